@@ -1,0 +1,593 @@
+// dpe_capi.cu — C-ABI layer (include/dpe_b200.h) over the sm_100a kernels: context,
+// scene-resident device state, per-stage orchestration.
+//
+// Where the reference rebuilds everything per (view, stage) — N+1 JPEG decodes, cv::resize,
+// 2(N+1) cudaMallocArray + texture objects, ~20 cudaMallocs, .dmb round trips
+// (DPE.cpp:733-1023, main.cpp:411-446) — this layer uploads a scene once: all pyramid
+// levels of all images as float textures + linear copies, cameras folded to per-pair
+// constants in double precision, prep arrays, and per-view PatchMatch state that never
+// leaves HBM between stages.  Source depth maps for geometric consistency live in one
+// "depth atlas" per scale ([slot][pixel] floats) so that a multi-GPU driver can all-gather
+// it in place.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include "dpe_kernels.cuh"
+#include "dpe_consts.h"
+
+using namespace dpe;
+
+namespace {
+
+struct ScaleImg {
+  float* lin = nullptr;          // W*H float
+  cudaArray_t arr = nullptr;
+  cudaTextureObject_t tex = 0;
+  uint8_t* edge = nullptr;       // edges_k (optional)
+  int32_t* label = nullptr;      // labels_k (optional)
+};
+
+struct ViewData {
+  HostCam cam;
+  bool have_img = false;
+  std::vector<int> src;
+  std::vector<ScaleImg> scales;
+  // state carried between stages (owner only)
+  float4* planes = nullptr;  // (world normal, depth)
+  uint8_t* state = nullptr;
+  uint32_t* selected = nullptr;
+  int cur_scale = -1;  // scale index of planes/state/selected
+  uint8_t* gray_full = nullptr;  // uploaded u8 image (device), freed after commit
+};
+
+struct Scratch {
+  float4* planes = nullptr; float* costs = nullptr; uint32_t* selected = nullptr; uint4* view_w = nullptr;
+  uint8_t* state = nullptr; float4* fit_planes = nullptr; int* radius = nullptr; short2* edge_neigh = nullptr;
+  float* complexity = nullptr; short2* label_boundary = nullptr; uint8_t* weak_reliable = nullptr;
+  short2* nearest_strong = nullptr; short2* neighbours = nullptr;
+  cudaStream_t stream = nullptr;
+};
+
+}  // namespace
+
+struct dpe_ctx {
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  long long launches = 0;
+  // scene
+  int n_views = 0, W = 0, H = 0, n_scales = 0;
+  std::vector<int> sw, sh;  // per scale index (0 = coarsest)
+  std::vector<ViewData> views;
+  bool committed = false;
+  // shard
+  int first_view = 0, n_local = 0, slots_per_rank = 0, n_ranks = 1;
+  // depth atlas per scale: front = committed (read by geom stages), back = being written
+  std::vector<float*> atlas_front, atlas_back;
+  int last_stage_scale = -1;
+  bool stage_pending = false;
+  // scratch
+  std::vector<Scratch> scratch;
+  uint8_t* zero_edge = nullptr;  // placeholder when no prep was supplied
+  int32_t* zero_label = nullptr;
+  unsigned long long* d_eval_units = nullptr;
+  bool count_evals = false;
+  double eval_units_total = 0.0;
+  double stage_ms = 0.0;
+  uint32_t stage_counter = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      char buf_[512];                                                                    \
+      snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      ctx->err = buf_;                                                                   \
+      return DPE_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define FAIL(code, msg) \
+  do { ctx->err = (msg); return (code); } while (0)
+
+static LaunchCfg cfg_of(dpe_ctx* ctx) { return LaunchCfg{ctx->num_sms, &ctx->launches}; }
+
+static void free_scene(dpe_ctx* ctx) {
+  for (auto& v : ctx->views) {
+    for (auto& s : v.scales) {
+      if (s.tex) cudaDestroyTextureObject(s.tex);
+      if (s.arr) cudaFreeArray(s.arr);
+      cudaFree(s.lin); cudaFree(s.edge); cudaFree(s.label);
+    }
+    cudaFree(v.planes); cudaFree(v.state); cudaFree(v.selected); cudaFree(v.gray_full);
+  }
+  ctx->views.clear();
+  for (auto p : ctx->atlas_front) cudaFree(p);
+  for (auto p : ctx->atlas_back) cudaFree(p);
+  ctx->atlas_front.clear(); ctx->atlas_back.clear();
+  for (auto& s : ctx->scratch) {
+    cudaFree(s.planes); cudaFree(s.costs); cudaFree(s.selected); cudaFree(s.view_w); cudaFree(s.state);
+    cudaFree(s.fit_planes); cudaFree(s.radius); cudaFree(s.edge_neigh); cudaFree(s.complexity);
+    cudaFree(s.label_boundary); cudaFree(s.weak_reliable); cudaFree(s.nearest_strong); cudaFree(s.neighbours);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  ctx->scratch.clear();
+  cudaFree(ctx->zero_edge); ctx->zero_edge = nullptr;
+  cudaFree(ctx->zero_label); ctx->zero_label = nullptr;
+  ctx->committed = false;
+}
+
+extern "C" {
+
+int dpe_ctx_create(dpe_ctx** out, int gpu_index) {
+  if (!out) return DPE_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return DPE_ERR_NO_DEVICE;
+  if (gpu_index < 0 || gpu_index >= n) return DPE_ERR_ARG;
+  if (cudaSetDevice(gpu_index) != cudaSuccess) return DPE_ERR_CUDA;
+  dpe_ctx* ctx = new dpe_ctx();
+  ctx->device = gpu_index;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, gpu_index) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
+  cudaMalloc(&ctx->d_eval_units, sizeof(unsigned long long));
+  cudaMemset(ctx->d_eval_units, 0, sizeof(unsigned long long));
+  *out = ctx;
+  return DPE_OK;
+}
+
+void dpe_ctx_destroy(dpe_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  free_scene(ctx);
+  cudaFree(ctx->d_eval_units);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  delete ctx;
+}
+
+const char* dpe_last_error(const dpe_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+long long dpe_kernel_launches(const dpe_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int dpe_scene_begin(dpe_ctx* ctx, int n_views, int width, int height, int n_scales) {
+  if (!ctx) return DPE_ERR_ARG;
+  if (n_views <= 0 || width <= 0 || height <= 0 || n_scales <= 0 || n_scales > 8) FAIL(DPE_ERR_ARG, "bad scene dimensions");
+  CK(cudaSetDevice(ctx->device));
+  free_scene(ctx);
+  ctx->n_views = n_views; ctx->W = width; ctx->H = height; ctx->n_scales = n_scales;
+  ctx->sw.assign(n_scales, 0); ctx->sh.assign(n_scales, 0);
+  for (int k = 0; k < n_scales; ++k) {
+    const int scale_size = 1 << (n_scales - 1 - k);
+    const float factor = 1.0f / (float)scale_size;  // DPE.cpp:800-802
+    ctx->sw[k] = (int)std::round(width * factor);
+    ctx->sh[k] = (int)std::round(height * factor);
+  }
+  ctx->views.assign(n_views, ViewData());
+  for (auto& v : ctx->views) v.scales.assign(n_scales, ScaleImg());
+  ctx->first_view = 0; ctx->n_local = n_views; ctx->slots_per_rank = n_views; ctx->n_ranks = 1;
+  ctx->stage_counter = 0; ctx->last_stage_scale = -1; ctx->stage_pending = false;
+  return DPE_OK;
+}
+
+int dpe_scene_set_view(dpe_ctx* ctx, int view, const uint8_t* gray, const float K[9], const float R[9],
+                       const float t[3], float depth_min, float depth_max) {
+  if (!ctx || view < 0 || view >= ctx->n_views || !gray || !K || !R || !t) return DPE_ERR_ARG;
+  if (ctx->committed) FAIL(DPE_ERR_STATE, "scene already committed");
+  CK(cudaSetDevice(ctx->device));
+  ViewData& v = ctx->views[view];
+  host_cam_set(&v.cam, K, R, t, depth_min, depth_max);
+  const size_t n = (size_t)ctx->W * ctx->H;
+  if (!v.gray_full) CK(cudaMalloc(&v.gray_full, n));
+  CK(cudaMemcpy(v.gray_full, gray, n, cudaMemcpyHostToDevice));
+  v.have_img = true;
+  return DPE_OK;
+}
+
+int dpe_scene_set_pairs(dpe_ctx* ctx, int view, const int* src_ids, int n_src) {
+  if (!ctx || view < 0 || view >= ctx->n_views || n_src < 0 || (n_src > 0 && !src_ids)) return DPE_ERR_ARG;
+  if (n_src > DPE_MAX_SRC) FAIL(DPE_ERR_TOO_MANY_IMAGES, "Can't process so much images");  // DPE.cpp:762-765
+  for (int i = 0; i < n_src; ++i)
+    if (src_ids[i] < 0 || src_ids[i] >= ctx->n_views) FAIL(DPE_ERR_ARG, "source id out of range");
+  ctx->views[view].src.assign(src_ids, src_ids + n_src);
+  return DPE_OK;
+}
+
+int dpe_scene_set_prep(dpe_ctx* ctx, int view, int scale, const uint8_t* edge, const int32_t* label) {
+  if (!ctx || view < 0 || view >= ctx->n_views || scale < 0 || scale >= ctx->n_scales) return DPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ScaleImg& s = ctx->views[view].scales[scale];
+  const size_t n = (size_t)ctx->sw[scale] * ctx->sh[scale];
+  if (edge) {
+    if (!s.edge) CK(cudaMalloc(&s.edge, n));
+    CK(cudaMemcpy(s.edge, edge, n, cudaMemcpyHostToDevice));
+  }
+  if (label) {
+    if (!s.label) CK(cudaMalloc(&s.label, n * sizeof(int32_t)));
+    CK(cudaMemcpy(s.label, label, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  return DPE_OK;
+}
+
+int dpe_scene_set_shard(dpe_ctx* ctx, int first_view, int count, int slots_per_rank, int n_ranks) {
+  if (!ctx || first_view < 0 || count < 0 || first_view + count > ctx->n_views || n_ranks < 1 ||
+      slots_per_rank * n_ranks < ctx->n_views)
+    return DPE_ERR_ARG;
+  if (ctx->committed) FAIL(DPE_ERR_STATE, "scene already committed");
+  ctx->first_view = first_view; ctx->n_local = count; ctx->slots_per_rank = slots_per_rank; ctx->n_ranks = n_ranks;
+  return DPE_OK;
+}
+
+int dpe_scene_commit(dpe_ctx* ctx) {
+  if (!ctx) return DPE_ERR_ARG;
+  if (ctx->committed) return DPE_OK;
+  CK(cudaSetDevice(ctx->device));
+  const LaunchCfg cfg = cfg_of(ctx);
+  const int top = ctx->n_scales - 1;
+  for (int vi = 0; vi < ctx->n_views; ++vi) {
+    ViewData& v = ctx->views[vi];
+    if (!v.have_img) FAIL(DPE_ERR_STATE, "view without image");
+    for (int k = 0; k < ctx->n_scales; ++k) {
+      ScaleImg& s = v.scales[k];
+      const int w = ctx->sw[k], h = ctx->sh[k];
+      CK(cudaMalloc(&s.lin, (size_t)w * h * sizeof(float)));
+    }
+    launch_u8_to_f32(v.gray_full, v.scales[top].lin, ctx->W * ctx->H, cfg, 0);
+    // every level is resized from the full-resolution image (DPE.cpp:798-820)
+    for (int k = 0; k < top; ++k)
+      launch_resize_linear(v.scales[top].lin, ctx->W, ctx->H, v.scales[k].lin, ctx->sw[k], ctx->sh[k], cfg, 0);
+    for (int k = 0; k < ctx->n_scales; ++k) {
+      ScaleImg& s = v.scales[k];
+      const int w = ctx->sw[k], h = ctx->sh[k];
+      cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+      CK(cudaMallocArray(&s.arr, &cd, w, h));
+      CK(cudaMemcpy2DToArrayAsync(s.arr, 0, 0, s.lin, (size_t)w * sizeof(float), (size_t)w * sizeof(float), h,
+                                  cudaMemcpyDeviceToDevice, 0));
+      cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+      rd.resType = cudaResourceTypeArray; rd.res.array.array = s.arr;
+      cudaTextureDesc td; memset(&td, 0, sizeof(td));
+      // the reference asks for Wrap with unnormalised coordinates, which CUDA turns into
+      // Clamp (DPE.cpp:929-933)
+      td.addressMode[0] = cudaAddressModeClamp; td.addressMode[1] = cudaAddressModeClamp;
+      td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+      CK(cudaCreateTextureObject(&s.tex, &rd, &td, nullptr));
+    }
+    CK(cudaFree(v.gray_full)); v.gray_full = nullptr;
+  }
+  // depth atlases
+  const int slots = ctx->slots_per_rank * ctx->n_ranks;
+  ctx->atlas_front.assign(ctx->n_scales, nullptr); ctx->atlas_back.assign(ctx->n_scales, nullptr);
+  for (int k = 0; k < ctx->n_scales; ++k) {
+    const size_t bytes = (size_t)slots * ctx->sw[k] * ctx->sh[k] * sizeof(float);
+    CK(cudaMalloc(&ctx->atlas_front[k], bytes)); CK(cudaMemset(ctx->atlas_front[k], 0, bytes));
+    CK(cudaMalloc(&ctx->atlas_back[k], bytes)); CK(cudaMemset(ctx->atlas_back[k], 0, bytes));
+  }
+  // scratch: one set per stream, sized for the finest scale
+  const size_t P = (size_t)ctx->W * ctx->H;
+  const int n_streams = 4;
+  ctx->scratch.assign(n_streams, Scratch());
+  for (auto& s : ctx->scratch) {
+    CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&s.planes, P * sizeof(float4))); CK(cudaMalloc(&s.costs, P * sizeof(float)));
+    CK(cudaMalloc(&s.selected, P * sizeof(uint32_t))); CK(cudaMalloc(&s.view_w, P * sizeof(uint4)));
+    CK(cudaMalloc(&s.state, P)); CK(cudaMalloc(&s.fit_planes, P * sizeof(float4)));
+    CK(cudaMalloc(&s.radius, P * sizeof(int))); CK(cudaMalloc(&s.edge_neigh, P * 8 * sizeof(short2)));
+    CK(cudaMalloc(&s.complexity, P * sizeof(float))); CK(cudaMalloc(&s.label_boundary, P * 8 * sizeof(short2)));
+    CK(cudaMalloc(&s.weak_reliable, P)); CK(cudaMalloc(&s.nearest_strong, P * sizeof(short2)));
+    CK(cudaMalloc(&s.neighbours, P * DPE_NEIGHBOUR_NUM * sizeof(short2)));
+    CK(cudaMemset(s.view_w, 0, P * sizeof(uint4)));
+    CK(cudaMemset(s.radius, 0, P * sizeof(int)));
+  }
+  CK(cudaMalloc(&ctx->zero_edge, P)); CK(cudaMemset(ctx->zero_edge, 0, P));
+  CK(cudaMalloc(&ctx->zero_label, P * sizeof(int32_t))); CK(cudaMemset(ctx->zero_label, 0xFF, P * sizeof(int32_t)));
+  CK(cudaDeviceSynchronize());
+  ctx->committed = true;
+  return DPE_OK;
+}
+
+}  // extern "C"
+
+static void build_ref_const(const dpe_ctx* ctx, int view, int k, bool geom, RefConst* rc) {
+  const ViewData& rv = ctx->views[view];
+  const int w = ctx->sw[k], h = ctx->sh[k];
+  fold_ref(rv.cam, w, h, ctx->W, ctx->H, view, rc);
+  rc->n_src = (int)rv.src.size();
+  const size_t P = (size_t)w * h;
+  for (int si = 0; si < rc->n_src; ++si) {
+    const int sv = rv.src[si];
+    SrcConst& sc = rc->src[si];
+    fold_pair(rv.cam, ctx->views[sv].cam, w, h, ctx->W, ctx->H, &sc);
+    sc.src_view = sv;
+    sc.tex = (unsigned long long)ctx->views[sv].scales[k].tex;
+    sc.depth = geom ? ctx->atlas_front[k] + (size_t)sv * P : nullptr;
+  }
+}
+
+static void fill_args(dpe_ctx* ctx, int view, int k, const dpe_stage_params* p, uint64_t seed, const Scratch& s,
+                      KernelParams* KP) {
+  memset(KP, 0, sizeof(*KP));
+  build_ref_const(ctx, view, k, p && p->geom_consistency, &KP->rc);
+  StageArgs& a = KP->a;
+  ViewData& v = ctx->views[view];
+  a.rc = nullptr;
+  a.ref_img = v.scales[k].lin;
+  a.W = ctx->sw[k]; a.H = ctx->sh[k];
+  a.planes = s.planes; a.costs = s.costs; a.selected = s.selected; a.view_w = s.view_w; a.state = s.state;
+  a.fit_planes = s.fit_planes; a.radius = s.radius;
+  a.edge = v.scales[k].edge ? v.scales[k].edge : ctx->zero_edge;
+  a.edge_low = v.scales[0].edge ? v.scales[0].edge : ctx->zero_edge;  // coarsest scale (DPE.cpp:1036-1045)
+  a.low_w = ctx->sw[0]; a.low_h = ctx->sh[0];
+  a.edge_neigh = s.edge_neigh; a.complexity = s.complexity;
+  a.label = v.scales[k].label ? v.scales[k].label : ctx->zero_label;
+  a.label_boundary = s.label_boundary; a.weak_reliable = s.weak_reliable; a.nearest_strong = s.nearest_strong;
+  a.neighbours = s.neighbours;
+  a.eval_units = ctx->count_evals ? ctx->d_eval_units : nullptr;
+  if (p) {
+    a.run_state = p->state; a.geom = p->geom_consistency; a.use_apd = p->use_apd; a.top_k = p->top_k;
+    a.weak_peak_radius = p->weak_peak_radius; a.rotate_time = p->rotate_time;
+    a.ransac_threshold = p->ransac_threshold; a.geom_factor = p->geom_factor;
+  }
+  // RNG key: depends only on (seed, view, stage index) so results do not depend on how
+  // views are scheduled over streams or GPUs
+  stage_key(seed, view, ctx->stage_counter, &a.key0, &a.key1);
+}
+
+extern "C" {
+
+int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed) {
+  if (!ctx || !p || k < 0 || k >= ctx->n_scales) return DPE_ERR_ARG;
+  if (!ctx->committed) FAIL(DPE_ERR_STATE, "scene not committed");
+  if (ctx->stage_pending) FAIL(DPE_ERR_STATE, "previous stage not committed (dpe_stage_commit)");
+  CK(cudaSetDevice(ctx->device));
+  const LaunchCfg cfg = cfg_of(ctx);
+  const size_t P = (size_t)ctx->sw[k] * ctx->sh[k];
+  const int ns = (int)ctx->scratch.size();
+  CK(cudaEventRecord(ctx->ev0, 0));
+  for (auto& s : ctx->scratch) CK(cudaStreamWaitEvent(s.stream, ctx->ev0, 0));
+  std::vector<cudaEvent_t> done(ns, nullptr);
+  std::vector<void*> to_free;  // previous-scale maps, released once the stage has drained
+  for (int li = 0; li < ctx->n_local; ++li) {
+    const int view = ctx->first_view + li;
+    ViewData& v = ctx->views[view];
+    if (p->state != DPE_FIRST_INIT && v.cur_scale < 0) FAIL(DPE_ERR_STATE, "refine stage before first init");
+    Scratch& s = ctx->scratch[li % ns];
+    KernelParams KP;
+    fill_args(ctx, view, k, p, seed, s, &KP);
+    StageArgs& a = KP.a;
+    // outputs: new buffers when the scale changes, in place otherwise
+    float4* new_planes = v.planes; uint8_t* new_state = v.state; uint32_t* new_sel = v.selected;
+    const bool realloc = (v.cur_scale != k);
+    if (realloc) {
+      CK(cudaMalloc(&new_planes, P * sizeof(float4))); CK(cudaMalloc(&new_state, P));
+      CK(cudaMalloc(&new_sel, P * sizeof(uint32_t)));
+    }
+    a.prev_planes = v.planes; a.prev_state = v.state; a.prev_selected = v.selected;
+    a.prev_W = v.cur_scale >= 0 ? ctx->sw[v.cur_scale] : a.W;
+    a.prev_H = v.cur_scale >= 0 ? ctx->sh[v.cur_scale] : a.H;
+    a.out_planes = new_planes; a.out_state = new_state; a.out_selected = new_sel;
+    a.atlas_out = ctx->atlas_back[k] + (size_t)view * P;
+
+    cudaStream_t st = s.stream;
+    if (p->state != DPE_FIRST_INIT) launch_load(KP, cfg, st);
+    if (p->use_apd) {
+      launch_edge_info(KP, cfg, st);
+      launch_nearest_strong(KP, cfg, st);
+      launch_gen_neighbours(KP, cfg, st);
+    }
+    launch_init(KP, cfg, st);
+    for (int it = 0; it < p->max_iterations; ++it) {
+      a.iter = it;
+      a.colour = 0; launch_strong(KP, cfg, st);
+      a.colour = 1; launch_strong(KP, cfg, st);
+      if (p->use_apd) {
+        launch_fit_plane(KP, cfg, st);
+        a.colour = 0; launch_weak(KP, cfg, st);
+        a.colour = 1; launch_weak(KP, cfg, st);
+      }
+    }
+    launch_extract(KP, cfg, st);
+    a.colour = 0; launch_median(KP, cfg, st);
+    a.colour = 1; launch_median(KP, cfg, st);
+    launch_classify_refine(KP, cfg, st);
+    launch_finish(KP, cfg, st);
+    if (realloc) {
+      to_free.push_back(v.planes); to_free.push_back(v.state); to_free.push_back(v.selected);
+      v.planes = new_planes; v.state = new_state; v.selected = new_sel; v.cur_scale = k;
+    }
+  }
+  CK(cudaGetLastError());
+  for (int i = 0; i < ns; ++i) {
+    CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    CK(cudaEventRecord(done[i], ctx->scratch[i].stream));
+    CK(cudaStreamWaitEvent(0, done[i], 0));
+  }
+  CK(cudaEventRecord(ctx->ev1, 0));
+  CK(cudaEventSynchronize(ctx->ev1));
+  for (int i = 0; i < ns; ++i) cudaEventDestroy(done[i]);
+  for (void* p_ : to_free) cudaFree(p_);
+  CK(cudaGetLastError());
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->stage_ms += ms;
+  ctx->stage_counter++;
+  ctx->last_stage_scale = k;
+  ctx->stage_pending = true;
+  return DPE_OK;
+}
+
+int dpe_stage_atlas(dpe_ctx* ctx, void** dev_ptr, size_t* chunk_bytes, size_t* total_bytes) {
+  if (!ctx || ctx->last_stage_scale < 0) return DPE_ERR_ARG;
+  const int k = ctx->last_stage_scale;
+  const size_t P = (size_t)ctx->sw[k] * ctx->sh[k];
+  if (dev_ptr) *dev_ptr = ctx->atlas_back[k];
+  if (chunk_bytes) *chunk_bytes = (size_t)ctx->slots_per_rank * P * sizeof(float);
+  if (total_bytes) *total_bytes = (size_t)ctx->slots_per_rank * ctx->n_ranks * P * sizeof(float);
+  return DPE_OK;
+}
+
+int dpe_stage_commit(dpe_ctx* ctx) {
+  if (!ctx) return DPE_ERR_ARG;
+  if (!ctx->stage_pending) return DPE_OK;
+  const int k = ctx->last_stage_scale;
+  std::swap(ctx->atlas_front[k], ctx->atlas_back[k]);
+  ctx->stage_pending = false;
+  return DPE_OK;
+}
+
+int dpe_cost_eval(dpe_ctx* ctx, int view, int k, int n_pix, const int* xy, const float* planes, int mode, float* out) {
+  if (!ctx || view < 0 || view >= ctx->n_views || k < 0 || k >= ctx->n_scales || n_pix <= 0 || !xy || !planes || !out)
+    return DPE_ERR_ARG;
+  if (!ctx->committed) FAIL(DPE_ERR_STATE, "scene not committed");
+  CK(cudaSetDevice(ctx->device));
+  KernelParams KP;
+  fill_args(ctx, view, k, nullptr, 0, ctx->scratch[0], &KP);
+  const int N = KP.rc.n_src;
+  int* d_xy; float4* d_pl; float* d_out;
+  CK(cudaMalloc(&d_xy, (size_t)n_pix * 2 * sizeof(int))); CK(cudaMalloc(&d_pl, (size_t)n_pix * sizeof(float4)));
+  CK(cudaMalloc(&d_out, (size_t)n_pix * N * sizeof(float)));
+  CK(cudaMemcpy(d_xy, xy, (size_t)n_pix * 2 * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_pl, planes, (size_t)n_pix * sizeof(float4), cudaMemcpyHostToDevice));
+  launch_cost_eval(KP, n_pix, d_xy, d_pl, mode, 0ull, d_out, cfg_of(ctx), 0);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, d_out, (size_t)n_pix * N * sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(d_xy); cudaFree(d_pl); cudaFree(d_out);
+  return DPE_OK;
+}
+
+int dpe_geom_eval(dpe_ctx* ctx, int view, int k, int n_pix, const int* xy, const float* planes, float* out) {
+  if (!ctx || view < 0 || view >= ctx->n_views || k < 0 || k >= ctx->n_scales || n_pix <= 0 || !xy || !planes || !out)
+    return DPE_ERR_ARG;
+  if (!ctx->committed) FAIL(DPE_ERR_STATE, "scene not committed");
+  CK(cudaSetDevice(ctx->device));
+  dpe_stage_params p; memset(&p, 0, sizeof(p)); p.geom_consistency = 1;
+  KernelParams KP;
+  fill_args(ctx, view, k, &p, 0, ctx->scratch[0], &KP);
+  const int N = KP.rc.n_src;
+  int* d_xy; float4* d_pl; float* d_out;
+  CK(cudaMalloc(&d_xy, (size_t)n_pix * 2 * sizeof(int))); CK(cudaMalloc(&d_pl, (size_t)n_pix * sizeof(float4)));
+  CK(cudaMalloc(&d_out, (size_t)n_pix * N * sizeof(float)));
+  CK(cudaMemcpy(d_xy, xy, (size_t)n_pix * 2 * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_pl, planes, (size_t)n_pix * sizeof(float4), cudaMemcpyHostToDevice));
+  launch_geom_eval(KP, n_pix, d_xy, d_pl, d_out, cfg_of(ctx), 0);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, d_out, (size_t)n_pix * N * sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(d_xy); cudaFree(d_pl); cudaFree(d_out);
+  return DPE_OK;
+}
+
+int dpe_get_size(dpe_ctx* ctx, int k, int* width, int* height) {
+  if (!ctx || k < 0 || k >= ctx->n_scales) return DPE_ERR_ARG;
+  if (width) *width = ctx->sw[k];
+  if (height) *height = ctx->sh[k];
+  return DPE_OK;
+}
+
+int dpe_get_maps(dpe_ctx* ctx, int view, float* depth, float* normal3, uint8_t* state, uint32_t* selected) {
+  if (!ctx || view < 0 || view >= ctx->n_views) return DPE_ERR_ARG;
+  ViewData& v = ctx->views[view];
+  if (v.cur_scale < 0 || !v.planes) FAIL(DPE_ERR_STATE, "view has no result on this context");
+  CK(cudaSetDevice(ctx->device));
+  const size_t P = (size_t)ctx->sw[v.cur_scale] * ctx->sh[v.cur_scale];
+  if (depth || normal3) {
+    std::vector<float4> h(P);
+    CK(cudaMemcpy(h.data(), v.planes, P * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < P; ++i) {
+      if (depth) depth[i] = h[i].w;
+      if (normal3) { normal3[3 * i] = h[i].x; normal3[3 * i + 1] = h[i].y; normal3[3 * i + 2] = h[i].z; }
+    }
+  }
+  if (state) CK(cudaMemcpy(state, v.state, P, cudaMemcpyDeviceToHost));
+  if (selected) CK(cudaMemcpy(selected, v.selected, P * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return DPE_OK;
+}
+
+int dpe_set_count_evals(dpe_ctx* ctx, int on) {
+  if (!ctx) return DPE_ERR_ARG;
+  ctx->count_evals = on != 0;
+  return DPE_OK;
+}
+
+double dpe_eval_units(dpe_ctx* ctx) {
+  if (!ctx) return 0.0;
+  cudaSetDevice(ctx->device);
+  unsigned long long h = 0;
+  if (cudaMemcpy(&h, ctx->d_eval_units, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return -1.0;
+  return (double)h;
+}
+
+double dpe_stage_gpu_ms(dpe_ctx* ctx) { return ctx ? ctx->stage_ms : 0.0; }
+
+int dpe_probe_tex_rate(dpe_ctx* ctx, int width, int height, int iters, double* taps_per_s) {
+  if (!ctx || width < 64 || height < 64 || iters <= 0 || !taps_per_s) return DPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  std::vector<float> h((size_t)width * height);
+  uint32_t s = 12345u;
+  for (auto& x : h) { s = s * 1664525u + 1013904223u; x = (float)(s >> 24); }
+  cudaArray_t arr; cudaTextureObject_t tex;
+  cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+  CK(cudaMallocArray(&arr, &cd, width, height));
+  CK(cudaMemcpy2DToArray(arr, 0, 0, h.data(), (size_t)width * 4, (size_t)width * 4, height, cudaMemcpyHostToDevice));
+  cudaResourceDesc rd; memset(&rd, 0, sizeof(rd)); rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+  cudaTextureDesc td; memset(&td, 0, sizeof(td));
+  td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp; td.filterMode = cudaFilterModeLinear;
+  td.readMode = cudaReadModeElementType;
+  CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+  float* sink; CK(cudaMalloc(&sink, 4));
+  const int blocks = ctx->num_sms * 8, threads = 256;
+  const LaunchCfg cfg = cfg_of(ctx);
+  launch_probe_tex((unsigned long long)tex, width, height, iters / 4 + 1, sink, blocks, threads, cfg, 0);  // warm-up
+  CK(cudaEventRecord(ctx->ev0, 0));
+  launch_probe_tex((unsigned long long)tex, width, height, iters, sink, blocks, threads, cfg, 0);
+  CK(cudaEventRecord(ctx->ev1, 0));
+  CK(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *taps_per_s = (double)blocks * threads * (double)iters * 36.0 / (ms * 1e-3);
+  cudaFree(sink); cudaDestroyTextureObject(tex); cudaFreeArray(arr);
+  return DPE_OK;
+}
+
+int dpe_probe_fma_rate(dpe_ctx* ctx, int iters, double* fma_per_s) {
+  if (!ctx || iters <= 0 || !fma_per_s) return DPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  float* sink; CK(cudaMalloc(&sink, 4));
+  const int blocks = ctx->num_sms * 8, threads = 256;
+  const LaunchCfg cfg = cfg_of(ctx);
+  launch_probe_fma(iters / 4 + 1, sink, blocks, threads, cfg, 0);
+  CK(cudaEventRecord(ctx->ev0, 0));
+  launch_probe_fma(iters, sink, blocks, threads, cfg, 0);
+  CK(cudaEventRecord(ctx->ev1, 0));
+  CK(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *fma_per_s = (double)blocks * threads * (double)iters * 128.0 / (ms * 1e-3);
+  cudaFree(sink);
+  return DPE_OK;
+}
+
+int dpe_probe_tex_weights(dpe_ctx* ctx, int n, float* weights) {
+  if (!ctx || n <= 0 || !weights) return DPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const float h[2] = {0.f, 1.f};
+  cudaArray_t arr; cudaTextureObject_t tex;
+  cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+  CK(cudaMallocArray(&arr, &cd, 2, 1));
+  CK(cudaMemcpy2DToArray(arr, 0, 0, h, 8, 8, 1, cudaMemcpyHostToDevice));
+  cudaResourceDesc rd; memset(&rd, 0, sizeof(rd)); rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+  cudaTextureDesc td; memset(&td, 0, sizeof(td));
+  td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp; td.filterMode = cudaFilterModeLinear;
+  td.readMode = cudaReadModeElementType;
+  CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+  float* d; CK(cudaMalloc(&d, (size_t)(n + 1) * 4));
+  launch_probe_weights((unsigned long long)tex, n, d, cfg_of(ctx), 0);
+  CK(cudaMemcpy(weights, d, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost));
+  cudaFree(d); cudaDestroyTextureObject(tex); cudaFreeArray(arr);
+  return DPE_OK;
+}
+
+}  // extern "C"

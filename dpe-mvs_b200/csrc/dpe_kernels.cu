@@ -1,0 +1,395 @@
+// dpe_kernels.cu — hand-written sm_100a kernels of the PatchMatch path.
+//
+// Kernel shape:
+//  * every image-space kernel is persistent: grid = #SMs x resident CTAs, each CTA loops
+//    over 32-wide pixel tiles;
+//  * per tile the reference-image window (tile + 5-pixel halo) is staged into shared
+//    memory with cp.async, and each thread derives the 36 hypothesis-invariant
+//    (weight, weight*ref) pairs of its pixel from it ONCE into a [tap][thread] shared
+//    table — the reference recomputes them (exp + sqrt + ref fetch per tap) for every one
+//    of the ~100 (hypothesis, view) evaluations a pixel makes per sweep;
+//  * per (hypothesis, view) the homography is 9 FMAs in registers (A - b m^T, with A and b
+//    in the constant bank via a __grid_constant__ parameter block), the 36 source taps go
+//    through the texture unit's bilinear filter, and the three moment sums are FMAs;
+//  * red/black sweeps read only the other colour, so a sweep is race-free and
+//    deterministic.
+#include <cuda_pipeline.h>
+#include "dpe_core.cuh"
+#include "dpe_weak.cuh"
+#include "dpe_kernels.cuh"
+
+namespace dpe {
+
+constexpr int NT = 128;      // threads per CTA
+constexpr int TILE_W = 32;
+constexpr int HALO = 5;
+constexpr int SMW = TILE_W + 2 * HALO;  // 42
+
+struct DevEnv {
+  const float2* tbl;  // &table[threadIdx.x]; tap t lives at tbl[t * NT]
+  const float* img;   // reference image (for the far-away anchor patches of the weak path)
+  int W, H;
+  __device__ __forceinline__ float ref(int x, int y) const {
+    return __ldg(&img[(size_t)iclamp(y, 0, H - 1) * W + iclamp(x, 0, W - 1)]);
+  }
+  __device__ __forceinline__ float tex(unsigned long long h, float u, float v) const {
+    return tex2D<float>((cudaTextureObject_t)h, u, v);
+  }
+  __device__ __forceinline__ float2 pw(int t) const { return tbl[t * NT]; }
+};
+
+// reference-image window in shared memory; clamp addressing reproduces the reference's
+// exact-texel tex2D fetches at image borders
+template <int TILE_H>
+struct RefTile {
+  static constexpr int SMH = TILE_H + 2 * HALO;
+  float* s;
+  int x0, y0;
+  __device__ __forceinline__ void stage(const float* __restrict__ img, int W, int H, int tx0, int ty0) {
+    x0 = tx0; y0 = ty0;
+    for (int i = threadIdx.x; i < SMW * SMH; i += NT) {
+      const int gx = iclamp(tx0 - HALO + (i % SMW), 0, W - 1);
+      const int gy = iclamp(ty0 - HALO + (i / SMW), 0, H - 1);
+      __pipeline_memcpy_async(&s[i], &img[(size_t)gy * W + gx], sizeof(float));
+    }
+    __pipeline_commit();
+  }
+  __device__ __forceinline__ float operator()(int x, int y) const {
+    return s[(y - y0 + HALO) * SMW + (x - x0 + HALO)];
+  }
+};
+
+struct TblStore {
+  float2* tbl;
+  __device__ __forceinline__ void operator()(int t, float w, float wr) const { tbl[t * NT] = make_float2(w, wr); }
+};
+
+__device__ __forceinline__ void flush_evals(unsigned long long* counter, unsigned evals) {
+  if (counter == nullptr) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) evals += __shfl_down_sync(0xffffffffu, evals, o);
+  if ((threadIdx.x & 31) == 0 && evals) atomicAdd(counter, (unsigned long long)evals);
+}
+
+// ---- full-image kernels: tile = 32 x 4 pixels, one thread per pixel ---------------------
+enum FullOp { OP_INIT = 0, OP_CLASSIFY = 1 };
+
+template <int OP>
+__global__ void __launch_bounds__(NT, 4) k_full(const __grid_constant__ KernelParams P) {
+  __shared__ float2 s_tbl[36 * NT];
+  __shared__ float s_tile[SMW * (4 + 2 * HALO)];
+  StageArgs a = P.a;
+  a.rc = &P.rc;
+  const int n_tiles = a.tiles_x * a.tiles_y;
+  unsigned evals = 0;
+  RefTile<4> tile;
+  tile.s = s_tile;
+  DevEnv env;
+  env.tbl = s_tbl + threadIdx.x;
+  env.img = a.ref_img; env.W = a.W; env.H = a.H;
+  TblStore st;
+  st.tbl = s_tbl + threadIdx.x;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int tx0 = (t % a.tiles_x) * TILE_W, ty0 = (t / a.tiles_x) * 4;
+    __syncthreads();
+    tile.stage(a.ref_img, a.W, a.H, tx0, ty0);
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    const int x = tx0 + (threadIdx.x & 31), y = ty0 + (threadIdx.x >> 5);
+    if (x < a.W && y < a.H) {
+      const PatchStats ps = build_patch(tile, x, y, st);
+      if (OP == OP_INIT) init_pixel(env, ps, a, x, y, evals);
+      else classify_refine_pixel(env, ps, a, x, y, evals);
+    }
+  }
+  flush_evals(a.eval_units, evals);
+}
+
+// ---- red/black half sweeps: tile = 32 x 8 pixels, one thread per pixel of one colour ----
+enum HalfOp { OP_STRONG = 0, OP_STRONG_EDGE = 1, OP_WEAK = 2 };
+
+template <int OP>
+__global__ void __launch_bounds__(NT, 4) k_half(const __grid_constant__ KernelParams P) {
+  __shared__ float2 s_tbl[36 * NT];
+  __shared__ float s_tile[SMW * (8 + 2 * HALO)];
+  StageArgs a = P.a;
+  a.rc = &P.rc;
+  const int n_tiles = a.tiles_x * a.tiles_y;
+  unsigned evals = 0;
+  RefTile<8> tile;
+  tile.s = s_tile;
+  DevEnv env;
+  env.tbl = s_tbl + threadIdx.x;
+  env.img = a.ref_img; env.W = a.W; env.H = a.H;
+  TblStore st;
+  st.tbl = s_tbl + threadIdx.x;
+  float cost_arr[9 * DPE_MAX_IMAGES];
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int tx0 = (t % a.tiles_x) * TILE_W, ty0 = (t / a.tiles_x) * 8;
+    __syncthreads();
+    tile.stage(a.ref_img, a.W, a.H, tx0, ty0);
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    const int lx = threadIdx.x & 31;
+    const int x = tx0 + lx, y = ty0 + 2 * (threadIdx.x >> 5) + ((lx + a.colour) & 1);
+    if (x < a.W && y < a.H) {
+      const bool weak = a.state[y * a.W + x] == DPE_WEAK;
+      if (OP == OP_WEAK) {
+        if (weak) {
+          const PatchStats ps = build_patch(tile, x, y, st);
+          weak_update_pixel(env, ps, a, x, y, cost_arr, evals);
+        }
+      } else if (!weak) {
+        const PatchStats ps = build_patch(tile, x, y, st);
+        strong_update_pixel<OP == OP_STRONG_EDGE>(env, ps, a, x, y, cost_arr, evals);
+      }
+    }
+  }
+  flush_evals(a.eval_units, evals);
+}
+
+// ---- light per-pixel kernels ------------------------------------------------------------
+enum LightOp { L_EXTRACT = 0, L_MEDIAN = 1, L_FINISH = 2, L_EDGE_INFO = 3, L_NEAREST = 4, L_NEIGH = 5, L_FIT = 6, L_LOAD = 7 };
+
+template <int OP>
+__global__ void __launch_bounds__(256) k_light(const __grid_constant__ KernelParams P) {
+  StageArgs a = P.a;
+  a.rc = &P.rc;
+  const int total = (OP == L_MEDIAN) ? a.W * ((a.H + 1) / 2) : a.W * a.H;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int x, y;
+    if (OP == L_MEDIAN) {
+      x = i % a.W;
+      y = 2 * (i / a.W) + ((x + a.colour) & 1);
+      if (y >= a.H) continue;
+      if (a.state[y * a.W + x] == DPE_WEAK) continue;  // DPE.cu:2081
+    } else {
+      x = i % a.W;
+      y = i / a.W;
+    }
+    if (OP == L_EXTRACT) extract_pixel(a, x, y);
+    else if (OP == L_MEDIAN) median_pixel(a, x, y);
+    else if (OP == L_FINISH) finish_pixel(a, x, y);
+    else if (OP == L_EDGE_INFO) edge_info_pixel(a, x, y);
+    else if (OP == L_NEAREST) nearest_strong_pixel(a, x, y);
+    else if (OP == L_NEIGH) gen_neighbours_pixel(a, x, y);
+    else if (OP == L_FIT) fit_plane_pixel(a, x, y);
+    else if (OP == L_LOAD) load_pixel(a, x, y);
+  }
+}
+
+// ---- launchers -----------------------------------------------------------------------------
+static inline int persistent_grid(int n_tiles, int num_sms, int per_sm) {
+  const int g = num_sms * per_sm;
+  return n_tiles < g ? (n_tiles > 0 ? n_tiles : 1) : g;
+}
+static inline void count(const LaunchCfg& cfg) {
+  if (cfg.launch_counter) ++*cfg.launch_counter;
+}
+
+void launch_init(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t stream) {
+  KernelParams P = P0;
+  P.a.tiles_x = (P.a.W + TILE_W - 1) / TILE_W;
+  P.a.tiles_y = (P.a.H + 3) / 4;
+  k_full<OP_INIT><<<persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, 4), NT, 0, stream>>>(P);
+  count(cfg);
+}
+void launch_classify_refine(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t stream) {
+  KernelParams P = P0;
+  P.a.tiles_x = (P.a.W + TILE_W - 1) / TILE_W;
+  P.a.tiles_y = (P.a.H + 3) / 4;
+  k_full<OP_CLASSIFY><<<persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, 4), NT, 0, stream>>>(P);
+  count(cfg);
+}
+void launch_strong(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t stream) {
+  KernelParams P = P0;
+  P.a.tiles_x = (P.a.W + TILE_W - 1) / TILE_W;
+  P.a.tiles_y = (P.a.H + 7) / 8;
+  const int g = persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, 4);
+  if (P.a.use_apd) k_half<OP_STRONG_EDGE><<<g, NT, 0, stream>>>(P);
+  else k_half<OP_STRONG><<<g, NT, 0, stream>>>(P);
+  count(cfg);
+}
+void launch_weak(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t stream) {
+  KernelParams P = P0;
+  P.a.tiles_x = (P.a.W + TILE_W - 1) / TILE_W;
+  P.a.tiles_y = (P.a.H + 7) / 8;
+  const int g = persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, 4);
+  k_half<OP_WEAK><<<g, NT, 0, stream>>>(P);
+  count(cfg);
+}
+template <int OP>
+static void launch_light(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream) {
+  k_light<OP><<<cfg.num_sms * 8, 256, 0, stream>>>(P);
+  count(cfg);
+}
+void launch_extract(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_EXTRACT>(P, cfg, s); }
+void launch_median(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_MEDIAN>(P, cfg, s); }
+void launch_finish(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_FINISH>(P, cfg, s); }
+void launch_edge_info(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_EDGE_INFO>(P, cfg, s); }
+void launch_nearest_strong(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_NEAREST>(P, cfg, s); }
+void launch_gen_neighbours(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_NEIGH>(P, cfg, s); }
+void launch_fit_plane(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_FIT>(P, cfg, s); }
+void launch_load(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_LOAD>(P, cfg, s); }
+
+// ---- scene preparation ---------------------------------------------------------------------
+__global__ void k_u8_to_f32(const uint8_t* __restrict__ src, float* __restrict__ dst, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = (float)src[i];
+}
+void launch_u8_to_f32(const uint8_t* src, float* dst, int n, const LaunchCfg& cfg, cudaStream_t stream) {
+  k_u8_to_f32<<<cfg.num_sms * 8, 256, 0, stream>>>(src, dst, n);
+  count(cfg);
+}
+
+// cv::resize INTER_LINEAR for CV_32FC1: source coordinate (d + 0.5) * scale - 0.5 with
+// scale = src/dst computed in double, floor, clamp of the tap index at the borders,
+// horizontal then vertical blend in float (the order OpenCV's separable resize uses).
+__global__ void k_resize_linear(const float* __restrict__ src, int sw, int sh, float* __restrict__ dst, int dw,
+                                int dh) {
+  const double scale_x = (double)sw / dw, scale_y = (double)sh / dh;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dw * dh; i += gridDim.x * blockDim.x) {
+    const int dx = i % dw, dy = i / dw;
+    float fx = (float)((dx + 0.5) * scale_x - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= sx;
+    if (sx < 0) { fx = 0.f; sx = 0; }
+    if (sx >= sw - 1) { fx = 0.f; sx = sw - 1; }
+    float fy = (float)((dy + 0.5) * scale_y - 0.5);
+    int sy = (int)floorf(fy);
+    fy -= sy;
+    if (sy < 0) { fy = 0.f; sy = 0; }
+    if (sy >= sh - 1) { fy = 0.f; sy = sh - 1; }
+    const int sx1 = imin(sx + 1, sw - 1), sy1 = imin(sy + 1, sh - 1);
+    const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
+    const float r0 = src[(size_t)sy * sw + sx] * a0 + src[(size_t)sy * sw + sx1] * a1;
+    const float r1 = src[(size_t)sy1 * sw + sx] * a0 + src[(size_t)sy1 * sw + sx1] * a1;
+    dst[i] = r0 * b0 + r1 * b1;
+  }
+}
+void launch_resize_linear(const float* src, int sw, int sh, float* dst, int dw, int dh, const LaunchCfg& cfg,
+                          cudaStream_t stream) {
+  k_resize_linear<<<cfg.num_sms * 8, 256, 0, stream>>>(src, sw, sh, dst, dw, dh);
+  count(cfg);
+}
+
+// ---- gate-1 hooks ---------------------------------------------------------------------------
+// mode 0: the product path (shared patch table + hardware bilinear).  mode 1: same
+// arithmetic, but each source tap is an exact fp32 bilinear blend of 4 point-sampled
+// texels (texture `point_tex` array is not needed: tex2Dgather is not available for
+// float textures with linear filtering, so the 4 taps are fetched at texel centres, where
+// the linear filter returns the texel itself).
+struct DevEnvExact {
+  const float2* tbl;
+  __device__ __forceinline__ float tex(unsigned long long h, float u, float v) const {
+    const float xb = u - 0.5f, yb = v - 0.5f;
+    const float fx0 = floorf(xb), fy0 = floorf(yb);
+    const float ax = xb - fx0, ay = yb - fy0;
+    const cudaTextureObject_t t = (cudaTextureObject_t)h;
+    const float t00 = tex2D<float>(t, fx0 + 0.5f, fy0 + 0.5f), t10 = tex2D<float>(t, fx0 + 1.5f, fy0 + 0.5f);
+    const float t01 = tex2D<float>(t, fx0 + 0.5f, fy0 + 1.5f), t11 = tex2D<float>(t, fx0 + 1.5f, fy0 + 1.5f);
+    return (1.f - ay) * ((1.f - ax) * t00 + ax * t10) + ay * ((1.f - ax) * t01 + ax * t11);
+  }
+  __device__ __forceinline__ float2 pw(int t) const { return tbl[t * NT]; }
+};
+
+struct GlobalRef {
+  const float* img;
+  int W, H;
+  __device__ __forceinline__ float operator()(int x, int y) const {
+    return img[(size_t)iclamp(y, 0, H - 1) * W + iclamp(x, 0, W - 1)];
+  }
+};
+
+__global__ void __launch_bounds__(NT) k_cost_eval(const __grid_constant__ KernelParams P, int n_pix,
+                                                  const int* __restrict__ xy, const float4* __restrict__ planes,
+                                                  int mode, float* __restrict__ out) {
+  __shared__ float2 s_tbl[36 * NT];
+  const RefConst& rc = P.rc;
+  const int i = blockIdx.x * NT + threadIdx.x;
+  if (i >= n_pix) return;
+  const int x = xy[2 * i], y = xy[2 * i + 1];
+  GlobalRef ref{P.a.ref_img, P.a.W, P.a.H};
+  TblStore st{s_tbl + threadIdx.x};
+  const PatchStats ps = build_patch(ref, x, y, st);
+  const float3 m = plane_to_m(rc, planes[i]);
+  if (mode == 0) {
+    DevEnv env{s_tbl + threadIdx.x, P.a.ref_img, P.a.W, P.a.H};
+    for (int v = 0; v < rc.n_src; ++v) out[(size_t)i * rc.n_src + v] = ncc_old(env, ps, rc.src[v], m, x, y);
+  } else {
+    DevEnvExact env{s_tbl + threadIdx.x};
+    for (int v = 0; v < rc.n_src; ++v) out[(size_t)i * rc.n_src + v] = ncc_old(env, ps, rc.src[v], m, x, y);
+  }
+}
+void launch_cost_eval(const KernelParams& P, int n_pix, const int* xy, const float4* planes, int mode,
+                      unsigned long long, float* out, const LaunchCfg& cfg, cudaStream_t stream) {
+  k_cost_eval<<<(n_pix + NT - 1) / NT, NT, 0, stream>>>(P, n_pix, xy, planes, mode, out);
+  count(cfg);
+}
+
+__global__ void k_geom_eval(const __grid_constant__ KernelParams P, int n_pix, const int* __restrict__ xy,
+                            const float4* __restrict__ planes, float* __restrict__ out) {
+  const RefConst& rc = P.rc;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pix) return;
+  for (int v = 0; v < rc.n_src; ++v)
+    out[(size_t)i * rc.n_src + v] = geom_cost(rc, rc.src[v], planes[i], xy[2 * i], xy[2 * i + 1]);
+}
+void launch_geom_eval(const KernelParams& P, int n_pix, const int* xy, const float4* planes, float* out,
+                      const LaunchCfg& cfg, cudaStream_t stream) {
+  k_geom_eval<<<(n_pix + 127) / 128, 128, 0, stream>>>(P, n_pix, xy, planes, out);
+  count(cfg);
+}
+
+// ---- micro-benchmarks (roofline denominators) ----------------------------------------------
+// Filtered fetch rate with an access pattern like the NCC's: each lane walks a 6x6 tap
+// grid with ~1-pixel steps around a base that differs by one pixel between lanes.
+__global__ void k_probe_tex(cudaTextureObject_t tex, int w, int h, int iters, float* sink) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  float bx = (float)((gid * 1) % (w - 16)) + 0.37f;
+  float by = (float)(((gid / 32) * 2) % (h - 16)) + 0.61f;
+  float acc = 0.f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+      for (int i = 0; i < 6; ++i) acc += tex2D<float>(tex, bx + 1.93f * i, by + 1.97f * j);
+    bx += 0.11f; by += 0.07f;
+    if (bx > w - 16) bx -= (w - 32);
+    if (by > h - 16) by -= (h - 32);
+  }
+  if (acc == 1234.5678f) sink[0] = acc;
+}
+void launch_probe_tex(unsigned long long tex, int w, int h, int iters, float* sink, int blocks, int threads,
+                      const LaunchCfg& cfg, cudaStream_t stream) {
+  k_probe_tex<<<blocks, threads, 0, stream>>>((cudaTextureObject_t)tex, w, h, iters, sink);
+  count(cfg);
+}
+__global__ void k_probe_fma(int iters, float* sink) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+  float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float b = 1.000001f, c = 1e-7f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+      a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+    }
+  }
+  const float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 1234.5678f) sink[0] = s;
+}
+void launch_probe_fma(int iters, float* sink, int blocks, int threads, const LaunchCfg& cfg, cudaStream_t stream) {
+  k_probe_fma<<<blocks, threads, 0, stream>>>(iters, sink);
+  count(cfg);
+}
+// texture is 2x1: texel 0 = 0.0, texel 1 = 1.0; sample at x = 0.5 + i/n
+__global__ void k_probe_weights(cudaTextureObject_t tex, int n, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n) out[i] = tex2D<float>(tex, 0.5f + (float)i / (float)n, 0.5f);
+}
+void launch_probe_weights(unsigned long long tex, int n, float* out, const LaunchCfg& cfg, cudaStream_t stream) {
+  k_probe_weights<<<(n + 256) / 256, 256, 0, stream>>>((cudaTextureObject_t)tex, n, out);
+  count(cfg);
+}
+
+}  // namespace dpe

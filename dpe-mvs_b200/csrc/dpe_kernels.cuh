@@ -1,0 +1,52 @@
+// dpe_kernels.cuh — launch interface between the C-ABI layer (dpe_capi.cu) and the
+// sm_100a kernels (dpe_kernels.cu).
+#pragma once
+#include "dpe_types.h"
+
+namespace dpe {
+
+struct KernelParams {
+  StageArgs a;
+  RefConst rc;
+};
+
+struct LaunchCfg {
+  int num_sms;
+  long long* launch_counter;  // host-side count of kernel launches
+};
+
+// stage kernels (one view, one stage); all asynchronous on `stream`
+void launch_load(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
+void launch_init(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
+void launch_strong(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);  // one colour, one iter
+void launch_extract(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
+void launch_median(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);  // one colour
+void launch_classify_refine(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
+void launch_finish(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
+// weak / edge path (DPE.cu kernels 2-5, 8, 9)
+void launch_edge_info(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
+void launch_nearest_strong(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
+void launch_gen_neighbours(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
+void launch_fit_plane(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
+void launch_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);  // one colour, one iter
+
+// scene preparation
+void launch_u8_to_f32(const uint8_t* src, float* dst, int n, const LaunchCfg& cfg, cudaStream_t stream);
+// cv::resize(INTER_LINEAR) of a float image (DPE.cpp:808)
+void launch_resize_linear(const float* src, int sw, int sh, float* dst, int dw, int dh,
+                          const LaunchCfg& cfg, cudaStream_t stream);
+
+// gate-1 hooks
+void launch_cost_eval(const KernelParams& P, int n_pix, const int* xy, const float4* planes, int mode,
+                      unsigned long long point_tex, float* out, const LaunchCfg& cfg, cudaStream_t stream);
+void launch_geom_eval(const KernelParams& P, int n_pix, const int* xy, const float4* planes, float* out,
+                      const LaunchCfg& cfg, cudaStream_t stream);
+
+// micro-benchmarks
+void launch_probe_tex(unsigned long long tex, int w, int h, int iters, float* sink, int blocks, int threads,
+                      const LaunchCfg& cfg, cudaStream_t stream);
+void launch_probe_fma(int iters, float* sink, int blocks, int threads, const LaunchCfg& cfg,
+                      cudaStream_t stream);
+void launch_probe_weights(unsigned long long tex, int n, float* out, const LaunchCfg& cfg, cudaStream_t stream);
+
+}  // namespace dpe

@@ -1,0 +1,145 @@
+/*
+ * dpe_b200.h — C ABI of the B200-native DPE-MVS PatchMatch path.
+ *
+ * The reference (shunkenney/DPE-MVS) exports no C symbols: its only exported
+ * symbol is PyInit__dpe (csrc/bindings.cpp:31) and the seam between host code
+ * and CUDA is the C++ class `DPE` (csrc/DPE-MVS/DPE.h:88-107).  This header is
+ * the thin C layer that replaces that seam: plain pointers and sizes, no C++
+ * or torch types.  Every entry point cites the reference interface it stands
+ * in for.  All functions return 0 on success or a negative dpe_status; none
+ * of them ever calls exit() (the reference does: DPE.cpp:633-641).
+ */
+#ifndef DPE_B200_H_
+#define DPE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPE_MAX_IMAGES 32 /* main.h:39 MAX_IMAGES (ref + <=31 sources)      */
+#define DPE_MAX_SRC 31
+#define DPE_NEIGHBOUR_NUM 9 /* main.h:40                                     */
+
+/* main.h:66-70 RunState */
+enum { DPE_FIRST_INIT = 0, DPE_REFINE_INIT = 1, DPE_REFINE_ITER = 2 };
+/* main.h:72-76 PixelState (values persisted in weak.bin) */
+enum { DPE_WEAK = 0, DPE_STRONG = 1, DPE_UNKNOWN = 2 };
+
+typedef enum dpe_status {
+  DPE_OK = 0,
+  DPE_ERR_ARG = -1,
+  DPE_ERR_CUDA = -2,
+  DPE_ERR_STATE = -3,
+  DPE_ERR_IO = -4,
+  DPE_ERR_TOO_MANY_IMAGES = -5, /* DPE.cpp:762-765 */
+  DPE_ERR_NO_DEVICE = -6
+} dpe_status;
+
+/* Per-stage parameters: the fields of PatchMatchParams (main.h:78-106) that
+ * RunDPEPipeline (main.cpp:508-567) varies, plus the always-on defaults. */
+typedef struct dpe_stage_params {
+  int state;            /* DPE_FIRST_INIT / REFINE_INIT / REFINE_ITER        */
+  int geom_consistency; /* main.cpp:526,553                                  */
+  int use_apd;          /* main.cpp:517,521  (also drives use_edge)          */
+  int max_iterations;   /* 3                                                 */
+  int top_k;            /* 4   main.h:83                                     */
+  int weak_peak_radius; /* 6 | 4,2,2   main.cpp:528,555                     */
+  int rotate_time;      /* min(2^i,4)   main.cpp:524,552                     */
+  float ransac_threshold; /* 0.01-0.00125 i  main.cpp:523,551                */
+  float geom_factor;    /* 0.2 main.h:104                                    */
+} dpe_stage_params;
+
+typedef struct dpe_ctx dpe_ctx;
+
+/* --- lifetime (replaces DPE::DPE / ~DPE, DPE.cpp:674-731, and
+ *     cudaSetDevice in RunDPEPipeline, main.cpp:478) ----------------------- */
+int dpe_ctx_create(dpe_ctx** out, int gpu_index);
+void dpe_ctx_destroy(dpe_ctx* ctx);
+const char* dpe_last_error(const dpe_ctx* ctx);
+/* how many CUDA kernels this context has launched so far */
+long long dpe_kernel_launches(const dpe_ctx* ctx);
+
+/* --- scene upload (replaces DPE::InuputInitialization DPE.cpp:733-914,
+ *     SupportInitialization :1025-1052, CudaSpaceInitialization :916-1023) -- */
+/* n_scales = ComputeRoundNum (main.cpp:390-408); scale index k has size
+ * round(W/2^(n_scales-1-k)) x round(H/2^(n_scales-1-k)); k=0 is the coarsest. */
+int dpe_scene_begin(dpe_ctx* ctx, int n_views, int width, int height, int n_scales);
+/* gray: H*W bytes (cv::IMREAD_GRAYSCALE image, DPE.cpp:745); K,R row-major;
+ * depth_min/max are the cam-file values (the 0.6/1.2 factors of
+ * DPE.cpp:788-789 are applied inside). */
+int dpe_scene_set_view(dpe_ctx* ctx, int view, const uint8_t* gray, const float K[9],
+                       const float R[9], const float t[3], float depth_min, float depth_max);
+/* src_ids index views of this scene (positions in pair.txt order), n_src<=31 */
+int dpe_scene_set_pairs(dpe_ctx* ctx, int view, const int* src_ids, int n_src);
+/* edge: edges_k (uchar 0/255), label: labels_k (int32) of GetProblemEdges
+ * (main.cpp:331-388) at scale index `scale` (0 = coarsest). */
+int dpe_scene_set_prep(dpe_ctx* ctx, int view, int scale, const uint8_t* edge,
+                       const int32_t* label);
+/* multi-GPU: this context owns views [first, first+count); depth-atlas slots
+ * are padded to slots_per_rank*n_ranks (NCCL all-gather needs equal chunks). */
+int dpe_scene_set_shard(dpe_ctx* ctx, int first_view, int count, int slots_per_rank,
+                        int n_ranks);
+/* builds pyramids, textures, per-pair constants; after this the scene is
+ * resident in HBM. */
+int dpe_scene_commit(dpe_ctx* ctx);
+
+/* --- the hot path (replaces DPE::RunPatchMatch DPE.cu:3126-3249 plus the
+ *     per-view host tail of ProcessProblem main.cpp:423-446, for every view
+ *     this context owns) ---------------------------------------------------- */
+int dpe_run_stage(dpe_ctx* ctx, int scale_idx, const dpe_stage_params* params, uint64_t seed);
+/* device pointer + byte size of the depth atlas this stage wrote (slots x P
+ * floats).  Between dpe_run_stage and dpe_stage_commit a multi-GPU driver
+ * all-gathers it in place (chunk = slots_per_rank*P floats at rank offset). */
+int dpe_stage_atlas(dpe_ctx* ctx, void** dev_ptr, size_t* chunk_bytes, size_t* total_bytes);
+/* publishes the atlas written by the last stage as the source depth maps of
+ * the next geometric-consistency stage (the reference does this through
+ * depths.dmb files, DPE.cpp:826-844). */
+int dpe_stage_commit(dpe_ctx* ctx);
+
+/* --- gate-1 hook: bilateral NCC of fixed plane hypotheses ------------------
+ * planes: n_pix x (nx,ny,nz,d) in reference-camera coordinates (n.X + d = 0,
+ * DPE.cu:337-342); xy: n_pix x (x,y); cost_out: n_pix x n_src floats =
+ * ComputeBilateralNCCOld (DPE.cu:692-778) per source view.  mode 0 = hardware
+ * bilinear (the product path), 1 = exact fp32 bilinear from 4 point taps. */
+int dpe_cost_eval(dpe_ctx* ctx, int view, int scale_idx, int n_pix, const int* xy,
+                  const float* planes, int mode, float* cost_out);
+/* ComputeGeomConsistencyCost (DPE.cu:915-953) against the committed atlas */
+int dpe_geom_eval(dpe_ctx* ctx, int view, int scale_idx, int n_pix, const int* xy,
+                  const float* planes, float* cost_out);
+
+/* --- results (replaces DPE::GetPlaneHypothesis/GetPixelStates/
+ *     GetSelectedViews DPE.cpp:1091-1105) -----------------------------------
+ * Maps of the last stage run for `view` at that stage's scale. Any pointer may
+ * be NULL.  depth: H*W (0 where out of range, main.cpp:431-434); normal: H*W*3
+ * world-space; state: H*W PixelState; selected: H*W bitmasks. */
+int dpe_get_size(dpe_ctx* ctx, int scale_idx, int* width, int* height);
+int dpe_get_maps(dpe_ctx* ctx, int view, float* depth, float* normal3, uint8_t* state,
+                 uint32_t* selected);
+/* number of (pixel,hypothesis,view) bilateral-NCC units evaluated so far
+ * (NCCOld = 1 unit = 36 taps, NCCNew = taps/36); 0 unless counting is on. */
+int dpe_set_count_evals(dpe_ctx* ctx, int on);
+double dpe_eval_units(dpe_ctx* ctx);
+/* GPU milliseconds spent inside dpe_run_stage so far (CUDA events). */
+double dpe_stage_gpu_ms(dpe_ctx* ctx);
+
+/* --- micro-benchmarks used for the roofline denominators ------------------ */
+/* filtered tex2D<float> taps per second on a WxH float texture */
+int dpe_probe_tex_rate(dpe_ctx* ctx, int width, int height, int iters, double* taps_per_s);
+int dpe_probe_fma_rate(dpe_ctx* ctx, int iters, double* fma_per_s);
+/* weights[i] = hardware bilinear result at fractional offset i/n between a
+ * texel holding 0 and a texel holding 1 (characterises the 1.8 fixed-point
+ * interpolation weights). */
+int dpe_probe_tex_weights(dpe_ctx* ctx, int n, float* weights);
+
+/* --- whole pipeline (replaces RunDPEPipeline main.cpp:474-600); same
+ *     argument meaning as the Python / CLI surface --------------------------- */
+int dpe_run_pipeline(const char* dense_folder, int gpu_index, int verbose, int fusion, int viz,
+                     int depth, int normal, int weak, int edge);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPE_B200_H_ */
