@@ -1,0 +1,255 @@
+"""ctypes binding of the C ABI (include/dpe_b200.h, lib/libdpe_b200.so).
+
+This is how tests and bench.py reach the CUDA path; there is no CPU fallback: without a GPU
+`Context()` raises (DPE_ERR_NO_DEVICE), without the built library `load()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "lib" / "libdpe_b200.so"
+
+FIRST_INIT, REFINE_INIT, REFINE_ITER = 0, 1, 2
+WEAK, STRONG, UNKNOWN = 0, 1, 2
+
+
+class StageParams(C.Structure):
+    """dpe_stage_params (include/dpe_b200.h)"""
+    _fields_ = [("state", C.c_int), ("geom_consistency", C.c_int), ("use_apd", C.c_int),
+                ("max_iterations", C.c_int), ("top_k", C.c_int), ("weak_peak_radius", C.c_int),
+                ("rotate_time", C.c_int), ("ransac_threshold", C.c_float), ("geom_factor", C.c_float)]
+
+
+# every symbol include/dpe_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "dpe_ctx_create", "dpe_ctx_destroy", "dpe_last_error", "dpe_kernel_launches", "dpe_scene_begin",
+    "dpe_scene_set_view", "dpe_scene_set_pairs", "dpe_scene_set_prep", "dpe_scene_set_shard", "dpe_scene_commit",
+    "dpe_run_stage", "dpe_stage_atlas", "dpe_stage_commit", "dpe_cost_eval", "dpe_geom_eval", "dpe_get_size",
+    "dpe_get_maps", "dpe_set_count_evals", "dpe_eval_units", "dpe_stage_gpu_ms", "dpe_probe_tex_rate",
+    "dpe_probe_fma_rate", "dpe_probe_tex_weights", "dpe_run_pipeline",
+]
+
+_lib = None
+
+
+def load(build=True):
+    """Loads libdpe_b200.so (building it in-tree first if asked and needed)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("dpe_build", HERE / "build.py")
+        b = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(b)
+        b.build_lib()
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} is missing: build the CUDA extension first (python dpe-mvs_b200/build.py)")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    lib.dpe_ctx_create.argtypes = [C.POINTER(vp), ci]
+    lib.dpe_ctx_destroy.argtypes = [vp]
+    lib.dpe_ctx_destroy.restype = None
+    lib.dpe_last_error.argtypes = [vp]
+    lib.dpe_last_error.restype = C.c_char_p
+    lib.dpe_kernel_launches.argtypes = [vp]
+    lib.dpe_kernel_launches.restype = C.c_longlong
+    lib.dpe_scene_begin.argtypes = [vp, ci, ci, ci, ci]
+    lib.dpe_scene_set_view.argtypes = [vp, ci, vp, vp, vp, vp, cf, cf]
+    lib.dpe_scene_set_pairs.argtypes = [vp, ci, vp, ci]
+    lib.dpe_scene_set_prep.argtypes = [vp, ci, ci, vp, vp]
+    lib.dpe_scene_set_shard.argtypes = [vp, ci, ci, ci, ci]
+    lib.dpe_scene_commit.argtypes = [vp]
+    lib.dpe_run_stage.argtypes = [vp, ci, C.POINTER(StageParams), C.c_uint64]
+    lib.dpe_stage_atlas.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.dpe_stage_commit.argtypes = [vp]
+    lib.dpe_cost_eval.argtypes = [vp, ci, ci, ci, vp, vp, ci, vp]
+    lib.dpe_geom_eval.argtypes = [vp, ci, ci, ci, vp, vp, vp]
+    lib.dpe_get_size.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci)]
+    lib.dpe_get_maps.argtypes = [vp, ci, vp, vp, vp, vp]
+    lib.dpe_set_count_evals.argtypes = [vp, ci]
+    lib.dpe_eval_units.argtypes = [vp]
+    lib.dpe_eval_units.restype = C.c_double
+    lib.dpe_stage_gpu_ms.argtypes = [vp]
+    lib.dpe_stage_gpu_ms.restype = C.c_double
+    lib.dpe_probe_tex_rate.argtypes = [vp, ci, ci, ci, C.POINTER(C.c_double)]
+    lib.dpe_probe_fma_rate.argtypes = [vp, ci, C.POINTER(C.c_double)]
+    lib.dpe_probe_tex_weights.argtypes = [vp, ci, vp]
+    lib.dpe_run_pipeline.argtypes = [C.c_char_p, ci, ci, ci, ci, ci, ci, ci, ci]
+    _lib = lib
+    return lib
+
+
+def stage_schedule(n_scales):
+    """The reference's coarse-to-fine schedule (main.cpp:508-567): list of (scale_idx, StageParams)."""
+    out = []
+    for i in range(n_scales):
+        p = StageParams(FIRST_INIT if i == 0 else REFINE_INIT, 0, int(i > 0), 3, 4, 6, 4, 0.005, 0.2)
+        if i > 0:
+            p.ransac_threshold = 0.01 - i * 0.00125
+            p.rotate_time = min(2 ** i, 4)
+        out.append((i, p))
+        for j in range(3):
+            out.append((i, StageParams(REFINE_ITER, 1, int(i > 0), 3, 4, max(4 - 2 * j, 2), min(2 ** i, 4),
+                                       0.01 - i * 0.00125, 0.2)))
+    return out
+
+
+def compute_round_num(width, height):
+    """ComputeRoundNum (main.cpp:390-408)."""
+    m = max(width, height)
+    r = 1
+    while m > 800:
+        m //= 2
+        r += 1
+    return max(r, 2)
+
+
+class DpeError(RuntimeError):
+    pass
+
+
+class Context:
+    """Owns a dpe_ctx.  Methods mirror the C ABI one to one."""
+
+    def __init__(self, gpu_index=0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        rc = self.lib.dpe_ctx_create(C.byref(self.h), gpu_index)
+        if rc != 0:
+            raise DpeError(f"dpe_ctx_create failed with code {rc} (no CUDA device / bad index)")
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise DpeError(f"code {rc}: {self.lib.dpe_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.dpe_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- scene ---------------------------------------------------------------------------
+    def scene_begin(self, n_views, width, height, n_scales):
+        self._ck(self.lib.dpe_scene_begin(self.h, n_views, width, height, n_scales))
+        self.n_views, self.n_scales = n_views, n_scales
+
+    def set_view(self, view, gray, K, R, t, dmin, dmax):
+        g = np.ascontiguousarray(gray, np.uint8)
+        K = np.ascontiguousarray(K, np.float32).reshape(9)
+        R = np.ascontiguousarray(R, np.float32).reshape(9)
+        t = np.ascontiguousarray(t, np.float32).reshape(3)
+        self._ck(self.lib.dpe_scene_set_view(self.h, view, g.ctypes.data, K.ctypes.data, R.ctypes.data, t.ctypes.data,
+                                             dmin, dmax))
+
+    def set_pairs(self, view, src):
+        s = np.ascontiguousarray(src, np.int32)
+        self._ck(self.lib.dpe_scene_set_pairs(self.h, view, s.ctypes.data, len(s)))
+
+    def set_prep(self, view, scale, edge=None, label=None):
+        e = np.ascontiguousarray(edge, np.uint8) if edge is not None else None
+        l = np.ascontiguousarray(label, np.int32) if label is not None else None
+        self._ck(self.lib.dpe_scene_set_prep(self.h, view, scale, e.ctypes.data if e is not None else None,
+                                             l.ctypes.data if l is not None else None))
+
+    def set_shard(self, first, count, slots_per_rank, n_ranks):
+        self._ck(self.lib.dpe_scene_set_shard(self.h, first, count, slots_per_rank, n_ranks))
+
+    def commit(self):
+        self._ck(self.lib.dpe_scene_commit(self.h))
+
+    # -- stages --------------------------------------------------------------------------
+    def run_stage(self, scale_idx, params, seed):
+        self._ck(self.lib.dpe_run_stage(self.h, scale_idx, C.byref(params), C.c_uint64(seed)))
+
+    def stage_atlas(self):
+        p, chunk, total = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        self._ck(self.lib.dpe_stage_atlas(self.h, C.byref(p), C.byref(chunk), C.byref(total)))
+        return p.value, chunk.value, total.value
+
+    def stage_commit(self):
+        self._ck(self.lib.dpe_stage_commit(self.h))
+
+    def size(self, scale_idx):
+        w, h = C.c_int(), C.c_int()
+        self._ck(self.lib.dpe_get_size(self.h, scale_idx, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def get_maps(self, view, scale_idx):
+        w, h = self.size(scale_idx)
+        depth = np.empty((h, w), np.float32)
+        normal = np.empty((h, w, 3), np.float32)
+        state = np.empty((h, w), np.uint8)
+        sel = np.empty((h, w), np.uint32)
+        self._ck(self.lib.dpe_get_maps(self.h, view, depth.ctypes.data, normal.ctypes.data, state.ctypes.data,
+                                       sel.ctypes.data))
+        return dict(depth=depth, normal=normal, state=state, selected=sel)
+
+    # -- gate-1 hooks --------------------------------------------------------------------
+    def cost_eval(self, view, scale_idx, xy, planes, n_src, mode=0):
+        xy = np.ascontiguousarray(xy, np.int32)
+        pl = np.ascontiguousarray(planes, np.float32)
+        out = np.empty((len(xy), n_src), np.float32)
+        self._ck(self.lib.dpe_cost_eval(self.h, view, scale_idx, len(xy), xy.ctypes.data, pl.ctypes.data, mode,
+                                        out.ctypes.data))
+        return out
+
+    def geom_eval(self, view, scale_idx, xy, planes, n_src):
+        xy = np.ascontiguousarray(xy, np.int32)
+        pl = np.ascontiguousarray(planes, np.float32)
+        out = np.empty((len(xy), n_src), np.float32)
+        self._ck(self.lib.dpe_geom_eval(self.h, view, scale_idx, len(xy), xy.ctypes.data, pl.ctypes.data,
+                                        out.ctypes.data))
+        return out
+
+    # -- counters / probes ---------------------------------------------------------------
+    def set_count_evals(self, on):
+        self._ck(self.lib.dpe_set_count_evals(self.h, int(on)))
+
+    def eval_units(self):
+        return self.lib.dpe_eval_units(self.h)
+
+    def stage_gpu_ms(self):
+        return self.lib.dpe_stage_gpu_ms(self.h)
+
+    def kernel_launches(self):
+        return self.lib.dpe_kernel_launches(self.h)
+
+    def probe_tex_rate(self, w=2048, h=2048, iters=200):
+        r = C.c_double()
+        self._ck(self.lib.dpe_probe_tex_rate(self.h, w, h, iters, C.byref(r)))
+        return r.value
+
+    def probe_fma_rate(self, iters=2000):
+        r = C.c_double()
+        self._ck(self.lib.dpe_probe_fma_rate(self.h, iters, C.byref(r)))
+        return r.value
+
+    def probe_tex_weights(self, n=4096):
+        w = np.empty(n + 1, np.float32)
+        self._ck(self.lib.dpe_probe_tex_weights(self.h, n, w.ctypes.data))
+        return w
+
+
+def upload_scene(ctx: Context, images, cams, depth_ranges, pairs, n_scales=None, shard=None):
+    """images: list of HxW uint8; cams: list of (K,R,t); pairs: list of source-id lists."""
+    H, W = images[0].shape
+    if n_scales is None:
+        n_scales = compute_round_num(W, H)
+    ctx.scene_begin(len(images), W, H, n_scales)
+    for v, (img, (K, R, t), (dmin, dmax)) in enumerate(zip(images, cams, depth_ranges)):
+        ctx.set_view(v, img, K, R, t, dmin, dmax)
+        ctx.set_pairs(v, pairs[v])
+    if shard is not None:
+        ctx.set_shard(*shard)
+    ctx.commit()
+    return n_scales

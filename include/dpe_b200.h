@@ -19,6 +19,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define DPE_API __attribute__((visibility("default")))
+#else
+#define DPE_API
+#endif
+
 #define DPE_MAX_IMAGES 32 /* main.h:39 MAX_IMAGES (ref + <=31 sources)      */
 #define DPE_MAX_SRC 31
 #define DPE_NEIGHBOUR_NUM 9 /* main.h:40                                     */
@@ -56,58 +62,58 @@ typedef struct dpe_ctx dpe_ctx;
 
 /* --- lifetime (replaces DPE::DPE / ~DPE, DPE.cpp:674-731, and
  *     cudaSetDevice in RunDPEPipeline, main.cpp:478) ----------------------- */
-int dpe_ctx_create(dpe_ctx** out, int gpu_index);
-void dpe_ctx_destroy(dpe_ctx* ctx);
-const char* dpe_last_error(const dpe_ctx* ctx);
+DPE_API int dpe_ctx_create(dpe_ctx** out, int gpu_index);
+DPE_API void dpe_ctx_destroy(dpe_ctx* ctx);
+DPE_API const char* dpe_last_error(const dpe_ctx* ctx);
 /* how many CUDA kernels this context has launched so far */
-long long dpe_kernel_launches(const dpe_ctx* ctx);
+DPE_API long long dpe_kernel_launches(const dpe_ctx* ctx);
 
 /* --- scene upload (replaces DPE::InuputInitialization DPE.cpp:733-914,
  *     SupportInitialization :1025-1052, CudaSpaceInitialization :916-1023) -- */
 /* n_scales = ComputeRoundNum (main.cpp:390-408); scale index k has size
  * round(W/2^(n_scales-1-k)) x round(H/2^(n_scales-1-k)); k=0 is the coarsest. */
-int dpe_scene_begin(dpe_ctx* ctx, int n_views, int width, int height, int n_scales);
+DPE_API int dpe_scene_begin(dpe_ctx* ctx, int n_views, int width, int height, int n_scales);
 /* gray: H*W bytes (cv::IMREAD_GRAYSCALE image, DPE.cpp:745); K,R row-major;
  * depth_min/max are the cam-file values (the 0.6/1.2 factors of
  * DPE.cpp:788-789 are applied inside). */
-int dpe_scene_set_view(dpe_ctx* ctx, int view, const uint8_t* gray, const float K[9],
+DPE_API int dpe_scene_set_view(dpe_ctx* ctx, int view, const uint8_t* gray, const float K[9],
                        const float R[9], const float t[3], float depth_min, float depth_max);
 /* src_ids index views of this scene (positions in pair.txt order), n_src<=31 */
-int dpe_scene_set_pairs(dpe_ctx* ctx, int view, const int* src_ids, int n_src);
+DPE_API int dpe_scene_set_pairs(dpe_ctx* ctx, int view, const int* src_ids, int n_src);
 /* edge: edges_k (uchar 0/255), label: labels_k (int32) of GetProblemEdges
  * (main.cpp:331-388) at scale index `scale` (0 = coarsest). */
-int dpe_scene_set_prep(dpe_ctx* ctx, int view, int scale, const uint8_t* edge,
+DPE_API int dpe_scene_set_prep(dpe_ctx* ctx, int view, int scale, const uint8_t* edge,
                        const int32_t* label);
 /* multi-GPU: this context owns views [first, first+count); depth-atlas slots
  * are padded to slots_per_rank*n_ranks (NCCL all-gather needs equal chunks). */
-int dpe_scene_set_shard(dpe_ctx* ctx, int first_view, int count, int slots_per_rank,
+DPE_API int dpe_scene_set_shard(dpe_ctx* ctx, int first_view, int count, int slots_per_rank,
                         int n_ranks);
 /* builds pyramids, textures, per-pair constants; after this the scene is
  * resident in HBM. */
-int dpe_scene_commit(dpe_ctx* ctx);
+DPE_API int dpe_scene_commit(dpe_ctx* ctx);
 
 /* --- the hot path (replaces DPE::RunPatchMatch DPE.cu:3126-3249 plus the
  *     per-view host tail of ProcessProblem main.cpp:423-446, for every view
  *     this context owns) ---------------------------------------------------- */
-int dpe_run_stage(dpe_ctx* ctx, int scale_idx, const dpe_stage_params* params, uint64_t seed);
+DPE_API int dpe_run_stage(dpe_ctx* ctx, int scale_idx, const dpe_stage_params* params, uint64_t seed);
 /* device pointer + byte size of the depth atlas this stage wrote (slots x P
  * floats).  Between dpe_run_stage and dpe_stage_commit a multi-GPU driver
  * all-gathers it in place (chunk = slots_per_rank*P floats at rank offset). */
-int dpe_stage_atlas(dpe_ctx* ctx, void** dev_ptr, size_t* chunk_bytes, size_t* total_bytes);
+DPE_API int dpe_stage_atlas(dpe_ctx* ctx, void** dev_ptr, size_t* chunk_bytes, size_t* total_bytes);
 /* publishes the atlas written by the last stage as the source depth maps of
  * the next geometric-consistency stage (the reference does this through
  * depths.dmb files, DPE.cpp:826-844). */
-int dpe_stage_commit(dpe_ctx* ctx);
+DPE_API int dpe_stage_commit(dpe_ctx* ctx);
 
 /* --- gate-1 hook: bilateral NCC of fixed plane hypotheses ------------------
  * planes: n_pix x (nx,ny,nz,d) in reference-camera coordinates (n.X + d = 0,
  * DPE.cu:337-342); xy: n_pix x (x,y); cost_out: n_pix x n_src floats =
  * ComputeBilateralNCCOld (DPE.cu:692-778) per source view.  mode 0 = hardware
  * bilinear (the product path), 1 = exact fp32 bilinear from 4 point taps. */
-int dpe_cost_eval(dpe_ctx* ctx, int view, int scale_idx, int n_pix, const int* xy,
+DPE_API int dpe_cost_eval(dpe_ctx* ctx, int view, int scale_idx, int n_pix, const int* xy,
                   const float* planes, int mode, float* cost_out);
 /* ComputeGeomConsistencyCost (DPE.cu:915-953) against the committed atlas */
-int dpe_geom_eval(dpe_ctx* ctx, int view, int scale_idx, int n_pix, const int* xy,
+DPE_API int dpe_geom_eval(dpe_ctx* ctx, int view, int scale_idx, int n_pix, const int* xy,
                   const float* planes, float* cost_out);
 
 /* --- results (replaces DPE::GetPlaneHypothesis/GetPixelStates/
@@ -115,28 +121,28 @@ int dpe_geom_eval(dpe_ctx* ctx, int view, int scale_idx, int n_pix, const int* x
  * Maps of the last stage run for `view` at that stage's scale. Any pointer may
  * be NULL.  depth: H*W (0 where out of range, main.cpp:431-434); normal: H*W*3
  * world-space; state: H*W PixelState; selected: H*W bitmasks. */
-int dpe_get_size(dpe_ctx* ctx, int scale_idx, int* width, int* height);
-int dpe_get_maps(dpe_ctx* ctx, int view, float* depth, float* normal3, uint8_t* state,
+DPE_API int dpe_get_size(dpe_ctx* ctx, int scale_idx, int* width, int* height);
+DPE_API int dpe_get_maps(dpe_ctx* ctx, int view, float* depth, float* normal3, uint8_t* state,
                  uint32_t* selected);
 /* number of (pixel,hypothesis,view) bilateral-NCC units evaluated so far
  * (NCCOld = 1 unit = 36 taps, NCCNew = taps/36); 0 unless counting is on. */
-int dpe_set_count_evals(dpe_ctx* ctx, int on);
-double dpe_eval_units(dpe_ctx* ctx);
+DPE_API int dpe_set_count_evals(dpe_ctx* ctx, int on);
+DPE_API double dpe_eval_units(dpe_ctx* ctx);
 /* GPU milliseconds spent inside dpe_run_stage so far (CUDA events). */
-double dpe_stage_gpu_ms(dpe_ctx* ctx);
+DPE_API double dpe_stage_gpu_ms(dpe_ctx* ctx);
 
 /* --- micro-benchmarks used for the roofline denominators ------------------ */
 /* filtered tex2D<float> taps per second on a WxH float texture */
-int dpe_probe_tex_rate(dpe_ctx* ctx, int width, int height, int iters, double* taps_per_s);
-int dpe_probe_fma_rate(dpe_ctx* ctx, int iters, double* fma_per_s);
+DPE_API int dpe_probe_tex_rate(dpe_ctx* ctx, int width, int height, int iters, double* taps_per_s);
+DPE_API int dpe_probe_fma_rate(dpe_ctx* ctx, int iters, double* fma_per_s);
 /* weights[i] = hardware bilinear result at fractional offset i/n between a
  * texel holding 0 and a texel holding 1 (characterises the 1.8 fixed-point
  * interpolation weights). */
-int dpe_probe_tex_weights(dpe_ctx* ctx, int n, float* weights);
+DPE_API int dpe_probe_tex_weights(dpe_ctx* ctx, int n, float* weights);
 
 /* --- whole pipeline (replaces RunDPEPipeline main.cpp:474-600); same
  *     argument meaning as the Python / CLI surface --------------------------- */
-int dpe_run_pipeline(const char* dense_folder, int gpu_index, int verbose, int fusion, int viz,
+DPE_API int dpe_run_pipeline(const char* dense_folder, int gpu_index, int verbose, int fusion, int viz,
                      int depth, int normal, int weak, int edge);
 
 #ifdef __cplusplus
