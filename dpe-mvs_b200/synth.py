@@ -261,7 +261,9 @@ def write_scene(spec: SceneSpec, out_dir, device=None, save_gt=True, jpeg_qualit
             # decoded pixels as cv2 (libjpeg-turbo) sees them: fed to the reference build's
             # imread stand-in so both implementations can be given identical pixels
             dec = cv2.imread(str(out / "images" / f"{v:08d}.jpg"), cv2.IMREAD_GRAYSCALE)
-            dec.tofile(str(out / "images" / f"{v:08d}.gray"))
+            with open(out / "images" / f"{v:08d}.gray", "wb") as fg:   # int32 rows, int32 cols, pixels
+                fg.write(np.array(dec.shape, np.int32).tobytes())
+                fg.write(dec.tobytes())
         valid = depth[depth > 0]
         dmin = float(np.percentile(valid, 1)) * 0.75   # colmap2mvsnet.py:407-408
         dmax = float(np.percentile(valid, 99)) * 1.25

@@ -1,0 +1,152 @@
+"""Gate-2 harness: run the UNMODIFIED reference build (oracle/_ref/DPE_ref, seed pinned) and
+this implementation on the same synthetic scene folder, same decoded pixels, same prep
+arrays; compare depth / normal / weak maps and time both.  Runs on the GPU box.
+
+usage: python tools/ref_compare.py <config> [--views N] [--scale S] [--ref-runs 2] [--out tag]
+"""
+import argparse, json, os, shutil, subprocess, sys, time
+from pathlib import Path
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "dpe-mvs_b200")); sys.path.insert(0, str(ROOT / "oracle"))
+import capi, synth, prep_cv2
+
+
+def write_prep(folder, n_views, n_scales, prep):
+    for v in range(n_views):
+        d = folder / "DPE" / f"{v:08d}"
+        d.mkdir(parents=True, exist_ok=True)
+        for j in range(n_scales):
+            prep_cv2.write_dmb(d / f"edges_{j}.dmb", prep[v][j][0])
+            prep_cv2.write_dmb(d / f"labels_{j}.dmb", prep[v][j][1])
+
+
+def compare(a_d, a_n, a_w, b_d, b_n, b_w):
+    valid = (a_d > 0) & (b_d > 0)
+    rel = np.abs(a_d - b_d) / np.maximum(b_d, 1e-9)
+    dot = np.clip((a_n * b_n).sum(-1), -1, 1)
+    ang = np.degrees(np.arccos(dot))
+    return dict(valid_frac=float(valid.mean()), both_or_neither=float(((a_d > 0) == (b_d > 0)).mean()),
+                depth_1pct=float((rel[valid] < 0.01).mean()), normal_1deg=float((ang[valid] < 1.0).mean()),
+                normal_5deg=float((ang[valid] < 5.0).mean()),
+                depth_and_normal=float(((rel < 0.01) & (ang < 1.0))[valid].mean()),
+                weak_agree=float((a_w == b_w).mean()))
+
+
+def vs_gt(d, n, gt_d, gt_n):
+    m = (gt_d > 0) & (d > 0)
+    rel = np.abs(d - gt_d) / np.maximum(gt_d, 1e-9)
+    ang = np.degrees(np.arccos(np.clip((n * gt_n).sum(-1), -1, 1)))
+    return dict(cover=float((d > 0).mean()), depth_1pct=float((rel[m] < 0.01).mean()), normal_5deg=float((ang[m] < 5).mean()),
+                depth_1pct_of_all=float(((rel < 0.01) & (d > 0))[gt_d > 0].mean()))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("config")
+    ap.add_argument("--views", type=int, default=None)
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--ref-runs", type=int, default=2)
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--no-hough", action="store_true")
+    args = ap.parse_args()
+    tag = args.out or args.config
+    OUT = ROOT / "gpurun_out"; OUT.mkdir(exist_ok=True)
+    folder = Path("/tmp") / f"scene_{tag}"
+    shutil.rmtree(folder, ignore_errors=True)
+    spec = synth.make_scene(args.config, scale=args.scale, n_views=args.views)
+    t0 = time.time()
+    pairs = synth.write_scene(spec, folder)
+    res = dict(config=args.config, views=spec.n_views, width=spec.width, height=spec.height, n_src=spec.n_src,
+               scene_gen_s=time.time() - t0, nproc=os.cpu_count())
+    V = spec.n_views
+    n_scales = capi.compute_round_num(spec.width, spec.height)
+    grays = []
+    for v in range(V):
+        raw = np.fromfile(folder / "images" / f"{v:08d}.gray", np.uint8)
+        grays.append(raw[8:].reshape(spec.height, spec.width))
+    t0 = time.time()
+    prep = [[prep_cv2.problem_edges(grays[v], 1 << j, hough=not args.no_hough)[1:] for j in range(n_scales)] for v in range(V)]
+    res["prep_cv2_s"] = time.time() - t0
+    gt = [(np.load(folder / "gt" / f"{v:08d}_depth.npy"), np.load(folder / "gt" / f"{v:08d}_normal.npy")) for v in range(V)]
+
+    # ---- reference runs
+    ref_out = []
+    for run in range(args.ref_runs):
+        shutil.rmtree(folder / "DPE", ignore_errors=True)
+        write_prep(folder, V, n_scales, prep)
+        t0 = time.time()
+        # argv: dense gpu verbose viz fusion depth normal weak edge   (main.cpp:602-635)
+        p = subprocess.run([str(ROOT / "oracle" / "_ref" / "DPE_ref"), str(folder), "0", "1", "0", "0", "1", "1", "1", "1"],
+                           capture_output=True, text=True)
+        dt = time.time() - t0
+        (OUT / f"ref_{tag}_run{run}.log").write_text(p.stdout[-4000:] + "\n--- stderr\n" + p.stderr[-4000:])
+        if p.returncode != 0:
+            res[f"ref_run{run}_rc"] = p.returncode
+            continue
+        maps = []
+        for v in range(V):
+            d = folder / "DPE" / f"{v:08d}"
+            maps.append((np.load(d / "depth.npy"), np.load(d / "normal.npy"), np.load(d / "weak.npy")))
+        ref_out.append(maps)
+        res[f"ref_run{run}_wall_s"] = dt
+        res[f"ref_run{run}_depth_maps_per_s"] = V / dt
+        print("ref run", run, dt, flush=True)
+
+    # ---- this implementation (same pixels, same prep)
+    cams, drs = [], []
+    for v in range(V):
+        K, R, t, dmin, dmax = synth.read_cam(folder / "cams" / f"{v:08d}_cam.txt")
+        cams.append((K, R, t)); drs.append((dmin, dmax))
+    rp = synth.read_pairs(folder / "pair.txt")
+    ctx = capi.Context(0)
+    t_all = time.time()
+    capi.upload_scene(ctx, grays, cams, drs, [s for (_, s) in rp], n_scales)
+    for v in range(V):
+        for k in range(n_scales):
+            j = n_scales - 1 - k
+            ctx.set_prep(v, k, prep[v][j][0], prep[v][j][1])
+    t_up = time.time() - t_all
+    ctx.set_count_evals(True)
+    stages = []
+    for (k, p) in capi.stage_schedule(n_scales):
+        m0, u0 = ctx.stage_gpu_ms(), ctx.eval_units()
+        ctx.run_stage(k, p, 20261018)
+        ctx.stage_commit()
+        stages.append(dict(scale=k, state=p.state, geom=p.geom_consistency, gpu_ms=ctx.stage_gpu_ms() - m0, units=ctx.eval_units() - u0))
+        print("ours", stages[-1], flush=True)
+    ours = []
+    for v in range(V):
+        m = ctx.get_maps(v, n_scales - 1)
+        d = m["depth"].copy(); d[m["state"] == capi.UNKNOWN] = 0      # ZeroDepthForUnknown, main.cpp:36-46
+        w = np.zeros(m["state"].shape, np.int8); w[m["state"] == capi.WEAK] = 1; w[m["state"] == capi.STRONG] = 2
+        ours.append((d, m["normal"], w))
+    res["ours_wall_s"] = time.time() - t_all
+    res["ours_upload_s"] = t_up
+    res["ours_gpu_ms"] = ctx.stage_gpu_ms()
+    res["ours_units"] = ctx.eval_units()
+    res["ours_stages"] = stages
+    res["ours_depth_maps_per_s"] = V / res["ours_wall_s"]
+
+    # ---- comparisons
+    if len(ref_out) >= 1:
+        res["ours_vs_ref"] = [compare(*ours[v], *ref_out[0][v]) for v in range(V)]
+        res["ref_vs_gt"] = [vs_gt(ref_out[0][v][0], ref_out[0][v][1], *gt[v]) for v in range(V)]
+        res["ref_weak_hist"] = [[float((ref_out[0][v][2] == k).mean()) for k in range(3)] for v in range(V)]
+    if len(ref_out) >= 2:
+        res["ref_vs_ref"] = [compare(*ref_out[1][v], *ref_out[0][v]) for v in range(V)]
+    res["ours_vs_gt"] = [vs_gt(ours[v][0], ours[v][1], *gt[v]) for v in range(V)]
+    res["ours_weak_hist"] = [[float((ours[v][2] == k).mean()) for k in range(3)] for v in range(V)]
+    np.savez_compressed(OUT / f"cmp_{tag}_view0.npz", ours_d=ours[0][0], ours_w=ours[0][2],
+                        ref_d=ref_out[0][0][0] if ref_out else 0, ref_w=ref_out[0][0][2] if ref_out else 0, gt_d=gt[0][0])
+    (OUT / f"cmp_{tag}.json").write_text(json.dumps(res, indent=1))
+    short = {k: v for k, v in res.items() if not isinstance(v, list)}
+    print(json.dumps(short, indent=1))
+    for key in ("ours_vs_ref", "ref_vs_ref", "ref_vs_gt", "ours_vs_gt"):
+        if key in res:
+            print(key, json.dumps(res[key][0]))
+
+
+if __name__ == "__main__":
+    main()
