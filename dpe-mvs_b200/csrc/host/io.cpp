@@ -1,0 +1,207 @@
+// io.cpp — see io.h.  Host C++ only (compiled by nvcc's host compiler; nvJPEG for decode).
+#include "io.h"
+
+#include <cuda_runtime.h>
+#include <nvjpeg.h>
+#include <string.h>
+#include <sys/stat.h>
+
+#include <fstream>
+#include <iomanip>
+#include <sstream>
+
+namespace dpe_host {
+
+std::string format_index(int index) {
+  std::stringstream ss;
+  ss << std::setw(8) << std::setfill('0') << index;
+  return ss.str();
+}
+
+bool file_exists(const std::string& path) {
+  struct stat st;
+  return stat(path.c_str(), &st) == 0;
+}
+
+// pair.txt: line 1 = V; per view: line "ref_id", line "n id1 s1 ... idn sn"; sources with a
+// score <= 0 are dropped (main.cpp:297-305).
+bool read_pairs(const std::string& path, std::vector<ProblemDesc>* problems) {
+  problems->clear();
+  std::ifstream file(path);
+  if (!file.good()) return false;
+  std::string line;
+  std::stringstream iss;
+  int num_images = 0;
+  std::getline(file, line);
+  iss.str(line);
+  iss >> num_images;
+  for (int i = 0; i < num_images; ++i) {
+    ProblemDesc p;
+    p.ref_image_id = 0;
+    iss.clear();
+    std::getline(file, line);
+    iss.str(line);
+    iss >> p.ref_image_id;
+    int n = 0;
+    iss.clear();
+    std::getline(file, line);
+    iss.str(line);
+    iss >> n;
+    for (int j = 0; j < n; ++j) {
+      int id = 0;
+      float score = 0.f;
+      iss >> id >> score;
+      if (score <= 0.0f) continue;
+      p.src_image_ids.push_back(id);
+    }
+    problems->push_back(p);
+  }
+  return true;
+}
+
+bool read_cam(const std::string& path, CamFile* cam) {
+  std::ifstream in(path);
+  if (!in.good()) return false;
+  std::string tok;
+  in >> tok;  // "extrinsic"
+  for (int i = 0; i < 3; ++i) in >> cam->R[3 * i + 0] >> cam->R[3 * i + 1] >> cam->R[3 * i + 2] >> cam->t[i];
+  float tmp[4];
+  in >> tmp[0] >> tmp[1] >> tmp[2] >> tmp[3];
+  in >> tok;  // "intrinsic"
+  for (int i = 0; i < 3; ++i) in >> cam->K[3 * i + 0] >> cam->K[3 * i + 1] >> cam->K[3 * i + 2];
+  float interval = 0.f, depth_num = 0.f;
+  in >> cam->depth_min >> interval >> depth_num >> cam->depth_max;
+  return !in.fail();
+}
+
+// NPY v1.0; header dict exactly as the reference writes it, space padded so that
+// 10 + header length is a multiple of 16 (main.cpp:71-85).
+bool write_npy(const std::string& path, const void* data, const char* descr, size_t elem_size, int rows, int cols,
+               int channels) {
+  std::ofstream out(path, std::ios::binary);
+  if (!out.is_open()) return false;
+  std::ostringstream shape;
+  shape << "(" << rows << ", " << cols;
+  if (channels > 1) shape << ", " << channels;
+  shape << ")";
+  std::string header = std::string("{'descr': '") + descr + "', 'fortran_order': False, 'shape': " + shape.str() + ", }";
+  const size_t header_len = header.size() + 1;
+  const size_t padding = (16 - ((10 + header_len) % 16)) % 16;
+  header.append(padding, ' ');
+  header.push_back('\n');
+  const char magic[] = "\x93NUMPY";
+  out.write(magic, 6);
+  out.put((char)1);
+  out.put((char)0);
+  const uint16_t hs = (uint16_t)header.size();
+  out.write((const char*)&hs, 2);
+  out.write(header.data(), header.size());
+  out.write((const char*)data, (size_t)rows * cols * channels * elem_size);
+  return out.good();
+}
+
+bool read_dmb(const std::string& path, int* rows, int* cols, int* type, std::vector<uint8_t>* data) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in.good()) return false;
+  int32_t h[4] = {0, 0, 0, 0};
+  in.read((char*)h, 16);
+  if (in.fail() || h[0] != 1 || h[1] <= 0 || h[2] <= 0) return false;
+  size_t es;
+  switch (h[3]) {
+    case DMB_8UC1: es = 1; break;
+    case DMB_32SC1: case DMB_32FC1: es = 4; break;
+    case DMB_32FC3: es = 12; break;
+    default: return false;
+  }
+  *rows = h[1]; *cols = h[2]; *type = h[3];
+  data->resize((size_t)h[1] * h[2] * es);
+  in.read((char*)data->data(), data->size());
+  return !in.fail();
+}
+
+bool write_dmb(const std::string& path, int rows, int cols, int type, const void* data, size_t bytes) {
+  std::ofstream out(path, std::ios::binary);
+  if (!out.is_open()) return false;
+  const int32_t h[4] = {1, rows, cols, type};
+  out.write((const char*)h, 16);
+  out.write((const char*)data, bytes);
+  return out.good();
+}
+
+// ---- nvJPEG ---------------------------------------------------------------------------------
+struct JpegDecoder {
+  nvjpegHandle_t handle = nullptr;
+  nvjpegJpegState_t state = nullptr;
+  cudaStream_t stream = nullptr;
+  unsigned char* dev = nullptr;
+  size_t dev_bytes = 0;
+  std::vector<unsigned char> file;
+};
+
+JpegDecoder* jpeg_decoder_create(std::string* err) {
+  JpegDecoder* d = new JpegDecoder();
+  if (nvjpegCreateSimple(&d->handle) != NVJPEG_STATUS_SUCCESS || nvjpegJpegStateCreate(d->handle, &d->state) != NVJPEG_STATUS_SUCCESS) {
+    if (err) *err = "nvjpeg initialisation failed";
+    delete d;
+    return nullptr;
+  }
+  cudaStreamCreate(&d->stream);
+  return d;
+}
+
+void jpeg_decoder_destroy(JpegDecoder* d) {
+  if (!d) return;
+  if (d->state) nvjpegJpegStateDestroy(d->state);
+  if (d->handle) nvjpegDestroy(d->handle);
+  if (d->stream) cudaStreamDestroy(d->stream);
+  cudaFree(d->dev);
+  delete d;
+}
+
+static bool jpeg_decode(JpegDecoder* d, const std::string& path, nvjpegOutputFormat_t fmt, int ch, std::vector<uint8_t>* out,
+                        int* width, int* height, std::string* err) {
+  std::ifstream in(path, std::ios::binary | std::ios::ate);
+  if (!in.good()) { if (err) *err = "cannot open " + path; return false; }
+  const std::streamsize n = in.tellg();
+  in.seekg(0);
+  d->file.resize((size_t)n);
+  in.read((char*)d->file.data(), n);
+  int comps = 0, ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
+  nvjpegChromaSubsampling_t ss;
+  if (nvjpegGetImageInfo(d->handle, d->file.data(), d->file.size(), &comps, &ss, ws, hs) != NVJPEG_STATUS_SUCCESS) {
+    if (err) *err = "not a decodable JPEG: " + path;
+    return false;
+  }
+  const int w = ws[0], h = hs[0];
+  const size_t need = (size_t)w * h * ch;
+  if (need > d->dev_bytes) {
+    cudaFree(d->dev);
+    if (cudaMalloc(&d->dev, need) != cudaSuccess) { if (err) *err = "cudaMalloc failed in jpeg decode"; d->dev_bytes = 0; return false; }
+    d->dev_bytes = need;
+  }
+  nvjpegImage_t img;
+  memset(&img, 0, sizeof(img));
+  img.channel[0] = d->dev;
+  img.pitch[0] = (size_t)w * ch;
+  if (nvjpegDecode(d->handle, d->state, d->file.data(), d->file.size(), fmt, &img, d->stream) != NVJPEG_STATUS_SUCCESS) {
+    if (err) *err = "nvjpegDecode failed: " + path;
+    return false;
+  }
+  out->resize(need);
+  if (cudaMemcpyAsync(out->data(), d->dev, need, cudaMemcpyDeviceToHost, d->stream) != cudaSuccess ||
+      cudaStreamSynchronize(d->stream) != cudaSuccess) {
+    if (err) *err = "copy after jpeg decode failed";
+    return false;
+  }
+  *width = w; *height = h;
+  return true;
+}
+
+bool jpeg_decode_gray(JpegDecoder* d, const std::string& path, std::vector<uint8_t>* gray, int* width, int* height, std::string* err) {
+  return jpeg_decode(d, path, NVJPEG_OUTPUT_Y, 1, gray, width, height, err);
+}
+bool jpeg_decode_bgr(JpegDecoder* d, const std::string& path, std::vector<uint8_t>* bgr, int* width, int* height, std::string* err) {
+  return jpeg_decode(d, path, NVJPEG_OUTPUT_BGRI, 3, bgr, width, height, err);
+}
+
+}  // namespace dpe_host
