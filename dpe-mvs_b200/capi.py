@@ -30,7 +30,7 @@ SYMBOLS = [
     "dpe_scene_set_view", "dpe_scene_set_pairs", "dpe_scene_set_prep", "dpe_scene_set_shard", "dpe_scene_commit",
     "dpe_run_stage", "dpe_stage_atlas", "dpe_stage_commit", "dpe_cost_eval", "dpe_geom_eval", "dpe_get_size",
     "dpe_get_maps", "dpe_set_count_evals", "dpe_eval_units", "dpe_stage_gpu_ms", "dpe_probe_tex_rate",
-    "dpe_probe_fma_rate", "dpe_probe_tex_weights", "dpe_run_pipeline",
+    "dpe_probe_fma_rate", "dpe_probe_tex_weights", "dpe_run_pipeline", "dpe_set_profile", "dpe_get_profile",
 ]
 
 _lib = None
@@ -79,6 +79,8 @@ def load(build=True):
     lib.dpe_probe_tex_rate.argtypes = [vp, ci, ci, ci, C.POINTER(C.c_double)]
     lib.dpe_probe_fma_rate.argtypes = [vp, ci, C.POINTER(C.c_double)]
     lib.dpe_probe_tex_weights.argtypes = [vp, ci, vp]
+    lib.dpe_set_profile.argtypes = [vp, ci]
+    lib.dpe_get_profile.argtypes = [vp, vp, vp, vp]
     lib.dpe_run_pipeline.argtypes = [C.c_char_p, ci, ci, ci, ci, ci, ci, ci, ci]
     _lib = lib
     return lib
@@ -223,6 +225,18 @@ class Context:
 
     def kernel_launches(self):
         return self.lib.dpe_kernel_launches(self.h)
+
+    KERNEL_CLASSES = ["load", "edge_info", "nearest_strong", "gen_neighbours", "init", "strong_sweep", "fit_plane",
+                      "weak_sweep", "extract", "median", "classify_refine", "finish"]
+
+    def set_profile(self, on):
+        self._ck(self.lib.dpe_set_profile(self.h, int(on)))
+
+    def get_profile(self):
+        n = len(self.KERNEL_CLASSES)
+        ms, units, launches = np.zeros(n), np.zeros(n), np.zeros(n, np.int64)
+        self._ck(self.lib.dpe_get_profile(self.h, ms.ctypes.data, units.ctypes.data, launches.ctypes.data))
+        return {k: dict(ms=float(ms[i]), units=float(units[i]), launches=int(launches[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
 
     def probe_tex_rate(self, w=2048, h=2048, iters=200):
         r = C.c_double()

@@ -79,6 +79,12 @@ struct dpe_ctx {
   double stage_ms = 0.0;
   uint32_t stage_counter = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // per-kernel-class profile (dpe_set_profile): single stream, CUDA events around each launch
+  bool profile = false;
+  double prof_ms[DPE_N_KERNEL_CLASSES] = {0};
+  double prof_units[DPE_N_KERNEL_CLASSES] = {0};
+  long long prof_launches[DPE_N_KERNEL_CLASSES] = {0};
+  cudaEvent_t pa = nullptr, pb = nullptr;
 };
 
 #define CK(call)                                                                         \
@@ -137,6 +143,8 @@ int dpe_ctx_create(dpe_ctx** out, int gpu_index) {
   if (cudaGetDeviceProperties(&prop, gpu_index) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
   cudaEventCreate(&ctx->ev0);
   cudaEventCreate(&ctx->ev1);
+  cudaEventCreate(&ctx->pa);
+  cudaEventCreate(&ctx->pb);
   cudaMalloc(&ctx->d_eval_units, sizeof(unsigned long long));
   cudaMemset(ctx->d_eval_units, 0, sizeof(unsigned long long));
   *out = ctx;
@@ -151,6 +159,8 @@ void dpe_ctx_destroy(dpe_ctx* ctx) {
   cudaFree(ctx->d_eval_units);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->pa) cudaEventDestroy(ctx->pa);
+  if (ctx->pb) cudaEventDestroy(ctx->pb);
   delete ctx;
 }
 
@@ -357,7 +367,7 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
     const int view = ctx->first_view + li;
     ViewData& v = ctx->views[view];
     if (p->state != DPE_FIRST_INIT && v.cur_scale < 0) FAIL(DPE_ERR_STATE, "refine stage before first init");
-    Scratch& s = ctx->scratch[li % ns];
+    Scratch& s = ctx->scratch[ctx->profile ? 0 : li % ns];
     KernelParams KP;
     fill_args(ctx, view, k, p, seed, s, &KP);
     StageArgs& a = KP.a;
@@ -375,28 +385,43 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
     a.atlas_out = ctx->atlas_back[k] + (size_t)view * P;
 
     cudaStream_t st = s.stream;
-    if (p->state != DPE_FIRST_INIT) launch_load(KP, cfg, st);
+    // in profile mode every launch is bracketed by CUDA events on its own stream and the
+    // eval-unit counter is read back after it
+    auto L = [&](int cls, void (*fn)(const KernelParams&, const LaunchCfg&, cudaStream_t)) {
+      if (!ctx->profile) { fn(KP, cfg, st); return; }
+      unsigned long long u0 = 0, u1 = 0;
+      cudaMemcpyAsync(&u0, ctx->d_eval_units, sizeof(u0), cudaMemcpyDeviceToHost, st);
+      cudaEventRecord(ctx->pa, st);
+      fn(KP, cfg, st);
+      cudaEventRecord(ctx->pb, st);
+      cudaMemcpyAsync(&u1, ctx->d_eval_units, sizeof(u1), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx->pa, ctx->pb);
+      ctx->prof_ms[cls] += ms; ctx->prof_units[cls] += (double)(u1 - u0); ctx->prof_launches[cls]++;
+    };
+    if (p->state != DPE_FIRST_INIT) L(DPE_K_LOAD, launch_load);
     if (p->use_apd) {
-      launch_edge_info(KP, cfg, st);
-      launch_nearest_strong(KP, cfg, st);
-      launch_gen_neighbours(KP, cfg, st);
+      L(DPE_K_EDGE_INFO, launch_edge_info);
+      L(DPE_K_NEAREST, launch_nearest_strong);
+      L(DPE_K_NEIGHBOURS, launch_gen_neighbours);
     }
-    launch_init(KP, cfg, st);
+    L(DPE_K_INIT, launch_init);
     for (int it = 0; it < p->max_iterations; ++it) {
       a.iter = it;
-      a.colour = 0; launch_strong(KP, cfg, st);
-      a.colour = 1; launch_strong(KP, cfg, st);
+      a.colour = 0; L(DPE_K_STRONG, launch_strong);
+      a.colour = 1; L(DPE_K_STRONG, launch_strong);
       if (p->use_apd) {
-        launch_fit_plane(KP, cfg, st);
-        a.colour = 0; launch_weak(KP, cfg, st);
-        a.colour = 1; launch_weak(KP, cfg, st);
+        L(DPE_K_FIT, launch_fit_plane);
+        a.colour = 0; L(DPE_K_WEAK, launch_weak);
+        a.colour = 1; L(DPE_K_WEAK, launch_weak);
       }
     }
-    launch_extract(KP, cfg, st);
-    a.colour = 0; launch_median(KP, cfg, st);
-    a.colour = 1; launch_median(KP, cfg, st);
-    launch_classify_refine(KP, cfg, st);
-    launch_finish(KP, cfg, st);
+    L(DPE_K_EXTRACT, launch_extract);
+    a.colour = 0; L(DPE_K_MEDIAN, launch_median);
+    a.colour = 1; L(DPE_K_MEDIAN, launch_median);
+    L(DPE_K_CLASSIFY, launch_classify_refine);
+    L(DPE_K_FINISH, launch_finish);
     if (realloc) {
       to_free.push_back(v.planes); to_free.push_back(v.state); to_free.push_back(v.selected);
       v.planes = new_planes; v.state = new_state; v.selected = new_sel; v.cur_scale = k;
@@ -523,6 +548,26 @@ double dpe_eval_units(dpe_ctx* ctx) {
 }
 
 double dpe_stage_gpu_ms(dpe_ctx* ctx) { return ctx ? ctx->stage_ms : 0.0; }
+
+int dpe_set_profile(dpe_ctx* ctx, int on) {
+  if (!ctx) return DPE_ERR_ARG;
+  ctx->profile = on != 0;
+  if (on) {
+    ctx->count_evals = true;
+    for (int i = 0; i < DPE_N_KERNEL_CLASSES; ++i) { ctx->prof_ms[i] = 0; ctx->prof_units[i] = 0; ctx->prof_launches[i] = 0; }
+  }
+  return DPE_OK;
+}
+
+int dpe_get_profile(dpe_ctx* ctx, double* ms, double* units, long long* launches) {
+  if (!ctx) return DPE_ERR_ARG;
+  for (int i = 0; i < DPE_N_KERNEL_CLASSES; ++i) {
+    if (ms) ms[i] = ctx->prof_ms[i];
+    if (units) units[i] = ctx->prof_units[i];
+    if (launches) launches[i] = ctx->prof_launches[i];
+  }
+  return DPE_OK;
+}
 
 int dpe_probe_tex_rate(dpe_ctx* ctx, int width, int height, int iters, double* taps_per_s) {
   if (!ctx || width < 64 || height < 64 || iters <= 0 || !taps_per_s) return DPE_ERR_ARG;

@@ -205,3 +205,44 @@ bool jpeg_decode_bgr(JpegDecoder* d, const std::string& path, std::vector<uint8_
 }
 
 }  // namespace dpe_host
+
+// C hooks for the CPU tests (tests/test_io.py)
+extern "C" {
+#define DPE_TEST_API __attribute__((visibility("default")))
+DPE_TEST_API int dpe_host_write_npy(const char* path, const void* data, const char* descr, int elem_size, int rows, int cols,
+                                    int channels) {
+  return dpe_host::write_npy(path, data, descr, (size_t)elem_size, rows, cols, channels) ? 0 : -1;
+}
+// out: K[9] R[9] t[3] depth_min depth_max (23 floats)
+DPE_TEST_API int dpe_host_read_cam(const char* path, float* out) {
+  dpe_host::CamFile c;
+  if (!dpe_host::read_cam(path, &c)) return -1;
+  memcpy(out, c.K, 36); memcpy(out + 9, c.R, 36); memcpy(out + 18, c.t, 12);
+  out[21] = c.depth_min; out[22] = c.depth_max;
+  return 0;
+}
+// out: per problem: ref_id, n_src, src ids...; returns number of ints written (or -1)
+DPE_TEST_API int dpe_host_read_pairs(const char* path, int* out, int cap) {
+  std::vector<dpe_host::ProblemDesc> p;
+  if (!dpe_host::read_pairs(path, &p)) return -1;
+  int n = 0;
+  for (const auto& q : p) {
+    if (n + 2 + (int)q.src_image_ids.size() > cap) return -1;
+    out[n++] = q.ref_image_id; out[n++] = (int)q.src_image_ids.size();
+    for (int s : q.src_image_ids) out[n++] = s;
+  }
+  return n;
+}
+}
+
+extern "C" DPE_TEST_API int dpe_host_decode_gray(const char* path, unsigned char* out, int cap, int* w, int* h) {
+  std::string err;
+  dpe_host::JpegDecoder* d = dpe_host::jpeg_decoder_create(&err);
+  if (!d) return -1;
+  std::vector<uint8_t> g;
+  const bool ok = dpe_host::jpeg_decode_gray(d, path, &g, w, h, &err);
+  dpe_host::jpeg_decoder_destroy(d);
+  if (!ok || (int)g.size() > cap) return -2;
+  memcpy(out, g.data(), g.size());
+  return 0;
+}

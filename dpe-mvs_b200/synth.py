@@ -271,7 +271,8 @@ def write_scene(spec: SceneSpec, out_dir, device=None, save_gt=True, jpeg_qualit
         write_cam(out / "cams" / f"{v:08d}_cam.txt", K, R, t, dmin, dmax)
         if save_gt:
             np.save(out / "gt" / f"{v:08d}_depth.npy", depth)
-            np.save(out / "gt" / f"{v:08d}_normal.npy", normal)
+            if save_gt != "depth":
+                np.save(out / "gt" / f"{v:08d}_normal.npy", normal)
     pairs = select_pairs(spec)
     with open(out / "pair.txt", "w") as f:
         f.write(f"{spec.n_views}\n")

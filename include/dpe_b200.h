@@ -131,6 +131,16 @@ DPE_API double dpe_eval_units(dpe_ctx* ctx);
 /* GPU milliseconds spent inside dpe_run_stage so far (CUDA events). */
 DPE_API double dpe_stage_gpu_ms(dpe_ctx* ctx);
 
+/* per-kernel-class profile: when on, dpe_run_stage runs its views on one stream with CUDA
+ * events around every launch and reads the eval-unit counter after it.  Classes index the
+ * arrays returned by dpe_get_profile (each DPE_N_KERNEL_CLASSES long). */
+enum {
+  DPE_K_LOAD = 0, DPE_K_EDGE_INFO, DPE_K_NEAREST, DPE_K_NEIGHBOURS, DPE_K_INIT, DPE_K_STRONG, DPE_K_FIT,
+  DPE_K_WEAK, DPE_K_EXTRACT, DPE_K_MEDIAN, DPE_K_CLASSIFY, DPE_K_FINISH, DPE_N_KERNEL_CLASSES
+};
+DPE_API int dpe_set_profile(dpe_ctx* ctx, int on);
+DPE_API int dpe_get_profile(dpe_ctx* ctx, double* ms, double* units, long long* launches);
+
 /* --- micro-benchmarks used for the roofline denominators ------------------ */
 /* filtered tex2D<float> taps per second on a WxH float texture */
 DPE_API int dpe_probe_tex_rate(dpe_ctx* ctx, int width, int height, int iters, double* taps_per_s);

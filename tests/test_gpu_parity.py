@@ -1,0 +1,276 @@
+"""Parity tests proper: the CUDA path through the C ABI against the float64 oracle, the golden
+vectors produced by the reference's own device code, the CPU logic simulator and ground truth.
+Need a B200 (`-m gpu`)."""
+import ctypes as C
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import capi
+import ncc_oracle as O
+import synth
+from scenes import seeded_hypotheses, small_scene
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+FIX = ROOT / "tests" / "golden" / "ref_probe_c1.npz"
+
+
+@pytest.fixture(scope="module")
+def ctx_c1():
+    spec, grays, cams, drs, pairs, gt = small_scene("c1", 0.5)
+    ctx = capi.Context(0)
+    ns = capi.upload_scene(ctx, grays, cams, drs, pairs)
+    yield ctx, ns, spec, grays, cams, drs, pairs, gt
+    ctx.close()
+
+
+def _oracle_costs(grays, cams, pairs, xy, planes, quant):
+    ref = grays[0].astype(np.float32)
+    return np.array([[O.bilateral_ncc_old(ref, grays[s].astype(np.float32), cams[0], cams[s], int(x), int(y),
+                                          planes[i].astype(np.float64), quant=quant) for s in pairs[0]]
+                     for i, (x, y) in enumerate(xy)])
+
+
+def test_gate1_cost_kernel_exact_bilinear(ctx_c1):
+    """Gate 1 (BASELINE.json): with fixed plane hypotheses the NCC kernel matches a float64
+    host evaluation of the reference formula within 1e-4 (source taps blended in fp32 from 4
+    point-sampled texels)."""
+    ctx, ns, spec, grays, cams, drs, pairs, gt = ctx_c1
+    xy, planes = seeded_hypotheses(spec, cams, gt, 400)
+    got = ctx.cost_eval(0, ns - 1, xy, planes, len(pairs[0]), mode=1)
+    want = _oracle_costs(grays, cams, pairs, xy, planes, quant=0)
+    assert np.abs(got - want).max() <= 1e-4
+
+
+def test_gate1_cost_kernel_hardware_filter(ctx_c1):
+    """The product path (texture-unit bilinear, 1.8 fixed-point weights) against the oracle
+    with the same weight model: equal except where an fp32 source coordinate falls into the
+    neighbouring 1/256 bin.  Tolerance: median 2e-4, 99th percentile 3e-3."""
+    ctx, ns, spec, grays, cams, drs, pairs, gt = ctx_c1
+    xy, planes = seeded_hypotheses(spec, cams, gt, 400, seed=1)
+    got = ctx.cost_eval(0, ns - 1, xy, planes, len(pairs[0]), mode=0)
+    want = _oracle_costs(grays, cams, pairs, xy, planes, quant=1)
+    d = np.abs(got - want)
+    assert np.median(d) < 2e-4 and np.percentile(d, 99) < 3e-3 and d.max() < 2e-2
+
+
+def test_cost_kernel_edge_cases(ctx_c1):
+    ctx, ns, spec, grays, cams, drs, pairs, gt = ctx_c1
+    W, H = spec.width, spec.height
+    # image corners and borders (clamp addressing of the reference taps), far / degenerate planes
+    xy = np.array([[0, 0], [W - 1, 0], [0, H - 1], [W - 1, H - 1], [3, H // 2], [W // 2, 2], [W // 2, H // 2]], np.int32)
+    _, planes = seeded_hypotheses(spec, cams, gt, len(xy), seed=2, margin=8)
+    planes[-1] = [0, 0, -1, 0.05]
+    got = ctx.cost_eval(0, ns - 1, xy, planes, len(pairs[0]), mode=1)
+    want = _oracle_costs(grays, cams, pairs, xy, planes, quant=0)
+    assert np.array_equal(got == 2.0, want == 2.0)
+    assert np.abs(got - want).max() <= 1e-4
+
+
+def test_cost_kernel_matches_reference_golden_vectors():
+    """The CUDA kernel against outputs of the reference's own ComputeBilateralNCCOld and
+    ComputeGeomConsistencyCost (tests/golden/ref_probe_c1.npz, made by oracle/make_golden.py)."""
+    fx = np.load(FIX)
+    imgs = [fx["images"][i] for i in range(4)]
+    cams = [(fx["K"][i], fx["R"][i], fx["t"][i]) for i in range(4)]
+    ctx = capi.Context(0)
+    H, W = imgs[0].shape
+    ctx.scene_begin(4, W, H, 1)
+    for v in range(4):
+        ctx.set_view(v, imgs[v], *cams[v], 1.0, 10.0)
+    ctx.set_pairs(0, [1, 2, 3])
+    ctx.commit()
+    got = ctx.cost_eval(0, 0, fx["xy"], fx["planes"], 3, mode=0)
+    ref = fx["ref_ncc"]
+    assert ((got >= 2.0) == (ref >= 2.0)).mean() > 0.995
+    both = (got < 2.0) & (ref < 2.0)
+    d = np.abs(got - ref)[both]
+    assert np.median(d) < 2e-4 and np.percentile(d, 99) < 3e-3, (np.median(d), np.percentile(d, 99))
+    ctx.close()
+
+
+def test_geom_eval_matches_oracle(ctx_c1):
+    ctx, ns, spec, grays, cams, drs, pairs, gt = ctx_c1
+    # run the first stage so that the atlas holds depth maps, then evaluate against them
+    sched = capi.stage_schedule(ns)
+    ctx.run_stage(*sched[0], 11)
+    ctx.stage_commit()
+    k = 0
+    w, h = ctx.size(k)
+    src_depth = [ctx.get_maps(s, k)["depth"] for s in pairs[0]]
+    rng = np.random.default_rng(4)
+    n = 200
+    xy = np.stack([rng.integers(8, w - 8, n), rng.integers(8, h - 8, n)], 1).astype(np.int32)
+    Kc = O.scale_camera(cams[0][0], w, h, spec.width, spec.height)
+    planes = np.zeros((n, 4), np.float32)
+    g = gt[0][0][::2, ::2]
+    for i, (x, y) in enumerate(xy):
+        d = float(g[y, x]) * (1 + rng.normal(0, 0.02))
+        nrm = np.array([0.0, 0.0, -1.0])
+        X = d * np.array([(x - Kc[0, 2]) / Kc[0, 0], (y - Kc[1, 2]) / Kc[1, 1], 1.0])
+        planes[i] = [*nrm, -float(nrm @ X)]
+    got = ctx.geom_eval(0, k, xy, planes, len(pairs[0]))
+    want = np.zeros_like(got)
+    for i, (x, y) in enumerate(xy):
+        for j, s in enumerate(pairs[0]):
+            Ks = O.scale_camera(cams[s][0], w, h, spec.width, spec.height)
+            want[i, j] = O.geom_consistency_cost((Kc, cams[0][1], cams[0][2]), (Ks, cams[s][1], cams[s][2]), src_depth[j], int(x), int(y), planes[i].astype(np.float64))
+    d = np.abs(got - want)
+    assert ((got == 3.0) == (want == 3.0)).mean() > 0.98
+    assert np.median(d) < 1e-3 and np.percentile(d, 95) < 5e-2
+
+
+def test_stage_matches_cpu_simulator():
+    """Same per-pixel code, same Philox stream: the GPU stage and its CPU simulation agree on
+    almost every pixel (they differ only in fp contraction and texture coordinate rounding)."""
+    import simpipe
+    spec, grays, cams, drs, pairs, gt = small_scene("c1", 0.25)
+    ctx = capi.Context(0)
+    ns = capi.upload_scene(ctx, grays, cams, drs, pairs)
+    k, p = capi.stage_schedule(ns)[0]
+    ctx.run_stage(k, p, 20261018)
+    ctx.stage_commit()
+    g = ctx.get_maps(0, 0)
+    st, _ = simpipe.run(grays, cams, drs, pairs, ns, stages=1, views=[0], seed=20261018)
+    s = st[0]
+    both = (g["depth"] > 0) & (s["depth"] > 0)
+    rel = np.abs(g["depth"] - s["depth"]) / np.maximum(s["depth"], 1e-6)
+    assert both.mean() > 0.8
+    assert (rel[both] < 0.01).mean() > 0.85
+    assert (g["state"] == s["state"]).mean() > 0.85
+    ctx.close()
+
+
+def _run_schedule(ctx, ns, seed=3):
+    for (k, p) in capi.stage_schedule(ns):
+        ctx.run_stage(k, p, seed)
+        ctx.stage_commit()
+
+
+def test_results_do_not_depend_on_sharding():
+    """Two contexts owning half of the views each, exchanging their atlas chunks after every
+    stage (what bench.py does with NCCL), give bit-identical maps to one context."""
+    import torch
+    spec, grays, cams, drs, pairs, gt = small_scene("c1", 0.25)
+    V = len(grays)
+    one = capi.Context(0)
+    ns = capi.upload_scene(one, grays, cams, drs, pairs)
+    _run_schedule(one, ns)
+    want = [one.get_maps(v, ns - 1) for v in range(V)]
+    one.close()
+    spr = (V + 1) // 2
+    ctxs = []
+    for r in range(2):
+        c = capi.Context(0)
+        first = r * spr
+        capi.upload_scene(c, grays, cams, drs, pairs, ns, shard=(first, min(spr, V - first), spr, 2))
+        ctxs.append(c)
+
+    def tensor(c):
+        ptr, chunk, total = c.stage_atlas()
+
+        class Raw:
+            __cuda_array_interface__ = {"shape": (total // 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(Raw(), device="cuda:0"), chunk // 4
+
+    for (k, p) in capi.stage_schedule(ns):
+        for c in ctxs:
+            c.run_stage(k, p, 3)
+        (t0, ch), (t1, _) = tensor(ctxs[0]), tensor(ctxs[1])
+        t1[0:ch] = t0[0:ch]
+        t0[ch:2 * ch] = t1[ch:2 * ch]
+        torch.cuda.synchronize()
+        for c in ctxs:
+            c.stage_commit()
+    for v in range(V):
+        got = ctxs[v // spr].get_maps(v, ns - 1)
+        for key in ("depth", "normal", "state", "selected"):
+            assert np.array_equal(got[key], want[v][key]), (v, key)
+    for c in ctxs:
+        c.close()
+
+
+def test_error_paths():
+    spec, grays, cams, drs, pairs, gt = small_scene("c1", 0.25)
+    ctx = capi.Context(0)
+    ctx.scene_begin(len(grays), spec.width, spec.height, 2)
+    with pytest.raises(capi.DpeError):          # > 31 sources (DPE.cpp:762-765)
+        ctx.set_pairs(0, [1] * 32)
+    with pytest.raises(capi.DpeError):          # stage before commit
+        ctx.run_stage(0, capi.stage_schedule(2)[0][1], 1)
+    for v in range(len(grays)):
+        ctx.set_view(v, grays[v], *cams[v], *drs[v])
+        ctx.set_pairs(v, pairs[v])
+    ctx.commit()
+    with pytest.raises(capi.DpeError):          # refine stage before the first initialisation
+        ctx.run_stage(0, capi.stage_schedule(2)[1][1], 1)
+    ctx.close()
+
+
+@pytest.fixture(scope="module")
+def c1_folder(tmp_path_factory):
+    folder = tmp_path_factory.mktemp("c1half")
+    spec = synth.make_scene("c1", scale=0.5)
+    synth.write_scene(spec, folder)
+    return spec, folder
+
+
+def test_jpeg_decode_close_to_cv2(c1_folder):
+    import cv2
+    spec, folder = c1_folder
+    lib = capi.load()
+    p = folder / "images" / "00000000.jpg"
+    buf = np.zeros(spec.width * spec.height, np.uint8)
+    w, h = C.c_int(), C.c_int()
+    assert lib.dpe_host_decode_gray(str(p).encode(), buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(w), C.byref(h)) == 0
+    assert (w.value, h.value) == (spec.width, spec.height)
+    ref = cv2.imread(str(p), cv2.IMREAD_GRAYSCALE)
+    d = np.abs(buf.reshape(ref.shape).astype(int) - ref.astype(int))
+    assert d.max() <= 2 and d.mean() < 0.25, (d.max(), d.mean())
+
+
+def test_pipeline_python_api_and_cli(c1_folder):
+    """DPE_MVS.dpe_mvs end to end: output files, shapes, dtypes, value sets, accuracy, cleanup,
+    determinism, and the CLI producing the same maps."""
+    import DPE_MVS
+    spec, folder = c1_folder
+    shutil.rmtree(folder / "DPE", ignore_errors=True)
+    assert DPE_MVS.dpe_mvs(str(folder), 0, False, False, False, True, True, True, True) == 0
+    H, W = spec.height, spec.width
+    out = {}
+    for v in range(spec.n_views):
+        d = folder / "DPE" / f"{v:08d}"
+        depth, normal, weak, edge = (np.load(d / f"{n}.npy") for n in ("depth", "normal", "weak", "edge"))
+        assert depth.shape == (H, W) and depth.dtype == np.dtype("<f4")
+        assert normal.shape == (H, W, 3) and normal.dtype == np.dtype("<f4")
+        assert weak.shape == (H, W) and weak.dtype == np.int8 and set(np.unique(weak)) <= {0, 1, 2}
+        assert edge.shape == (H, W) and edge.dtype == np.int8 and set(np.unique(edge)) <= {0, 1}
+        assert (depth[weak == 0] == 0).all()                       # ZeroDepthForUnknown
+        assert sorted(p.name for p in d.iterdir()) == ["depth.npy", "edge.npy", "normal.npy", "weak.npy"]
+        out[v] = (depth, normal, weak)
+    gt_d = np.load(folder / "gt" / "00000000_depth.npy")
+    m = (gt_d > 0) & (out[0][0] > 0)
+    rel = np.abs(out[0][0] - gt_d) / np.maximum(gt_d, 1e-6)
+    assert m.mean() > 0.8 and (rel[m] < 0.01).mean() > 0.85
+    # same seed, same result; the CLI (argument order: dense gpu verbose viz fusion depth normal weak edge)
+    exe = ROOT / "dpe-mvs_b200" / "bin" / "DPE"
+    shutil.rmtree(folder / "DPE")
+    p = subprocess.run([str(exe), str(folder), "0", "1", "0", "0", "1", "1", "1", "0"], capture_output=True, text=True)
+    assert p.returncode == 0
+    assert "There are 5 images to be processed!" in p.stdout and "Iteration 8 / 8 done" in p.stdout and "All done" in p.stdout
+    for v in range(spec.n_views):
+        d = folder / "DPE" / f"{v:08d}"
+        assert np.array_equal(np.load(d / "depth.npy"), out[v][0])
+        assert np.array_equal(np.load(d / "weak.npy"), out[v][2])
+        assert not (d / "edge.npy").exists()
+
+
+def test_pipeline_rejects_bad_input(tmp_path):
+    import DPE_MVS
+    (tmp_path / "pair.txt").write_text("1\n0\n0\n")
+    with pytest.raises(RuntimeError, match="DPE-MVS failed with code 1"):
+        DPE_MVS.dpe_mvs(str(tmp_path), verbose=False)

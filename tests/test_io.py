@@ -1,0 +1,47 @@
+"""Input / output contract of the host pipeline: pair.txt, cam files, .npy writer.  CPU only."""
+import ctypes as C
+
+import numpy as np
+
+import capi
+import synth
+
+
+def test_npy_writer_matches_reference_header(tmp_path):
+    lib = capi.load()
+    for arr, descr in [(np.arange(12, dtype=np.float32).reshape(3, 4), b"<f4"),
+                       (np.arange(24, dtype=np.float32).reshape(2, 4, 3), b"<f4"),
+                       (np.arange(12, dtype=np.int8).reshape(3, 4), b"|i1")]:
+        p = tmp_path / "a.npy"
+        ch = arr.shape[2] if arr.ndim == 3 else 1
+        assert lib.dpe_host_write_npy(str(p).encode(), arr.ctypes.data_as(C.c_void_p), descr, arr.itemsize, arr.shape[0], arr.shape[1], ch) == 0
+        raw = p.read_bytes()
+        assert raw[:8] == b"\x93NUMPY\x01\x00"
+        hlen = int.from_bytes(raw[8:10], "little")
+        assert (10 + hlen) % 16 == 0                       # main.cpp:78-81
+        header = raw[10:10 + hlen].decode()
+        shape = ", ".join(str(s) for s in arr.shape)
+        assert header.startswith("{'descr': '%s', 'fortran_order': False, 'shape': (%s), }" % (descr.decode(), shape))
+        assert header.endswith("\n")
+        back = np.load(p)
+        assert back.dtype == arr.dtype and np.array_equal(back, arr)
+
+
+def test_cam_and_pair_parsers(tmp_path):
+    lib = capi.load()
+    K = np.array([[576.0, 0, 320], [0, 577.5, 240], [0, 0, 1]])
+    R = np.eye(3)[[1, 0, 2]].astype(float)
+    t = np.array([0.1, -0.2, 3.0])
+    synth.write_cam(tmp_path / "c.txt", K, R, t, 1.25, 9.5)
+    out = np.zeros(23, np.float32)
+    assert lib.dpe_host_read_cam(str(tmp_path / "c.txt").encode(), out.ctypes.data_as(C.c_void_p)) == 0
+    assert np.allclose(out[:9].reshape(3, 3), K) and np.allclose(out[9:18].reshape(3, 3), R) and np.allclose(out[18:21], t)
+    assert abs(out[21] - 1.25) < 1e-6 and abs(out[22] - 9.5) < 1e-6
+    Kp, Rp, tp, dmin, dmax = synth.read_cam(tmp_path / "c.txt")
+    assert np.allclose(Kp, K) and np.allclose(tp, t) and (dmin, dmax) == (1.25, 9.5)
+    # pair.txt: sources with score <= 0 are dropped (main.cpp:301-303); ragged lists; empty list
+    (tmp_path / "pair.txt").write_text("3\n7\n3 1 10.5 2 0.0 3 2.0\n1\n0\n2\n2 7 -1 1 5\n")
+    buf = np.zeros(64, np.int32)
+    n = lib.dpe_host_read_pairs(str(tmp_path / "pair.txt").encode(), buf.ctypes.data_as(C.c_void_p), 64)
+    assert list(buf[:n]) == [7, 2, 1, 3, 1, 0, 2, 1, 1]
+    assert lib.dpe_host_read_pairs(str(tmp_path / "missing.txt").encode(), buf.ctypes.data_as(C.c_void_p), 64) == -1

@@ -1,0 +1,115 @@
+"""Host logic of the PatchMatch path through the TEST-ONLY CPU simulator (same per-pixel code
+as the kernels, compiled for the host) against the float64 oracle and against ground truth.
+CPU only."""
+import numpy as np
+import pytest
+
+import hostsim
+import ncc_oracle as O
+import simpipe
+from scenes import seeded_hypotheses, small_scene
+
+
+def test_cost_core_matches_oracle_exact_bilinear():
+    """Gate 1 on the CPU build of the kernel's cost routine: fp32 with exact bilinear weights
+    vs float64 of the reference formula, tolerance 1e-4 (BASELINE.json north_star)."""
+    spec, grays, cams, drs, pairs, gt = small_scene()
+    xy, planes = seeded_hypotheses(spec, cams, gt, 150)
+    ids = [0] + pairs[0]
+    imgs = [grays[i].astype(np.float32) for i in ids]
+    cc = [cams[i] for i in ids]
+    got = hostsim.cost_eval(imgs, cc, (spec.width, spec.height), xy, planes, quant=0)
+    for i, (x, y) in enumerate(xy):
+        for v in range(len(ids) - 1):
+            want = O.bilateral_ncc_old(imgs[0], imgs[v + 1], cc[0], cc[v + 1], int(x), int(y), planes[i].astype(np.float64), quant=0)
+            assert abs(got[i, v] - want) <= 1e-4
+
+
+def test_cost_core_texture_model_statistics():
+    """With the 1.8 fixed-point weight model on both sides the only difference is fp32 vs
+    float64 coordinates landing in neighbouring 1/256 bins."""
+    spec, grays, cams, drs, pairs, gt = small_scene()
+    xy, planes = seeded_hypotheses(spec, cams, gt, 100, seed=3)
+    ids = [0] + pairs[0]
+    imgs = [grays[i].astype(np.float32) for i in ids]
+    cc = [cams[i] for i in ids]
+    got = hostsim.cost_eval(imgs, cc, (spec.width, spec.height), xy, planes, quant=1)
+    want = np.array([[O.bilateral_ncc_old(imgs[0], imgs[v + 1], cc[0], cc[v + 1], int(x), int(y), planes[i].astype(np.float64), quant=1)
+                      for v in range(len(ids) - 1)] for i, (x, y) in enumerate(xy)])
+    d = np.abs(got - want)
+    assert np.median(d) < 1e-5 and np.percentile(d, 99) < 2e-3
+
+
+def test_out_of_image_and_flat_patch_give_cost_max():
+    spec, grays, cams, drs, pairs, gt = small_scene()
+    ids = [0] + pairs[0]
+    imgs = [grays[i].astype(np.float32) for i in ids]
+    cc = [cams[i] for i in ids]
+    # a plane far behind the scene projects outside every source image
+    xy = np.array([[5, 5], [80, 60]], np.int32)
+    planes = np.array([[0, 0, -1, 0.05], [0, 0, -1, 0.05]], np.float32)
+    got = hostsim.cost_eval(imgs, cc, (spec.width, spec.height), xy, planes, quant=0)
+    want = np.array([[O.bilateral_ncc_old(imgs[0], imgs[v + 1], cc[0], cc[v + 1], int(x), int(y), planes[i].astype(np.float64), quant=0)
+                      for v in range(len(ids) - 1)] for i, (x, y) in enumerate(xy)])
+    assert np.array_equal(got == 2.0, want == 2.0)
+    flat = [np.full_like(imgs[0], 77.0)] + imgs[1:]
+    xy2, pl2 = seeded_hypotheses(spec, cams, gt, 5)
+    assert (hostsim.cost_eval(flat, cc, (spec.width, spec.height), xy2, pl2, quant=0) == 2.0).all()   # var_ref < 1e-5
+
+
+def test_first_stage_converges_to_ground_truth():
+    spec, grays, cams, drs, pairs, gt = small_scene()
+    st, units = simpipe.run(grays, cams, drs, pairs, 2, stages=1, views=[0])
+    d = st[0]["depth"]
+    g = gt[0][0][::2, ::2]
+    assert d.shape == g.shape == (60, 80)
+    rel = np.abs(d - g) / np.maximum(g, 1e-6)
+    assert (rel[g > 0] < 0.05).mean() > 0.55
+    # eval accounting: init N + 3 iterations x 2 colours... between 200 and 500 units per pixel (N = 4)
+    assert 200 < units[0] / d.size < 500
+    # outputs are well-formed
+    assert set(np.unique(st[0]["state"])) <= {0, 1, 2}
+    n = st[0]["planes"][..., :3]
+    assert np.allclose(np.linalg.norm(n, axis=-1), 1.0, atol=1e-3)
+    assert (st[0]["selected"] < (1 << 4)).all()
+    assert (st[0]["state"][:6] == hostsim.UNKNOWN).all() and (st[0]["state"][:, :6] == hostsim.UNKNOWN).all()   # 6-px border (Q15)
+
+
+def test_stage_is_deterministic_and_seed_dependent():
+    spec, grays, cams, drs, pairs, gt = small_scene()
+    a, _ = simpipe.run(grays, cams, drs, pairs, 2, stages=1, views=[0], seed=5)
+    b, _ = simpipe.run(grays, cams, drs, pairs, 2, stages=1, views=[0], seed=5)
+    c, _ = simpipe.run(grays, cams, drs, pairs, 2, stages=1, views=[0], seed=6)
+    assert np.array_equal(a[0]["planes"], b[0]["planes"]) and np.array_equal(a[0]["state"], b[0]["state"])
+    assert not np.array_equal(a[0]["planes"], c[0]["planes"])
+
+
+@pytest.mark.timeout(600)
+def test_full_schedule_with_weak_path():
+    """All 8 stages (2 scales) including the weak/edge path on a scene with low-texture
+    planes; prep arrays from the product's C++ prep."""
+    import ctypes as C
+    import capi
+    spec, grays, cams, drs, pairs, gt = small_scene("c4", 0.05, 5)      # 151 x 101
+    lib = capi.load()
+    H, W = grays[0].shape
+    sizes = simpipe.level_sizes(W, H, 2)
+    prep = []
+    for g in grays:
+        per = []
+        for k in range(2):
+            e = np.empty((sizes[k][1], sizes[k][0]), np.uint8)
+            l = np.empty((sizes[k][1], sizes[k][0]), np.int32)
+            gg = np.ascontiguousarray(g)
+            lib.dpe_host_problem_edges(gg.ctypes.data_as(C.c_void_p), W, H, 1 << (1 - k), e.ctypes.data_as(C.c_void_p), l.ctypes.data_as(C.c_void_p))
+            per.append((e, l))
+        prep.append(per)
+    st, units = simpipe.run(grays, cams, drs, pairs, 2, prep=prep)
+    assert len(units) == 8 and all(u > 0 for u in units)
+    d, g = st[0]["depth"], gt[0][0]
+    assert d.shape == g.shape
+    valid = (g > 0) & (d > 0)
+    rel = np.abs(d - g) / np.maximum(g, 1e-6)
+    assert valid.mean() > 0.5
+    assert (rel[valid] < 0.05).mean() > 0.6
+    assert set(np.unique(st[0]["state"])) <= {0, 1, 2}
