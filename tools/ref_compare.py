@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--ref-runs", type=int, default=2)
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-hough", action="store_true")
+    ap.add_argument("--seed2", action="store_true", help="one more reference run with a different pinned RNG seed")
     args = ap.parse_args()
     tag = args.out or args.config
     OUT = ROOT / "gpurun_out"; OUT.mkdir(exist_ok=True)
@@ -73,12 +74,14 @@ def main():
 
     # ---- reference runs
     ref_out = []
-    for run in range(args.ref_runs):
+    seed2_out = None
+    for run in range(args.ref_runs + (1 if args.seed2 else 0)):
         shutil.rmtree(folder / "DPE", ignore_errors=True)
         write_prep(folder, V, n_scales, prep)
         t0 = time.time()
+        exe = "DPE_ref_seed2" if run >= args.ref_runs else "DPE_ref"
         # argv: dense gpu verbose viz fusion depth normal weak edge   (main.cpp:602-635)
-        p = subprocess.run([str(ROOT / "oracle" / "_ref" / "DPE_ref"), str(folder), "0", "1", "0", "0", "1", "1", "1", "1"],
+        p = subprocess.run([str(ROOT / "oracle" / "_ref" / exe), str(folder), "0", "1", "0", "0", "1", "1", "1", "1"],
                            capture_output=True, text=True)
         dt = time.time() - t0
         (OUT / f"ref_{tag}_run{run}.log").write_text(p.stdout[-4000:] + "\n--- stderr\n" + p.stderr[-4000:])
@@ -89,6 +92,10 @@ def main():
         for v in range(V):
             d = folder / "DPE" / f"{v:08d}"
             maps.append((np.load(d / "depth.npy"), np.load(d / "normal.npy"), np.load(d / "weak.npy")))
+        if run >= args.ref_runs:
+            seed2_out = maps
+            print("ref seed2 run", dt, flush=True)
+            continue
         ref_out.append(maps)
         res[f"ref_run{run}_wall_s"] = dt
         res[f"ref_run{run}_depth_maps_per_s"] = V / dt
@@ -136,6 +143,8 @@ def main():
         res["ref_weak_hist"] = [[float((ref_out[0][v][2] == k).mean()) for k in range(3)] for v in range(V)]
     if len(ref_out) >= 2:
         res["ref_vs_ref"] = [compare(*ref_out[1][v], *ref_out[0][v]) for v in range(V)]
+    if seed2_out is not None and ref_out:
+        res["refseed2_vs_ref"] = [compare(*seed2_out[v], *ref_out[0][v]) for v in range(V)]
     res["ours_vs_gt"] = [vs_gt(ours[v][0], ours[v][1], *gt[v]) for v in range(V)]
     res["ours_weak_hist"] = [[float((ours[v][2] == k).mean()) for k in range(3)] for v in range(V)]
     np.savez_compressed(OUT / f"cmp_{tag}_view0.npz", ours_d=ours[0][0], ours_w=ours[0][2],
@@ -143,9 +152,10 @@ def main():
     (OUT / f"cmp_{tag}.json").write_text(json.dumps(res, indent=1))
     short = {k: v for k, v in res.items() if not isinstance(v, list)}
     print(json.dumps(short, indent=1))
-    for key in ("ours_vs_ref", "ref_vs_ref", "ref_vs_gt", "ours_vs_gt"):
+    for key in ("ours_vs_ref", "ref_vs_ref", "refseed2_vs_ref", "ref_vs_gt", "ours_vs_gt"):
         if key in res:
             print(key, json.dumps(res[key][0]))
+            print(key, "mean over views", json.dumps({k: float(np.mean([r[k] for r in res[key]])) for k in res[key][0]}))
 
 
 if __name__ == "__main__":
