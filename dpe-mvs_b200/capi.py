@@ -30,7 +30,7 @@ SYMBOLS = [
     "dpe_scene_set_view", "dpe_scene_set_pairs", "dpe_scene_set_prep", "dpe_scene_set_shard", "dpe_scene_commit",
     "dpe_run_stage", "dpe_stage_atlas", "dpe_stage_commit", "dpe_cost_eval", "dpe_geom_eval", "dpe_get_size",
     "dpe_get_maps", "dpe_set_count_evals", "dpe_eval_units", "dpe_stage_gpu_ms", "dpe_probe_tex_rate",
-    "dpe_probe_fma_rate", "dpe_probe_tex_weights", "dpe_run_pipeline", "dpe_set_profile", "dpe_get_profile",
+    "dpe_probe_fma_rate", "dpe_probe_tex_pattern", "dpe_probe_tex_weights", "dpe_run_pipeline", "dpe_set_profile", "dpe_get_profile",
 ]
 
 _lib = None
@@ -78,6 +78,7 @@ def load(build=True):
     lib.dpe_stage_gpu_ms.restype = C.c_double
     lib.dpe_probe_tex_rate.argtypes = [vp, ci, ci, ci, C.POINTER(C.c_double)]
     lib.dpe_probe_fma_rate.argtypes = [vp, ci, C.POINTER(C.c_double)]
+    lib.dpe_probe_tex_pattern.argtypes = [vp, ci, ci, ci, ci, ci, vp, ci, ci, C.POINTER(C.c_double)]
     lib.dpe_probe_tex_weights.argtypes = [vp, ci, vp]
     lib.dpe_set_profile.argtypes = [vp, ci]
     lib.dpe_get_profile.argtypes = [vp, vp, vp, vp]
@@ -241,6 +242,12 @@ class Context:
     def probe_tex_rate(self, w=2048, h=2048, iters=200):
         r = C.c_double()
         self._ck(self.lib.dpe_probe_tex_rate(self.h, w, h, iters, C.byref(r)))
+        return r.value
+
+    def probe_tex_pattern(self, fmt, layout, m=(1, 0, 0, 1), w=2048, h=2048, iters=200, threads=128, blocks_per_sm=4):
+        r = C.c_double()
+        mm = np.asarray(m, np.float32)
+        self._ck(self.lib.dpe_probe_tex_pattern(self.h, fmt, layout, w, h, iters, mm.ctypes.data, threads, blocks_per_sm, C.byref(r)))
         return r.value
 
     def probe_fma_rate(self, iters=2000):

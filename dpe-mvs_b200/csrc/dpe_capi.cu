@@ -10,6 +10,8 @@
 // "depth atlas" per scale ([slot][pixel] floats) so that a multi-GPU driver can all-gather
 // it in place.
 #include <cuda_runtime.h>
+#include <cuda_profiler_api.h>
+#include <cuda_fp16.h>
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
@@ -81,6 +83,7 @@ struct dpe_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // per-kernel-class profile (dpe_set_profile): single stream, CUDA events around each launch
   bool profile = false;
+  int profile_views = 0;  // profile only the first n local views (the others run normally)
   double prof_ms[DPE_N_KERNEL_CLASSES] = {0};
   double prof_units[DPE_N_KERNEL_CLASSES] = {0};
   long long prof_launches[DPE_N_KERNEL_CLASSES] = {0};
@@ -367,7 +370,11 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
     const int view = ctx->first_view + li;
     ViewData& v = ctx->views[view];
     if (p->state != DPE_FIRST_INIT && v.cur_scale < 0) FAIL(DPE_ERR_STATE, "refine stage before first init");
-    Scratch& s = ctx->scratch[ctx->profile ? 0 : li % ns];
+    const bool prof_view = ctx->profile && li < ctx->profile_views;
+    // an external profiler started with --profile-from-start off sees exactly the profiled views
+    if (ctx->profile && li == 0) cudaProfilerStart();
+    if (ctx->profile && li == ctx->profile_views) cudaProfilerStop();
+    Scratch& s = ctx->scratch[prof_view ? 0 : li % ns];
     KernelParams KP;
     fill_args(ctx, view, k, p, seed, s, &KP);
     StageArgs& a = KP.a;
@@ -388,7 +395,7 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
     // in profile mode every launch is bracketed by CUDA events on its own stream and the
     // eval-unit counter is read back after it
     auto L = [&](int cls, void (*fn)(const KernelParams&, const LaunchCfg&, cudaStream_t)) {
-      if (!ctx->profile) { fn(KP, cfg, st); return; }
+      if (!prof_view) { fn(KP, cfg, st); return; }
       unsigned long long u0 = 0, u1 = 0;
       cudaMemcpyAsync(&u0, ctx->d_eval_units, sizeof(u0), cudaMemcpyDeviceToHost, st);
       cudaEventRecord(ctx->pa, st);
@@ -427,6 +434,7 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
       v.planes = new_planes; v.state = new_state; v.selected = new_sel; v.cur_scale = k;
     }
   }
+  if (ctx->profile && ctx->n_local <= ctx->profile_views) cudaProfilerStop();
   CK(cudaGetLastError());
   for (int i = 0; i < ns; ++i) {
     CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
@@ -552,6 +560,7 @@ double dpe_stage_gpu_ms(dpe_ctx* ctx) { return ctx ? ctx->stage_ms : 0.0; }
 int dpe_set_profile(dpe_ctx* ctx, int on) {
   if (!ctx) return DPE_ERR_ARG;
   ctx->profile = on != 0;
+  ctx->profile_views = on;
   if (on) {
     ctx->count_evals = true;
     for (int i = 0; i < DPE_N_KERNEL_CLASSES; ++i) { ctx->prof_ms[i] = 0; ctx->prof_units[i] = 0; ctx->prof_launches[i] = 0; }
@@ -590,6 +599,52 @@ int dpe_probe_tex_rate(dpe_ctx* ctx, int width, int height, int iters, double* t
   launch_probe_tex((unsigned long long)tex, width, height, iters / 4 + 1, sink, blocks, threads, cfg, 0);  // warm-up
   CK(cudaEventRecord(ctx->ev0, 0));
   launch_probe_tex((unsigned long long)tex, width, height, iters, sink, blocks, threads, cfg, 0);
+  CK(cudaEventRecord(ctx->ev1, 0));
+  CK(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *taps_per_s = (double)blocks * threads * (double)iters * 36.0 / (ms * 1e-3);
+  cudaFree(sink); cudaDestroyTextureObject(tex); cudaFreeArray(arr);
+  return DPE_OK;
+}
+
+int dpe_probe_tex_pattern(dpe_ctx* ctx, int fmt, int layout, int width, int height, int iters, const float m[4],
+                          int threads, int blocks_per_sm, double* taps_per_s) {
+  if (!ctx || width < 128 || height < 128 || iters <= 0 || !taps_per_s || !m || fmt < 0 || fmt > 2) return DPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)width * height;
+  std::vector<float> h(n);
+  uint32_t s = 12345u;
+  for (auto& x : h) { s = s * 1664525u + 1013904223u; x = (float)(s >> 24); }
+  cudaArray_t arr; cudaTextureObject_t tex;
+  cudaTextureDesc td; memset(&td, 0, sizeof(td));
+  td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp; td.filterMode = cudaFilterModeLinear;
+  td.readMode = cudaReadModeElementType;
+  if (fmt == 0) {
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+    CK(cudaMallocArray(&arr, &cd, width, height));
+    CK(cudaMemcpy2DToArray(arr, 0, 0, h.data(), (size_t)width * 4, (size_t)width * 4, height, cudaMemcpyHostToDevice));
+  } else if (fmt == 1) {
+    std::vector<__half> hh(n);
+    for (size_t i = 0; i < n; ++i) hh[i] = __float2half(h[i]);
+    cudaChannelFormatDesc cd = cudaCreateChannelDescHalf();
+    CK(cudaMallocArray(&arr, &cd, width, height));
+    CK(cudaMemcpy2DToArray(arr, 0, 0, hh.data(), (size_t)width * 2, (size_t)width * 2, height, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<uint8_t> hb(n);
+    for (size_t i = 0; i < n; ++i) hb[i] = (uint8_t)h[i];
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+    CK(cudaMallocArray(&arr, &cd, width, height));
+    CK(cudaMemcpy2DToArray(arr, 0, 0, hb.data(), (size_t)width, (size_t)width, height, cudaMemcpyHostToDevice));
+    td.readMode = cudaReadModeNormalizedFloat;
+  }
+  cudaResourceDesc rd; memset(&rd, 0, sizeof(rd)); rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+  CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+  float* sink; CK(cudaMalloc(&sink, 4));
+  const int blocks = ctx->num_sms * blocks_per_sm;
+  const LaunchCfg cfg = cfg_of(ctx);
+  launch_probe_tex_pattern((unsigned long long)tex, width, height, iters / 4 + 1, layout, m, sink, blocks, threads, cfg, 0);
+  CK(cudaEventRecord(ctx->ev0, 0));
+  launch_probe_tex_pattern((unsigned long long)tex, width, height, iters, layout, m, sink, blocks, threads, cfg, 0);
   CK(cudaEventRecord(ctx->ev1, 0));
   CK(cudaEventSynchronize(ctx->ev1));
   float ms = 0.f; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));

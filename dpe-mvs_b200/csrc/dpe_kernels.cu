@@ -364,6 +364,39 @@ void launch_probe_tex(unsigned long long tex, int w, int h, int iters, float* si
   k_probe_tex<<<blocks, threads, 0, stream>>>((cudaTextureObject_t)tex, w, h, iters, sink);
   count(cfg);
 }
+// Lane-layout / footprint study: `layout` maps the 32 lanes of a warp to reference pixels
+// (0: 32 consecutive x; 1: red/black zig-zag over two rows, the half-sweep layout; 2: 8x4 block;
+// 3: one colour of an 8-wide x 8-tall block; 4: 16x2 block), the 2x2 matrix m maps reference
+// offsets to source offsets (rotation / scale / shear of a plane-induced homography), taps are
+// the NCC's {-5,-3,..,5}^2.
+__global__ void k_probe_tex_pattern(cudaTextureObject_t tex, int w, int h, int iters, int layout, float m00, float m01,
+                                    float m10, float m11, float* sink) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lx, ly;
+  if (layout == 0) { lx = lane; ly = 0; }
+  else if (layout == 1) { lx = lane; ly = lane & 1; }
+  else if (layout == 2) { lx = lane & 7; ly = lane >> 3; }
+  else if (layout == 3) { lx = lane & 7; ly = 2 * (lane >> 3) + (lane & 1); }
+  else { lx = lane & 15; ly = lane >> 4; }
+  const int span = w - 96;
+  float bx = 48.f + (float)((warp * 37) % span) + lx * m00 + ly * m01 + 0.37f;
+  float by = 48.f + (float)((warp * 11) % (h - 96)) + lx * m10 + ly * m11 + 0.61f;
+  float acc = 0.f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = -5; j <= 5; j += 2)
+#pragma unroll
+      for (int i = -5; i <= 5; i += 2) acc += tex2D<float>(tex, bx + m00 * i + m01 * j, by + m10 * i + m11 * j);
+    bx += 0.11f; by += 0.07f;
+  }
+  if (acc == 1234.5678f) sink[0] = acc;
+}
+void launch_probe_tex_pattern(unsigned long long tex, int w, int h, int iters, int layout, const float m[4], float* sink,
+                              int blocks, int threads, const LaunchCfg& cfg, cudaStream_t stream) {
+  k_probe_tex_pattern<<<blocks, threads, 0, stream>>>((cudaTextureObject_t)tex, w, h, iters, layout, m[0], m[1], m[2], m[3], sink);
+  count(cfg);
+}
 __global__ void k_probe_fma(int iters, float* sink) {
   float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
   float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;

@@ -45,6 +45,8 @@ void launch_geom_eval(const KernelParams& P, int n_pix, const int* xy, const flo
 // micro-benchmarks
 void launch_probe_tex(unsigned long long tex, int w, int h, int iters, float* sink, int blocks, int threads,
                       const LaunchCfg& cfg, cudaStream_t stream);
+void launch_probe_tex_pattern(unsigned long long tex, int w, int h, int iters, int layout, const float m[4], float* sink,
+                              int blocks, int threads, const LaunchCfg& cfg, cudaStream_t stream);
 void launch_probe_fma(int iters, float* sink, int blocks, int threads, const LaunchCfg& cfg,
                       cudaStream_t stream);
 void launch_probe_weights(unsigned long long tex, int n, float* out, const LaunchCfg& cfg, cudaStream_t stream);

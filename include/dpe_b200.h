@@ -131,8 +131,10 @@ DPE_API double dpe_eval_units(dpe_ctx* ctx);
 /* GPU milliseconds spent inside dpe_run_stage so far (CUDA events). */
 DPE_API double dpe_stage_gpu_ms(dpe_ctx* ctx);
 
-/* per-kernel-class profile: when on, dpe_run_stage runs its views on one stream with CUDA
- * events around every launch and reads the eval-unit counter after it.  Classes index the
+/* per-kernel-class profile: dpe_set_profile(ctx, n) with n > 0 makes dpe_run_stage bracket every
+ * launch of its first n local views with CUDA events (those views run on one stream, the eval-unit
+ * counter is read after each launch); the remaining views run as usual so that the stage still sees
+ * every view's depth map.  n = 0 switches it off.  Classes index the
  * arrays returned by dpe_get_profile (each DPE_N_KERNEL_CLASSES long). */
 enum {
   DPE_K_LOAD = 0, DPE_K_EDGE_INFO, DPE_K_NEAREST, DPE_K_NEIGHBOURS, DPE_K_INIT, DPE_K_STRONG, DPE_K_FIT,
@@ -144,6 +146,10 @@ DPE_API int dpe_get_profile(dpe_ctx* ctx, double* ms, double* units, long long* 
 /* --- micro-benchmarks used for the roofline denominators ------------------ */
 /* filtered tex2D<float> taps per second on a WxH float texture */
 DPE_API int dpe_probe_tex_rate(dpe_ctx* ctx, int width, int height, int iters, double* taps_per_s);
+/* same with a texel format (0 f32, 1 f16, 2 u8 normalised), a lane layout (0 row of 32, 1 red/black
+ * zig-zag, 2 8x4 block, 3 one colour of 8x8, 4 16x2) and a 2x2 reference->source map m */
+DPE_API int dpe_probe_tex_pattern(dpe_ctx* ctx, int fmt, int layout, int width, int height, int iters, const float m[4],
+                          int threads, int blocks_per_sm, double* taps_per_s);
 DPE_API int dpe_probe_fma_rate(dpe_ctx* ctx, int iters, double* fma_per_s);
 /* weights[i] = hardware bilinear result at fractional offset i/n between a
  * texel holding 0 and a texel holding 1 (characterises the 1.8 fixed-point

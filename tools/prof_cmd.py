@@ -9,7 +9,7 @@ sys.path.insert(0, str(ROOT / "dpe-mvs_b200")); sys.path.insert(0, str(ROOT))
 import capi
 from bench import ensure_scene, load_scene_arrays, product_prep
 
-n_own = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+n_prof = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 folder = ensure_scene("c2", 12, "c2v12")
 grays, cams, drs, pairs = load_scene_arrays(folder)
 V = len(grays); H, W = grays[0].shape
@@ -19,15 +19,20 @@ ns = capi.compute_round_num(W, H)
 ctx.scene_begin(V, W, H, ns)
 for v in range(V):
     ctx.set_view(v, grays[v], *cams[v], *drs[v]); ctx.set_pairs(v, pairs[v])
-for v in range(n_own):
     for k, (e, l) in enumerate(product_prep(lib, grays[v], ns)):
         ctx.set_prep(v, k, e, l)
-ctx.set_shard(0, n_own, V, 1)
+ctx.set_shard(0, V, V, 1)
 ctx.commit()
-ctx.set_profile(True)
-t0 = time.time()
-for (k, p) in capi.stage_schedule(ns):
+sched = capi.stage_schedule(ns)
+for (k, p) in sched:                      # warm pass: every view gets real depth maps
     ctx.run_stage(k, p, 20261018); ctx.stage_commit()
+# ncu --profile-from-start off: dpe_run_stage brackets the profiled views with
+# cudaProfilerStart/Stop, so only they are captured; the other views of each stage run after them
+ctx.set_profile(n_prof)
+t0 = time.time()
+for (k, p) in sched:
+    ctx.run_stage(k, p, 20261018)
+    ctx.stage_commit()
 print("wall", time.time() - t0, "gpu_ms", ctx.stage_gpu_ms(), "launches", ctx.kernel_launches())
 for k, v in ctx.get_profile().items():
     print(f"{k:16s} ms={v['ms']:10.3f} launches={v['launches']:4d} units={v['units']:.4g}" + (f"  Gunits/s={v['units']/v['ms']/1e6:.2f}" if v['units'] else ""))
