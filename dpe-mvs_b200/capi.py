@@ -30,7 +30,7 @@ SYMBOLS = [
     "dpe_scene_set_view", "dpe_scene_set_pairs", "dpe_scene_set_prep", "dpe_scene_set_shard", "dpe_scene_commit",
     "dpe_run_stage", "dpe_stage_atlas", "dpe_stage_commit", "dpe_cost_eval", "dpe_geom_eval", "dpe_get_size",
     "dpe_get_maps", "dpe_set_count_evals", "dpe_eval_units", "dpe_stage_gpu_ms", "dpe_probe_tex_rate",
-    "dpe_probe_fma_rate", "dpe_probe_tex_pattern", "dpe_probe_tex_weights", "dpe_run_pipeline", "dpe_set_profile", "dpe_get_profile",
+    "dpe_probe_fma_rate", "dpe_probe_tex_pattern", "dpe_probe_tex_weights", "dpe_run_pipeline", "dpe_set_profile", "dpe_get_profile", "dpe_set_view_order", "dpe_bench_ncc",
 ]
 
 _lib = None
@@ -81,6 +81,8 @@ def load(build=True):
     lib.dpe_probe_tex_pattern.argtypes = [vp, ci, ci, ci, ci, ci, vp, ci, ci, C.POINTER(C.c_double)]
     lib.dpe_probe_tex_weights.argtypes = [vp, ci, vp]
     lib.dpe_set_profile.argtypes = [vp, ci]
+    lib.dpe_set_view_order.argtypes = [vp, ci]
+    lib.dpe_bench_ncc.argtypes = [vp, ci, ci, ci, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.dpe_get_profile.argtypes = [vp, vp, vp, vp]
     lib.dpe_run_pipeline.argtypes = [C.c_char_p, ci, ci, ci, ci, ci, ci, ci, ci]
     _lib = lib
@@ -229,6 +231,14 @@ class Context:
 
     KERNEL_CLASSES = ["load", "edge_info", "nearest_strong", "gen_neighbours", "init", "strong_sweep", "fit_plane",
                       "weak_sweep", "extract", "median", "classify_refine", "finish"]
+
+    def set_view_order(self, sequential):
+        self._ck(self.lib.dpe_set_view_order(self.h, int(sequential)))
+
+    def bench_ncc(self, view, variant, n_cand=8, reps=3):
+        r, c = C.c_double(), C.c_double()
+        self._ck(self.lib.dpe_bench_ncc(self.h, view, variant, n_cand, reps, C.byref(r), C.byref(c)))
+        return r.value, c.value
 
     def set_profile(self, on):
         self._ck(self.lib.dpe_set_profile(self.h, int(on)))

@@ -50,6 +50,8 @@ struct Scratch {
   uint8_t* state = nullptr; float4* fit_planes = nullptr; int* radius = nullptr; short2* edge_neigh = nullptr;
   float* complexity = nullptr; short2* label_boundary = nullptr; uint8_t* weak_reliable = nullptr;
   short2* nearest_strong = nullptr; short2* neighbours = nullptr;
+  Xorwow* rng = nullptr;
+  int* weak_list = nullptr; int* weak_count = nullptr;
   cudaStream_t stream = nullptr;
 };
 
@@ -71,8 +73,13 @@ struct dpe_ctx {
   std::vector<float*> atlas_front, atlas_back;
   int last_stage_scale = -1;
   bool stage_pending = false;
+  bool gauss_seidel = false;  // dpe_set_view_order
   // scratch
   std::vector<Scratch> scratch;
+  // initial XORWOW states per scale for rng_seed (dpe_rng.h): table[k][y*w+x] = curand_init(seed, y, x)
+  std::vector<Xorwow*> rng_table;
+  uint64_t rng_seed = 0;
+  bool rng_ready = false;
   uint8_t* zero_edge = nullptr;  // placeholder when no prep was supplied
   int32_t* zero_label = nullptr;
   unsigned long long* d_eval_units = nullptr;
@@ -123,9 +130,12 @@ static void free_scene(dpe_ctx* ctx) {
     cudaFree(s.planes); cudaFree(s.costs); cudaFree(s.selected); cudaFree(s.view_w); cudaFree(s.state);
     cudaFree(s.fit_planes); cudaFree(s.radius); cudaFree(s.edge_neigh); cudaFree(s.complexity);
     cudaFree(s.label_boundary); cudaFree(s.weak_reliable); cudaFree(s.nearest_strong); cudaFree(s.neighbours);
+    cudaFree(s.rng); cudaFree(s.weak_list); cudaFree(s.weak_count);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   ctx->scratch.clear();
+  for (auto p : ctx->rng_table) cudaFree(p);
+  ctx->rng_table.clear(); ctx->rng_ready = false;
   cudaFree(ctx->zero_edge); ctx->zero_edge = nullptr;
   cudaFree(ctx->zero_label); ctx->zero_label = nullptr;
   ctx->committed = false;
@@ -295,6 +305,9 @@ int dpe_scene_commit(dpe_ctx* ctx) {
     CK(cudaMalloc(&s.complexity, P * sizeof(float))); CK(cudaMalloc(&s.label_boundary, P * 8 * sizeof(short2)));
     CK(cudaMalloc(&s.weak_reliable, P)); CK(cudaMalloc(&s.nearest_strong, P * sizeof(short2)));
     CK(cudaMalloc(&s.neighbours, P * DPE_NEIGHBOUR_NUM * sizeof(short2)));
+    CK(cudaMalloc(&s.rng, P * sizeof(Xorwow)));
+    CK(cudaMalloc(&s.weak_list, 2 * P * sizeof(int))); CK(cudaMalloc(&s.weak_count, 2 * sizeof(int)));
+    CK(cudaMemset(s.weak_count, 0, 2 * sizeof(int)));
     CK(cudaMemset(s.view_w, 0, P * sizeof(uint4)));
     CK(cudaMemset(s.radius, 0, P * sizeof(int)));
   }
@@ -323,6 +336,22 @@ static void build_ref_const(const dpe_ctx* ctx, int view, int k, bool geom, RefC
   }
 }
 
+// (re)builds the per-scale initial-state tables for `seed`
+static int ensure_rng_tables(dpe_ctx* ctx, uint64_t seed) {
+  if (ctx->rng_ready && ctx->rng_seed == seed) return DPE_OK;
+  if (ctx->rng_table.empty()) ctx->rng_table.assign(ctx->n_scales, nullptr);
+  std::vector<Xorwow> host;
+  for (int k = 0; k < ctx->n_scales; ++k) {
+    const size_t P = (size_t)ctx->sw[k] * ctx->sh[k];
+    host.resize(P);
+    xorwow_init_table(seed, ctx->sw[k], ctx->sh[k], host.data());
+    if (!ctx->rng_table[k]) CK(cudaMalloc(&ctx->rng_table[k], P * sizeof(Xorwow)));
+    CK(cudaMemcpy(ctx->rng_table[k], host.data(), P * sizeof(Xorwow), cudaMemcpyHostToDevice));
+  }
+  ctx->rng_seed = seed; ctx->rng_ready = true;
+  return DPE_OK;
+}
+
 static void fill_args(dpe_ctx* ctx, int view, int k, const dpe_stage_params* p, uint64_t seed, const Scratch& s,
                       KernelParams* KP) {
   memset(KP, 0, sizeof(*KP));
@@ -341,15 +370,15 @@ static void fill_args(dpe_ctx* ctx, int view, int k, const dpe_stage_params* p, 
   a.label = v.scales[k].label ? v.scales[k].label : ctx->zero_label;
   a.label_boundary = s.label_boundary; a.weak_reliable = s.weak_reliable; a.nearest_strong = s.nearest_strong;
   a.neighbours = s.neighbours;
+  a.rng = s.rng;
+  a.weak_list = s.weak_list; a.weak_count = s.weak_count; a.list_stride = ctx->W * ctx->H;
   a.eval_units = ctx->count_evals ? ctx->d_eval_units : nullptr;
   if (p) {
     a.run_state = p->state; a.geom = p->geom_consistency; a.use_apd = p->use_apd; a.top_k = p->top_k;
     a.weak_peak_radius = p->weak_peak_radius; a.rotate_time = p->rotate_time;
     a.ransac_threshold = p->ransac_threshold; a.geom_factor = p->geom_factor;
   }
-  // RNG key: depends only on (seed, view, stage index) so results do not depend on how
-  // views are scheduled over streams or GPUs
-  stage_key(seed, view, ctx->stage_counter, &a.key0, &a.key1);
+  (void)seed;
 }
 
 extern "C" {
@@ -362,6 +391,7 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
   const LaunchCfg cfg = cfg_of(ctx);
   const size_t P = (size_t)ctx->sw[k] * ctx->sh[k];
   const int ns = (int)ctx->scratch.size();
+  if (int rc = ensure_rng_tables(ctx, seed)) return rc;
   CK(cudaEventRecord(ctx->ev0, 0));
   for (auto& s : ctx->scratch) CK(cudaStreamWaitEvent(s.stream, ctx->ev0, 0));
   std::vector<cudaEvent_t> done(ns, nullptr);
@@ -374,7 +404,7 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
     // an external profiler started with --profile-from-start off sees exactly the profiled views
     if (ctx->profile && li == 0) cudaProfilerStart();
     if (ctx->profile && li == ctx->profile_views) cudaProfilerStop();
-    Scratch& s = ctx->scratch[prof_view ? 0 : li % ns];
+    Scratch& s = ctx->scratch[(prof_view || ctx->gauss_seidel) ? 0 : li % ns];
     KernelParams KP;
     fill_args(ctx, view, k, p, seed, s, &KP);
     StageArgs& a = KP.a;
@@ -389,9 +419,13 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
     a.prev_W = v.cur_scale >= 0 ? ctx->sw[v.cur_scale] : a.W;
     a.prev_H = v.cur_scale >= 0 ? ctx->sh[v.cur_scale] : a.H;
     a.out_planes = new_planes; a.out_state = new_state; a.out_selected = new_sel;
-    a.atlas_out = ctx->atlas_back[k] + (size_t)view * P;
+    // sequential order: publish straight into the committed atlas, so that later views of this stage
+    // read it (the reference's depths.dmb files)
+    a.atlas_out = (ctx->gauss_seidel ? ctx->atlas_front[k] : ctx->atlas_back[k]) + (size_t)view * P;
 
     cudaStream_t st = s.stream;
+    // every (view, stage) starts from curand_init(seed, y, x) like the reference (DPE.cu:1020-1033)
+    CK(cudaMemcpyAsync(s.rng, ctx->rng_table[k], P * sizeof(Xorwow), cudaMemcpyDeviceToDevice, st));
     // in profile mode every launch is bracketed by CUDA events on its own stream and the
     // eval-unit counter is read back after it
     auto L = [&](int cls, void (*fn)(const KernelParams&, const LaunchCfg&, cudaStream_t)) {
@@ -412,6 +446,7 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
       L(DPE_K_EDGE_INFO, launch_edge_info);
       L(DPE_K_NEAREST, launch_nearest_strong);
       L(DPE_K_NEIGHBOURS, launch_gen_neighbours);
+      L(DPE_K_NEIGHBOURS, launch_compact_weak);
     }
     L(DPE_K_INIT, launch_init);
     for (int it = 0; it < p->max_iterations; ++it) {
@@ -459,7 +494,7 @@ int dpe_stage_atlas(dpe_ctx* ctx, void** dev_ptr, size_t* chunk_bytes, size_t* t
   if (!ctx || ctx->last_stage_scale < 0) return DPE_ERR_ARG;
   const int k = ctx->last_stage_scale;
   const size_t P = (size_t)ctx->sw[k] * ctx->sh[k];
-  if (dev_ptr) *dev_ptr = ctx->atlas_back[k];
+  if (dev_ptr) *dev_ptr = ctx->gauss_seidel ? ctx->atlas_front[k] : ctx->atlas_back[k];
   if (chunk_bytes) *chunk_bytes = (size_t)ctx->slots_per_rank * P * sizeof(float);
   if (total_bytes) *total_bytes = (size_t)ctx->slots_per_rank * ctx->n_ranks * P * sizeof(float);
   return DPE_OK;
@@ -469,8 +504,16 @@ int dpe_stage_commit(dpe_ctx* ctx) {
   if (!ctx) return DPE_ERR_ARG;
   if (!ctx->stage_pending) return DPE_OK;
   const int k = ctx->last_stage_scale;
-  std::swap(ctx->atlas_front[k], ctx->atlas_back[k]);
+  if (!ctx->gauss_seidel) std::swap(ctx->atlas_front[k], ctx->atlas_back[k]);
   ctx->stage_pending = false;
+  return DPE_OK;
+}
+
+int dpe_set_view_order(dpe_ctx* ctx, int sequential) {
+  if (!ctx) return DPE_ERR_ARG;
+  if (ctx->stage_pending) FAIL(DPE_ERR_STATE, "stage not committed");
+  if (sequential && ctx->n_ranks > 1) FAIL(DPE_ERR_ARG, "sequential view order needs all views on one GPU");
+  ctx->gauss_seidel = sequential != 0;
   return DPE_OK;
 }
 
@@ -574,6 +617,34 @@ int dpe_get_profile(dpe_ctx* ctx, double* ms, double* units, long long* launches
     if (ms) ms[i] = ctx->prof_ms[i];
     if (units) units[i] = ctx->prof_units[i];
     if (launches) launches[i] = ctx->prof_launches[i];
+  }
+  return DPE_OK;
+}
+
+int dpe_bench_ncc(dpe_ctx* ctx, int view, int variant, int n_cand, int reps, double* units_per_s, double* checksum) {
+  if (!ctx || view < 0 || view >= ctx->n_views || n_cand <= 0 || reps <= 0 || !units_per_s) return DPE_ERR_ARG;
+  ViewData& v = ctx->views[view];
+  if (v.cur_scale < 0 || !v.planes) FAIL(DPE_ERR_STATE, "view has no result on this context");
+  CK(cudaSetDevice(ctx->device));
+  const int k = v.cur_scale;
+  KernelParams KP;
+  fill_args(ctx, view, k, nullptr, 0, ctx->scratch[0], &KP);
+  const size_t P = (size_t)ctx->sw[k] * ctx->sh[k];
+  float* out = ctx->scratch[0].costs;
+  const LaunchCfg cfg = cfg_of(ctx);
+  launch_ncc_bench(KP, v.planes, n_cand, variant, out, cfg, 0);
+  CK(cudaEventRecord(ctx->ev0, 0));
+  for (int r = 0; r < reps; ++r) launch_ncc_bench(KP, v.planes, n_cand, variant, out, cfg, 0);
+  CK(cudaEventRecord(ctx->ev1, 0));
+  CK(cudaEventSynchronize(ctx->ev1));
+  CK(cudaGetLastError());
+  float ms = 0.f; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *units_per_s = (double)(P / 2) * n_cand * KP.rc.n_src * reps / (ms * 1e-3);
+  if (checksum) {
+    std::vector<float> h(P);
+    CK(cudaMemcpy(h.data(), out, P * sizeof(float), cudaMemcpyDeviceToHost));
+    double s = 0; for (size_t i = 0; i < P; ++i) if (((i % ctx->sw[k]) + (i / ctx->sw[k])) % 2 == 0 && h[i] == h[i]) s += h[i];
+    *checksum = s;
   }
   return DPE_OK;
 }

@@ -87,11 +87,4 @@ inline void fold_pair(const HostCam& r, const HostCam& s, int w, int h, int full
   sc->width = (float)w; sc->height = (float)h;
 }
 
-// stage RNG key: depends only on (seed, view, stage index)
-inline void stage_key(uint64_t seed, int view, uint32_t stage_counter, uint32_t* k0, uint32_t* k1) {
-  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(view + 1) + 0xD1B54A32D192ED03ull * (uint64_t)(stage_counter + 1);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= (z >> 31);
-  *k0 = (uint32_t)z; *k1 = (uint32_t)(z >> 32);
-}
-
 }  // namespace dpe

@@ -144,7 +144,10 @@ int dpe_hostsim_stage(int W, int H, int full_w, int full_h, int n_src, const flo
   a.run_state = p->state; a.geom = p->geom_consistency; a.use_apd = p->use_apd; a.top_k = p->top_k;
   a.weak_peak_radius = p->weak_peak_radius; a.rotate_time = p->rotate_time; a.ransac_threshold = p->ransac_threshold;
   a.geom_factor = p->geom_factor;
-  stage_key(seed, view, stage_counter, &a.key0, &a.key1);
+  (void)stage_counter;
+  std::vector<Xorwow> rng_states(P);
+  xorwow_init_table(seed, W, H, rng_states.data());
+  a.rng = rng_states.data();
   double units = 0.0;
 
   HostRef ref{images[0], W, H};

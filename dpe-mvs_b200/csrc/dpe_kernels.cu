@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(NT, 4) k_full(const __grid_constant__ KernelPa
 }
 
 // ---- red/black half sweeps: tile = 32 x 8 pixels, one thread per pixel of one colour ----
-enum HalfOp { OP_STRONG = 0, OP_STRONG_EDGE = 1, OP_WEAK = 2 };
+enum HalfOp { OP_STRONG = 0, OP_STRONG_EDGE = 1 };
 
 template <int OP>
 __global__ void __launch_bounds__(NT, 4) k_half(const __grid_constant__ KernelParams P) {
@@ -133,17 +133,72 @@ __global__ void __launch_bounds__(NT, 4) k_half(const __grid_constant__ KernelPa
     const int lx = threadIdx.x & 31;
     const int x = tx0 + lx, y = ty0 + 2 * (threadIdx.x >> 5) + ((lx + a.colour) & 1);
     if (x < a.W && y < a.H) {
-      const bool weak = a.state[y * a.W + x] == DPE_WEAK;
-      if (OP == OP_WEAK) {
-        if (weak) {
-          const PatchStats ps = build_patch(tile, x, y, st);
-          weak_update_pixel(env, ps, a, x, y, cost_arr, evals);
-        }
-      } else if (!weak) {
+      if (a.state[y * a.W + x] != DPE_WEAK) {
         const PatchStats ps = build_patch(tile, x, y, st);
         strong_update_pixel<OP == OP_STRONG_EDGE>(env, ps, a, x, y, cost_arr, evals);
       }
     }
+  }
+  flush_evals(a.eval_units, evals);
+}
+
+// ---- WEAK pixels: compacted lists ------------------------------------------------------------
+// Only a few per cent of the pixels are WEAK, scattered over the image; sweeping them through
+// the image-tile kernel leaves most lanes idle behind a handful of long-running ones (the
+// reference does exactly that, DPE.cu:1864-1898).  The stage therefore compacts the WEAK pixels
+// of each colour once (after GenNeighbours has demoted the unreliable ones) and the weak sweep
+// runs over the dense list.  List order varies from run to run (warp-aggregated atomics); the
+// result does not depend on it, a sweep only reads the other colour.
+struct GlobalRef {
+  const float* img;
+  int W, H;
+  __device__ __forceinline__ float operator()(int x, int y) const {
+    return __ldg(&img[(size_t)iclamp(y, 0, H - 1) * W + iclamp(x, 0, W - 1)]);
+  }
+};
+
+__global__ void __launch_bounds__(256) k_compact_weak(const __grid_constant__ KernelParams P) {
+  const StageArgs& a = P.a;
+  const int total = a.W * a.H;
+  const int lane = threadIdx.x & 31;
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total; base += gridDim.x * blockDim.x) {
+    const int i = base + lane;
+    const bool weak = i < total && a.state[i] == DPE_WEAK;
+    const int colour = weak ? (((i % a.W) + (i / a.W)) & 1) : 0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const unsigned m = __ballot_sync(0xffffffffu, weak && colour == c);
+      if (m == 0u) continue;
+      int off = 0;
+      if (lane == (__ffs(m) - 1)) off = atomicAdd(&a.weak_count[c], __popc(m));
+      off = __shfl_sync(0xffffffffu, off, __ffs(m) - 1);
+      if (weak && colour == c) a.weak_list[c * a.list_stride + off + __popc(m & ((1u << lane) - 1u))] = i;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT, 4) k_weak_list(const __grid_constant__ KernelParams P) {
+  __shared__ float2 s_tbl[36 * NT];
+  StageArgs a = P.a;
+  a.rc = &P.rc;
+  const int count = a.weak_count[a.colour];
+  const int* list = a.weak_list + a.colour * a.list_stride;
+  unsigned evals = 0;
+  DevEnv env;
+  env.tbl = s_tbl + threadIdx.x;
+  env.img = a.ref_img; env.W = a.W; env.H = a.H;
+  TblStore st;
+  st.tbl = s_tbl + threadIdx.x;
+  GlobalRef ref{a.ref_img, a.W, a.H};
+  float cost_arr[9 * DPE_MAX_IMAGES];
+  // consecutive 32-entry chunks go to different CTAs first, so a short list still spreads over all SMs
+  const int warps_per_cta = NT / 32;
+  const int gwarp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+  for (int i = gwarp * 32 + (threadIdx.x & 31); i < count; i += gridDim.x * warps_per_cta * 32) {
+    const int center = list[i];
+    const int x = center % a.W, y = center / a.W;
+    const PatchStats ps = build_patch(ref, x, y, st);
+    weak_update_pixel(env, ps, a, x, y, cost_arr, evals);
   }
   flush_evals(a.eval_units, evals);
 }
@@ -210,12 +265,13 @@ void launch_strong(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t st
   else k_half<OP_STRONG><<<g, NT, 0, stream>>>(P);
   count(cfg);
 }
-void launch_weak(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t stream) {
-  KernelParams P = P0;
-  P.a.tiles_x = (P.a.W + TILE_W - 1) / TILE_W;
-  P.a.tiles_y = (P.a.H + 7) / 8;
-  const int g = persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, 4);
-  k_half<OP_WEAK><<<g, NT, 0, stream>>>(P);
+void launch_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream) {
+  k_weak_list<<<cfg.num_sms * 4, NT, 0, stream>>>(P);
+  count(cfg);
+}
+void launch_compact_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream) {
+  cudaMemsetAsync(P.a.weak_count, 0, 2 * sizeof(int), stream);
+  k_compact_weak<<<cfg.num_sms * 8, 256, 0, stream>>>(P);
   count(cfg);
 }
 template <int OP>
@@ -292,14 +348,6 @@ struct DevEnvExact {
   __device__ __forceinline__ float2 pw(int t) const { return tbl[t * NT]; }
 };
 
-struct GlobalRef {
-  const float* img;
-  int W, H;
-  __device__ __forceinline__ float operator()(int x, int y) const {
-    return img[(size_t)iclamp(y, 0, H - 1) * W + iclamp(x, 0, W - 1)];
-  }
-};
-
 __global__ void __launch_bounds__(NT) k_cost_eval(const __grid_constant__ KernelParams P, int n_pix,
                                                   const int* __restrict__ xy, const float4* __restrict__ planes,
                                                   int mode, float* __restrict__ out) {
@@ -337,6 +385,128 @@ __global__ void k_geom_eval(const __grid_constant__ KernelParams P, int n_pix, c
 void launch_geom_eval(const KernelParams& P, int n_pix, const int* xy, const float4* planes, float* out,
                       const LaunchCfg& cfg, cudaStream_t stream) {
   k_geom_eval<<<(n_pix + 127) / 128, 128, 0, stream>>>(P, n_pix, xy, planes, out);
+  count(cfg);
+}
+
+// ---- NCC throughput study --------------------------------------------------------------------
+// The candidate loop of the strong sweep in isolation: every pixel of a view scores the planes
+// of n_cand neighbours (carried (world normal, depth) maps of the last stage) against all source
+// views.  ROWS = tap rows fetched before any is consumed (texture results in flight per thread =
+// 6 * ROWS); MINB = CTAs per SM the register allocation is tuned for.
+template <int ROWS, class Env>
+__device__ __forceinline__ float ncc_old_rows(const Env& env, const PatchStats& ps, const SrcConst& sc, const float3 m,
+                                              const int x, const int y) {
+  float h0 = sc.A[0] - sc.b[0] * m.x, h1 = sc.A[1] - sc.b[0] * m.y, h2 = sc.A[2] - sc.b[0] * m.z;
+  float h3 = sc.A[3] - sc.b[1] * m.x, h4 = sc.A[4] - sc.b[1] * m.y, h5 = sc.A[5] - sc.b[1] * m.z;
+  const float h6 = sc.A[6] - sc.b[2] * m.x, h7 = sc.A[7] - sc.b[2] * m.y, h8 = sc.A[8] - sc.b[2] * m.z;
+  {
+    const float Z = h6 * x + h7 * y + h8;
+    const float px = (h0 * x + h1 * y + h2) / Z;
+    const float py = (h3 * x + h4 * y + h5) / Z;
+    if (px >= sc.width || px < 0.0f || py >= sc.height || py < 0.0f) return 2.0f;
+  }
+  h0 = fmaf(0.5f, h6, h0); h1 = fmaf(0.5f, h7, h1); h2 = fmaf(0.5f, h8, h2);
+  h3 = fmaf(0.5f, h6, h3); h4 = fmaf(0.5f, h7, h4); h5 = fmaf(0.5f, h8, h5);
+  const float x0 = (float)(x - 5), y0 = (float)(y - 5);
+  float Xr = h0 * x0 + h1 * y0 + h2;
+  float Yr = h3 * x0 + h4 * y0 + h5;
+  float Zr = h6 * x0 + h7 * y0 + h8;
+  const float dXi = 2.0f * h0, dYi = 2.0f * h3, dZi = 2.0f * h6;
+  const float dXj = 2.0f * h1, dYj = 2.0f * h4, dZj = 2.0f * h7;
+  float ss = 0.f, sss = 0.f, srs = 0.f;
+#pragma unroll
+  for (int jb = 0; jb < 6; jb += ROWS) {
+    float sv[6 * ROWS];
+#pragma unroll
+    for (int jy = 0; jy < ROWS; ++jy) {
+      float X = Xr, Y = Yr, Z = Zr;
+#pragma unroll
+      for (int ix = 0; ix < 6; ++ix) {
+        const float iz = fast_rcp(Z);
+        sv[jy * 6 + ix] = env.tex(sc.tex, X * iz, Y * iz);
+        X += dXi; Y += dYi; Z += dZi;
+      }
+      Xr += dXj; Yr += dYj; Zr += dZj;
+    }
+#pragma unroll
+    for (int t = 0; t < 6 * ROWS; ++t) {
+      const float sdiff = sv[t] - ps.r0;
+      const float2 ww = env.pw(jb * 6 + t);
+      const float ws = ww.x * sdiff;
+      ss += ws;
+      sss = fmaf(ws, sdiff, sss);
+      srs = fmaf(ww.y, sdiff, srs);
+    }
+  }
+  const float ms = ss * ps.inv_sw;
+  const float var_s = sss * ps.inv_sw - ms * ms;
+  const float kMinVar = 1e-5f;
+  if (ps.var_r < kMinVar || var_s < kMinVar) return 2.0f;
+  const float cov = srs * ps.inv_sw - ps.mean_r * ms;
+  return fmaxf(0.0f, fminf(2.0f, 1.0f - cov * fast_rsqrt(ps.var_r * var_s)));
+}
+
+template <int ROWS, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_ncc_bench(const __grid_constant__ KernelParams P, const float4* __restrict__ world_planes,
+                                                        int n_cand, float* __restrict__ out) {
+  __shared__ float2 s_tbl[36 * NT];
+  __shared__ float s_tile[SMW * (8 + 2 * HALO)];
+  StageArgs a = P.a;
+  const RefConst& rc = P.rc;
+  const int tiles_x = (a.W + TILE_W - 1) / TILE_W, tiles_y = (a.H + 7) / 8;
+  RefTile<8> tile;
+  tile.s = s_tile;
+  DevEnv env;
+  env.tbl = s_tbl + threadIdx.x;
+  env.img = a.ref_img; env.W = a.W; env.H = a.H;
+  TblStore st;
+  st.tbl = s_tbl + threadIdx.x;
+  const int offx[8] = {0, 0, -1, 1, -3, 3, 5, -7}, offy[8] = {-1, 1, 0, 0, 5, -5, 3, 2};
+  for (int t = blockIdx.x; t < tiles_x * tiles_y; t += gridDim.x) {
+    const int tx0 = (t % tiles_x) * TILE_W, ty0 = (t / tiles_x) * 8;
+    __syncthreads();
+    tile.stage(a.ref_img, a.W, a.H, tx0, ty0);
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    const int lx = threadIdx.x & 31;
+    const int x = tx0 + lx, y = ty0 + 2 * (threadIdx.x >> 5) + (lx & 1);
+    if (x < a.W && y < a.H) {
+      const PatchStats ps = build_patch(tile, x, y, st);
+      float acc = 0.f;
+      for (int c = 0; c < n_cand; ++c) {
+        const int nx = iclamp(x + offx[c & 7], 0, a.W - 1), ny = iclamp(y + offy[c & 7], 0, a.H - 1);
+        const float4 pw = world_planes[ny * a.W + nx];
+        float4 pl = world_to_cam_normal(rc, pw);
+        pl.w = dist2origin(rc, nx, ny, pw.w > 0.f ? pw.w : 1.0f, pl);
+        const float3 m = plane_to_m(rc, pl);
+        for (int v = 0; v < rc.n_src; ++v) {
+          if (ROWS == 0) acc += ncc_old(env, ps, rc.src[v], m, x, y);
+          else acc += ncc_old_rows<(ROWS == 0 ? 1 : ROWS)>(env, ps, rc.src[v], m, x, y);
+        }
+      }
+      out[y * a.W + x] = acc;
+    }
+  }
+}
+void launch_ncc_bench(const KernelParams& P, const float4* world_planes, int n_cand, int variant, float* out,
+                      const LaunchCfg& cfg, cudaStream_t stream) {
+  const int tiles = ((P.a.W + TILE_W - 1) / TILE_W) * ((P.a.H + 7) / 8);
+  auto g = [&](int per_sm) { return persistent_grid(tiles, cfg.num_sms, per_sm); };
+  switch (variant) {
+    case 0: k_ncc_bench<0, 4><<<g(4), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
+    case 1: k_ncc_bench<1, 4><<<g(4), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
+    case 2: k_ncc_bench<2, 4><<<g(4), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
+    case 3: k_ncc_bench<3, 4><<<g(4), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
+    case 4: k_ncc_bench<6, 4><<<g(4), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
+    case 5: k_ncc_bench<0, 3><<<g(3), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
+    case 6: k_ncc_bench<2, 3><<<g(3), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
+    case 7: k_ncc_bench<3, 3><<<g(3), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
+    case 8: k_ncc_bench<6, 3><<<g(3), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
+    case 9: k_ncc_bench<6, 2><<<g(2), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
+    case 10: k_ncc_bench<2, 5><<<g(5), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
+    case 11: k_ncc_bench<1, 6><<<g(6), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
+    default: break;
+  }
   count(cfg);
 }
 

@@ -27,6 +27,7 @@ void launch_finish(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t str
 void launch_edge_info(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
 void launch_nearest_strong(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
 void launch_gen_neighbours(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
+void launch_compact_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);  // after gen_neighbours
 void launch_fit_plane(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
 void launch_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);  // one colour, one iter
 
@@ -40,6 +41,10 @@ void launch_resize_linear(const float* src, int sw, int sh, float* dst, int dw, 
 void launch_cost_eval(const KernelParams& P, int n_pix, const int* xy, const float4* planes, int mode,
                       unsigned long long point_tex, float* out, const LaunchCfg& cfg, cudaStream_t stream);
 void launch_geom_eval(const KernelParams& P, int n_pix, const int* xy, const float4* planes, float* out,
+                      const LaunchCfg& cfg, cudaStream_t stream);
+
+// NCC throughput study (variants of the tap loop; see dpe_kernels.cu)
+void launch_ncc_bench(const KernelParams& P, const float4* world_planes, int n_cand, int variant, float* out,
                       const LaunchCfg& cfg, cudaStream_t stream);
 
 // micro-benchmarks

@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 #include "../../include/dpe_b200.h"
+#include "dpe_rng.h"
 
 namespace dpe {
 
@@ -62,6 +63,11 @@ struct StageArgs {
   uint8_t* weak_reliable;
   short2* nearest_strong;
   short2* neighbours;       // 9 per pixel (not compacted; neighbours_map is the identity)
+  // WEAK pixels of this stage, compacted per colour after GenNeighbours: weak_list[c * list_stride + i],
+  // i < weak_count[c], colour c = (x + y) & 1
+  int* weak_list;
+  int* weak_count;
+  int list_stride;
   // state carried in from the previous stage (possibly at the previous scale)
   const float4* prev_planes;  // (world normal, depth)
   const uint8_t* prev_state;
@@ -76,7 +82,7 @@ struct StageArgs {
   int run_state, geom, use_apd, top_k, weak_peak_radius, rotate_time;
   float ransac_threshold, geom_factor;
   int iter, colour;
-  uint32_t key0, key1;  // RNG key = f(seed, view, stage)
+  Xorwow* rng;  // per-pixel XORWOW state of this stage (dpe_rng.h), starts as curand_init(seed, y, x)
   unsigned long long* eval_units;  // optional counter (36-tap units)
   int tiles_x, tiles_y;
 };

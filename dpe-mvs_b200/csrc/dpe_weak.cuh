@@ -145,7 +145,7 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
   for (int i = 0; i < MAXP; ++i) { strong_points[i] = make_short2(-1, -1); dir_valid[i] = false; }
   int strong_point_size = 0;
   Rng rng;
-  rng.init(a.key0, a.key1, (uint32_t)center, 0x300u);
+  rng.load(a.rng + center);
 
   const int rotate_time = a.rotate_time;
   const float angle = 45.0f / rotate_time;
@@ -255,7 +255,7 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
     }
   }
 
-  if (strong_point_size <= 3) { a.weak_reliable[center] = 0; a.state[center] = DPE_UNKNOWN; return; }
+  if (strong_point_size <= 3) { rng.store(a.rng + center); a.weak_reliable[center] = 0; a.state[center] = DPE_UNKNOWN; return; }
 
   float4 best_plane = make_float4(0.f, 0.f, 0.f, 0.f);
   bool has_valid_plane = false;
@@ -365,6 +365,7 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
     }
   }
 
+  rng.store(a.rng + center);
   if (!has_valid_plane) { a.weak_reliable[center] = 0; a.state[center] = DPE_UNKNOWN; return; }
 
   float weight[MAXP];
@@ -393,7 +394,7 @@ DPE_HDN void fit_plane_pixel(const StageArgs& a, const int x, const int y) {
   const int W = a.W, center = y * W + x;
   if (a.state[center] != DPE_WEAK) { a.fit_planes[center] = a.planes[center]; return; }
   Rng rng;
-  rng.init(a.key0, a.key1, (uint32_t)center, 0x400u + (uint32_t)a.iter);
+  rng.load(a.rng + center);
   bool edge_limit = true;
   if (a.use_apd) {
     const float cv = a.complexity[center];
@@ -417,7 +418,7 @@ DPE_HDN void fit_plane_pixel(const StageArgs& a, const int x, const int y) {
     spn[sc] = make_float3(pl.x, pl.y, pl.z);
     sc++;
   }
-  if (sc < 3) { a.fit_planes[center] = a.planes[center]; return; }
+  if (sc < 3) { rng.store(a.rng + center); a.fit_planes[center] = a.planes[center]; return; }
 
   int iteration = 50, ua = -1, ub = -1, uc = -1;
   float min_cost = FLT_MAX;
@@ -473,6 +474,7 @@ DPE_HDN void fit_plane_pixel(const StageArgs& a, const int x, const int y) {
     }
   }
 
+  rng.store(a.rng + center);
   if (!has_best) {
     a.fit_planes[center] = make_float4(0.f, 0.f, 0.f, 0.f);
     a.radius[center] = 5;
@@ -642,7 +644,7 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
     for (int v = 0; v < N; ++v) cost_arr[i * DPE_MAX_IMAGES + v] = ncc_new(env, ps, a, rc.src[v], v, m, x, y, units);
   }
   Rng rng;
-  rng.init(a.key0, a.key1, (uint32_t)center, 0x500u + (uint32_t)(a.iter * 2 + a.colour));
+  rng.load(a.rng + center);
   ViewW vw;
   float weight_norm;
   uint32_t sel_bits;
@@ -712,6 +714,7 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
       }
     }
   }
+  rng.store(a.rng + center);
   float4 final_plane = a.planes[center];
   if (a.run_state == DPE_REFINE_INIT) {
     if (cost_now < cost_before - 0.1f) { final_plane = plane_now; a.planes[center] = plane_now; }

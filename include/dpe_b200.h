@@ -95,6 +95,8 @@ DPE_API int dpe_scene_commit(dpe_ctx* ctx);
 /* --- the hot path (replaces DPE::RunPatchMatch DPE.cu:3126-3249 plus the
  *     per-view host tail of ProcessProblem main.cpp:423-446, for every view
  *     this context owns) ---------------------------------------------------- */
+/* seed: the reference's curand_init seed (clock64() there, DPE.cu:1032): every (view, stage) starts
+ * pixel (x, y) from the cuRAND XORWOW state curand_init(seed, y, x). */
 DPE_API int dpe_run_stage(dpe_ctx* ctx, int scale_idx, const dpe_stage_params* params, uint64_t seed);
 /* device pointer + byte size of the depth atlas this stage wrote (slots x P
  * floats).  Between dpe_run_stage and dpe_stage_commit a multi-GPU driver
@@ -104,6 +106,13 @@ DPE_API int dpe_stage_atlas(dpe_ctx* ctx, void** dev_ptr, size_t* chunk_bytes, s
  * the next geometric-consistency stage (the reference does this through
  * depths.dmb files, DPE.cpp:826-844). */
 DPE_API int dpe_stage_commit(dpe_ctx* ctx);
+
+/* View order inside a stage.  0 (default): every view reads the depth maps the PREVIOUS stage
+ * committed (Jacobi) — independent of scheduling, required when views are sharded.  1: views run one
+ * after the other and each publishes its depth map immediately, so view k reads this stage's maps of
+ * views < k and the previous stage's of views > k — the order the reference gets from processing
+ * problems serially through depths.dmb files (main.cpp:509-558, DPE.cpp:826-844).  Single GPU only. */
+DPE_API int dpe_set_view_order(dpe_ctx* ctx, int sequential);
 
 /* --- gate-1 hook: bilateral NCC of fixed plane hypotheses ------------------
  * planes: n_pix x (nx,ny,nz,d) in reference-camera coordinates (n.X + d = 0,
@@ -142,6 +151,12 @@ enum {
 };
 DPE_API int dpe_set_profile(dpe_ctx* ctx, int on);
 DPE_API int dpe_get_profile(dpe_ctx* ctx, double* ms, double* units, long long* launches);
+
+/* tap-loop study: the candidate-scoring loop of the strong sweep in isolation on `view`'s current
+ * maps (n_cand neighbour planes x all source views per pixel of one colour); variant selects how many
+ * tap rows are fetched before use and the register budget (dpe_kernels.cu: launch_ncc_bench). */
+DPE_API int dpe_bench_ncc(dpe_ctx* ctx, int view, int variant, int n_cand, int reps, double* units_per_s,
+                  double* checksum);
 
 /* --- micro-benchmarks used for the roofline denominators ------------------ */
 /* filtered tex2D<float> taps per second on a WxH float texture */

@@ -50,6 +50,8 @@ def main():
     ap.add_argument("--ref-runs", type=int, default=2)
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-hough", action="store_true")
+    ap.add_argument("--match", action="store_true", help="run ours in the reference's view order (sequential) — the RNG stream is the reference's anyway")
+    ap.add_argument("--ours-seed", type=int, default=20261018)
     ap.add_argument("--seed2", action="store_true", help="one more reference run with a different pinned RNG seed")
     args = ap.parse_args()
     tag = args.out or args.config
@@ -116,10 +118,12 @@ def main():
             ctx.set_prep(v, k, prep[v][j][0], prep[v][j][1])
     t_up = time.time() - t_all
     ctx.set_count_evals(True)
+    if args.match:
+        ctx.set_view_order(1)
     stages = []
     for (k, p) in capi.stage_schedule(n_scales):
         m0, u0 = ctx.stage_gpu_ms(), ctx.eval_units()
-        ctx.run_stage(k, p, 20261018)
+        ctx.run_stage(k, p, args.ours_seed)
         ctx.stage_commit()
         stages.append(dict(scale=k, state=p.state, geom=p.geom_consistency, gpu_ms=ctx.stage_gpu_ms() - m0, units=ctx.eval_units() - u0))
         print("ours", stages[-1], flush=True)
