@@ -26,8 +26,6 @@ namespace {
 
 struct ScaleImg {
   float* lin = nullptr;          // W*H float
-  cudaArray_t arr = nullptr;
-  cudaTextureObject_t tex = 0;
   uint8_t* edge = nullptr;       // edges_k (optional)
   int32_t* label = nullptr;      // labels_k (optional)
 };
@@ -66,6 +64,9 @@ struct dpe_ctx {
   int n_views = 0, W = 0, H = 0, n_scales = 0;
   std::vector<int> sw, sh;  // per scale index (0 = coarsest)
   std::vector<ViewData> views;
+  // one layered array + texture object per scale: layer v = image of view v (float, linear filter)
+  std::vector<cudaArray_t> scale_arr;
+  std::vector<cudaTextureObject_t> scale_tex;
   bool committed = false;
   // shard
   int first_view = 0, n_local = 0, slots_per_rank = 0, n_ranks = 1;
@@ -115,14 +116,13 @@ static LaunchCfg cfg_of(dpe_ctx* ctx) { return LaunchCfg{ctx->num_sms, &ctx->lau
 
 static void free_scene(dpe_ctx* ctx) {
   for (auto& v : ctx->views) {
-    for (auto& s : v.scales) {
-      if (s.tex) cudaDestroyTextureObject(s.tex);
-      if (s.arr) cudaFreeArray(s.arr);
-      cudaFree(s.lin); cudaFree(s.edge); cudaFree(s.label);
-    }
+    for (auto& s : v.scales) { cudaFree(s.lin); cudaFree(s.edge); cudaFree(s.label); }
     cudaFree(v.planes); cudaFree(v.state); cudaFree(v.selected); cudaFree(v.gray_full);
   }
   ctx->views.clear();
+  for (auto t : ctx->scale_tex) if (t) cudaDestroyTextureObject(t);
+  for (auto a : ctx->scale_arr) if (a) cudaFreeArray(a);
+  ctx->scale_tex.clear(); ctx->scale_arr.clear();
   for (auto p : ctx->atlas_front) cudaFree(p);
   for (auto p : ctx->atlas_back) cudaFree(p);
   ctx->atlas_front.clear(); ctx->atlas_back.clear();
@@ -254,6 +254,19 @@ int dpe_scene_commit(dpe_ctx* ctx) {
   CK(cudaSetDevice(ctx->device));
   const LaunchCfg cfg = cfg_of(ctx);
   const int top = ctx->n_scales - 1;
+  ctx->scale_arr.assign(ctx->n_scales, nullptr); ctx->scale_tex.assign(ctx->n_scales, 0);
+  for (int k = 0; k < ctx->n_scales; ++k) {
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+    CK(cudaMalloc3DArray(&ctx->scale_arr[k], &cd, make_cudaExtent(ctx->sw[k], ctx->sh[k], ctx->n_views), cudaArrayLayered));
+    cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray; rd.res.array.array = ctx->scale_arr[k];
+    cudaTextureDesc td; memset(&td, 0, sizeof(td));
+    // the reference asks for Wrap with unnormalised coordinates, which CUDA turns into
+    // Clamp (DPE.cpp:929-933)
+    td.addressMode[0] = cudaAddressModeClamp; td.addressMode[1] = cudaAddressModeClamp; td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+    CK(cudaCreateTextureObject(&ctx->scale_tex[k], &rd, &td, nullptr));
+  }
   for (int vi = 0; vi < ctx->n_views; ++vi) {
     ViewData& v = ctx->views[vi];
     if (!v.have_img) FAIL(DPE_ERR_STATE, "view without image");
@@ -267,20 +280,14 @@ int dpe_scene_commit(dpe_ctx* ctx) {
     for (int k = 0; k < top; ++k)
       launch_resize_linear(v.scales[top].lin, ctx->W, ctx->H, v.scales[k].lin, ctx->sw[k], ctx->sh[k], cfg, 0);
     for (int k = 0; k < ctx->n_scales; ++k) {
-      ScaleImg& s = v.scales[k];
       const int w = ctx->sw[k], h = ctx->sh[k];
-      cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
-      CK(cudaMallocArray(&s.arr, &cd, w, h));
-      CK(cudaMemcpy2DToArrayAsync(s.arr, 0, 0, s.lin, (size_t)w * sizeof(float), (size_t)w * sizeof(float), h,
-                                  cudaMemcpyDeviceToDevice, 0));
-      cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
-      rd.resType = cudaResourceTypeArray; rd.res.array.array = s.arr;
-      cudaTextureDesc td; memset(&td, 0, sizeof(td));
-      // the reference asks for Wrap with unnormalised coordinates, which CUDA turns into
-      // Clamp (DPE.cpp:929-933)
-      td.addressMode[0] = cudaAddressModeClamp; td.addressMode[1] = cudaAddressModeClamp;
-      td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
-      CK(cudaCreateTextureObject(&s.tex, &rd, &td, nullptr));
+      cudaMemcpy3DParms cp; memset(&cp, 0, sizeof(cp));
+      cp.srcPtr = make_cudaPitchedPtr(v.scales[k].lin, (size_t)w * sizeof(float), w, h);
+      cp.dstArray = ctx->scale_arr[k];
+      cp.dstPos = make_cudaPos(0, 0, vi);
+      cp.extent = make_cudaExtent(w, h, 1);
+      cp.kind = cudaMemcpyDeviceToDevice;
+      CK(cudaMemcpy3DAsync(&cp, 0));
     }
     CK(cudaFree(v.gray_full)); v.gray_full = nullptr;
   }
@@ -331,7 +338,7 @@ static void build_ref_const(const dpe_ctx* ctx, int view, int k, bool geom, RefC
     SrcConst& sc = rc->src[si];
     fold_pair(rv.cam, ctx->views[sv].cam, w, h, ctx->W, ctx->H, &sc);
     sc.src_view = sv;
-    sc.tex = (unsigned long long)ctx->views[sv].scales[k].tex;
+    sc.tex = 0;
     sc.depth = geom ? ctx->atlas_front[k] + (size_t)sv * P : nullptr;
   }
 }
@@ -392,6 +399,9 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
   const size_t P = (size_t)ctx->sw[k] * ctx->sh[k];
   const int ns = (int)ctx->scratch.size();
   if (int rc = ensure_rng_tables(ctx, seed)) return rc;
+  // all views of a scale are layers of one texture (layer = view, linear filter, clamp)
+  CK(cudaDeviceSynchronize());
+  launch_set_scale_tex((unsigned long long)ctx->scale_tex[k], 0);
   CK(cudaEventRecord(ctx->ev0, 0));
   for (auto& s : ctx->scratch) CK(cudaStreamWaitEvent(s.stream, ctx->ev0, 0));
   std::vector<cudaEvent_t> done(ns, nullptr);
@@ -530,6 +540,8 @@ int dpe_cost_eval(dpe_ctx* ctx, int view, int k, int n_pix, const int* xy, const
   CK(cudaMalloc(&d_out, (size_t)n_pix * N * sizeof(float)));
   CK(cudaMemcpy(d_xy, xy, (size_t)n_pix * 2 * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_pl, planes, (size_t)n_pix * sizeof(float4), cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize());
+  launch_set_scale_tex((unsigned long long)ctx->scale_tex[k], 0);
   launch_cost_eval(KP, n_pix, d_xy, d_pl, mode, 0ull, d_out, cfg_of(ctx), 0);
   CK(cudaGetLastError());
   CK(cudaMemcpy(out, d_out, (size_t)n_pix * N * sizeof(float), cudaMemcpyDeviceToHost));
@@ -632,6 +644,8 @@ int dpe_bench_ncc(dpe_ctx* ctx, int view, int variant, int n_cand, int reps, dou
   const size_t P = (size_t)ctx->sw[k] * ctx->sh[k];
   float* out = ctx->scratch[0].costs;
   const LaunchCfg cfg = cfg_of(ctx);
+  CK(cudaDeviceSynchronize());
+  launch_set_scale_tex((unsigned long long)ctx->scale_tex[k], 0);
   launch_ncc_bench(KP, v.planes, n_cand, variant, out, cfg, 0);
   CK(cudaEventRecord(ctx->ev0, 0));
   for (int r = 0; r < reps; ++r) launch_ncc_bench(KP, v.planes, n_cand, variant, out, cfg, 0);

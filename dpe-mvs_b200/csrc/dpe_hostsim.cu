@@ -44,7 +44,7 @@ struct HostEnv {
   float2 tbl[36];
   const float* img;
   int W, H;
-  float tex(unsigned long long h, float u, float v) const { return host_tex((const HostImage*)h, u, v); }
+  float tex(const SrcConst& sc, float u, float v) const { return host_tex((const HostImage*)sc.tex, u, v); }
   float2 pw(int t) const { return tbl[t]; }
   float ref(int x, int y) const { return img[(size_t)iclamp(y, 0, H - 1) * W + iclamp(x, 0, W - 1)]; }
 };

@@ -25,6 +25,13 @@ constexpr int TILE_W = 32;
 constexpr int HALO = 5;
 constexpr int SMW = TILE_W + 2 * HALO;  // 42
 
+// The layered image texture of the scale a stage runs at.  It lives in the constant bank at a fixed
+// address (set by launch_set_scale_tex before the stage's kernels are queued) so that the handle of every
+// TEX instruction is warp-uniform by construction, also inside non-inlined cost functions; a handle that
+// arrives through a pointer or a struct makes the compiler wrap each fetch in a serialising
+// per-unique-handle loop.
+__constant__ cudaTextureObject_t c_scale_tex;
+
 struct DevEnv {
   const float2* tbl;  // &table[threadIdx.x]; tap t lives at tbl[t * NT]
   const float* img;   // reference image (for the far-away anchor patches of the weak path)
@@ -32,8 +39,8 @@ struct DevEnv {
   __device__ __forceinline__ float ref(int x, int y) const {
     return __ldg(&img[(size_t)iclamp(y, 0, H - 1) * W + iclamp(x, 0, W - 1)]);
   }
-  __device__ __forceinline__ float tex(unsigned long long h, float u, float v) const {
-    return tex2D<float>((cudaTextureObject_t)h, u, v);
+  __device__ __forceinline__ float tex(const SrcConst& sc, float u, float v) const {
+    return tex2DLayered<float>(c_scale_tex, u, v, sc.src_view);
   }
   __device__ __forceinline__ float2 pw(int t) const { return tbl[t * NT]; }
 };
@@ -233,6 +240,10 @@ __global__ void __launch_bounds__(256) k_light(const __grid_constant__ KernelPar
   }
 }
 
+void launch_set_scale_tex(unsigned long long tex, cudaStream_t stream) {
+  cudaMemcpyToSymbolAsync(c_scale_tex, &tex, sizeof(tex), 0, cudaMemcpyHostToDevice, stream);
+}
+
 // ---- launchers -----------------------------------------------------------------------------
 static inline int persistent_grid(int n_tiles, int num_sms, int per_sm) {
   const int g = num_sms * per_sm;
@@ -336,13 +347,14 @@ void launch_resize_linear(const float* src, int sw, int sh, float* dst, int dw, 
 // the linear filter returns the texel itself).
 struct DevEnvExact {
   const float2* tbl;
-  __device__ __forceinline__ float tex(unsigned long long h, float u, float v) const {
+  __device__ __forceinline__ float tex(const SrcConst& sc, float u, float v) const {
     const float xb = u - 0.5f, yb = v - 0.5f;
     const float fx0 = floorf(xb), fy0 = floorf(yb);
     const float ax = xb - fx0, ay = yb - fy0;
-    const cudaTextureObject_t t = (cudaTextureObject_t)h;
-    const float t00 = tex2D<float>(t, fx0 + 0.5f, fy0 + 0.5f), t10 = tex2D<float>(t, fx0 + 1.5f, fy0 + 0.5f);
-    const float t01 = tex2D<float>(t, fx0 + 0.5f, fy0 + 1.5f), t11 = tex2D<float>(t, fx0 + 1.5f, fy0 + 1.5f);
+    const cudaTextureObject_t t = c_scale_tex;
+    const int l = sc.src_view;
+    const float t00 = tex2DLayered<float>(t, fx0 + 0.5f, fy0 + 0.5f, l), t10 = tex2DLayered<float>(t, fx0 + 1.5f, fy0 + 0.5f, l);
+    const float t01 = tex2DLayered<float>(t, fx0 + 0.5f, fy0 + 1.5f, l), t11 = tex2DLayered<float>(t, fx0 + 1.5f, fy0 + 1.5f, l);
     return (1.f - ay) * ((1.f - ax) * t00 + ax * t10) + ay * ((1.f - ax) * t01 + ax * t11);
   }
   __device__ __forceinline__ float2 pw(int t) const { return tbl[t * NT]; }
@@ -423,7 +435,7 @@ __device__ __forceinline__ float ncc_old_rows(const Env& env, const PatchStats& 
 #pragma unroll
       for (int ix = 0; ix < 6; ++ix) {
         const float iz = fast_rcp(Z);
-        sv[jy * 6 + ix] = env.tex(sc.tex, X * iz, Y * iz);
+        sv[jy * 6 + ix] = env.tex(sc, X * iz, Y * iz);
         X += dXi; Y += dYi; Z += dZi;
       }
       Xr += dXj; Yr += dYj; Zr += dZj;
@@ -494,17 +506,7 @@ void launch_ncc_bench(const KernelParams& P, const float4* world_planes, int n_c
   auto g = [&](int per_sm) { return persistent_grid(tiles, cfg.num_sms, per_sm); };
   switch (variant) {
     case 0: k_ncc_bench<0, 4><<<g(4), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
-    case 1: k_ncc_bench<1, 4><<<g(4), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
-    case 2: k_ncc_bench<2, 4><<<g(4), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
-    case 3: k_ncc_bench<3, 4><<<g(4), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
-    case 4: k_ncc_bench<6, 4><<<g(4), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
-    case 5: k_ncc_bench<0, 3><<<g(3), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
-    case 6: k_ncc_bench<2, 3><<<g(3), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
-    case 7: k_ncc_bench<3, 3><<<g(3), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
-    case 8: k_ncc_bench<6, 3><<<g(3), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
-    case 9: k_ncc_bench<6, 2><<<g(2), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
-    case 10: k_ncc_bench<2, 5><<<g(5), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
-    case 11: k_ncc_bench<1, 6><<<g(6), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
+    case 1: k_ncc_bench<6, 3><<<g(3), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
     default: break;
   }
   count(cfg);

@@ -15,6 +15,10 @@ struct LaunchCfg {
   long long* launch_counter;  // host-side count of kernel launches
 };
 
+// selects the scale whose layered image texture the following kernels sample (device-wide constant:
+// all kernels in flight on a device must be of the same scale — a stage is)
+void launch_set_scale_tex(unsigned long long tex, cudaStream_t stream);
+
 // stage kernels (one view, one stage); all asynchronous on `stream`
 void launch_load(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
 void launch_init(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);

@@ -23,8 +23,8 @@ struct SrcConst {
   float bi[3];
   float baseline;        // |C_ref - C_src|  (DPE.cu:2640-2645)
   float width, height;   // source image size at this scale
-  int src_view;          // index of the source view in the scene
-  unsigned long long tex;  // cudaTextureObject_t of the source image (host sim: HostImage*)
+  int src_view;          // index of the source view in the scene = its layer in the scale's layered texture
+  unsigned long long tex;  // host simulator: HostImage* of the source image (unused on the GPU)
   const float* depth;      // source depth map in the committed atlas (nullptr if none)
 };
 

@@ -533,27 +533,61 @@ DPE_HDN void fit_plane_pixel(const StageArgs& a, const int x, const int y) {
 // ---- deformable NCC, ComputeBilateralNCCNew DPE.cu:557-690 ---------------------------------
 // Env additionally provides ref(x,y): clamped reference-image fetch.  `units` accumulates
 // evaluated taps / 36.
+// One patch of NTAP x NTAP taps at offsets first + t*inc around (px, py), weights relative to the
+// centre pixel's intensity r0 (DPE.cu:619-663).  NTAP is a compile-time constant so that the
+// fetches of a patch are independent instructions in flight together: the adaptive radius is 0
+// or a multiple of 5 with inc = 2r/5, i.e. always 1 or 6 taps per axis; anchor
+// patches are 3 x 3.
+template <int NTAP, class Env>
+DPE_HD float patch_cost_new(const Env& env, const PatchStats& ps, const SrcConst& sc, const float* h, const int px,
+                            const int py, const int first, const int inc) {
+  float sw = 0.f, sr = 0.f, srr = 0.f, ss = 0.f, sss = 0.f, srs = 0.f;
+#pragma unroll
+  for (int ti = 0; ti < NTAP; ++ti) {
+#pragma unroll
+    for (int tj = 0; tj < NTAP; ++tj) {
+      const int i = first + ti * inc, j = first + tj * inc;
+      const int rx = px + i, ry = py + j;
+      const float r = env.ref(rx, ry);
+      const float Z = h[6] * rx + h[7] * ry + h[8];
+      const float iz = fast_rcp(Z);
+      const float s = env.tex(sc, (h[0] * rx + h[1] * ry + h[2]) * iz + 0.5f, (h[3] * rx + h[4] * ry + h[5]) * iz + 0.5f) - ps.r0;
+      const float w = fast_exp(-sqrtf((float)(i * i + j * j)) * (1.0f / 50.0f) - fabsf(r - ps.r0) * (1.0f / 18.0f));
+      const float rp = r - ps.r0;
+      const float wr = w * rp, ws = w * s;
+      sw += w; sr += wr; srr = fmaf(wr, rp, srr); ss += ws; sss = fmaf(ws, s, sss); srs = fmaf(wr, s, srs);
+    }
+  }
+  const float inv = 1.0f / sw;
+  const float mr = sr * inv, ms = ss * inv;
+  const float var_r = srr * inv - mr * mr, var_s = sss * inv - ms * ms;
+  if (var_r < 1e-5f || var_s < 1e-5f) return 2.0f;
+  return fmaxf(0.0f, fminf(2.0f, 1.0f - (srs * inv - mr * ms) * fast_rsqrt(var_r * var_s)));
+}
+
 template <class Env>
-DPE_HDN float ncc_new(const Env& env, const PatchStats& ps, const StageArgs& a, const SrcConst& sc, const int v,
+__noinline__ DPE_HDN float ncc_new(const Env& env, const PatchStats& ps, const StageArgs& a, const SrcConst& sc, const int v,
                       const float3 m, const int x, const int y, float& units) {
   const int W = a.W, H = a.H, center = y * W + x;
-  const float h0 = sc.A[0] - sc.b[0] * m.x, h1 = sc.A[1] - sc.b[0] * m.y, h2 = sc.A[2] - sc.b[0] * m.z;
-  const float h3 = sc.A[3] - sc.b[1] * m.x, h4 = sc.A[4] - sc.b[1] * m.y, h5 = sc.A[5] - sc.b[1] * m.z;
-  const float h6 = sc.A[6] - sc.b[2] * m.x, h7 = sc.A[7] - sc.b[2] * m.y, h8 = sc.A[8] - sc.b[2] * m.z;
+  float h[9];
+  h[0] = sc.A[0] - sc.b[0] * m.x; h[1] = sc.A[1] - sc.b[0] * m.y; h[2] = sc.A[2] - sc.b[0] * m.z;
+  h[3] = sc.A[3] - sc.b[1] * m.x; h[4] = sc.A[4] - sc.b[1] * m.y; h[5] = sc.A[5] - sc.b[1] * m.z;
+  h[6] = sc.A[6] - sc.b[2] * m.x; h[7] = sc.A[7] - sc.b[2] * m.y; h[8] = sc.A[8] - sc.b[2] * m.z;
   {
-    const float Z = h6 * x + h7 * y + h8;
-    const float px = (h0 * x + h1 * y + h2) / Z, py = (h3 * x + h4 * y + h5) / Z;
+    const float Z = h[6] * x + h[7] * y + h[8];
+    const float px = (h[0] * x + h[1] * y + h[2]) / Z, py = (h[3] * x + h[4] * y + h[5]) / Z;
     if (px >= sc.width || px < 0.0f || py >= sc.height || py < 0.0f) return 2.0f;
   }
   const short2* nbrs = a.neighbours + (size_t)center * DPE_NEIGHBOUR_NUM;
   float center_cost = 0.f, strong_cost = 0.f;
   int strong_count = 0;
+#pragma unroll 1
   for (int k = 0; k < DPE_NEIGHBOUR_NUM; ++k) {
     const short2 np = nbrs[k];
     if (np.x == -1 || np.y == -1) continue;
     {
-      const float Z = h6 * np.x + h7 * np.y + h8;
-      const float qx = (h0 * np.x + h1 * np.y + h2) / Z, qy = (h3 * np.x + h4 * np.y + h5) / Z;
+      const float Z = h[6] * np.x + h[7] * np.y + h[8];
+      const float qx = (h[0] * np.x + h[1] * np.y + h[2]) / Z, qy = (h[3] * np.x + h[4] * np.y + h[5]) / Z;
       if (qx < 0 || qy < 0 || qx >= W || qy >= H) {  // sic: reference-image size (DPE.cu:596)
         if (k != 0) {
           if ((a.selected[np.x + np.y * W] >> v) & 1u) { strong_cost += 2.0f; strong_count++; }
@@ -562,33 +596,23 @@ DPE_HDN float ncc_new(const Env& env, const PatchStats& ps, const StageArgs& a, 
         return 2.0f;
       }
     }
-    int radius = 5, inc = (k == 0) ? 2 : 5;
-    if (k == 0) { radius = a.radius[center]; inc = imax(2, (int)(2.0 * radius / 5.0)); }
-    float sw = 0.f, sr = 0.f, srr = 0.f, ss = 0.f, sss = 0.f, srs = 0.f;
-    int taps = 0;
-    for (int i = -radius; i <= radius; i += inc) {
-      for (int j = -radius; j <= radius; j += inc) {
-        const int rx = np.x + i, ry = np.y + j;
-        const float r = env.ref(rx, ry);
-        const float Z = h6 * rx + h7 * ry + h8;
-        const float iz = fast_rcp(Z);
-        const float s = env.tex(sc.tex, (h0 * rx + h1 * ry + h2) * iz + 0.5f, (h3 * rx + h4 * ry + h5) * iz + 0.5f) - ps.r0;
-        const float w = fast_exp(-sqrtf((float)(i * i + j * j)) * (1.0f / 50.0f) - fabsf(r - ps.r0) * (1.0f / 18.0f));
-        const float rp = r - ps.r0;
-        const float wr = w * rp, ws = w * s;
-        sw += w; sr += wr; srr = fmaf(wr, rp, srr); ss += ws; sss = fmaf(ws, s, sss); srs = fmaf(wr, s, srs);
-        taps++;
-      }
-    }
-    units += taps * (1.0f / 36.0f);
-    const float inv = 1.0f / sw;
-    const float mr = sr * inv, ms = ss * inv;
-    const float var_r = srr * inv - mr * mr, var_s = sss * inv - ms * ms;
     float tc;
-    if (var_r < 1e-5f || var_s < 1e-5f) tc = 2.0f;
-    else tc = fmaxf(0.0f, fminf(2.0f, 1.0f - (srs * inv - mr * ms) * fast_rsqrt(var_r * var_s)));
-    if (k == 0) center_cost = tc;
-    else { strong_cost += tc; strong_count++; }
+    if (k == 0) {
+      const int radius = a.radius[center];
+      const int inc = imax(2, (int)(2.0 * radius / 5.0));
+      if (radius < inc) {  // a single tap (radius 0)
+        tc = patch_cost_new<1>(env, ps, sc, h, np.x, np.y, -radius, inc);
+        units += 1.0f / 36.0f;
+      } else {
+        tc = patch_cost_new<6>(env, ps, sc, h, np.x, np.y, -radius, inc);
+        units += 1.0f;
+      }
+      center_cost = tc;
+    } else {
+      tc = patch_cost_new<3>(env, ps, sc, h, np.x, np.y, -5, 5);
+      units += 9.0f / 36.0f;
+      strong_cost += tc; strong_count++;
+    }
   }
   if (strong_count == 0) return center_cost;
   strong_cost /= strong_count;

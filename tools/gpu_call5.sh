@@ -1,0 +1,7 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 600 python tools/prof_cmd.py 1 > gpurun_out/prof_cmd5.log 2>&1 && \
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:k_weak_list -s 8 -c 1 -f -o gpurun_out/r01c_weak python tools/prof_cmd.py 1 > gpurun_out/ncu_full5a.log 2>&1
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:k_half -s 30 -c 1 -f -o gpurun_out/r01c_strong_edge python tools/prof_cmd.py 1 > gpurun_out/ncu_full5b.log 2>&1
+echo done

@@ -19,8 +19,7 @@ for v in range(V):
 ctx.commit()
 for (k, p) in capi.stage_schedule(ns):
     ctx.run_stage(k, p, 20261018); ctx.stage_commit()
-names = {0: "as-is/4", 1: "rows1/4", 2: "rows2/4", 3: "rows3/4", 4: "rows6/4", 5: "as-is/3", 6: "rows2/3", 7: "rows3/3", 8: "rows6/3",
-         9: "rows6/2", 10: "rows2/5", 11: "rows1/6"}
+names = {0: "as-is/4", 1: "rows6/3"}
 out = []
 for var in sorted(names):
     best, cs = 0.0, None
