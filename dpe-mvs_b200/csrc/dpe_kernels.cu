@@ -184,31 +184,292 @@ __global__ void __launch_bounds__(256) k_compact_weak(const __grid_constant__ Ke
   }
 }
 
-__global__ void __launch_bounds__(NT, 4) k_weak_list(const __grid_constant__ KernelParams P) {
-  __shared__ float2 s_tbl[36 * NT];
+// One WARP per WEAK pixel.  A WEAK pixel scores 8 anchor planes x N views plus ~7 hypotheses x
+// sampled views, each over up to 108 taps; one thread per pixel leaves that as a single long
+// dependent chain on a few thousand threads.  Here the (hypothesis, view) pairs of a phase are
+// spread over the 32 lanes, the reference-side table (WeakTab) is built once per pixel in shared
+// memory, and the serial parts (view sampling with its RNG draws, accept chains) run on values every
+// lane holds.  Per-pair arithmetic and all summation orders are those of weak_update_pixel
+// (dpe_weak.cuh), which stays the definition (CPU simulator) — tests compare the two.
+struct WarpEnv {
+  const float2* tbl36;  // strong-patch table of the centre pixel (final re-score), shared memory
+  const float* img;
+  int W, H;
+  __device__ __forceinline__ float ref(int x, int y) const {
+    return __ldg(&img[(size_t)iclamp(y, 0, H - 1) * W + iclamp(x, 0, W - 1)]);
+  }
+  __device__ __forceinline__ float tex(const SrcConst& sc, float u, float v) const {
+    return tex2DLayered<float>(c_scale_tex, u, v, sc.src_view);
+  }
+  __device__ __forceinline__ float2 pw(int t) const { return tbl36[t]; }
+};
+
+struct WeakWarpSmem {
+  WeakTab T;
+  float cost[8 * DPE_MAX_IMAGES];   // candidate costs (cost_array of DPE.cu:1690)
+  float hcost[7 * DPE_MAX_IMAGES];  // per-view costs of: current plane, fit plane, 5 refinement hypotheses
+  float4 hplane[7];
+  float4 cand[8];
+  float2 tbl36[36];
+};
+
+struct Tbl36Store {
+  float2* t;
+  __device__ __forceinline__ void operator()(int i, float w, float wr) const { t[i] = make_float2(w, wr); }
+};
+
+__device__ __forceinline__ float bcast(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// PHASE_SYNC(): the warps of a CTA (each on its own pixel) enter every phase together, so that an SM
+// executes a few code regions at a time instead of one per warp — the weak sweep's code is far larger
+// than the instruction cache close to the schedulers, and un-synchronised warps spent two thirds of
+// their time waiting for instruction fetches (profiles/r01_ncu_weak_warp.txt).
+#define PHASE_SYNC() __syncthreads()
+__device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const int x, const int y, WeakWarpSmem& S, int& taps,
+                                 const bool live) {
+  const int lane = threadIdx.x & 31;
+  const bool writer = live && lane == 0;  // the lane that publishes this pixel's results
+  const int W = a.W, H = a.H, N = rc.n_src, center = y * W + x;
+  const int iter = a.iter;
+  WarpEnv env{S.tbl36, a.ref_img, W, H};
+  GlobalRef ref{a.ref_img, W, H};
+  WeakTab& T = S.T;
+  // ---- set-up: anchors, strong-patch table + statistics (lane 0), deformable table (lanes 0..8)
+  int first0 = 0, inc0 = 2;
+  if (lane < DPE_NEIGHBOUR_NUM) init_weak_tab_entry(a, center, T, lane, first0, inc0);
+  first0 = __shfl_sync(0xffffffffu, first0, 0); inc0 = __shfl_sync(0xffffffffu, inc0, 0);
+  // strong-patch table (build_patch, dpe_core.cuh): one tap per lane, summed by lane 0 in tap order
+  PatchStats ps;
+  ps.r0 = ref(x, y);
+  for (int t = lane; t < 36; t += 32) {
+    const int jy = t / 6, ixx = t - jy * 6;
+    const int i = 2 * ixx - 5, j = 2 * jy - 5;
+    const float r = ref(x + i, y + j);
+    const float sd = sqrtf((float)(i * i + j * j));
+    const float w = fast_exp(-sd * (1.0f / 50.0f) - fabsf(r - ps.r0) * (1.0f / 18.0f));
+    const float rp = r - ps.r0;
+    S.tbl36[t] = make_float2(w, w * rp);
+    S.hcost[t] = rp;
+  }
+  __syncwarp();
+  {
+    float sw = 0.f, swr = 0.f, swrr = 0.f;
+    if (lane == 0) {
+      for (int t = 0; t < 36; ++t) {
+        const float2 ww = S.tbl36[t];
+        sw += ww.x; swr += ww.y; swrr = fmaf(ww.y, S.hcost[t], swrr);
+      }
+    }
+    sw = bcast(sw, 0); swr = bcast(swr, 0); swrr = bcast(swrr, 0);
+    ps.inv_sw = 1.0f / sw;
+    ps.mean_r = swr * ps.inv_sw;
+    ps.var_r = swrr * ps.inv_sw - ps.mean_r * ps.mean_r;
+  }
+  __syncwarp();
+  if (lane < DPE_NEIGHBOUR_NUM) build_weak_patch(ref, ps.r0, T, lane, lane == 0 ? first0 : -5, lane == 0 ? inc0 : 5);
+  for (int i = lane; i < 8 * DPE_MAX_IMAGES; i += 32) S.cost[i] = 0.f;
+  __syncwarp();
+  if (lane == 0) S.cost[0] = 2.0f;
+  // candidates = planes of the STRONG anchors
+  bool my_flag = false;
+  int my_pos = 0;
+  if (lane < 8) {
+    const short2 np = T.anchor[lane + 1];
+    if (!(np.x == -1 || np.y == -1)) {
+      const int npc = np.x + np.y * W;
+      if (a.state[npc] == DPE_STRONG) { my_flag = true; my_pos = npc; S.cand[lane] = a.planes[npc]; }
+    }
+  }
+  const unsigned flags = __ballot_sync(0xffffffffu, my_flag) & 0xffu;
+  __syncwarp();
+  PHASE_SYNC();
+  // ---- phase 1: 8 candidates x N views
+  for (int p = lane; p < 8 * N; p += 32) {
+    const int j = p / N, v = p - j * N;
+    if ((flags >> j) & 1u) {
+      const float3 m = plane_to_m(rc, S.cand[j]);
+      S.cost[j * DPE_MAX_IMAGES + v] = ncc_new(env, ps.r0, T, rc.src[v], v, m, x, y, W, H, taps);
+    }
+  }
+  __syncwarp();
+  PHASE_SYNC();
+  // ---- phase 2: priors + view sampling (serial, lane 0 holds the pixel's RNG state)
+  ViewW vw;
+  float weight_norm = 0.f;
+  uint32_t sel_bits = 0u;
+  Rng rng;
+  if (lane == 0) {
+    float priors[DPE_MAX_IMAGES];
+    for (int v = 0; v < N; ++v) priors[v] = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      const short2 np = T.anchor[i + 1];
+      if (np.x == -1 || np.y == -1) continue;
+      const uint32_t sv = T.asel[i + 1];
+      for (int v = 0; v < N; ++v) priors[v] += ((sv >> v) & 1u) ? 0.9f : 0.1f;
+    }
+    rng.load(a.rng + center);
+    sample_views(S.cost, priors, N, iter, rng, vw, weight_norm, sel_bits);
+    if (live) a.view_w[center] = vw.pack();
+  }
+  vw.lo = __shfl_sync(0xffffffffu, vw.lo, 0); vw.hi = __shfl_sync(0xffffffffu, vw.hi, 0);
+  weight_norm = bcast(weight_norm, 0);
+  sel_bits = __shfl_sync(0xffffffffu, sel_bits, 0);
+  // sampled views, ascending
+  int nv = 0;
+  int vlist_lo = 0;  // this lane's entry of the list (lane i holds the i-th sampled view)
+  for (int v = 0; v < N; ++v)
+    if (vw.get(v) > 0) { if (nv == lane) vlist_lo = v; nv++; }
+  // ---- phase 3: final candidate costs (lane j), arg-min with "<=" (last minimum wins)
+  float my_final = 0.f;
+  if (lane < 8) {
+    const bool fl = (flags >> lane) & 1u;
+    float4 cand = make_float4(0.f, 0.f, 1.f, 1.f);
+    if (fl) cand = S.cand[lane];
+    float f = 0.f;
+    for (int v = 0; v < N; ++v) {
+      const int w = vw.get(v);
+      if (w > 0) {
+        float c = S.cost[lane * DPE_MAX_IMAGES + v];
+        if (a.geom) c += a.geom_factor * (fl ? geom_cost(rc, rc.src[v], cand, x, y) : 3.0f);
+        f += w * c;
+      }
+    }
+    my_final = f / weight_norm;
+  }
+  int min_idx = 0;
+  float min_final = bcast(my_final, 0);
+  for (int j = 1; j < 8; ++j) {
+    const float fj = bcast(my_final, j);
+    if (fj <= min_final) { min_final = fj; min_idx = j; }
+  }
+  PHASE_SYNC();
+  // ---- phase 4: current plane and fit plane over the sampled views
+  float4 plane_now = a.planes[center];
+  const float4 fit = a.fit_planes[center];
+  const bool has_fit = !(fit.x == 0 && fit.y == 0 && fit.z == 0);
+  if (lane == 0) { S.hplane[0] = plane_now; S.hplane[1] = fit; }
+  __syncwarp();
+  // lane i < nv knows the i-th sampled view; spread it to a small shared list through registers
+  int vlist[DPE_MAX_SRC > 15 ? 15 : DPE_MAX_SRC];  // at most 15 draws => at most 15 sampled views
+#pragma unroll
+  for (int i = 0; i < 15; ++i) vlist[i] = __shfl_sync(0xffffffffu, vlist_lo, i);
+  auto view_at = [&](const int i) {
+    int v = vlist[0];
+#pragma unroll
+    for (int q = 1; q < 15; ++q) if (i == q) v = vlist[q];
+    return v;
+  };
+  auto score = [&](const int h0, const int nh) {
+    for (int p = lane; p < nh * nv; p += 32) {
+      const int hi = p / nv;
+      const int v = view_at(p - hi * nv);
+      const float4 pl = S.hplane[h0 + hi];
+      const float3 m = plane_to_m(rc, pl);
+      float cv = ncc_new(env, ps.r0, T, rc.src[v], v, m, x, y, W, H, taps);
+      if (a.geom) cv += a.geom_factor * geom_cost(rc, rc.src[v], pl, x, y);
+      S.hcost[(h0 + hi) * DPE_MAX_IMAGES + v] = cv;
+    }
+    __syncwarp();
+  };
+  auto weighted = [&](const int h) {  // same order as weighted_cost_weak
+    float c = 0.f;
+    for (int v = 0; v < N; ++v) {
+      const int w = vw.get(v);
+      if (w > 0) c += w * S.hcost[h * DPE_MAX_IMAGES + v];
+    }
+    return c / weight_norm;
+  };
+  score(0, has_fit ? 2 : 1);
+  float cost_now = weighted(0);
+  const float cost_before = cost_now;
+  float depth_now = depth_from_plane(rc, plane_now, x, y);
+  if ((flags >> min_idx) & 1u) {
+    const float4 cand = S.cand[min_idx];
+    const float db = depth_from_plane(rc, cand, x, y);
+    if (db >= rc.depth_min && db <= rc.depth_max && min_final < cost_now) {
+      depth_now = db; plane_now = cand; cost_now = min_final;
+      if (writer) a.selected[center] = sel_bits;
+    }
+  }
+  PHASE_SYNC();
+  // ---- phase 5: PlaneHypothesisRefinementWeak (DPE.cu:1120-1212)
+  if (has_fit) {
+    const float dmin = rc.depth_min, dmax = rc.depth_max;
+    {
+      const float c = weighted(1);
+      const float db = depth_from_plane(rc, fit, x, y);
+      if (db >= dmin && db <= dmax && c < cost_now) { depth_now = db; plane_now = fit; cost_now = c; }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const float depth_rand = rng.uniform() * (dmax - dmin) + dmin;
+      const float4 n_rand = random_normal(rc, x, y, rng, depth_now);
+      const float lo = (1 - 0.02f) * depth_now, hi = (1 + 0.02f) * depth_now;
+      const float depth_pert = rng.uniform() * (hi - lo) + lo;
+      const float4 n_pert = perturbed_normal(rc, x, y, plane_now, rng, 0.02f * 3.14159265358979323846f);
+      for (int i = 0; i < 5; ++i) {
+        const float d = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : depth_now);
+        float4 n = (i == 1 || i == 2) ? n_rand : (i == 3 ? n_pert : plane_now);
+        n.w = dist2origin(rc, x, y, d, n);
+        S.hplane[2 + i] = n;
+      }
+    }
+    __syncwarp();
+    score(2, 5);
+    for (int i = 0; i < 5; ++i) {
+      const float4 n = S.hplane[2 + i];
+      const float c = weighted(2 + i);
+      const float db = depth_from_plane(rc, n, x, y);
+      if (db >= dmin && db <= dmax && c < cost_now) { depth_now = db; plane_now = n; cost_now = c; }
+    }
+  }
+  PHASE_SYNC();
+  if (writer) rng.store(a.rng + center);
+  float4 final_plane = a.planes[center];
+  if (a.run_state == DPE_REFINE_INIT) {
+    if (cost_now < cost_before - 0.1f) { final_plane = plane_now; if (writer) a.planes[center] = plane_now; }
+  } else {
+    final_plane = plane_now;
+    if (writer) a.planes[center] = plane_now;
+  }
+  // ---- phase 6: costs[] re-scored with the plain 6x6 NCC (DPE.cu:1845-1861)
+  __syncwarp();
+  {
+    const float3 m = plane_to_m(rc, final_plane);
+    if (lane < nv) {
+      const int v = vlist_lo;
+      S.hcost[v] = ncc_old(env, ps, rc.src[v], m, x, y);
+      taps += 36;
+    }
+    __syncwarp();
+    if (writer) a.costs[center] = weighted(0);
+  }
+  __syncwarp();
+}
+
+constexpr int NTW = 256;  // threads per CTA of the weak sweep: 8 warps = 8 pixels in phase lock-step
+__global__ void __launch_bounds__(NTW, 2) k_weak_list(const __grid_constant__ KernelParams P) {
+  __shared__ WeakWarpSmem s_w[NTW / 32];
   StageArgs a = P.a;
   a.rc = &P.rc;
   const int count = a.weak_count[a.colour];
   const int* list = a.weak_list + a.colour * a.list_stride;
-  unsigned evals = 0;
-  DevEnv env;
-  env.tbl = s_tbl + threadIdx.x;
-  env.img = a.ref_img; env.W = a.W; env.H = a.H;
-  TblStore st;
-  st.tbl = s_tbl + threadIdx.x;
-  GlobalRef ref{a.ref_img, a.W, a.H};
-  float cost_arr[9 * DPE_MAX_IMAGES];
-  // consecutive 32-entry chunks go to different CTAs first, so a short list still spreads over all SMs
-  const int warps_per_cta = NT / 32;
-  const int gwarp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
-  for (int i = gwarp * 32 + (threadIdx.x & 31); i < count; i += gridDim.x * warps_per_cta * 32) {
-    const int center = list[i];
-    const int x = center % a.W, y = center / a.W;
-    const PatchStats ps = build_patch(ref, x, y, st);
-    weak_update_pixel(env, ps, a, x, y, cost_arr, evals);
+  int taps = 0;
+  const int warps_per_cta = NTW / 32;
+  // consecutive list entries go to different CTAs first, so a short list still spreads over all SMs
+  // CTA-uniform loop (the phases synchronise the CTA): group g = one list entry per
+  // warp.  In the ragged last group a warp without an entry shadows the last one with its stores off.
+  const int wid = threadIdx.x >> 5;
+  const int groups = (count + warps_per_cta - 1) / warps_per_cta;
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+    const int i = g * warps_per_cta + wid;
+    const bool live = i < count;
+    const int center = list[live ? i : count - 1];
+    weak_update_warp(a, P.rc, center % a.W, center / a.W, s_w[wid], taps, live);
   }
-  flush_evals(a.eval_units, evals);
+  flush_evals(a.eval_units, (unsigned)((taps + 18) / 36));
 }
+#undef PHASE_SYNC
 
 // ---- light per-pixel kernels ------------------------------------------------------------
 enum LightOp { L_EXTRACT = 0, L_MEDIAN = 1, L_FINISH = 2, L_EDGE_INFO = 3, L_NEAREST = 4, L_NEIGH = 5, L_FIT = 6, L_LOAD = 7 };
@@ -277,7 +538,7 @@ void launch_strong(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t st
   count(cfg);
 }
 void launch_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream) {
-  k_weak_list<<<cfg.num_sms * 4, NT, 0, stream>>>(P);
+  k_weak_list<<<cfg.num_sms * 2, NTW, 0, stream>>>(P);
   count(cfg);
 }
 void launch_compact_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream) {

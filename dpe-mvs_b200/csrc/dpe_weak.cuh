@@ -531,44 +531,96 @@ DPE_HDN void fit_plane_pixel(const StageArgs& a, const int x, const int y) {
 }
 
 // ---- deformable NCC, ComputeBilateralNCCNew DPE.cu:557-690 ---------------------------------
-// Env additionally provides ref(x,y): clamped reference-image fetch.  `units` accumulates
-// evaluated taps / 36.
-// One patch of NTAP x NTAP taps at offsets first + t*inc around (px, py), weights relative to the
-// centre pixel's intensity r0 (DPE.cu:619-663).  NTAP is a compile-time constant so that the
-// fetches of a patch are independent instructions in flight together: the adaptive radius is 0
-// or a multiple of 5 with inc = 2r/5, i.e. always 1 or 6 taps per axis; anchor
-// patches are 3 x 3.
-template <int NTAP, class Env>
-DPE_HD float patch_cost_new(const Env& env, const PatchStats& ps, const SrcConst& sc, const float* h, const int px,
-                            const int py, const int first, const int inc) {
-  float sw = 0.f, sr = 0.f, srr = 0.f, ss = 0.f, sss = 0.f, srs = 0.f;
-#pragma unroll
-  for (int ti = 0; ti < NTAP; ++ti) {
-#pragma unroll
-    for (int tj = 0; tj < NTAP; ++tj) {
+// The reference recomputes, for every (hypothesis, view) it scores at a WEAK pixel, the reference
+// intensities, bilateral weights and reference moments of all nine patches (centre patch with
+// the adaptive radius + up to 8 anchor patches of 3 x 3 taps; weights relative to the centre
+// pixel's intensity, DPE.cu:619-663).  None of that depends on the hypothesis or the view, so it
+// is built once per pixel and sweep into a WeakTab and every evaluation only does the source
+// fetches and the source-side sums.  The adaptive radius is 0 or a multiple of 5 with
+// inc = max(2, 2r/5): the centre patch has 1 or 6 taps per axis.
+struct WeakTab {
+  float2 ww[108];     // (w, w * (r - r0)) per tap; patch k starts at tab_offset(k)
+  short2 xy[108];     // reference pixel of the tap
+  float inv_sw[9], mean_r[9], var_r[9];
+  short2 anchor[9];   // anchor[0] = the pixel itself; (-1,-1) = absent
+  uint32_t asel[9];   // selected-view bits of the anchors (constant during a weak sweep: anchors are STRONG)
+  uint8_t ntap[9];    // taps per axis: 0 = absent, 1, 3 or 6
+};
+DPE_HD int tab_offset(const int k) { return k == 0 ? 0 : 36 + (k - 1) * 9; }
+
+// reference side of patch k (tap order: x offset outer, y offset inner, as DPE.cu:619-621)
+template <class RefFetch>
+DPE_HD void build_weak_patch(const RefFetch& ref, const float r0, WeakTab& T, const int k, const int first, const int inc) {
+  const int n = T.ntap[k];
+  if (n == 0) return;
+  const short2 np = T.anchor[k];
+  const int off = tab_offset(k);
+  float sw = 0.f, sr = 0.f, srr = 0.f;
+  for (int ti = 0; ti < n; ++ti) {
+    for (int tj = 0; tj < n; ++tj) {
       const int i = first + ti * inc, j = first + tj * inc;
-      const int rx = px + i, ry = py + j;
-      const float r = env.ref(rx, ry);
-      const float Z = h[6] * rx + h[7] * ry + h[8];
-      const float iz = fast_rcp(Z);
-      const float s = env.tex(sc, (h[0] * rx + h[1] * ry + h[2]) * iz + 0.5f, (h[3] * rx + h[4] * ry + h[5]) * iz + 0.5f) - ps.r0;
-      const float w = fast_exp(-sqrtf((float)(i * i + j * j)) * (1.0f / 50.0f) - fabsf(r - ps.r0) * (1.0f / 18.0f));
-      const float rp = r - ps.r0;
-      const float wr = w * rp, ws = w * s;
-      sw += w; sr += wr; srr = fmaf(wr, rp, srr); ss += ws; sss = fmaf(ws, s, sss); srs = fmaf(wr, s, srs);
+      const int rx = np.x + i, ry = np.y + j;
+      const float r = ref(rx, ry);
+      const float w = fast_exp(-sqrtf((float)(i * i + j * j)) * (1.0f / 50.0f) - fabsf(r - r0) * (1.0f / 18.0f));
+      const float rp = r - r0;
+      const float wr = w * rp;
+      T.ww[off + ti * n + tj] = make_float2(w, wr);
+      T.xy[off + ti * n + tj] = make_short2((short)rx, (short)ry);
+      sw += w; sr += wr; srr = fmaf(wr, rp, srr);
     }
   }
   const float inv = 1.0f / sw;
-  const float mr = sr * inv, ms = ss * inv;
-  const float var_r = srr * inv - mr * mr, var_s = sss * inv - ms * ms;
+  const float mr = sr * inv;
+  T.inv_sw[k] = inv; T.mean_r[k] = mr; T.var_r[k] = srr * inv - mr * mr;
+}
+
+// anchors, their selected views, tap counts: everything of the WeakTab but the patches
+DPE_HD void init_weak_tab_entry(const StageArgs& a, const int center, WeakTab& T, const int k, int& first0, int& inc0) {
+  const short2 np = a.neighbours[(size_t)center * DPE_NEIGHBOUR_NUM + k];
+  T.anchor[k] = np;
+  const bool present = !(np.x == -1 || np.y == -1);
+  T.asel[k] = present ? a.selected[np.x + np.y * a.W] : 0u;
+  if (k == 0) {
+    const int radius = a.radius[center];
+    const int inc = imax(2, (int)(2.0 * radius / 5.0));
+    T.ntap[0] = present ? (radius < inc ? 1 : 6) : 0;
+    first0 = -radius; inc0 = inc;
+  } else {
+    T.ntap[k] = present ? 3 : 0;
+  }
+}
+
+// source side of one patch: NTAP x NTAP independent fetches
+template <int NTAP, class Env>
+DPE_HD float patch_cost_tab(const Env& env, const float r0, const WeakTab& T, const int k, const SrcConst& sc, const float* h) {
+  const int off = tab_offset(k);
+  float ss = 0.f, sss = 0.f, srs = 0.f;
+  // one row of taps (NTAP independent fetches) per iteration: the code stays small enough for the
+  // instruction cache when every warp of an SM is at a different place of the weak sweep
+#pragma unroll 1
+  for (int tr = 0; tr < NTAP; ++tr)
+#pragma unroll
+  for (int tc = 0; tc < NTAP; ++tc) {
+    const int t = tr * NTAP + tc;
+    const short2 q = T.xy[off + t];
+    const float Z = h[6] * q.x + h[7] * q.y + h[8];
+    const float iz = fast_rcp(Z);
+    const float s = env.tex(sc, (h[0] * q.x + h[1] * q.y + h[2]) * iz + 0.5f, (h[3] * q.x + h[4] * q.y + h[5]) * iz + 0.5f) - r0;
+    const float2 ww = T.ww[off + t];
+    const float ws = ww.x * s;
+    ss += ws; sss = fmaf(ws, s, sss); srs = fmaf(ww.y, s, srs);
+  }
+  const float inv = T.inv_sw[k], mr = T.mean_r[k], var_r = T.var_r[k];
+  const float ms = ss * inv;
+  const float var_s = sss * inv - ms * ms;
   if (var_r < 1e-5f || var_s < 1e-5f) return 2.0f;
   return fmaxf(0.0f, fminf(2.0f, 1.0f - (srs * inv - mr * ms) * fast_rsqrt(var_r * var_s)));
 }
 
+// `taps` accumulates evaluated source taps
 template <class Env>
-__noinline__ DPE_HDN float ncc_new(const Env& env, const PatchStats& ps, const StageArgs& a, const SrcConst& sc, const int v,
-                      const float3 m, const int x, const int y, float& units) {
-  const int W = a.W, H = a.H, center = y * W + x;
+__noinline__ DPE_HDN float ncc_new(const Env& env, const float r0, const WeakTab& T, const SrcConst& sc, const int v, const float3 m,
+                                   const int x, const int y, const int W, const int H, int& taps) {
   float h[9];
   h[0] = sc.A[0] - sc.b[0] * m.x; h[1] = sc.A[1] - sc.b[0] * m.y; h[2] = sc.A[2] - sc.b[0] * m.z;
   h[3] = sc.A[3] - sc.b[1] * m.x; h[4] = sc.A[4] - sc.b[1] * m.y; h[5] = sc.A[5] - sc.b[1] * m.z;
@@ -578,40 +630,31 @@ __noinline__ DPE_HDN float ncc_new(const Env& env, const PatchStats& ps, const S
     const float px = (h[0] * x + h[1] * y + h[2]) / Z, py = (h[3] * x + h[4] * y + h[5]) / Z;
     if (px >= sc.width || px < 0.0f || py >= sc.height || py < 0.0f) return 2.0f;
   }
-  const short2* nbrs = a.neighbours + (size_t)center * DPE_NEIGHBOUR_NUM;
   float center_cost = 0.f, strong_cost = 0.f;
   int strong_count = 0;
 #pragma unroll 1
   for (int k = 0; k < DPE_NEIGHBOUR_NUM; ++k) {
-    const short2 np = nbrs[k];
-    if (np.x == -1 || np.y == -1) continue;
+    const int n = T.ntap[k];
+    if (n == 0) continue;
+    const short2 np = T.anchor[k];
     {
       const float Z = h[6] * np.x + h[7] * np.y + h[8];
       const float qx = (h[0] * np.x + h[1] * np.y + h[2]) / Z, qy = (h[3] * np.x + h[4] * np.y + h[5]) / Z;
       if (qx < 0 || qy < 0 || qx >= W || qy >= H) {  // sic: reference-image size (DPE.cu:596)
         if (k != 0) {
-          if ((a.selected[np.x + np.y * W] >> v) & 1u) { strong_cost += 2.0f; strong_count++; }
+          if ((T.asel[k] >> v) & 1u) { strong_cost += 2.0f; strong_count++; }
           continue;
         }
         return 2.0f;
       }
     }
-    float tc;
     if (k == 0) {
-      const int radius = a.radius[center];
-      const int inc = imax(2, (int)(2.0 * radius / 5.0));
-      if (radius < inc) {  // a single tap (radius 0)
-        tc = patch_cost_new<1>(env, ps, sc, h, np.x, np.y, -radius, inc);
-        units += 1.0f / 36.0f;
-      } else {
-        tc = patch_cost_new<6>(env, ps, sc, h, np.x, np.y, -radius, inc);
-        units += 1.0f;
-      }
-      center_cost = tc;
+      center_cost = (n == 1) ? patch_cost_tab<1>(env, r0, T, 0, sc, h) : patch_cost_tab<6>(env, r0, T, 0, sc, h);
+      taps += n * n;
     } else {
-      tc = patch_cost_new<3>(env, ps, sc, h, np.x, np.y, -5, 5);
-      units += 9.0f / 36.0f;
-      strong_cost += tc; strong_count++;
+      strong_cost += patch_cost_tab<3>(env, r0, T, k, sc, h);
+      strong_count++;
+      taps += 9;
     }
   }
   if (strong_count == 0) return center_cost;
@@ -622,15 +665,15 @@ __noinline__ DPE_HDN float ncc_new(const Env& env, const PatchStats& ps, const S
 
 // weighted (photometric + geometric) cost of one hypothesis over the sampled views
 template <class Env>
-DPE_HD float weighted_cost_weak(const Env& env, const PatchStats& ps, const StageArgs& a, const float4 pl, const int x,
-                                const int y, const ViewW& vw, const float weight_norm, float& units) {
+DPE_HD float weighted_cost_weak(const Env& env, const PatchStats& ps, const WeakTab& T, const StageArgs& a, const float4 pl,
+                                const int x, const int y, const ViewW& vw, const float weight_norm, int& taps) {
   const RefConst& rc = *a.rc;
   const float3 m = plane_to_m(rc, pl);
   float c = 0.f;
   for (int v = 0; v < rc.n_src; ++v) {
     const int w = vw.get(v);
     if (w > 0) {
-      float cv = ncc_new(env, ps, a, rc.src[v], v, m, x, y, units);
+      float cv = ncc_new(env, ps.r0, T, rc.src[v], v, m, x, y, a.W, a.H, taps);
       if (a.geom) cv += a.geom_factor * geom_cost(rc, rc.src[v], pl, x, y);
       c += w * cv;
     }
@@ -645,7 +688,14 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
   const RefConst& rc = *a.rc;
   const int W = a.W, N = rc.n_src, center = y * W + x;
   const int iter = a.iter;
-  float units = 0.f;
+  int taps = 0;
+  WeakTab T;
+  {
+    int first0 = 0, inc0 = 2;
+    for (int k = 0; k < DPE_NEIGHBOUR_NUM; ++k) init_weak_tab_entry(a, center, T, k, first0, inc0);
+    auto ref = [&](int rx, int ry) { return env.ref(rx, ry); };
+    for (int k = 0; k < DPE_NEIGHBOUR_NUM; ++k) build_weak_patch(ref, ps.r0, T, k, k == 0 ? first0 : -5, k == 0 ? inc0 : 5);
+  }
   for (int j = 0; j < 8; ++j)
     for (int v = 0; v < N; ++v) cost_arr[j * DPE_MAX_IMAGES + v] = 0.f;
   cost_arr[0] = 2.0f;
@@ -665,7 +715,7 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
     if (a.state[npc] != DPE_STRONG) continue;
     positions[i] = npc; flag[i] = true;
     const float3 m = plane_to_m(rc, a.planes[npc]);
-    for (int v = 0; v < N; ++v) cost_arr[i * DPE_MAX_IMAGES + v] = ncc_new(env, ps, a, rc.src[v], v, m, x, y, units);
+    for (int v = 0; v < N; ++v) cost_arr[i * DPE_MAX_IMAGES + v] = ncc_new(env, ps.r0, T, rc.src[v], v, m, x, y, a.W, a.H, taps);
   }
   Rng rng;
   rng.load(a.rng + center);
@@ -698,7 +748,7 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
       if (final_costs[j] <= mc) { mc = final_costs[j]; min_idx = j; }
   }
   float4 plane_now = a.planes[center];
-  float cost_now = weighted_cost_weak(env, ps, a, plane_now, x, y, vw, weight_norm, units);
+  float cost_now = weighted_cost_weak(env, ps, T, a, plane_now, x, y, vw, weight_norm, taps);
   const float cost_before = cost_now;
   float depth_now = depth_from_plane(rc, plane_now, x, y);
   if (flag[min_idx]) {
@@ -716,7 +766,7 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
     const bool has_fit = !(fit.x == 0 && fit.y == 0 && fit.z == 0);
     if (has_fit) {  // without a fit plane the reference returns before the random refinement
       {
-        const float c = weighted_cost_weak(env, ps, a, fit, x, y, vw, weight_norm, units);
+        const float c = weighted_cost_weak(env, ps, T, a, fit, x, y, vw, weight_norm, taps);
         const float db = depth_from_plane(rc, fit, x, y);
         if (db >= dmin && db <= dmax && c < cost_now) { depth_now = db; plane_now = fit; cost_now = c; }
       }
@@ -732,7 +782,7 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
         const float d = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : depth_in);
         float4 n = (i == 1 || i == 2) ? n_rand : (i == 3 ? n_pert : plane_in);
         n.w = dist2origin(rc, x, y, d, n);
-        const float c = weighted_cost_weak(env, ps, a, n, x, y, vw, weight_norm, units);
+        const float c = weighted_cost_weak(env, ps, T, a, n, x, y, vw, weight_norm, taps);
         const float db = depth_from_plane(rc, n, x, y);
         if (db >= dmin && db <= dmax && c < cost_now) { depth_now = db; plane_now = n; cost_now = c; }
       }
@@ -752,11 +802,11 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
     float c = 0.f;
     for (int v = 0; v < N; ++v) {
       const int w = vw.get(v);
-      if (w > 0) { c += w * ncc_old(env, ps, rc.src[v], m, x, y); units += 1.f; }
+      if (w > 0) { c += w * ncc_old(env, ps, rc.src[v], m, x, y); taps += 36; }
     }
     a.costs[center] = c / weight_norm;
   }
-  evals += (unsigned)(units + 0.5f);
+  evals += (unsigned)((taps + 18) / 36);
 }
 
 }  // namespace dpe

@@ -125,7 +125,7 @@ def test_geom_eval_matches_oracle(ctx_c1):
 
 
 def test_stage_matches_cpu_simulator():
-    """Same per-pixel code, same Philox stream: the GPU stage and its CPU simulation agree on
+    """Same per-pixel code, same XORWOW stream: the GPU stage and its CPU simulation agree on
     almost every pixel (they differ only in fp contraction and texture coordinate rounding)."""
     import simpipe
     spec, grays, cams, drs, pairs, gt = small_scene("c1", 0.25)
@@ -142,6 +142,71 @@ def test_stage_matches_cpu_simulator():
     assert both.mean() > 0.8
     assert (rel[both] < 0.01).mean() > 0.85
     assert (g["state"] == s["state"]).mean() > 0.85
+    ctx.close()
+
+
+def test_weak_path_stages_match_cpu_simulator():
+    """The DPE weak/edge path (anchor search, fit plane, warp-cooperative weak sweep, classifier) on the GPU
+    against the per-pixel CPU simulation of the same stage, started from the GPU's own previous-stage maps:
+    stage 4 (first stage with WEAK pixels, REFINE_INIT) and stage 5 (REFINE_ITER with geometric consistency).
+    Same code per (hypothesis, view), same XORWOW stream; differences come from fp contraction / texture
+    coordinate rounding only, so the maps agree on most pixels."""
+    import ctypes as C
+    import hostsim
+    import simpipe
+    spec, grays, cams, drs, pairs, gt = small_scene("c4", 0.05, 5)      # 151 x 101, low-texture planes
+    lib = capi.load()
+    H, W = grays[0].shape
+    sizes = simpipe.level_sizes(W, H, 2)
+    prep = []
+    for g in grays:
+        per = []
+        for k in range(2):
+            e = np.empty((sizes[k][1], sizes[k][0]), np.uint8)
+            l = np.empty((sizes[k][1], sizes[k][0]), np.int32)
+            gg = np.ascontiguousarray(g)
+            lib.dpe_host_problem_edges(gg.ctypes.data_as(C.c_void_p), W, H, 1 << (1 - k), e.ctypes.data_as(C.c_void_p), l.ctypes.data_as(C.c_void_p))
+            per.append((e, l))
+        prep.append(per)
+    ctx = capi.Context(0)
+    ns = capi.upload_scene(ctx, grays, cams, drs, pairs, 2)
+    for v in range(len(grays)):
+        for k in range(2):
+            ctx.set_prep(v, k, *prep[v][k])
+    sched = capi.stage_schedule(ns)
+    seed = 20261018
+
+    for si in range(4):
+        ctx.run_stage(*sched[si], seed); ctx.stage_commit()
+    pyr = [hostsim.resize_linear(g.astype(np.float32), *sizes[0]) for g in grays]
+    full = [g.astype(np.float32) for g in grays]
+    n_weak_total = 0
+    for si in (4, 5):
+        prev = [ctx.get_maps(v, 0 if si == 4 else 1) for v in range(len(grays))]
+        ctx.run_stage(*sched[si], seed); ctx.stage_commit()
+        k, p = sched[si]
+        for v in (0, 2):
+            got = ctx.get_maps(v, 1)
+            ids = [v] + list(pairs[v])
+            pv = prev[v]
+            planes = np.concatenate([pv["normal"], pv["depth"][..., None]], -1)
+            sd = [prev[i]["depth"] for i in pairs[v]] if p.geom_consistency else None
+            r = hostsim.run_stage([full[i] for i in ids], [cams[i] for i in ids], drs[v], (W, H), p, seed, view=v,
+                                  prev=(planes, pv["state"], pv["selected"]), src_depths=sd, edge=prep[v][1][0],
+                                  edge_low=prep[v][0][0], label=prep[v][1][1])
+            weak_in = pv["state"] == capi.WEAK
+            if si == 4:   # previous maps are at the coarse scale: the stage upsamples them
+                weak_in = np.zeros((H, W), bool) | (r["state"] == capi.WEAK) | (got["state"] == capi.WEAK)
+            n_weak_total += int(weak_in.sum())
+            assert (got["state"] == r["state"]).mean() > 0.93, (si, v, (got["state"] == r["state"]).mean())
+            both = (got["depth"] > 0) & (r["depth"] > 0)
+            rel = np.abs(got["depth"] - r["depth"]) / np.maximum(r["depth"], 1e-6)
+            assert (rel[both] < 0.01).mean() > 0.93, (si, v, (rel[both] < 0.01).mean())
+            # the WEAK pixels themselves (where the weak sweep acted)
+            m = both & weak_in
+            if m.sum() > 50:
+                assert (rel[m] < 0.01).mean() > 0.8, (si, v, (rel[m] < 0.01).mean(), int(m.sum()))
+    assert n_weak_total > 200      # the scene does exercise the weak path
     ctx.close()
 
 
