@@ -21,6 +21,10 @@
 namespace dpe {
 
 constexpr int NT = 128;      // threads per CTA
+#ifndef DPE_CTAS_PER_SM
+#define DPE_CTAS_PER_SM 4
+#endif
+constexpr int CTAS_PER_SM = DPE_CTAS_PER_SM;  // resident CTAs per SM of the image-tile kernels (register budget 65536 / (128 * n))
 constexpr int TILE_W = 32;
 constexpr int HALO = 5;
 constexpr int SMW = TILE_W + 2 * HALO;  // 42
@@ -82,7 +86,7 @@ __device__ __forceinline__ void flush_evals(unsigned long long* counter, unsigne
 enum FullOp { OP_INIT = 0, OP_CLASSIFY = 1 };
 
 template <int OP>
-__global__ void __launch_bounds__(NT, 4) k_full(const __grid_constant__ KernelParams P) {
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) k_full(const __grid_constant__ KernelParams P) {
   __shared__ float2 s_tbl[36 * NT];
   __shared__ float s_tile[SMW * (4 + 2 * HALO)];
   StageArgs a = P.a;
@@ -116,7 +120,7 @@ __global__ void __launch_bounds__(NT, 4) k_full(const __grid_constant__ KernelPa
 enum HalfOp { OP_STRONG = 0, OP_STRONG_EDGE = 1 };
 
 template <int OP>
-__global__ void __launch_bounds__(NT, 4) k_half(const __grid_constant__ KernelParams P) {
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) k_half(const __grid_constant__ KernelParams P) {
   __shared__ float2 s_tbl[36 * NT];
   __shared__ float s_tile[SMW * (8 + 2 * HALO)];
   StageArgs a = P.a;
@@ -447,8 +451,9 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
   __syncwarp();
 }
 
-constexpr int NTW = 256;  // threads per CTA of the weak sweep: 8 warps = 8 pixels in phase lock-step
-__global__ void __launch_bounds__(NTW, 2) k_weak_list(const __grid_constant__ KernelParams P) {
+constexpr int NTW = 128;  // threads per CTA of the weak sweep: 4 warps = 4 pixels in phase lock-step
+constexpr int WEAK_CTAS_PER_SM = 6;
+__global__ void __launch_bounds__(NTW, WEAK_CTAS_PER_SM) k_weak_list(const __grid_constant__ KernelParams P) {
   __shared__ WeakWarpSmem s_w[NTW / 32];
   StageArgs a = P.a;
   a.rc = &P.rc;
@@ -518,27 +523,27 @@ void launch_init(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t stre
   KernelParams P = P0;
   P.a.tiles_x = (P.a.W + TILE_W - 1) / TILE_W;
   P.a.tiles_y = (P.a.H + 3) / 4;
-  k_full<OP_INIT><<<persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, 4), NT, 0, stream>>>(P);
+  k_full<OP_INIT><<<persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, CTAS_PER_SM), NT, 0, stream>>>(P);
   count(cfg);
 }
 void launch_classify_refine(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t stream) {
   KernelParams P = P0;
   P.a.tiles_x = (P.a.W + TILE_W - 1) / TILE_W;
   P.a.tiles_y = (P.a.H + 3) / 4;
-  k_full<OP_CLASSIFY><<<persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, 4), NT, 0, stream>>>(P);
+  k_full<OP_CLASSIFY><<<persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, CTAS_PER_SM), NT, 0, stream>>>(P);
   count(cfg);
 }
 void launch_strong(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t stream) {
   KernelParams P = P0;
   P.a.tiles_x = (P.a.W + TILE_W - 1) / TILE_W;
   P.a.tiles_y = (P.a.H + 7) / 8;
-  const int g = persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, 4);
+  const int g = persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, CTAS_PER_SM);
   if (P.a.use_apd) k_half<OP_STRONG_EDGE><<<g, NT, 0, stream>>>(P);
   else k_half<OP_STRONG><<<g, NT, 0, stream>>>(P);
   count(cfg);
 }
 void launch_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream) {
-  k_weak_list<<<cfg.num_sms * 2, NTW, 0, stream>>>(P);
+  k_weak_list<<<cfg.num_sms * WEAK_CTAS_PER_SM, NTW, 0, stream>>>(P);
   count(cfg);
 }
 void launch_compact_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream) {
