@@ -159,6 +159,9 @@ def run_ours(args):
     if use_dist:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # host-side barrier for the phases in which one rank works alone: an NCCL barrier would leave a
+        # spinning kernel on the idle ranks' GPUs, which rank 0's in-process multi-GPU e2e run also uses
+        cpu_group = dist.new_group(backend="gloo")
     lib = capi.load()
 
     tag = "c2"
@@ -275,7 +278,8 @@ def run_ours(args):
     # ---- e2e through the public API (rank 0 drives; N > 1: in-process multi-GPU, DPE_GPUS)
     e2e = None
     if use_dist:
-        dist.barrier()
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
     if rank == 0:
         import DPE_MVS
         shutil.rmtree(folder / "DPE", ignore_errors=True)
@@ -296,7 +300,7 @@ def run_ours(args):
         except Exception:
             pass
     if use_dist:
-        dist.barrier()
+        dist.barrier(group=cpu_group)
 
     # ---- cpu baseline: float64 oracle port of the NCC, one core, bounded sample
     cpu = None

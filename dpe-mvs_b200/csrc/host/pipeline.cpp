@@ -137,23 +137,38 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
   std::vector<ImageU8> grays(n_views);
   std::vector<CamFile> cams(n_views);
   int width = 0, height = 0;
-  for (int v = 0; v < n_views; ++v) {
-    int w = 0, h = 0;
-    const std::string ip = dense + "/images/" + format_index(view_ids[v]) + ".jpg";
-    if (!jpeg_decode_gray(dec, ip, &grays[v].d, &w, &h, &err)) {
+  {
+    // one nvJPEG decoder per loader thread (Huffman decoding is host work, the rest runs on gpus[0])
+    const int n_load = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 8, n_views}));
+    std::vector<JpegDecoder*> decs(n_load, nullptr);
+    decs[0] = dec;
+    std::vector<int> ws(n_views, 0), hs(n_views, 0);
+    std::atomic<int> bad(0), next_dec(0);
+    parallel_for(n_views, n_load, [&](int v) {
+      thread_local int my = -1;
+      thread_local const void* owner = nullptr;
+      if (my < 0 || owner != (const void*)&decs) {
+        my = next_dec++; owner = (const void*)&decs;
+        cudaSetDevice(gpus[0]);
+        if (my > 0) { std::string e; decs[my] = jpeg_decoder_create(&e); }
+      }
+      std::string e;
+      const std::string ip = dense + "/images/" + format_index(view_ids[v]) + ".jpg";
+      if (!decs[my] || !jpeg_decode_gray(decs[my], ip, &grays[v].d, &ws[v], &hs[v], &e)) { bad++; return; }
+      grays[v].cols = ws[v]; grays[v].rows = hs[v];
+      if (!read_cam(dense + "/cams/" + format_index(view_ids[v]) + "_cam.txt", &cams[v])) bad += 1000;
+    });
+    for (int i = 1; i < n_load; ++i) jpeg_decoder_destroy(decs[i]);
+    width = ws[0]; height = hs[0];
+    bool same = bad.load() % 1000 == 0;
+    for (int v = 0; v < n_views && same; ++v) same = (ws[v] == width && hs[v] == height);
+    if (!same) {  // CheckImages (main.cpp:310-329)
       std::cerr << "Images may error, check it!\n";
       jpeg_decoder_destroy(dec);
       return 1;
     }
-    grays[v].cols = w; grays[v].rows = h;
-    if (v == 0) { width = w; height = h; }
-    else if (w != width || h != height) {
-      std::cerr << "Images may error, check it!\n";
-      jpeg_decoder_destroy(dec);
-      return 1;
-    }
-    if (!read_cam(dense + "/cams/" + format_index(view_ids[v]) + "_cam.txt", &cams[v])) {
-      std::cerr << "DPE-MVS: cannot read camera of image " << view_ids[v] << "\n";
+    if (bad.load() >= 1000) {
+      std::cerr << "DPE-MVS: cannot read a camera file\n";
       jpeg_decoder_destroy(dec);
       return 1;
     }
@@ -211,29 +226,40 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     return 1;
   };
   const int slots_per_rank = slots;
-  for (int g = 0; g < G; ++g) {
-    if (dpe_ctx_create(&ctxs[g], gpus[g]) != DPE_OK) return fail("cannot create context", nullptr);
-    dpe_ctx* c = ctxs[g];
-    if (dpe_scene_begin(c, n_views, width, height, round_num)) return fail("scene_begin", c);
-    for (int v = 0; v < n_views; ++v) {
-      if (dpe_scene_set_view(c, v, grays[v].d.data(), cams[v].K, cams[v].R, cams[v].t, cams[v].depth_min, cams[v].depth_max))
-        return fail("set_view", c);
-    }
-    for (int v = 0; v < n_problems; ++v) {
-      std::vector<int> src;
-      for (int s : problems[v].src_image_ids) src.push_back(id_to_view[s]);
-      if (dpe_scene_set_pairs(c, v, src.data(), (int)src.size())) return fail("set_pairs", c);
-    }
-    const int first = std::min(g * slots, n_problems), count = std::max(0, std::min(slots, n_problems - first));
-    for (int v = first; v < first + count; ++v)
-      for (int k = 0; k < round_num; ++k) {
-        const int j = round_num - 1 - k;
-        if (dpe_scene_set_prep(c, v, k, prep[v].edge[j].d.data(), prep[v].label[j].data()))
-          return fail("set_prep", c);
+  {
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) th.emplace_back([&, g]() {
+      auto bad = [&](const char* what) { errs[g] = std::string(what) + ": " + (ctxs[g] ? dpe_last_error(ctxs[g]) : ""); };
+      if (dpe_ctx_create(&ctxs[g], gpus[g]) != DPE_OK) { errs[g] = "cannot create context"; return; }
+      dpe_ctx* c = ctxs[g];
+      if (dpe_scene_begin(c, n_views, width, height, round_num)) return bad("scene_begin");
+      for (int v = 0; v < n_views; ++v)
+        if (dpe_scene_set_view(c, v, grays[v].d.data(), cams[v].K, cams[v].R, cams[v].t, cams[v].depth_min, cams[v].depth_max))
+          return bad("set_view");
+      for (int v = 0; v < n_problems; ++v) {
+        std::vector<int> src;
+        for (int s : problems[v].src_image_ids) src.push_back(id_to_view[s]);
+        if (dpe_scene_set_pairs(c, v, src.data(), (int)src.size())) return bad("set_pairs");
       }
-    // the coarsest edge map is needed for every owned view (edge_low_res), set above with k = 0
-    if (dpe_scene_set_shard(c, first, count, slots_per_rank, G)) return fail("set_shard", c);
-    if (dpe_scene_commit(c)) return fail("commit", c);
+      const int first = std::min(g * slots, n_problems), count = std::max(0, std::min(slots, n_problems - first));
+      for (int v = first; v < first + count; ++v)
+        for (int k = 0; k < round_num; ++k) {
+          const int j = round_num - 1 - k;
+          if (dpe_scene_set_prep(c, v, k, prep[v].edge[j].d.data(), prep[v].label[j].data())) return bad("set_prep");
+        }
+      if (dpe_scene_set_shard(c, first, count, slots_per_rank, G)) return bad("set_shard");
+      if (dpe_scene_commit(c)) return bad("commit");
+    });
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G; ++g)
+      if (!errs[g].empty()) {
+        std::cerr << "DPE-MVS: " << errs[g] << "\n";
+        for (auto* x : ctxs) dpe_ctx_destroy(x);
+        jpeg_decoder_destroy(dec);
+        return 1;
+      }
+    cudaSetDevice(gpus[0]);
   }
   tm.upload = now_s() - t0;
 
@@ -244,7 +270,18 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
 
   // ---- stage loop (main.cpp:507-567) ------------------------------------------------------------
   t0 = now_s();
-  const uint64_t seed = 20261018ull;
+  // RNG seed: the reference seeds cuRAND with clock64() (DPE.cu:1032); any value is "the reference's";
+  // a fixed default makes runs reproducible, DPE_SEED overrides it.
+  uint64_t seed = 20261018ull;
+  if (const char* e = getenv("DPE_SEED")) seed = strtoull(e, nullptr, 10);
+  // view order inside a stage: single GPU defaults to the reference's sequential order (view k reads
+  // this stage's depth maps of views < k); several GPUs need the order-independent one.
+  // DPE_VIEW_ORDER=parallel|sequential overrides.
+  {
+    bool sequential = (G == 1);
+    if (const char* e = getenv("DPE_VIEW_ORDER")) sequential = (std::string(e) == "sequential") && G == 1;
+    if (sequential) dpe_set_view_order(ctxs[0], 1);
+  }
   int iteration_index = 0;
   auto run_stage_all = [&](int k, const dpe_stage_params& p) -> int {
     std::vector<int> rcs(G, 0);
@@ -309,30 +346,58 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
   std::vector<std::vector<uint8_t>> all_state;
   if (fusion) { all_depth.resize(n_problems); all_normal.resize(n_problems); all_state.resize(n_problems); }
   {
-    std::vector<float> d(P), n3(P * 3);
-    std::vector<uint8_t> st(P);
-    std::vector<int8_t> i8(P);
-    for (int v = 0; v < n_problems; ++v) {
-      const int g = std::min(v / slots, G - 1);
-      if (dpe_get_maps(ctxs[g], v, d.data(), n3.data(), st.data(), nullptr)) return fail("get_maps", ctxs[g]);
+    // one reader thread per GPU pulls its views' maps off the device; the .npy files are written by
+    // a few writer tasks behind it
+    struct Job { int v; std::vector<float> d, n3; std::vector<uint8_t> st; };
+    std::vector<std::string> errs(G);
+    std::atomic<int> write_fail(0);
+    auto write_view = [&](Job* job) {
+      const int v = job->v;
       const std::string dir = out_root + "/" + format_index(view_ids[v]);
-      if (fusion) { all_depth[v] = d; all_normal[v] = n3; all_state[v] = st; }
+      std::vector<int8_t> i8;
+      bool ok = true;
       if (depth) {
-        std::vector<float> dz(d);
-        for (size_t i = 0; i < P; ++i) if (st[i] == DPE_UNKNOWN) dz[i] = 0.0f;  // ZeroDepthForUnknown
-        write_npy(dir + "/depth.npy", dz.data(), "<f4", 4, height, width, 1);
+        std::vector<float> dz(job->d);
+        for (size_t i = 0; i < P; ++i) if (job->st[i] == DPE_UNKNOWN) dz[i] = 0.0f;  // ZeroDepthForUnknown
+        ok &= write_npy(dir + "/depth.npy", dz.data(), "<f4", 4, height, width, 1);
       }
-      if (normal) write_npy(dir + "/normal.npy", n3.data(), "<f4", 4, height, width, 3);
+      if (normal) ok &= write_npy(dir + "/normal.npy", job->n3.data(), "<f4", 4, height, width, 3);
       if (weak) {
-        for (size_t i = 0; i < P; ++i) i8[i] = st[i] == DPE_UNKNOWN ? 0 : (st[i] == DPE_WEAK ? 1 : (st[i] == DPE_STRONG ? 2 : 0));
-        write_npy(dir + "/weak.npy", i8.data(), "|i1", 1, height, width, 1);
+        i8.resize(P);
+        for (size_t i = 0; i < P; ++i) { const uint8_t st = job->st[i]; i8[i] = st == DPE_WEAK ? 1 : (st == DPE_STRONG ? 2 : 0); }
+        ok &= write_npy(dir + "/weak.npy", i8.data(), "|i1", 1, height, width, 1);
       }
       if (edge) {
+        i8.resize(P);
         const ImageU8& e = prep[v].edge[0];
         for (size_t i = 0; i < P; ++i) i8[i] = e.d[i] > 0 ? 1 : 0;
-        write_npy(dir + "/edge.npy", i8.data(), "|i1", 1, height, width, 1);
+        ok &= write_npy(dir + "/edge.npy", i8.data(), "|i1", 1, height, width, 1);
       }
-    }
+      if (!ok) write_fail++;
+      if (fusion) { all_depth[v].swap(job->d); all_normal[v].swap(job->n3); all_state[v].swap(job->st); }
+      delete job;
+    };
+    std::vector<std::thread> readers;
+    for (int g = 0; g < G; ++g) readers.emplace_back([&, g]() {
+      cudaSetDevice(gpus[g]);
+      const int first = std::min(g * slots, n_problems), count = std::max(0, std::min(slots, n_problems - first));
+      std::vector<std::thread> writers;
+      for (int v = first; v < first + count; ++v) {
+        Job* job = new Job{v, std::vector<float>(P), std::vector<float>((normal || fusion) ? P * 3 : 0), std::vector<uint8_t>(P)};
+        if (dpe_get_maps(ctxs[g], v, job->d.data(), job->n3.empty() ? nullptr : job->n3.data(), job->st.data(), nullptr)) {
+          errs[g] = dpe_last_error(ctxs[g]);
+          delete job;
+          break;
+        }
+        if (writers.size() >= 4) { writers.front().join(); writers.erase(writers.begin()); }
+        writers.emplace_back(write_view, job);
+      }
+      for (auto& w : writers) w.join();
+    });
+    for (auto& r : readers) r.join();
+    cudaSetDevice(gpus[0]);
+    for (int g = 0; g < G; ++g) if (!errs[g].empty()) { std::cerr << "DPE-MVS: get_maps: " << errs[g] << "\n"; return fail("get_maps", nullptr); }
+    if (write_fail.load()) { std::cerr << "DPE-MVS: cannot write the .npy outputs\n"; return fail("write", nullptr); }
   }
   tm.output = now_s() - t0;
   for (auto* c : ctxs) dpe_ctx_destroy(c);
