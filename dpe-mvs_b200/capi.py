@@ -30,7 +30,7 @@ SYMBOLS = [
     "dpe_scene_set_view", "dpe_scene_set_pairs", "dpe_scene_set_prep", "dpe_scene_set_shard", "dpe_scene_commit",
     "dpe_run_stage", "dpe_stage_atlas", "dpe_stage_commit", "dpe_cost_eval", "dpe_geom_eval", "dpe_get_size",
     "dpe_get_maps", "dpe_set_count_evals", "dpe_eval_units", "dpe_stage_gpu_ms", "dpe_probe_tex_rate",
-    "dpe_probe_fma_rate", "dpe_probe_tex_pattern", "dpe_probe_tex_weights", "dpe_run_pipeline", "dpe_set_profile", "dpe_get_profile", "dpe_set_view_order", "dpe_bench_ncc",
+    "dpe_probe_fma_rate", "dpe_probe_tex_pattern", "dpe_probe_tex_weights", "dpe_run_pipeline", "dpe_set_profile", "dpe_get_profile", "dpe_set_view_order", "dpe_bench_ncc", "dpe_set_reference_race", "dpe_debug_read", "dpe_set_cost_arithmetic",
 ]
 
 _lib = None
@@ -82,6 +82,9 @@ def load(build=True):
     lib.dpe_probe_tex_weights.argtypes = [vp, ci, vp]
     lib.dpe_set_profile.argtypes = [vp, ci]
     lib.dpe_set_view_order.argtypes = [vp, ci]
+    lib.dpe_set_reference_race.argtypes = [vp, ci]
+    lib.dpe_set_cost_arithmetic.argtypes = [vp, ci]
+    lib.dpe_debug_read.argtypes = [vp, ci, vp, C.c_size_t]
     lib.dpe_bench_ncc.argtypes = [vp, ci, ci, ci, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.dpe_get_profile.argtypes = [vp, vp, vp, vp]
     lib.dpe_run_pipeline.argtypes = [C.c_char_p, ci, ci, ci, ci, ci, ci, ci, ci]
@@ -239,6 +242,18 @@ class Context:
         r, c = C.c_double(), C.c_double()
         self._ck(self.lib.dpe_bench_ncc(self.h, view, variant, n_cand, reps, C.byref(r), C.byref(c)))
         return r.value, c.value
+
+    def set_cost_arithmetic(self, mode):
+        """0 = centred (precise), 1 = the reference's raw fp32 accumulation (default)."""
+        self._ck(self.lib.dpe_set_cost_arithmetic(self.h, int(mode)))
+
+    def set_reference_race(self, on):
+        self._ck(self.lib.dpe_set_reference_race(self.h, int(on)))
+
+    def debug_read(self, what, shape, dtype):
+        out = np.empty(shape, dtype)
+        self._ck(self.lib.dpe_debug_read(self.h, what, out.ctypes.data, out.nbytes))
+        return out
 
     def set_profile(self, on):
         self._ck(self.lib.dpe_set_profile(self.h, int(on)))

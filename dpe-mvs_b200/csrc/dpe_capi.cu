@@ -75,6 +75,8 @@ struct dpe_ctx {
   int last_stage_scale = -1;
   bool stage_pending = false;
   bool gauss_seidel = false;  // dpe_set_view_order
+  bool ref_race = false;      // dpe_set_reference_race
+  bool cost_raw = true;       // dpe_set_cost_arithmetic
   // scratch
   std::vector<Scratch> scratch;
   // initial XORWOW states per scale for rng_seed (dpe_rng.h): table[k][y*w+x] = curand_init(seed, y, x)
@@ -378,6 +380,8 @@ static void fill_args(dpe_ctx* ctx, int view, int k, const dpe_stage_params* p, 
   a.label_boundary = s.label_boundary; a.weak_reliable = s.weak_reliable; a.nearest_strong = s.nearest_strong;
   a.neighbours = s.neighbours;
   a.rng = s.rng;
+  a.ref_race = ctx->ref_race ? 1 : 0;
+  a.cost_raw = ctx->cost_raw ? 1 : 0;
   a.weak_list = s.weak_list; a.weak_count = s.weak_count; a.list_stride = ctx->W * ctx->H;
   a.eval_units = ctx->count_evals ? ctx->d_eval_units : nullptr;
   if (p) {
@@ -524,6 +528,41 @@ int dpe_set_view_order(dpe_ctx* ctx, int sequential) {
   if (ctx->stage_pending) FAIL(DPE_ERR_STATE, "stage not committed");
   if (sequential && ctx->n_ranks > 1) FAIL(DPE_ERR_ARG, "sequential view order needs all views on one GPU");
   ctx->gauss_seidel = sequential != 0;
+  return DPE_OK;
+}
+
+int dpe_set_cost_arithmetic(dpe_ctx* ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 1) return DPE_ERR_ARG;
+  ctx->cost_raw = mode == DPE_COST_REFERENCE;
+  return DPE_OK;
+}
+
+int dpe_set_reference_race(dpe_ctx* ctx, int on) {
+  if (!ctx) return DPE_ERR_ARG;
+  ctx->ref_race = on != 0;
+  return DPE_OK;
+}
+
+// scratch buffers of the last stage run for `view` (test hook; only meaningful when the view ran on the
+// first stream: sequential view order, or a shard of one view)
+int dpe_debug_read(dpe_ctx* ctx, int what, void* out, size_t bytes) {
+  if (!ctx || !out || ctx->scratch.empty() || ctx->last_stage_scale < 0) return DPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const Scratch& s = ctx->scratch[0];
+  const size_t P = (size_t)ctx->sw[ctx->last_stage_scale] * ctx->sh[ctx->last_stage_scale];
+  const void* src = nullptr; size_t n = 0;
+  switch (what) {
+    case 0: src = s.neighbours; n = P * DPE_NEIGHBOUR_NUM * sizeof(short2); break;
+    case 1: src = s.fit_planes; n = P * sizeof(float4); break;
+    case 2: src = s.radius; n = P * sizeof(int); break;
+    case 3: src = s.costs; n = P * sizeof(float); break;
+    case 4: src = s.weak_reliable; n = P; break;
+    case 5: src = s.nearest_strong; n = P * sizeof(short2); break;
+    case 6: src = s.complexity; n = P * sizeof(float); break;
+    default: return DPE_ERR_ARG;
+  }
+  if (bytes < n) return DPE_ERR_ARG;
+  CK(cudaMemcpy(out, src, n, cudaMemcpyDeviceToHost));
   return DPE_OK;
 }
 

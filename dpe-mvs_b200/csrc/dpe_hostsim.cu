@@ -83,7 +83,7 @@ int dpe_hostsim_cost_eval(int W, int H, int full_w, int full_h, const float* ref
     HostRef ref{ref_img, W, H};
     HostStore st{env.tbl};
     const int x = xy[2 * i], y = xy[2 * i + 1];
-    const PatchStats ps = build_patch(ref, x, y, st);
+    const PatchStats ps = build_patch(ref, x, y, st, getenv("DPE_HOSTSIM_CENTRED") == nullptr);
     const float4 pl = make_float4(planes[4 * i], planes[4 * i + 1], planes[4 * i + 2], planes[4 * i + 3]);
     const float3 m = plane_to_m(*rc, pl);
     for (int v = 0; v < n_src; ++v) out[(size_t)i * n_src + v] = ncc_old(env, ps, rc->src[v], m, x, y);
@@ -95,14 +95,24 @@ int dpe_hostsim_cost_eval(int W, int H, int full_w, int full_h, const float* ref
 // One (view, stage) of the PatchMatch path on the CPU.  images: n_src+1 float images at
 // this stage's scale (index 0 = reference); cameras likewise.  src_depths: n_src maps or
 // NULL.  prev_*: maps of the previous stage (NULL for FIRST_INIT).  Outputs are W*H.
-int dpe_hostsim_stage(int W, int H, int full_w, int full_h, int n_src, const float* const* images, const float* K,
+// Raw state after a step (per-kernel differential tests against oracle/ref_stage_probe.cu).  Steps:
+// 0 anchors (GenNeighbours + NeigbourUpdate), 1 init, 2+3i strong sweeps of iteration i, 3+3i fit plane,
+// 4+3i weak sweeps, 11 final.
+struct HostsimDbg {
+  int stop_step;
+  float* planes; float* costs; uint32_t* selected; uint8_t* state; float* fit; int32_t* radius;
+  int16_t* neighbours;  // P x 9 x 2
+  uint8_t* reliable;
+};
+
+static int hostsim_stage_impl(int W, int H, int full_w, int full_h, int n_src, const float* const* images, const float* K,
                       const float* R, const float* t, float depth_min, float depth_max,
                       const float* const* src_depths, const float* prev_planes, const uint8_t* prev_state,
                       const uint32_t* prev_selected, int prev_W, int prev_H, const uint8_t* edge,
                       const uint8_t* edge_low, int low_w, int low_h, const int32_t* label,
                       const dpe_stage_params* p, uint64_t seed, int view, uint32_t stage_counter, int quant,
                       float* out_planes, uint8_t* out_state, uint32_t* out_selected, float* out_depth,
-                      double* eval_units) {
+                      double* eval_units, const HostsimDbg* dbg) {
   if (n_src > DPE_MAX_SRC) return DPE_ERR_TOO_MANY_IMAGES;
   const size_t P = (size_t)W * H;
   std::vector<HostCam> cams(n_src + 1);
@@ -144,11 +154,25 @@ int dpe_hostsim_stage(int W, int H, int full_w, int full_h, int n_src, const flo
   a.run_state = p->state; a.geom = p->geom_consistency; a.use_apd = p->use_apd; a.top_k = p->top_k;
   a.weak_peak_radius = p->weak_peak_radius; a.rotate_time = p->rotate_time; a.ransac_threshold = p->ransac_threshold;
   a.geom_factor = p->geom_factor;
+  a.ref_race = getenv("DPE_HOSTSIM_REF_RACE") ? 1 : 0;
+  a.cost_raw = getenv("DPE_HOSTSIM_CENTRED") ? 0 : 1;
   (void)stage_counter;
   std::vector<Xorwow> rng_states(P);
   xorwow_init_table(seed, W, H, rng_states.data());
   a.rng = rng_states.data();
   double units = 0.0;
+  auto stop_at = [&](int step) {
+    if (!dbg || dbg->stop_step != step) return false;
+    memcpy(dbg->planes, planes.data(), P * sizeof(float4));
+    memcpy(dbg->costs, costs.data(), P * sizeof(float));
+    memcpy(dbg->selected, selected.data(), P * sizeof(uint32_t));
+    memcpy(dbg->state, state.data(), P);
+    memcpy(dbg->fit, fit.data(), P * sizeof(float4));
+    memcpy(dbg->radius, radius.data(), P * sizeof(int));
+    memcpy(dbg->neighbours, neighbours.data(), P * DPE_NEIGHBOUR_NUM * sizeof(short2));
+    memcpy(dbg->reliable, reliable.data(), P);
+    return true;
+  };
 
   HostRef ref{images[0], W, H};
   auto for_all = [&](auto&& fn) {
@@ -164,7 +188,7 @@ int dpe_hostsim_stage(int W, int H, int full_w, int full_h, int n_src, const flo
   auto with_patch = [&](int x, int y, auto&& fn) {
     HostEnv env; env.img = images[0]; env.W = W; env.H = H;
     HostStore st{env.tbl};
-    const PatchStats ps = build_patch(ref, x, y, st);
+    const PatchStats ps = build_patch(ref, x, y, st, a.cost_raw != 0);
     unsigned ev = 0;
     fn(env, ps, ev);
     if (ev) {
@@ -179,7 +203,9 @@ int dpe_hostsim_stage(int W, int H, int full_w, int full_h, int n_src, const flo
     for_all([&](int x, int y) { nearest_strong_pixel(a, x, y); });
     for_all([&](int x, int y) { gen_neighbours_pixel(a, x, y); });
   }
+  if (stop_at(0)) { delete rc; return 0; }
   for_all([&](int x, int y) { with_patch(x, y, [&](HostEnv& env, const PatchStats& ps, unsigned& ev) { init_pixel(env, ps, a, x, y, ev); }); });
+  if (stop_at(1)) { delete rc; return 0; }
   for (int it = 0; it < p->max_iterations; ++it) {
     a.iter = it;
     for (int colour = 0; colour < 2; ++colour) {
@@ -193,8 +219,10 @@ int dpe_hostsim_stage(int W, int H, int full_w, int full_h, int n_src, const flo
         });
       });
     }
+    if (stop_at(2 + 3 * it)) { delete rc; return 0; }
     if (p->use_apd) {
       for_all([&](int x, int y) { fit_plane_pixel(a, x, y); });
+      if (stop_at(3 + 3 * it)) { delete rc; return 0; }
       for (int colour = 0; colour < 2; ++colour) {
         a.colour = colour;
         for_colour(colour, [&](int x, int y) {
@@ -206,6 +234,7 @@ int dpe_hostsim_stage(int W, int H, int full_w, int full_h, int n_src, const flo
         });
       }
     }
+    if (stop_at(4 + 3 * it)) { delete rc; return 0; }
   }
   for_all([&](int x, int y) { extract_pixel(a, x, y); });
   for (int colour = 0; colour < 2; ++colour) {
@@ -217,6 +246,11 @@ int dpe_hostsim_stage(int W, int H, int full_w, int full_h, int n_src, const flo
   }
   for_all([&](int x, int y) { with_patch(x, y, [&](HostEnv& env, const PatchStats& ps, unsigned& ev) { classify_refine_pixel(env, ps, a, x, y, ev); }); });
   for_all([&](int x, int y) { finish_pixel(a, x, y); });
+  if (dbg && dbg->stop_step == 11) {
+    memcpy(dbg->planes, outp.data(), P * sizeof(float4));
+    memcpy(dbg->selected, outsel.data(), P * sizeof(uint32_t));
+    memcpy(dbg->state, outst.data(), P);
+  }
 
   memcpy(out_planes, outp.data(), P * sizeof(float4));
   memcpy(out_state, outst.data(), P);
@@ -225,6 +259,39 @@ int dpe_hostsim_stage(int W, int H, int full_w, int full_h, int n_src, const flo
   if (eval_units) *eval_units = units;
   delete rc;
   return 0;
+}
+
+int dpe_hostsim_stage(int W, int H, int full_w, int full_h, int n_src, const float* const* images, const float* K,
+                      const float* R, const float* t, float depth_min, float depth_max,
+                      const float* const* src_depths, const float* prev_planes, const uint8_t* prev_state,
+                      const uint32_t* prev_selected, int prev_W, int prev_H, const uint8_t* edge,
+                      const uint8_t* edge_low, int low_w, int low_h, const int32_t* label,
+                      const dpe_stage_params* p, uint64_t seed, int view, uint32_t stage_counter, int quant,
+                      float* out_planes, uint8_t* out_state, uint32_t* out_selected, float* out_depth,
+                      double* eval_units) {
+  return hostsim_stage_impl(W, H, full_w, full_h, n_src, images, K, R, t, depth_min, depth_max, src_depths, prev_planes,
+                            prev_state, prev_selected, prev_W, prev_H, edge, edge_low, low_w, low_h, label, p, seed, view,
+                            stage_counter, quant, out_planes, out_state, out_selected, out_depth, eval_units, nullptr);
+}
+
+// same, stopping after `stop_step` and returning the raw state at that point
+int dpe_hostsim_stage_dbg(int W, int H, int full_w, int full_h, int n_src, const float* const* images, const float* K,
+                          const float* R, const float* t, float depth_min, float depth_max,
+                          const float* const* src_depths, const float* prev_planes, const uint8_t* prev_state,
+                          const uint32_t* prev_selected, int prev_W, int prev_H, const uint8_t* edge,
+                          const uint8_t* edge_low, int low_w, int low_h, const int32_t* label,
+                          const dpe_stage_params* p, uint64_t seed, int quant, int stop_step, float* planes, float* costs,
+                          uint32_t* selected, uint8_t* state, float* fit, int32_t* radius, int16_t* neighbours,
+                          uint8_t* reliable) {
+  const size_t P = (size_t)W * H;
+  std::vector<float> op(P * 4), od(P);
+  std::vector<uint8_t> os(P);
+  std::vector<uint32_t> ol(P);
+  double u = 0;
+  HostsimDbg dbg{stop_step, planes, costs, selected, state, fit, radius, neighbours, reliable};
+  return hostsim_stage_impl(W, H, full_w, full_h, n_src, images, K, R, t, depth_min, depth_max, src_depths, prev_planes,
+                            prev_state, prev_selected, prev_W, prev_H, edge, edge_low, low_w, low_h, label, p, seed, 0, 0,
+                            quant, op.data(), os.data(), ol.data(), od.data(), &u, &dbg);
 }
 
 // cv::resize(INTER_LINEAR) on float, host mirror of k_resize_linear (same arithmetic)

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_full(const __grid_constant_
     __syncthreads();
     const int x = tx0 + (threadIdx.x & 31), y = ty0 + (threadIdx.x >> 5);
     if (x < a.W && y < a.H) {
-      const PatchStats ps = build_patch(tile, x, y, st);
+      const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0);
       if (OP == OP_INIT) init_pixel(env, ps, a, x, y, evals);
       else classify_refine_pixel(env, ps, a, x, y, evals);
     }
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_half(const __grid_constant_
     const int x = tx0 + lx, y = ty0 + 2 * (threadIdx.x >> 5) + ((lx + a.colour) & 1);
     if (x < a.W && y < a.H) {
       if (a.state[y * a.W + x] != DPE_WEAK) {
-        const PatchStats ps = build_patch(tile, x, y, st);
+        const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0);
         strong_update_pixel<OP == OP_STRONG_EDGE>(env, ps, a, x, y, cost_arr, evals);
       }
     }
@@ -245,32 +245,37 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
   // strong-patch table (build_patch, dpe_core.cuh): one tap per lane, summed by lane 0 in tap order
   PatchStats ps;
   ps.r0 = ref(x, y);
+  ps.c0 = a.cost_raw ? 0.0f : ps.r0;
   for (int t = lane; t < 36; t += 32) {
-    const int jy = t / 6, ixx = t - jy * 6;
+    const int ixx = t / 6, jy = t - ixx * 6;
     const int i = 2 * ixx - 5, j = 2 * jy - 5;
     const float r = ref(x + i, y + j);
     const float sd = sqrtf((float)(i * i + j * j));
     const float w = fast_exp(-sd * (1.0f / 50.0f) - fabsf(r - ps.r0) * (1.0f / 18.0f));
-    const float rp = r - ps.r0;
-    S.tbl36[t] = make_float2(w, w * rp);
+    const float rp = r - ps.c0;
+    S.tbl36[t] = make_float2(w, mul_rn(w, rp));
     S.hcost[t] = rp;
   }
   __syncwarp();
   {
     float sw = 0.f, swr = 0.f, swrr = 0.f;
     if (lane == 0) {
-      for (int t = 0; t < 36; ++t) {
-        const float2 ww = S.tbl36[t];
-        sw += ww.x; swr += ww.y; swrr = fmaf(ww.y, S.hcost[t], swrr);
+      for (int ixx = 0; ixx < 6; ++ixx) {
+        float sw_c = 0.f, swr_c = 0.f, swrr_c = 0.f;
+        for (int jy = 0; jy < 6; ++jy) {
+          const float2 ww = S.tbl36[ixx * 6 + jy];
+          sw_c += ww.x; swr_c += ww.y; swrr_c = fmaf(ww.y, S.hcost[ixx * 6 + jy], swrr_c);
+        }
+        sw += sw_c; swr += swr_c; swrr += swrr_c;
       }
     }
     sw = bcast(sw, 0); swr = bcast(swr, 0); swrr = bcast(swrr, 0);
-    ps.inv_sw = 1.0f / sw;
-    ps.mean_r = swr * ps.inv_sw;
-    ps.var_r = swrr * ps.inv_sw - ps.mean_r * ps.mean_r;
+    ps.inv_sw = fast_rcp(sw);
+    ps.mean_r = ps.inv_sw * swr;
+    ps.var_r = fmaf(ps.inv_sw, swrr, -mul_rn(ps.mean_r, ps.mean_r));
   }
   __syncwarp();
-  if (lane < DPE_NEIGHBOUR_NUM) build_weak_patch(ref, ps.r0, T, lane, lane == 0 ? first0 : -5, lane == 0 ? inc0 : 5);
+  if (lane < DPE_NEIGHBOUR_NUM) build_weak_patch(ref, ps.r0, ps.c0, T, lane, lane == 0 ? first0 : -5, lane == 0 ? inc0 : 5);
   for (int i = lane; i < 8 * DPE_MAX_IMAGES; i += 32) S.cost[i] = 0.f;
   __syncwarp();
   if (lane == 0) S.cost[0] = 2.0f;
@@ -292,7 +297,7 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
     const int j = p / N, v = p - j * N;
     if ((flags >> j) & 1u) {
       const float3 m = plane_to_m(rc, S.cand[j]);
-      S.cost[j * DPE_MAX_IMAGES + v] = ncc_new(env, ps.r0, T, rc.src[v], v, m, x, y, W, H, taps);
+      S.cost[j * DPE_MAX_IMAGES + v] = ncc_new(env, ps.c0, T, rc.src[v], v, m, x, y, W, H, taps);
     }
   }
   __syncwarp();
@@ -369,7 +374,7 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
       const int v = view_at(p - hi * nv);
       const float4 pl = S.hplane[h0 + hi];
       const float3 m = plane_to_m(rc, pl);
-      float cv = ncc_new(env, ps.r0, T, rc.src[v], v, m, x, y, W, H, taps);
+      float cv = ncc_new(env, ps.c0, T, rc.src[v], v, m, x, y, W, H, taps);
       if (a.geom) cv += a.geom_factor * geom_cost(rc, rc.src[v], pl, x, y);
       S.hcost[(h0 + hi) * DPE_MAX_IMAGES + v] = cv;
     }
@@ -636,7 +641,7 @@ __global__ void __launch_bounds__(NT) k_cost_eval(const __grid_constant__ Kernel
   const int x = xy[2 * i], y = xy[2 * i + 1];
   GlobalRef ref{P.a.ref_img, P.a.W, P.a.H};
   TblStore st{s_tbl + threadIdx.x};
-  const PatchStats ps = build_patch(ref, x, y, st);
+  const PatchStats ps = build_patch(ref, x, y, st, P.a.cost_raw != 0);
   const float3 m = plane_to_m(rc, planes[i]);
   if (mode == 0) {
     DevEnv env{s_tbl + threadIdx.x, P.a.ref_img, P.a.W, P.a.H};
@@ -671,59 +676,6 @@ void launch_geom_eval(const KernelParams& P, int n_pix, const int* xy, const flo
 // of n_cand neighbours (carried (world normal, depth) maps of the last stage) against all source
 // views.  ROWS = tap rows fetched before any is consumed (texture results in flight per thread =
 // 6 * ROWS); MINB = CTAs per SM the register allocation is tuned for.
-template <int ROWS, class Env>
-__device__ __forceinline__ float ncc_old_rows(const Env& env, const PatchStats& ps, const SrcConst& sc, const float3 m,
-                                              const int x, const int y) {
-  float h0 = sc.A[0] - sc.b[0] * m.x, h1 = sc.A[1] - sc.b[0] * m.y, h2 = sc.A[2] - sc.b[0] * m.z;
-  float h3 = sc.A[3] - sc.b[1] * m.x, h4 = sc.A[4] - sc.b[1] * m.y, h5 = sc.A[5] - sc.b[1] * m.z;
-  const float h6 = sc.A[6] - sc.b[2] * m.x, h7 = sc.A[7] - sc.b[2] * m.y, h8 = sc.A[8] - sc.b[2] * m.z;
-  {
-    const float Z = h6 * x + h7 * y + h8;
-    const float px = (h0 * x + h1 * y + h2) / Z;
-    const float py = (h3 * x + h4 * y + h5) / Z;
-    if (px >= sc.width || px < 0.0f || py >= sc.height || py < 0.0f) return 2.0f;
-  }
-  h0 = fmaf(0.5f, h6, h0); h1 = fmaf(0.5f, h7, h1); h2 = fmaf(0.5f, h8, h2);
-  h3 = fmaf(0.5f, h6, h3); h4 = fmaf(0.5f, h7, h4); h5 = fmaf(0.5f, h8, h5);
-  const float x0 = (float)(x - 5), y0 = (float)(y - 5);
-  float Xr = h0 * x0 + h1 * y0 + h2;
-  float Yr = h3 * x0 + h4 * y0 + h5;
-  float Zr = h6 * x0 + h7 * y0 + h8;
-  const float dXi = 2.0f * h0, dYi = 2.0f * h3, dZi = 2.0f * h6;
-  const float dXj = 2.0f * h1, dYj = 2.0f * h4, dZj = 2.0f * h7;
-  float ss = 0.f, sss = 0.f, srs = 0.f;
-#pragma unroll
-  for (int jb = 0; jb < 6; jb += ROWS) {
-    float sv[6 * ROWS];
-#pragma unroll
-    for (int jy = 0; jy < ROWS; ++jy) {
-      float X = Xr, Y = Yr, Z = Zr;
-#pragma unroll
-      for (int ix = 0; ix < 6; ++ix) {
-        const float iz = fast_rcp(Z);
-        sv[jy * 6 + ix] = env.tex(sc, X * iz, Y * iz);
-        X += dXi; Y += dYi; Z += dZi;
-      }
-      Xr += dXj; Yr += dYj; Zr += dZj;
-    }
-#pragma unroll
-    for (int t = 0; t < 6 * ROWS; ++t) {
-      const float sdiff = sv[t] - ps.r0;
-      const float2 ww = env.pw(jb * 6 + t);
-      const float ws = ww.x * sdiff;
-      ss += ws;
-      sss = fmaf(ws, sdiff, sss);
-      srs = fmaf(ww.y, sdiff, srs);
-    }
-  }
-  const float ms = ss * ps.inv_sw;
-  const float var_s = sss * ps.inv_sw - ms * ms;
-  const float kMinVar = 1e-5f;
-  if (ps.var_r < kMinVar || var_s < kMinVar) return 2.0f;
-  const float cov = srs * ps.inv_sw - ps.mean_r * ms;
-  return fmaxf(0.0f, fminf(2.0f, 1.0f - cov * fast_rsqrt(ps.var_r * var_s)));
-}
-
 template <int ROWS, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_ncc_bench(const __grid_constant__ KernelParams P, const float4* __restrict__ world_planes,
                                                         int n_cand, float* __restrict__ out) {
@@ -749,7 +701,7 @@ __global__ void __launch_bounds__(NT, MINB) k_ncc_bench(const __grid_constant__ 
     const int lx = threadIdx.x & 31;
     const int x = tx0 + lx, y = ty0 + 2 * (threadIdx.x >> 5) + (lx & 1);
     if (x < a.W && y < a.H) {
-      const PatchStats ps = build_patch(tile, x, y, st);
+      const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0);
       float acc = 0.f;
       for (int c = 0; c < n_cand; ++c) {
         const int nx = iclamp(x + offx[c & 7], 0, a.W - 1), ny = iclamp(y + offy[c & 7], 0, a.H - 1);
@@ -758,8 +710,7 @@ __global__ void __launch_bounds__(NT, MINB) k_ncc_bench(const __grid_constant__ 
         pl.w = dist2origin(rc, nx, ny, pw.w > 0.f ? pw.w : 1.0f, pl);
         const float3 m = plane_to_m(rc, pl);
         for (int v = 0; v < rc.n_src; ++v) {
-          if (ROWS == 0) acc += ncc_old(env, ps, rc.src[v], m, x, y);
-          else acc += ncc_old_rows<(ROWS == 0 ? 1 : ROWS)>(env, ps, rc.src[v], m, x, y);
+          acc += ncc_old(env, ps, rc.src[v], m, x, y);
         }
       }
       out[y * a.W + x] = acc;
@@ -772,7 +723,7 @@ void launch_ncc_bench(const KernelParams& P, const float4* world_planes, int n_c
   auto g = [&](int per_sm) { return persistent_grid(tiles, cfg.num_sms, per_sm); };
   switch (variant) {
     case 0: k_ncc_bench<0, 4><<<g(4), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
-    case 1: k_ncc_bench<6, 3><<<g(3), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
+    case 1: k_ncc_bench<0, 3><<<g(3), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
     default: break;
   }
   count(cfg);

@@ -82,6 +82,8 @@ struct StageArgs {
   int run_state, geom, use_apd, top_k, weak_peak_radius, rotate_time;
   float ransac_threshold, geom_factor;
   int iter, colour;
+  int cost_raw;  // cost arithmetic: 1 = moments on raw intensities like the reference, 0 = centred (dpe_core.cuh)
+  int ref_race;  // 1: edge-mode direction 4 samples its own colour like the reference, racy
   Xorwow* rng;  // per-pixel XORWOW state of this stage (dpe_rng.h), starts as curand_init(seed, y, x)
   unsigned long long* eval_units;  // optional counter (36-tap units)
   int tiles_x, tiles_y;

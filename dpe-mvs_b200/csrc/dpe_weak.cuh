@@ -550,28 +550,31 @@ DPE_HD int tab_offset(const int k) { return k == 0 ? 0 : 36 + (k - 1) * 9; }
 
 // reference side of patch k (tap order: x offset outer, y offset inner, as DPE.cu:619-621)
 template <class RefFetch>
-DPE_HD void build_weak_patch(const RefFetch& ref, const float r0, WeakTab& T, const int k, const int first, const int inc) {
+DPE_HD void build_weak_patch(const RefFetch& ref, const float r0, const float c0, WeakTab& T, const int k, const int first,
+                             const int inc) {
   const int n = T.ntap[k];
   if (n == 0) return;
   const short2 np = T.anchor[k];
   const int off = tab_offset(k);
   float sw = 0.f, sr = 0.f, srr = 0.f;
   for (int ti = 0; ti < n; ++ti) {
+    float sw_c = 0.f, sr_c = 0.f, srr_c = 0.f;  // one partial sum per tap column, as the reference
     for (int tj = 0; tj < n; ++tj) {
       const int i = first + ti * inc, j = first + tj * inc;
       const int rx = np.x + i, ry = np.y + j;
       const float r = ref(rx, ry);
       const float w = fast_exp(-sqrtf((float)(i * i + j * j)) * (1.0f / 50.0f) - fabsf(r - r0) * (1.0f / 18.0f));
-      const float rp = r - r0;
-      const float wr = w * rp;
+      const float rp = r - c0;
+      const float wr = mul_rn(w, rp);
       T.ww[off + ti * n + tj] = make_float2(w, wr);
       T.xy[off + ti * n + tj] = make_short2((short)rx, (short)ry);
-      sw += w; sr += wr; srr = fmaf(wr, rp, srr);
+      sw_c += w; sr_c += wr; srr_c = fmaf(wr, rp, srr_c);
     }
+    sw += sw_c; sr += sr_c; srr += srr_c;
   }
-  const float inv = 1.0f / sw;
-  const float mr = sr * inv;
-  T.inv_sw[k] = inv; T.mean_r[k] = mr; T.var_r[k] = srr * inv - mr * mr;
+  const float inv = fast_rcp(sw);
+  const float mr = inv * sr;
+  T.inv_sw[k] = inv; T.mean_r[k] = mr; T.var_r[k] = fmaf(inv, srr, -mul_rn(mr, mr));
 }
 
 // anchors, their selected views, tap counts: everything of the WeakTab but the patches
@@ -592,34 +595,33 @@ DPE_HD void init_weak_tab_entry(const StageArgs& a, const int center, WeakTab& T
 
 // source side of one patch: NTAP x NTAP independent fetches
 template <int NTAP, class Env>
-DPE_HD float patch_cost_tab(const Env& env, const float r0, const WeakTab& T, const int k, const SrcConst& sc, const float* h) {
+DPE_HD float patch_cost_tab(const Env& env, const float c0, const WeakTab& T, const int k, const SrcConst& sc, const float* h) {
   const int off = tab_offset(k);
   float ss = 0.f, sss = 0.f, srs = 0.f;
-  // one row of taps (NTAP independent fetches) per iteration: the code stays small enough for the
+  // one column of taps (NTAP independent fetches) per iteration: the code stays small enough for the
   // instruction cache when every warp of an SM is at a different place of the weak sweep
 #pragma unroll 1
-  for (int tr = 0; tr < NTAP; ++tr)
+  for (int tr = 0; tr < NTAP; ++tr) {
+    float ss_c = 0.f, sss_c = 0.f, srs_c = 0.f;
 #pragma unroll
-  for (int tc = 0; tc < NTAP; ++tc) {
-    const int t = tr * NTAP + tc;
-    const short2 q = T.xy[off + t];
-    const float Z = h[6] * q.x + h[7] * q.y + h[8];
-    const float iz = fast_rcp(Z);
-    const float s = env.tex(sc, (h[0] * q.x + h[1] * q.y + h[2]) * iz + 0.5f, (h[3] * q.x + h[4] * q.y + h[5]) * iz + 0.5f) - r0;
-    const float2 ww = T.ww[off + t];
-    const float ws = ww.x * s;
-    ss += ws; sss = fmaf(ws, s, sss); srs = fmaf(ww.y, s, srs);
+    for (int tc = 0; tc < NTAP; ++tc) {
+      const int t = tr * NTAP + tc;
+      const short2 q = T.xy[off + t];
+      const float Z = h[6] * q.x + h[7] * q.y + h[8];
+      const float iz = fast_rcp(Z);
+      const float s = env.tex(sc, (h[0] * q.x + h[1] * q.y + h[2]) * iz + 0.5f, (h[3] * q.x + h[4] * q.y + h[5]) * iz + 0.5f) - c0;
+      const float2 ww = T.ww[off + t];
+      const float ws = mul_rn(ww.x, s);
+      ss_c += ws; sss_c = fmaf(ws, s, sss_c); srs_c = fmaf(ww.y, s, srs_c);
+    }
+    ss += ss_c; sss += sss_c; srs += srs_c;
   }
-  const float inv = T.inv_sw[k], mr = T.mean_r[k], var_r = T.var_r[k];
-  const float ms = ss * inv;
-  const float var_s = sss * inv - ms * ms;
-  if (var_r < 1e-5f || var_s < 1e-5f) return 2.0f;
-  return fmaxf(0.0f, fminf(2.0f, 1.0f - (srs * inv - mr * ms) * fast_rsqrt(var_r * var_s)));
+  return ncc_finish(T.inv_sw[k], T.mean_r[k], T.var_r[k], ss, sss, srs);
 }
 
 // `taps` accumulates evaluated source taps
 template <class Env>
-__noinline__ DPE_HDN float ncc_new(const Env& env, const float r0, const WeakTab& T, const SrcConst& sc, const int v, const float3 m,
+__noinline__ DPE_HDN float ncc_new(const Env& env, const float c0, const WeakTab& T, const SrcConst& sc, const int v, const float3 m,
                                    const int x, const int y, const int W, const int H, int& taps) {
   float h[9];
   h[0] = sc.A[0] - sc.b[0] * m.x; h[1] = sc.A[1] - sc.b[0] * m.y; h[2] = sc.A[2] - sc.b[0] * m.z;
@@ -649,10 +651,10 @@ __noinline__ DPE_HDN float ncc_new(const Env& env, const float r0, const WeakTab
       }
     }
     if (k == 0) {
-      center_cost = (n == 1) ? patch_cost_tab<1>(env, r0, T, 0, sc, h) : patch_cost_tab<6>(env, r0, T, 0, sc, h);
+      center_cost = (n == 1) ? patch_cost_tab<1>(env, c0, T, 0, sc, h) : patch_cost_tab<6>(env, c0, T, 0, sc, h);
       taps += n * n;
     } else {
-      strong_cost += patch_cost_tab<3>(env, r0, T, k, sc, h);
+      strong_cost += patch_cost_tab<3>(env, c0, T, k, sc, h);
       strong_count++;
       taps += 9;
     }
@@ -673,7 +675,7 @@ DPE_HD float weighted_cost_weak(const Env& env, const PatchStats& ps, const Weak
   for (int v = 0; v < rc.n_src; ++v) {
     const int w = vw.get(v);
     if (w > 0) {
-      float cv = ncc_new(env, ps.r0, T, rc.src[v], v, m, x, y, a.W, a.H, taps);
+      float cv = ncc_new(env, ps.c0, T, rc.src[v], v, m, x, y, a.W, a.H, taps);
       if (a.geom) cv += a.geom_factor * geom_cost(rc, rc.src[v], pl, x, y);
       c += w * cv;
     }
@@ -694,7 +696,7 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
     int first0 = 0, inc0 = 2;
     for (int k = 0; k < DPE_NEIGHBOUR_NUM; ++k) init_weak_tab_entry(a, center, T, k, first0, inc0);
     auto ref = [&](int rx, int ry) { return env.ref(rx, ry); };
-    for (int k = 0; k < DPE_NEIGHBOUR_NUM; ++k) build_weak_patch(ref, ps.r0, T, k, k == 0 ? first0 : -5, k == 0 ? inc0 : 5);
+    for (int k = 0; k < DPE_NEIGHBOUR_NUM; ++k) build_weak_patch(ref, ps.r0, ps.c0, T, k, k == 0 ? first0 : -5, k == 0 ? inc0 : 5);
   }
   for (int j = 0; j < 8; ++j)
     for (int v = 0; v < N; ++v) cost_arr[j * DPE_MAX_IMAGES + v] = 0.f;
@@ -715,7 +717,7 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
     if (a.state[npc] != DPE_STRONG) continue;
     positions[i] = npc; flag[i] = true;
     const float3 m = plane_to_m(rc, a.planes[npc]);
-    for (int v = 0; v < N; ++v) cost_arr[i * DPE_MAX_IMAGES + v] = ncc_new(env, ps.r0, T, rc.src[v], v, m, x, y, a.W, a.H, taps);
+    for (int v = 0; v < N; ++v) cost_arr[i * DPE_MAX_IMAGES + v] = ncc_new(env, ps.c0, T, rc.src[v], v, m, x, y, a.W, a.H, taps);
   }
   Rng rng;
   rng.load(a.rng + center);

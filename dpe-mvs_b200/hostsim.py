@@ -70,7 +70,7 @@ def resize_linear(img, dw, dh):
     return dst
 
 
-def cost_eval(images, cams, full_wh, xy, planes, quant=1):
+def cost_eval(images, cams, full_wh, xy, planes, quant=1, centred=True):
     """images: [ref, src...] float32 HxW; cams: [(K,R,t)...]; returns n_pix x n_src costs."""
     imgs = [np.ascontiguousarray(i, np.float32) for i in images]
     H, W = imgs[0].shape
@@ -81,9 +81,16 @@ def cost_eval(images, cams, full_wh, xy, planes, quant=1):
     xy = np.ascontiguousarray(xy, np.int32)
     planes = np.ascontiguousarray(planes, np.float32)
     out = np.empty((len(xy), n_src), np.float32)
+    import os
+    # cost arithmetic (dpe_core.cuh): centred by default here — this entry point serves the float64 comparisons
+    if centred:
+        os.environ["DPE_HOSTSIM_CENTRED"] = "1"
+    else:
+        os.environ.pop("DPE_HOSTSIM_CENTRED", None)
     lib().dpe_hostsim_cost_eval(W, H, full_wh[0], full_wh[1], _fp(imgs[0]), n_src, _ptr_array(imgs[1:]), _fp(K),
                                 _fp(R), _fp(t), quant, len(xy), xy.ctypes.data_as(C.POINTER(C.c_int)), _fp(planes),
                                 _fp(out))
+    os.environ.pop("DPE_HOSTSIM_CENTRED", None)
     return out
 
 
@@ -136,3 +143,56 @@ def run_stage(images, cams, depth_range, full_wh, params, seed, view=0, stage_co
     if rc != 0:
         raise RuntimeError(f"hostsim stage failed: {rc}")
     return dict(planes=planes, state=state, selected=sel, depth=depth, units=units.value)
+
+
+def run_stage_dbg(images, cams, depth_range, full_wh, params, seed, stop_step, prev=None, src_depths=None, edge=None,
+                  edge_low=None, label=None, quant=1):
+    """Like run_stage but stops after `stop_step` (0 anchors, 1 init, 2+3i strong, 3+3i fit, 4+3i weak, 11 final)
+    and returns the raw state there: dict(planes HxWx4, costs, selected, state, fit HxWx4, radius, neighbours HxWx9x2,
+    reliable)."""
+    imgs = [np.ascontiguousarray(i, np.float32) for i in images]
+    H, W = imgs[0].shape
+    n_src = len(imgs) - 1
+    K = np.ascontiguousarray(np.stack([c[0] for c in cams]).reshape(-1), np.float32)
+    R = np.ascontiguousarray(np.stack([c[1] for c in cams]).reshape(-1), np.float32)
+    t = np.ascontiguousarray(np.stack([c[2] for c in cams]).reshape(-1), np.float32)
+    null_f = C.POINTER(C.c_float)()
+    null_b = C.POINTER(C.c_uint8)()
+    null_u = C.POINTER(C.c_uint32)()
+    null_i = C.POINTER(C.c_int32)()
+    if prev is not None:
+        pp = np.ascontiguousarray(prev[0], np.float32)
+        ps = np.ascontiguousarray(prev[1], np.uint8)
+        pl = np.ascontiguousarray(prev[2], np.uint32)
+        pH, pW = ps.shape
+        a_pp, a_ps, a_pl = _fp(pp), ps.ctypes.data_as(C.POINTER(C.c_uint8)), pl.ctypes.data_as(C.POINTER(C.c_uint32))
+    else:
+        pH, pW = H, W
+        a_pp, a_ps, a_pl = null_f, null_b, null_u
+    sd = None
+    if src_depths is not None:
+        sdl = [np.ascontiguousarray(d, np.float32) for d in src_depths]
+        sd = _ptr_array(sdl)
+    e = np.ascontiguousarray(edge, np.uint8) if edge is not None else None
+    el = np.ascontiguousarray(edge_low, np.uint8) if edge_low is not None else None
+    lb = np.ascontiguousarray(label, np.int32) if label is not None else None
+    out = dict(planes=np.zeros((H, W, 4), np.float32), costs=np.zeros((H, W), np.float32), selected=np.zeros((H, W), np.uint32),
+               state=np.zeros((H, W), np.uint8), fit=np.zeros((H, W, 4), np.float32), radius=np.zeros((H, W), np.int32),
+               neighbours=np.zeros((H, W, 9, 2), np.int16), reliable=np.zeros((H, W), np.uint8))
+    fn = lib().dpe_hostsim_stage_dbg
+    fn.restype = C.c_int
+    rc = fn(W, H, full_wh[0], full_wh[1], n_src, _ptr_array(imgs), _fp(K), _fp(R), _fp(t),
+            C.c_float(depth_range[0]), C.c_float(depth_range[1]), sd if sd is not None else C.POINTER(C.POINTER(C.c_float))(),
+            a_pp, a_ps, a_pl, pW, pH,
+            e.ctypes.data_as(C.POINTER(C.c_uint8)) if e is not None else null_b,
+            el.ctypes.data_as(C.POINTER(C.c_uint8)) if el is not None else null_b,
+            el.shape[1] if el is not None else 0, el.shape[0] if el is not None else 0,
+            lb.ctypes.data_as(C.POINTER(C.c_int32)) if lb is not None else null_i,
+            C.byref(params), C.c_uint64(seed), quant, int(stop_step),
+            _fp(out["planes"]), _fp(out["costs"]), out["selected"].ctypes.data_as(C.POINTER(C.c_uint32)),
+            out["state"].ctypes.data_as(C.POINTER(C.c_uint8)), _fp(out["fit"]),
+            out["radius"].ctypes.data_as(C.POINTER(C.c_int32)), out["neighbours"].ctypes.data_as(C.POINTER(C.c_int16)),
+            out["reliable"].ctypes.data_as(C.POINTER(C.c_uint8)))
+    if rc != 0:
+        raise RuntimeError(f"hostsim stage failed: {rc}")
+    return out

@@ -114,6 +114,21 @@ DPE_API int dpe_stage_commit(dpe_ctx* ctx);
  * problems serially through depths.dmb files (main.cpp:509-558, DPE.cpp:826-844).  Single GPU only. */
 DPE_API int dpe_set_view_order(dpe_ctx* ctx, int sequential);
 
+/* fp32 arithmetic of the NCC moments.  DPE_COST_REFERENCE (default): accumulated on the raw intensities in
+ * the reference's operation order (DPE.cu:716-775), costs within ~1e-6 of the reference's own;
+ * DPE_COST_CENTRED: intensities centred on the centre pixel first, costs within 1e-4 of the float64
+ * formula also on low-contrast patches (where the reference's E[x^2]-E[x]^2 loses ~3 digits). */
+enum { DPE_COST_CENTRED = 0, DPE_COST_REFERENCE = 1 };
+DPE_API int dpe_set_cost_arithmetic(dpe_ctx* ctx, int mode);
+/* Edge-mode propagation, direction 4: 0 (default) samples the other colour like directions 5-7, which
+ * makes a sweep race-free and bit-reproducible; 1 samples the reference's positions (own colour, read while
+ * the same launch writes it: DPE.cu:1274-1278) for parity runs. */
+DPE_API int dpe_set_reference_race(dpe_ctx* ctx, int on);
+/* test hook: scratch arrays of the view that ran last on the first stream.  what: 0 anchors (P x 9 short2),
+ * 1 fit planes (P float4), 2 radius (P int32), 3 costs (P float), 4 weak_reliable (P u8), 5 nearest strong
+ * (P short2), 6 complexity (P float). */
+DPE_API int dpe_debug_read(dpe_ctx* ctx, int what, void* out, size_t bytes);
+
 /* --- gate-1 hook: bilateral NCC of fixed plane hypotheses ------------------
  * planes: n_pix x (nx,ny,nz,d) in reference-camera coordinates (n.X + d = 0,
  * DPE.cu:337-342); xy: n_pix x (x,y); cost_out: n_pix x n_src floats =

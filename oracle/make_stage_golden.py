@@ -1,0 +1,184 @@
+"""TEST INFRASTRUCTURE — golden per-step states of ONE (view, stage) computed by the reference's own
+kernels (oracle/_ref/ref_stage_probe, built from /root/reference), for two cases:
+
+  first   stage 0 (FIRST_INIT, coarse scale, no weak path, no geometric consistency)
+  weak    stage 6 (REFINE_ITER at the fine scale: weak/edge path + geometric consistency), started from
+          the maps this implementation produced for stages 0..5 on the GPU
+
+Runs on a GPU box:   python oracle/make_stage_golden.py      -> tests/golden/ref_stage_{first,weak}.npz
+tests/test_stage_golden.py replays the stored inputs through the CPU logic simulator step by step.
+"""
+import ctypes as C
+import struct
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "dpe-mvs_b200")); sys.path.insert(0, str(ROOT / "tests"))
+import capi, hostsim, synth  # noqa: E402
+from scenes import small_scene  # noqa: E402
+import simpipe  # noqa: E402
+
+SEED = 20261018          # = DPE_REF_SEED of oracle/cvshim (the probe's curand seed)
+FIELDS = [("planes", np.float32, 4), ("costs", np.float32, 1), ("selected", np.uint32, 1), ("state", np.uint8, 1),
+          ("fit", np.float32, 4), ("radius", np.int32, 1), ("neighbours", np.int16, 18), ("reliable", np.uint8, 1)]
+
+
+def camera_bytes(K, R, t, w, h, full_w, full_h, dmin, dmax):
+    """struct Camera (main.h:50-59) at the stage's scale (K scaled as DPE.cpp:804-817, float arithmetic)."""
+    K = np.array(K, np.float32).copy()
+    R, t = np.asarray(R, np.float32), np.asarray(t, np.float32)
+    if (w, h) != (full_w, full_h):
+        sx, sy = np.float32(w) / np.float32(full_w), np.float32(h) / np.float32(full_h)
+        K[0, 0] *= sx; K[0, 2] *= sx; K[1, 1] *= sy; K[1, 2] *= sy
+    c = -(R.astype(np.float64).T @ t.astype(np.float64)).astype(np.float32)
+    return K.tobytes() + R.tobytes() + t.tobytes() + c.tobytes() + struct.pack("<iiff", h, w, dmin, dmax)
+
+
+def run_probe(tag, imgs, cams, full_wh, drange, p, planes, state, selected, src_depths, edge, edge_low, label):
+    H, W = imgs[0].shape
+    N = len(imgs)
+    lw, lh = edge_low.shape[1], edge_low.shape[0]
+    blob = struct.pack("<11i", W, H, N, lw, lh, p.state, p.geom_consistency, p.use_apd, p.max_iterations, p.weak_peak_radius, p.rotate_time)
+    blob += struct.pack("<3f", p.ransac_threshold, np.float32(drange[0]) * np.float32(0.6), np.float32(drange[1]) * np.float32(1.2))
+    blob += np.stack(imgs).astype(np.float32).tobytes()
+    if p.geom_consistency:
+        blob += np.stack([np.zeros((H, W), np.float32)] + [d.astype(np.float32) for d in src_depths]).tobytes()
+    for (K, R, t) in cams:
+        blob += camera_bytes(K, R, t, W, H, full_wh[0], full_wh[1], drange[0], drange[1])
+    blob += planes.astype(np.float32).tobytes() + state.astype(np.uint8).tobytes() + selected.astype(np.uint32).tobytes()
+    blob += edge.astype(np.uint8).tobytes() + edge_low.astype(np.uint8).tobytes() + label.astype(np.int32).tobytes()
+    fin, fout = Path(f"/tmp/stage_{tag}_in.bin"), Path(f"/tmp/stage_{tag}_out.bin")
+    fin.write_bytes(blob)
+    subprocess.check_call([str(ROOT / "oracle" / "_ref" / "ref_stage_probe"), str(fin), str(fout)])
+    raw = fout.read_bytes()
+    P = W * H
+    out, off = {}, 0
+    while off < len(raw):
+        (step,) = struct.unpack_from("<i", raw, off); off += 4
+        rec = {}
+        for name, dt, ch in FIELDS:
+            n = P * ch
+            a = np.frombuffer(raw, dt, n, off).copy(); off += n * np.dtype(dt).itemsize
+            rec[name] = a.reshape((H, W) if ch == 1 else (H, W, ch) if name != "neighbours" else (H, W, 9, 2))
+        out[step] = rec
+    return out
+
+
+def main():
+    spec, grays, cams, drs, pairs, gt = small_scene("c4", 0.05, 5)      # 151 x 101, low-texture planes
+    lib = capi.load()
+    H, W = grays[0].shape
+    sizes = simpipe.level_sizes(W, H, 2)
+    prep = []
+    for g in grays:
+        per = []
+        for k in range(2):
+            e = np.empty((sizes[k][1], sizes[k][0]), np.uint8)
+            l = np.empty((sizes[k][1], sizes[k][0]), np.int32)
+            gg = np.ascontiguousarray(g)
+            lib.dpe_host_problem_edges(gg.ctypes.data_as(C.c_void_p), W, H, 1 << (1 - k), e.ctypes.data_as(C.c_void_p), l.ctypes.data_as(C.c_void_p))
+            per.append((e, l))
+        prep.append(per)
+    v = 0
+    ids = [v] + list(pairs[v])
+    sched = capi.stage_schedule(2)
+    report = {}
+    # ---- case "first": stage 0 at the coarse scale
+    k, p = sched[0]
+    cw, ch = sizes[0]
+    imgs0 = [hostsim.resize_linear(grays[i].astype(np.float32), cw, ch) for i in ids]
+    zero_e = np.zeros((ch, cw), np.uint8)
+    dumps = run_probe("first", imgs0, [cams[i] for i in ids], (W, H), drs[v], p, np.zeros((ch, cw, 4), np.float32),
+                      np.ones((ch, cw), np.uint8), np.zeros((ch, cw), np.uint32), None, zero_e, zero_e, np.full((ch, cw), -1, np.int32))
+    rec = dict(images=np.stack(imgs0), K=np.stack([cams[i][0] for i in ids]), R=np.stack([cams[i][1] for i in ids]),
+               t=np.stack([cams[i][2] for i in ids]), drange=np.array(drs[v], np.float32), full_wh=np.array([W, H]))
+    for s in (1, 2, 8, 11):
+        for name in ("planes", "costs", "selected", "state"):
+            rec[f"s{s}_{name}"] = dumps[s][name]
+    np.savez_compressed(ROOT / "tests" / "golden" / "ref_stage_first.npz", **rec)
+    print("first: steps", sorted(dumps))
+    # ---- case "weak": stage 6, inputs = this implementation's maps after stages 0..5 (GPU)
+    ctx = capi.Context(0)
+    capi.upload_scene(ctx, grays, cams, drs, pairs, 2)
+    for vv in range(len(grays)):
+        for kk in range(2):
+            ctx.set_prep(vv, kk, *prep[vv][kk])
+    for si in range(6):
+        ctx.run_stage(*sched[si], SEED); ctx.stage_commit()
+    maps = [ctx.get_maps(i, 1) for i in range(len(grays))]
+    # the weak case uses the LAST view: the GPU run of stage 6 below keeps its scratch arrays readable
+    v = len(grays) - 1
+    ids = [v] + list(pairs[v])
+    k, p = sched[6]
+    pv = maps[v]
+    planes = np.concatenate([pv["normal"], pv["depth"][..., None]], -1).astype(np.float32)
+    src_d = [maps[i]["depth"] for i in pairs[v]]
+    imgs1 = [grays[i].astype(np.float32) for i in ids]
+    dumps = run_probe("weak", imgs1, [cams[i] for i in ids], (W, H), drs[v], p, planes, pv["state"], pv["selected"], src_d,
+                      prep[v][1][0], prep[v][0][0], prep[v][1][1])
+    rec = dict(images=np.stack([grays[i] for i in ids]), K=np.stack([cams[i][0] for i in ids]), R=np.stack([cams[i][1] for i in ids]),
+               t=np.stack([cams[i][2] for i in ids]), drange=np.array(drs[v], np.float32), full_wh=np.array([W, H]),
+               prev_planes=planes, prev_state=pv["state"], prev_selected=pv["selected"], src_depths=np.stack(src_d),
+               edge=prep[v][1][0], edge_low=prep[v][0][0], label=prep[v][1][1])
+    want = {0: ("state", "neighbours", "reliable"), 1: ("planes", "costs", "selected"), 2: ("planes", "costs", "selected"),
+            3: ("fit", "radius"), 4: ("planes", "costs", "selected"), 10: ("planes", "costs", "selected"), 11: ("planes", "state", "selected")}
+    for s, names in want.items():
+        for name in names:
+            rec[f"s{s}_{name}"] = dumps[s][name]
+    np.savez_compressed(ROOT / "tests" / "golden" / "ref_stage_weak.npz", **rec)
+    nweak = int((pv["state"] == 0).sum())
+    print("weak: steps", sorted(dumps), "weak pixels in", nweak, "of", pv["state"].size)
+    # ---- the same stage on the GPU (this implementation), all views on the first stream so that the last
+    # view's scratch arrays survive; compared with the reference's dumps
+    import json
+    for race in (0, 1):
+        c2 = capi.Context(0)
+        capi.upload_scene(c2, grays, cams, drs, pairs, 2)
+        for vv in range(len(grays)):
+            for kk in range(2):
+                c2.set_prep(vv, kk, *prep[vv][kk])
+        for si in range(6):
+            c2.run_stage(*sched[si], SEED); c2.stage_commit()
+        c2.set_profile(len(grays))
+        c2.set_reference_race(race)
+        c2.run_stage(*sched[6], SEED); c2.stage_commit()
+        nb = c2.debug_read(0, (H, W, 9, 2), np.int16)
+        fit = c2.debug_read(1, (H, W, 4), np.float32)
+        rad = c2.debug_read(2, (H, W), np.int32)
+        rel = c2.debug_read(4, (H, W), np.uint8)
+        fin = c2.get_maps(v, 1)
+        c2.close()
+        wm = pv["state"] == 0
+        r = {}
+        eq = (nb[wm] == dumps[0]["neighbours"][wm]).all(-1)
+        r["anchors_equal"] = float(eq.mean()); r["anchor_sets_equal"] = float(eq.all(-1).mean())
+        r["reliable_equal"] = float((rel[wm] == dumps[0]["reliable"][wm]).mean())
+        r["radius_equal_weak"] = float((rad[wm] == dumps[9]["radius"][wm]).mean())
+        dn = np.abs(fit[..., :3] - dumps[9]["fit"][..., :3]).max(-1)
+        r["fit_normal_equal_weak"] = float((dn[wm] < 1e-4).mean())
+        ref_fin = dumps[11]
+        rd = ref_fin["planes"][..., 3].copy()
+        rst = ref_fin["state"].copy()
+        dmin, dmax = np.float32(drs[v][0]) * np.float32(0.6), np.float32(drs[v][1]) * np.float32(1.2)
+        oob = (rd < dmin) | (rd > dmax)                       # host tail of ProcessProblem (main.cpp:427-437)
+        rd[oob] = 0; rst[oob] = 2
+        both = (fin["depth"] > 0) & (rd > 0)
+        rel_d = np.abs(fin["depth"] - rd) / np.maximum(rd, 1e-9)
+        dn = np.abs(fin["normal"] - ref_fin["planes"][..., :3]).max(-1)
+        r["final_state_equal"] = float((fin["state"] == rst).mean())
+        r["final_depth_1e-3"] = float((rel_d[both] < 1e-3).mean()); r["final_depth_1pct"] = float((rel_d[both] < 1e-2).mean())
+        r["final_normal_identical"] = float((dn[both] < 1e-4).mean())
+        ang = np.degrees(np.arccos(np.clip((fin["normal"] * ref_fin["planes"][..., :3]).sum(-1), -1, 1)))
+        r["final_normal_1deg"] = float((ang[both] < 1).mean())
+        r["final_weakpx_depth_1pct"] = float((rel_d[both & wm] < 1e-2).mean())
+        report[f"gpu_vs_ref_stage6_race{race}"] = r
+        print(f"GPU vs reference kernels, stage 6, view {v}, ref_race={race}:", json.dumps(r))
+    (ROOT / "gpurun_out" / "stage_diff.json").write_text(json.dumps(report, indent=1))
+
+
+if __name__ == "__main__":
+    main()

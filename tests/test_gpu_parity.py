@@ -41,9 +41,15 @@ def test_gate1_cost_kernel_exact_bilinear(ctx_c1):
     point-sampled texels)."""
     ctx, ns, spec, grays, cams, drs, pairs, gt = ctx_c1
     xy, planes = seeded_hypotheses(spec, cams, gt, 400)
+    ctx.set_cost_arithmetic(0)          # centred moments: the precise arithmetic (include/dpe_b200.h)
     got = ctx.cost_eval(0, ns - 1, xy, planes, len(pairs[0]), mode=1)
+    ctx.set_cost_arithmetic(1)
     want = _oracle_costs(grays, cams, pairs, xy, planes, quant=0)
     assert np.abs(got - want).max() <= 1e-4
+    # the reference's own arithmetic (raw fp32 moments) on the same hypotheses: E[x^2]-E[x]^2 around
+    # intensity 128 loses ~3 digits, so it only holds ~1e-3 against float64 — like the reference itself
+    got_ref = ctx.cost_eval(0, ns - 1, xy, planes, len(pairs[0]), mode=1)
+    assert np.abs(got_ref - want).max() <= 5e-3 and np.median(np.abs(got_ref - want)) < 2e-4
 
 
 def test_gate1_cost_kernel_hardware_filter(ctx_c1):
@@ -52,7 +58,9 @@ def test_gate1_cost_kernel_hardware_filter(ctx_c1):
     neighbouring 1/256 bin.  Tolerance: median 2e-4, 99th percentile 3e-3."""
     ctx, ns, spec, grays, cams, drs, pairs, gt = ctx_c1
     xy, planes = seeded_hypotheses(spec, cams, gt, 400, seed=1)
+    ctx.set_cost_arithmetic(0)
     got = ctx.cost_eval(0, ns - 1, xy, planes, len(pairs[0]), mode=0)
+    ctx.set_cost_arithmetic(1)
     want = _oracle_costs(grays, cams, pairs, xy, planes, quant=1)
     d = np.abs(got - want)
     assert np.median(d) < 2e-4 and np.percentile(d, 99) < 3e-3 and d.max() < 2e-2
@@ -65,7 +73,9 @@ def test_cost_kernel_edge_cases(ctx_c1):
     xy = np.array([[0, 0], [W - 1, 0], [0, H - 1], [W - 1, H - 1], [3, H // 2], [W // 2, 2], [W // 2, H // 2]], np.int32)
     _, planes = seeded_hypotheses(spec, cams, gt, len(xy), seed=2, margin=8)
     planes[-1] = [0, 0, -1, 0.05]
+    ctx.set_cost_arithmetic(0)
     got = ctx.cost_eval(0, ns - 1, xy, planes, len(pairs[0]), mode=1)
+    ctx.set_cost_arithmetic(1)
     want = _oracle_costs(grays, cams, pairs, xy, planes, quant=0)
     assert np.array_equal(got == 2.0, want == 2.0)
     assert np.abs(got - want).max() <= 1e-4
@@ -84,12 +94,21 @@ def test_cost_kernel_matches_reference_golden_vectors():
         ctx.set_view(v, imgs[v], *cams[v], 1.0, 10.0)
     ctx.set_pairs(0, [1, 2, 3])
     ctx.commit()
+    # product default = the reference's arithmetic: half of the costs within 1e-6 of the reference's own
+    # (a third bit-identical); the rest differ through the source coordinates (per-tap rcp.approx and an
+    # incrementally stepped homography here, --use_fast_math divides there), which move a tap across a 1/256
+    # filter-weight bin now and then.  Measured on B200: median 9.3e-7, p90 2.2e-5, p99 2.0e-4.
     got = ctx.cost_eval(0, 0, fx["xy"], fx["planes"], 3, mode=0)
     ref = fx["ref_ncc"]
     assert ((got >= 2.0) == (ref >= 2.0)).mean() > 0.995
     both = (got < 2.0) & (ref < 2.0)
     d = np.abs(got - ref)[both]
-    assert np.median(d) < 2e-4 and np.percentile(d, 99) < 3e-3, (np.median(d), np.percentile(d, 99))
+    assert np.median(d) < 5e-6 and np.percentile(d, 90) < 1e-4 and np.percentile(d, 99) < 1e-3, (np.median(d), np.percentile(d, 99))
+    assert (d == 0).mean() > 0.15
+    ctx.set_cost_arithmetic(0)
+    got0 = ctx.cost_eval(0, 0, fx["xy"], fx["planes"], 3, mode=0)
+    d0 = np.abs(got0 - ref)[(got0 < 2.0) & (ref < 2.0)]
+    assert np.median(d0) < 2e-5 and np.percentile(d0, 99) < 1e-3
     ctx.close()
 
 

@@ -1,0 +1,31 @@
+"""GPU cost kernel vs the reference's own device outputs (tests/golden/ref_probe_c1.npz) in both cost
+arithmetics."""
+import sys, json
+from pathlib import Path
+import numpy as np
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "dpe-mvs_b200"))
+import capi
+fx = np.load(ROOT / "tests" / "golden" / "ref_probe_c1.npz")
+imgs = [fx["images"][i] for i in range(4)]
+cams = [(fx["K"][i], fx["R"][i], fx["t"][i]) for i in range(4)]
+out = {}
+for mode, name in ((1, "reference"), (0, "centred")):
+    ctx = capi.Context(0)
+    H, W = imgs[0].shape
+    ctx.scene_begin(4, W, H, 1)
+    for v in range(4):
+        ctx.set_view(v, imgs[v], *cams[v], 1.0, 10.0)
+    ctx.set_pairs(0, [1, 2, 3])
+    ctx.commit()
+    ctx.set_cost_arithmetic(mode)
+    got = ctx.cost_eval(0, 0, fx["xy"], fx["planes"], 3, mode=0)
+    ref = fx["ref_ncc"]
+    both = (got < 2.0) & (ref < 2.0)
+    d = np.abs(got - ref)[both]
+    out[name] = dict(n=int(both.sum()), same_invalid=float(((got >= 2.0) == (ref >= 2.0)).mean()), median=float(np.median(d)),
+                     p90=float(np.percentile(d, 90)), p99=float(np.percentile(d, 99)), max=float(d.max()), exact=float((d == 0).mean()),
+                     below_1e6=float((d < 1e-6).mean()), below_1e5=float((d < 1e-5).mean()))
+    print(name, json.dumps(out[name]))
+    ctx.close()
+(ROOT / "gpurun_out" / "cost_diff.json").write_text(json.dumps(out, indent=1))

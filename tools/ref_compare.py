@@ -34,12 +34,21 @@ def compare(a_d, a_n, a_w, b_d, b_n, b_w):
                 weak_agree=float((a_w == b_w).mean()))
 
 
-def vs_gt(d, n, gt_d, gt_n):
+def vs_gt(d, n, gt_d, gt_n, w=None):
     m = (gt_d > 0) & (d > 0)
     rel = np.abs(d - gt_d) / np.maximum(gt_d, 1e-9)
     ang = np.degrees(np.arccos(np.clip((n * gt_n).sum(-1), -1, 1)))
-    return dict(cover=float((d > 0).mean()), depth_1pct=float((rel[m] < 0.01).mean()), normal_5deg=float((ang[m] < 5).mean()),
-                depth_1pct_of_all=float(((rel < 0.01) & (d > 0))[gt_d > 0].mean()))
+    out = dict(cover=float((d > 0).mean()), depth_1pct=float((rel[m] < 0.01).mean()), normal_5deg=float((ang[m] < 5).mean()),
+               normal_2deg=float((ang[m] < 2).mean()), normal_10deg=float((ang[m] < 10).mean()),
+               depth_1pct_of_all=float(((rel < 0.01) & (d > 0))[gt_d > 0].mean()))
+    if w is not None:      # by this implementation's own pixel class (1 weak, 2 strong)
+        for name, cls in (("weak", 1), ("strong", 2)):
+            mm = m & (w == cls)
+            if mm.sum() > 0:
+                out[f"{name}_frac"] = float((w == cls).mean())
+                out[f"{name}_depth_1pct"] = float((rel[mm] < 0.01).mean())
+                out[f"{name}_normal_5deg"] = float((ang[mm] < 5).mean())
+    return out
 
 
 def main():
@@ -120,6 +129,7 @@ def main():
     ctx.set_count_evals(True)
     if args.match:
         ctx.set_view_order(1)
+        ctx.set_reference_race(1)
     stages = []
     for (k, p) in capi.stage_schedule(n_scales):
         m0, u0 = ctx.stage_gpu_ms(), ctx.eval_units()
@@ -143,23 +153,24 @@ def main():
     # ---- comparisons
     if len(ref_out) >= 1:
         res["ours_vs_ref"] = [compare(*ours[v], *ref_out[0][v]) for v in range(V)]
-        res["ref_vs_gt"] = [vs_gt(ref_out[0][v][0], ref_out[0][v][1], *gt[v]) for v in range(V)]
+        res["ref_vs_gt"] = [vs_gt(ref_out[0][v][0], ref_out[0][v][1], *gt[v], ref_out[0][v][2]) for v in range(V)]
         res["ref_weak_hist"] = [[float((ref_out[0][v][2] == k).mean()) for k in range(3)] for v in range(V)]
     if len(ref_out) >= 2:
         res["ref_vs_ref"] = [compare(*ref_out[1][v], *ref_out[0][v]) for v in range(V)]
     if seed2_out is not None and ref_out:
         res["refseed2_vs_ref"] = [compare(*seed2_out[v], *ref_out[0][v]) for v in range(V)]
-    res["ours_vs_gt"] = [vs_gt(ours[v][0], ours[v][1], *gt[v]) for v in range(V)]
+        res["refseed2_vs_gt"] = [vs_gt(seed2_out[v][0], seed2_out[v][1], *gt[v], seed2_out[v][2]) for v in range(V)]
+    res["ours_vs_gt"] = [vs_gt(ours[v][0], ours[v][1], *gt[v], ours[v][2]) for v in range(V)]
     res["ours_weak_hist"] = [[float((ours[v][2] == k).mean()) for k in range(3)] for v in range(V)]
     np.savez_compressed(OUT / f"cmp_{tag}_view0.npz", ours_d=ours[0][0], ours_w=ours[0][2],
                         ref_d=ref_out[0][0][0] if ref_out else 0, ref_w=ref_out[0][0][2] if ref_out else 0, gt_d=gt[0][0])
     (OUT / f"cmp_{tag}.json").write_text(json.dumps(res, indent=1))
     short = {k: v for k, v in res.items() if not isinstance(v, list)}
     print(json.dumps(short, indent=1))
-    for key in ("ours_vs_ref", "ref_vs_ref", "refseed2_vs_ref", "ref_vs_gt", "ours_vs_gt"):
+    for key in ("ours_vs_ref", "ref_vs_ref", "refseed2_vs_ref", "ref_vs_gt", "refseed2_vs_gt", "ours_vs_gt"):
         if key in res:
             print(key, json.dumps(res[key][0]))
-            print(key, "mean over views", json.dumps({k: float(np.mean([r[k] for r in res[key]])) for k in res[key][0]}))
+            print(key, "mean over views", json.dumps({k: round(float(np.mean([r[k] for r in res[key] if k in r])), 4) for k in res[key][0]}))
 
 
 if __name__ == "__main__":
