@@ -52,7 +52,7 @@ def build_lib(verbose=False, force=False) -> Path:
     OBJ.mkdir(exist_ok=True)
     hdrs = _headers()
     objs = []
-    cu = [CSRC / "dpe_kernels.cu", CSRC / "dpe_capi.cu"]
+    cu = [CSRC / "dpe_kernels.cu", CSRC / "dpe_capi.cu", CSRC / "dpe_fusion.cu"]
     cpp = sorted((CSRC / "host").glob("*.cpp"))
     for src in cu + cpp:
         o = OBJ / (src.stem + ".o")

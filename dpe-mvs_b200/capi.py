@@ -30,7 +30,7 @@ SYMBOLS = [
     "dpe_scene_set_view", "dpe_scene_set_pairs", "dpe_scene_set_prep", "dpe_scene_set_shard", "dpe_scene_commit",
     "dpe_run_stage", "dpe_stage_atlas", "dpe_stage_commit", "dpe_cost_eval", "dpe_geom_eval", "dpe_get_size",
     "dpe_get_maps", "dpe_set_count_evals", "dpe_eval_units", "dpe_stage_gpu_ms", "dpe_probe_tex_rate",
-    "dpe_probe_fma_rate", "dpe_probe_tex_pattern", "dpe_probe_tex_weights", "dpe_run_pipeline", "dpe_set_profile", "dpe_get_profile", "dpe_set_view_order", "dpe_bench_ncc", "dpe_set_reference_race", "dpe_debug_read", "dpe_set_cost_arithmetic",
+    "dpe_probe_fma_rate", "dpe_probe_tex_pattern", "dpe_probe_tex_weights", "dpe_run_pipeline", "dpe_set_profile", "dpe_get_profile", "dpe_set_view_order", "dpe_bench_ncc", "dpe_set_reference_race", "dpe_debug_read", "dpe_set_cost_arithmetic", "dpe_fuse_set_view", "dpe_fuse_run", "dpe_fuse_get",
 ]
 
 _lib = None
@@ -84,6 +84,9 @@ def load(build=True):
     lib.dpe_set_view_order.argtypes = [vp, ci]
     lib.dpe_set_reference_race.argtypes = [vp, ci]
     lib.dpe_set_cost_arithmetic.argtypes = [vp, ci]
+    lib.dpe_fuse_set_view.argtypes = [vp, ci, vp, vp, vp, vp]
+    lib.dpe_fuse_run.argtypes = [vp, C.POINTER(C.c_size_t)]
+    lib.dpe_fuse_get.argtypes = [vp, vp, vp]
     lib.dpe_debug_read.argtypes = [vp, ci, vp, C.c_size_t]
     lib.dpe_bench_ncc.argtypes = [vp, ci, ci, ci, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.dpe_get_profile.argtypes = [vp, vp, vp, vp]
@@ -242,6 +245,22 @@ class Context:
         r, c = C.c_double(), C.c_double()
         self._ck(self.lib.dpe_bench_ncc(self.h, view, variant, n_cand, reps, C.byref(r), C.byref(c)))
         return r.value, c.value
+
+    def fuse(self, maps, colours):
+        """maps[v] = dict(depth, normal, state) at full resolution (None = no maps), colours[v] = HxWx3 uint8 BGR.
+        Returns (xyz Nx3 float32, bgr Nx3 uint8)."""
+        for v, m in enumerate(maps):
+            if m is None:
+                continue
+            d = np.ascontiguousarray(m["depth"], np.float32); n = np.ascontiguousarray(m["normal"], np.float32)
+            st = np.ascontiguousarray(m["state"], np.uint8); c = np.ascontiguousarray(colours[v], np.uint8)
+            self._ck(self.lib.dpe_fuse_set_view(self.h, v, d.ctypes.data, n.ctypes.data, st.ctypes.data, c.ctypes.data))
+        n = C.c_size_t()
+        self._ck(self.lib.dpe_fuse_run(self.h, C.byref(n)))
+        xyz = np.empty((n.value, 3), np.float32); bgr = np.empty((n.value, 3), np.uint8)
+        if n.value:
+            self._ck(self.lib.dpe_fuse_get(self.h, xyz.ctypes.data, bgr.ctypes.data))
+        return xyz, bgr
 
     def set_cost_arithmetic(self, mode):
         """0 = centred (precise), 1 = the reference's raw fp32 accumulation (default)."""

@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 #include "dpe_kernels.cuh"
+#include "dpe_fusion.cuh"
 #include "dpe_consts.h"
 
 using namespace dpe;
@@ -41,6 +42,10 @@ struct ViewData {
   uint32_t* selected = nullptr;
   int cur_scale = -1;  // scale index of planes/state/selected
   uint8_t* gray_full = nullptr;  // uploaded u8 image (device), freed after commit
+};
+
+struct FuseData {
+  float* depth = nullptr; float* normal = nullptr; uint8_t* state = nullptr; uint8_t* bgr = nullptr; uint8_t* mask = nullptr;
 };
 
 struct Scratch {
@@ -79,6 +84,9 @@ struct dpe_ctx {
   bool cost_raw = true;       // dpe_set_cost_arithmetic
   // scratch
   std::vector<Scratch> scratch;
+  // device fusion (dpe_fuse_*): per-view maps at full resolution + the fused cloud (host)
+  std::vector<FuseData> fuse;
+  std::vector<FusedPointDev> cloud;
   // initial XORWOW states per scale for rng_seed (dpe_rng.h): table[k][y*w+x] = curand_init(seed, y, x)
   std::vector<Xorwow*> rng_table;
   uint64_t rng_seed = 0;
@@ -136,6 +144,8 @@ static void free_scene(dpe_ctx* ctx) {
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   ctx->scratch.clear();
+  for (auto& f : ctx->fuse) { cudaFree(f.depth); cudaFree(f.normal); cudaFree(f.state); cudaFree(f.bgr); cudaFree(f.mask); }
+  ctx->fuse.clear(); ctx->cloud.clear();
   for (auto p : ctx->rng_table) cudaFree(p);
   ctx->rng_table.clear(); ctx->rng_ready = false;
   cudaFree(ctx->zero_edge); ctx->zero_edge = nullptr;
@@ -528,6 +538,82 @@ int dpe_set_view_order(dpe_ctx* ctx, int sequential) {
   if (ctx->stage_pending) FAIL(DPE_ERR_STATE, "stage not committed");
   if (sequential && ctx->n_ranks > 1) FAIL(DPE_ERR_ARG, "sequential view order needs all views on one GPU");
   ctx->gauss_seidel = sequential != 0;
+  return DPE_OK;
+}
+
+// ---- device fusion (RunFusion, DPE.cpp:1220-1370) ---------------------------------------------
+int dpe_fuse_set_view(dpe_ctx* ctx, int view, const float* depth, const float* normal3, const uint8_t* state, const uint8_t* bgr) {
+  if (!ctx || view < 0 || view >= ctx->n_views || !depth || !normal3 || !state || !bgr) return DPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->fuse.empty()) ctx->fuse.assign(ctx->n_views, FuseData());
+  FuseData& f = ctx->fuse[view];
+  const size_t P = (size_t)ctx->W * ctx->H;
+  if (!f.depth) {
+    CK(cudaMalloc(&f.depth, P * 4)); CK(cudaMalloc(&f.normal, P * 12)); CK(cudaMalloc(&f.state, P)); CK(cudaMalloc(&f.bgr, P * 3));
+    CK(cudaMalloc(&f.mask, P));
+  }
+  CK(cudaMemcpy(f.depth, depth, P * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(f.normal, normal3, P * 12, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(f.state, state, P, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(f.bgr, bgr, P * 3, cudaMemcpyHostToDevice));
+  return DPE_OK;
+}
+
+int dpe_fuse_run(dpe_ctx* ctx, size_t* n_points) {
+  if (!ctx || !n_points) return DPE_ERR_ARG;
+  if (ctx->fuse.empty()) FAIL(DPE_ERR_STATE, "no fusion inputs (dpe_fuse_set_view)");
+  CK(cudaSetDevice(ctx->device));
+  const int V = ctx->n_views, W = ctx->W, H = ctx->H;
+  const size_t P = (size_t)W * H;
+  std::vector<FuseView> hv(V);
+  for (int v = 0; v < V; ++v) {
+    FuseView& fv = hv[v];
+    memset(&fv, 0, sizeof(fv));
+    const FuseData& f = ctx->fuse[v];
+    fv.depth = f.depth; fv.normal = f.normal; fv.state = f.state; fv.bgr = f.bgr; fv.mask = f.mask;
+    if (f.mask) CK(cudaMemset(f.mask, 0, P));
+    const HostCam& c = ctx->views[v].cam;
+    for (int i = 0; i < 9; ++i) { fv.K[i] = (float)c.K[i]; fv.R[i] = (float)c.R[i]; }
+    for (int i = 0; i < 3; ++i) fv.t[i] = (float)c.t[i];
+    // camera centre as the reference's fusion computes it: float arithmetic (DPE.cpp:1170-1194)
+    for (int j = 0; j < 3; ++j) fv.C[j] = -(fv.R[0 + j] * fv.t[0] + fv.R[3 + j] * fv.t[1] + fv.R[6 + j] * fv.t[2]);
+  }
+  FuseView* dv; CK(cudaMalloc(&dv, V * sizeof(FuseView)));
+  CK(cudaMemcpy(dv, hv.data(), V * sizeof(FuseView), cudaMemcpyHostToDevice));
+  FusedPointDev *pts, *sel; uint8_t* accept; int* d_n; void* temp;
+  CK(cudaMalloc(&pts, P * sizeof(FusedPointDev))); CK(cudaMalloc(&sel, P * sizeof(FusedPointDev)));
+  CK(cudaMalloc(&accept, P)); CK(cudaMalloc(&d_n, sizeof(int)));
+  const size_t temp_bytes = fuse_select_temp_bytes((int)P);
+  CK(cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
+  ctx->cloud.clear();
+  for (int i = 0; i < V; ++i) {  // views in order: a view sees every mark of the views before it
+    if (!hv[i].depth) continue;
+    FuseSrcList sl; memset(&sl, 0, sizeof(sl));
+    const std::vector<int>& src = ctx->views[i].src;
+    sl.n = (int)src.size();
+    for (int j = 0; j < sl.n; ++j) sl.id[j] = ctx->fuse[src[j]].depth ? src[j] : -1;
+    launch_fuse_view(dv, i, sl, W, H, pts, accept, ctx->num_sms, 0);
+    launch_fuse_select(temp, temp_bytes, pts, accept, sel, d_n, (int)P, 0);
+    ctx->launches += 2;
+    int n = 0;
+    CK(cudaMemcpy(&n, d_n, sizeof(int), cudaMemcpyDeviceToHost));
+    const size_t at = ctx->cloud.size();
+    ctx->cloud.resize(at + n);
+    if (n) CK(cudaMemcpy(ctx->cloud.data() + at, sel, (size_t)n * sizeof(FusedPointDev), cudaMemcpyDeviceToHost));
+  }
+  CK(cudaGetLastError());
+  cudaFree(dv); cudaFree(pts); cudaFree(sel); cudaFree(accept); cudaFree(d_n); cudaFree(temp);
+  *n_points = ctx->cloud.size();
+  return DPE_OK;
+}
+
+int dpe_fuse_get(dpe_ctx* ctx, float* xyz, uint8_t* bgr) {
+  if (!ctx || !xyz || !bgr) return DPE_ERR_ARG;
+  for (size_t i = 0; i < ctx->cloud.size(); ++i) {
+    const FusedPointDev& p = ctx->cloud[i];
+    xyz[3 * i] = p.x; xyz[3 * i + 1] = p.y; xyz[3 * i + 2] = p.z;
+    bgr[3 * i] = (uint8_t)(p.bgr & 255u); bgr[3 * i + 1] = (uint8_t)((p.bgr >> 8) & 255u); bgr[3 * i + 2] = (uint8_t)((p.bgr >> 16) & 255u);
+  }
   return DPE_OK;
 }
 

@@ -1,0 +1,115 @@
+// dpe_fusion.cu — depth-map fusion on the device (RunFusion, DPE.cpp:1220-1370).
+//
+// The reference fuses on one CPU core: for every view in order, for every pixel in raster order, project the
+// pixel's 3-D point into each source view, check reprojection error (< 2 px), relative depth difference
+// (< 1 %) and normal angle (< 10 deg), accept the point if sum exp(-(e + 200 dd + 10 ang)) exceeds
+// 0.3 (0.45 for WEAK pixels) per consistent view, and mark the source pixels it used so that later
+// pixels / views skip them.  Here views are still processed in order (one launch per view: a later view
+// sees every mark of an earlier one), the pixels of a view in parallel; marks are plain byte stores.  The
+// one semantic difference: two pixels of the SAME view that land on the same source pixel can both use it,
+// where the reference's raster order gives it to the first — a slightly denser cloud, same points.
+// Accepted points are compacted per view with cub::DeviceSelect (stable: points come out in raster
+// order, like the reference's) and appended to the host cloud.
+#include <cuda_runtime.h>
+#include <cub/device/device_select.cuh>
+
+#include "dpe_fusion.cuh"
+
+namespace dpe {
+
+__device__ __forceinline__ void fuse_world_point(const FuseView& c, float x, float y, float depth, float X[3]) {  // DPE.cpp:1170-1194
+  const float px = depth * (x - c.K[2]) / c.K[0], py = depth * (y - c.K[5]) / c.K[4], pz = depth;
+  X[0] = c.R[0] * px + c.R[3] * py + c.R[6] * pz + c.C[0];
+  X[1] = c.R[1] * px + c.R[4] * py + c.R[7] * pz + c.C[1];
+  X[2] = c.R[2] * px + c.R[5] * py + c.R[8] * pz + c.C[2];
+}
+__device__ __forceinline__ void fuse_project(const FuseView& c, const float X[3], float* u, float* v, float* d) {  // DPE.cpp:1196-1206
+  const float tx = c.R[0] * X[0] + c.R[1] * X[1] + c.R[2] * X[2] + c.t[0];
+  const float ty = c.R[3] * X[0] + c.R[4] * X[1] + c.R[5] * X[2] + c.t[1];
+  const float tz = c.R[6] * X[0] + c.R[7] * X[1] + c.R[8] * X[2] + c.t[2];
+  *d = c.K[6] * tx + c.K[7] * ty + c.K[8] * tz;
+  *u = (c.K[0] * tx + c.K[1] * ty + c.K[2] * tz) / *d;
+  *v = (c.K[3] * tx + c.K[4] * ty + c.K[5] * tz) / *d;
+}
+
+__global__ void __launch_bounds__(256) k_fuse_view(const FuseView* __restrict__ views, const int i, const FuseSrcList srcs, const int W,
+                                                   const int H, FusedPointDev* __restrict__ pts, uint8_t* __restrict__ accept) {
+  const FuseView& ref = views[i];
+  const int total = W * H;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    accept[idx] = 0;
+    if (ref.mask[idx] == 1) continue;
+    const float ref_depth = ref.depth[idx];
+    if (ref_depth <= 0.0f) continue;
+    const int r = idx / W, c = idx - r * W;
+    const float rn0 = ref.normal[3 * idx], rn1 = ref.normal[3 * idx + 1], rn2 = ref.normal[3 * idx + 2];
+    float X[3];
+    fuse_world_point(ref, (float)c, (float)r, ref_depth, X);
+    int num_consistent = 0;
+    float dynamic_consistency = 0.0f;
+    int used[DPE_MAX_SRC];
+    for (int j = 0; j < srcs.n; ++j) {
+      used[j] = -1;
+      const int s = srcs.id[j];
+      if (s < 0) continue;
+      const FuseView& sv = views[s];
+      if (sv.depth == nullptr) continue;
+      float u, v, pd;
+      fuse_project(sv, X, &u, &v, &pd);
+      const int sr = (int)(v + 0.5f), sc = (int)(u + 0.5f);
+      if (!(sc >= 0 && sc < W && sr >= 0 && sr < H)) continue;
+      const int sidx = sr * W + sc;
+      if (sv.mask[sidx] == 1) continue;
+      const float sd = sv.depth[sidx];
+      if (sd <= 0.0f) continue;
+      float Y[3], bu, bv;
+      fuse_world_point(sv, (float)sc, (float)sr, sd, Y);
+      fuse_project(ref, Y, &bu, &bv, &pd);
+      const float reproj = sqrtf((c - bu) * (c - bu) + (r - bv) * (r - bv));
+      const float rel = fabsf(pd - ref_depth) / ref_depth;
+      float angle = acosf(rn0 * sv.normal[3 * sidx] + rn1 * sv.normal[3 * sidx + 1] + rn2 * sv.normal[3 * sidx + 2]);
+      if (angle != angle) angle = 0.0f;
+      if (reproj < 2.0f && rel < 0.01f && angle < 0.174533f) {
+        used[j] = sidx;
+        dynamic_consistency += expf(-(reproj + 200 * rel + angle * 10));
+        num_consistent++;
+      }
+    }
+    const float factor = (ref.state[idx] == DPE_WEAK ? 0.45f : 0.3f);
+    if (num_consistent >= 1 && dynamic_consistency > factor * num_consistent) {
+      const uint8_t* px = ref.bgr + 3 * (size_t)idx;
+      float col[3] = {(float)px[0], (float)px[1], (float)px[2]};
+      for (int j = 0; j < srcs.n; ++j) {
+        if (used[j] < 0) continue;
+        const FuseView& sv = views[srcs.id[j]];
+        sv.mask[used[j]] = 1;
+        const uint8_t* sp = sv.bgr + 3 * (size_t)used[j];
+        col[0] += sp[0]; col[1] += sp[1]; col[2] += sp[2];
+      }
+      FusedPointDev p;
+      p.x = X[0]; p.y = X[1]; p.z = X[2];
+      const uint32_t b = (uint32_t)(uint8_t)(col[0] / (num_consistent + 1)), g = (uint32_t)(uint8_t)(col[1] / (num_consistent + 1)),
+                     rr = (uint32_t)(uint8_t)(col[2] / (num_consistent + 1));
+      p.bgr = b | (g << 8) | (rr << 16);
+      pts[idx] = p;
+      accept[idx] = 1;
+    }
+  }
+}
+
+void launch_fuse_view(const FuseView* views, int i, const FuseSrcList& srcs, int W, int H, FusedPointDev* pts, uint8_t* accept,
+                      int num_sms, cudaStream_t stream) {
+  k_fuse_view<<<num_sms * 8, 256, 0, stream>>>(views, i, srcs, W, H, pts, accept);
+}
+
+size_t fuse_select_temp_bytes(int n) {
+  size_t bytes = 0;
+  cub::DeviceSelect::Flagged(nullptr, bytes, (const FusedPointDev*)nullptr, (const uint8_t*)nullptr, (FusedPointDev*)nullptr, (int*)nullptr, n);
+  return bytes;
+}
+void launch_fuse_select(void* temp, size_t temp_bytes, const FusedPointDev* pts, const uint8_t* accept, FusedPointDev* out, int* n_out, int n,
+                        cudaStream_t stream) {
+  cub::DeviceSelect::Flagged(temp, temp_bytes, pts, accept, out, n_out, n, stream);
+}
+
+}  // namespace dpe

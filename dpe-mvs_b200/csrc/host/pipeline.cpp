@@ -66,6 +66,7 @@ void parallel_for(int n, int n_threads, const std::function<void(int)>& fn) {
 
 struct Timing {
   double load = 0, prep = 0, upload = 0, stages = 0, output = 0, fusion = 0, total = 0, gpu_ms = 0;
+  double up_create = 0, up_views = 0, up_commit = 0;  // parts of `upload` on the first GPU
   long long launches = 0;
 };
 
@@ -231,8 +232,10 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     std::vector<std::thread> th;
     for (int g = 0; g < G; ++g) th.emplace_back([&, g]() {
       auto bad = [&](const char* what) { errs[g] = std::string(what) + ": " + (ctxs[g] ? dpe_last_error(ctxs[g]) : ""); };
+      const double tu0 = now_s();
       if (dpe_ctx_create(&ctxs[g], gpus[g]) != DPE_OK) { errs[g] = "cannot create context"; return; }
       dpe_ctx* c = ctxs[g];
+      const double tu1 = now_s();
       if (dpe_scene_begin(c, n_views, width, height, round_num)) return bad("scene_begin");
       for (int v = 0; v < n_views; ++v)
         if (dpe_scene_set_view(c, v, grays[v].d.data(), cams[v].K, cams[v].R, cams[v].t, cams[v].depth_min, cams[v].depth_max))
@@ -249,7 +252,9 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
           if (dpe_scene_set_prep(c, v, k, prep[v].edge[j].d.data(), prep[v].label[j].data())) return bad("set_prep");
         }
       if (dpe_scene_set_shard(c, first, count, slots_per_rank, G)) return bad("set_shard");
+      const double tu2 = now_s();
       if (dpe_scene_commit(c)) return bad("commit");
+      if (g == 0) { tm.up_create = tu1 - tu0; tm.up_views = tu2 - tu1; tm.up_commit = now_s() - tu2; }
     });
     for (auto& t : th) t.join();
     for (int g = 0; g < G; ++g)
@@ -400,34 +405,31 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     if (write_fail.load()) { std::cerr << "DPE-MVS: cannot write the .npy outputs\n"; return fail("write", nullptr); }
   }
   tm.output = now_s() - t0;
-  for (auto* c : ctxs) dpe_ctx_destroy(c);
-  ctxs.assign(G, nullptr);
-
   if (fusion) {
+    // on the device of the first context: maps of every problem view + colour images go up, the cloud comes back
     t0 = now_s();
-    FusionInput fi;
-    fi.width = width; fi.height = height;
-    fi.n_views = n_problems;
-    fi.depth = &all_depth; fi.normal = &all_normal; fi.state = &all_state;
-    fi.cams = &cams;
-    for (int v = 0; v < n_problems; ++v) {
-      std::vector<int> src;
-      for (int s : problems[v].src_image_ids) { const int sv = id_to_view[s]; if (sv < n_problems) src.push_back(sv); else src.push_back(-1); }
-      fi.src.push_back(src);
-    }
-    std::vector<std::vector<uint8_t>> colors(n_problems);
+    dpe_ctx* fc = ctxs[0];
+    cudaSetDevice(gpus[0]);
+    std::vector<uint8_t> color;
     for (int v = 0; v < n_problems; ++v) {
       int w, h;
-      if (!jpeg_decode_bgr(dec, dense + "/images/" + format_index(view_ids[v]) + ".jpg", &colors[v], &w, &h, &err)) {
-        // grey-only JPEG: replicate luma
-        colors[v].resize(P * 3);
-        for (size_t i = 0; i < P; ++i) colors[v][3 * i] = colors[v][3 * i + 1] = colors[v][3 * i + 2] = grays[v].d[i];
+      if (!jpeg_decode_bgr(dec, dense + "/images/" + format_index(view_ids[v]) + ".jpg", &color, &w, &h, &err)) {
+        color.resize(P * 3);  // grey-only JPEG: replicate luma
+        for (size_t i = 0; i < P; ++i) color[3 * i] = color[3 * i + 1] = color[3 * i + 2] = grays[v].d[i];
       }
+      if (dpe_fuse_set_view(fc, v, all_depth[v].data(), all_normal[v].data(), all_state[v].data(), color.data())) return fail("fuse_set_view", fc);
+      std::vector<float>().swap(all_depth[v]); std::vector<float>().swap(all_normal[v]);
     }
-    fi.bgr = &colors;
-    run_fusion(fi, dense + "/DPE/DPE.ply");
+    size_t n_points = 0;
+    if (dpe_fuse_run(fc, &n_points)) return fail("fuse_run", fc);
+    std::vector<float> xyz(n_points * 3);
+    std::vector<uint8_t> bgr(n_points * 3);
+    if (n_points && dpe_fuse_get(fc, xyz.data(), bgr.data())) return fail("fuse_get", fc);
+    if (!write_ply(dense + "/DPE/DPE.ply", xyz.data(), bgr.data(), n_points)) { std::cerr << "DPE-MVS: cannot write DPE.ply\n"; return fail("write_ply", nullptr); }
     tm.fusion = now_s() - t0;
   }
+  for (auto* c : ctxs) dpe_ctx_destroy(c);
+  ctxs.assign(G, nullptr);
   jpeg_decoder_destroy(dec);
 
   // ---- cleanup of intermediates the reference deletes (main.cpp:581-595) ------------------------
@@ -444,9 +446,9 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     if (f) {
       fprintf(f,
               "{\"views\": %d, \"gpus\": %d, \"width\": %d, \"height\": %d, \"load_s\": %.6f, \"prep_s\": %.6f, "
-              "\"upload_s\": %.6f, \"stages_s\": %.6f, \"output_s\": %.6f, \"fusion_s\": %.6f, \"total_s\": %.6f, "
+              "\"upload_s\": %.6f, \"upload_parts_s\": [%.6f, %.6f, %.6f], \"stages_s\": %.6f, \"output_s\": %.6f, \"fusion_s\": %.6f, \"total_s\": %.6f, "
               "\"gpu_ms\": %.3f, \"kernel_launches\": %lld}\n",
-              n_problems, G, width, height, tm.load, tm.prep, tm.upload, tm.stages, tm.output, tm.fusion, tm.total,
+              n_problems, G, width, height, tm.load, tm.prep, tm.upload, tm.up_create, tm.up_views, tm.up_commit, tm.stages, tm.output, tm.fusion, tm.total,
               tm.gpu_ms, tm.launches);
       fclose(f);
     }

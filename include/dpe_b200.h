@@ -173,6 +173,17 @@ DPE_API int dpe_get_profile(dpe_ctx* ctx, double* ms, double* units, long long* 
 DPE_API int dpe_bench_ncc(dpe_ctx* ctx, int view, int variant, int n_cand, int reps, double* units_per_s,
                   double* checksum);
 
+/* --- depth-map fusion on the device (replaces DPE::RunFusion, DPE.cpp:1220-1370, and the point list
+ *     ExportPointCloud writes, DPE.cpp:532-572) -----------------------------------------------------
+ * Inputs are the final maps of every problem view at full resolution (as dpe_get_maps returns them,
+ * depth already zeroed where the pixel state is UNKNOWN) and the colour image (B,G,R interleaved);
+ * cameras and source lists are the scene's.  Views without maps are skipped as sources.  dpe_fuse_run
+ * fuses the views in index order; dpe_fuse_get copies the cloud out (n_points x 3 each). */
+DPE_API int dpe_fuse_set_view(dpe_ctx* ctx, int view, const float* depth, const float* normal3, const uint8_t* state,
+                      const uint8_t* bgr);
+DPE_API int dpe_fuse_run(dpe_ctx* ctx, size_t* n_points);
+DPE_API int dpe_fuse_get(dpe_ctx* ctx, float* xyz, uint8_t* bgr);
+
 /* --- micro-benchmarks used for the roofline denominators ------------------ */
 /* filtered tex2D<float> taps per second on a WxH float texture */
 DPE_API int dpe_probe_tex_rate(dpe_ctx* ctx, int width, int height, int iters, double* taps_per_s);

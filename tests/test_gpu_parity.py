@@ -353,6 +353,74 @@ def test_pipeline_python_api_and_cli(c1_folder):
         assert not (d / "edge.npy").exists()
 
 
+def _read_ply(path):
+    raw = Path(path).read_bytes()
+    head, body = raw.split(b"end_header\n", 1)
+    n = int([l for l in head.decode().split("\n") if l.startswith("element vertex")][0].split()[-1])
+    assert len(body) == n * 15
+    rec = np.frombuffer(body, np.dtype([("xyz", "<f4", 3), ("bgr", "u1", 3)]))
+    return rec["xyz"].copy(), rec["bgr"].copy()
+
+
+def test_device_fusion_matches_cpu_oracle(c1_folder):
+    """dpe_fuse_* (csrc/dpe_fusion.cu) against the CPU restatement of the reference's RunFusion
+    (oracle/fusion_oracle.cpp) on this implementation's own maps: same points up to the one documented
+    difference (two pixels of one view may both use a source pixel), and DPE.ply through the pipeline."""
+    import cv2
+    import DPE_MVS
+    spec, folder = c1_folder
+    V, H, W = spec.n_views, spec.height, spec.width
+    shutil.rmtree(folder / "DPE", ignore_errors=True)
+    assert DPE_MVS.dpe_mvs(str(folder), 0, False, True, False, True, True, True, False) == 0
+    xyz_p, bgr_p = _read_ply(folder / "DPE" / "DPE.ply")
+    assert len(xyz_p) > 0.5 * H * W
+    # the same maps through the C ABI and through the oracle
+    rp = synth.read_pairs(folder / "pair.txt")
+    cams = [synth.read_cam(folder / "cams" / f"{v:08d}_cam.txt") for v in range(V)]
+    maps, cols = [], []
+    for v in range(V):
+        d = folder / "DPE" / f"{v:08d}"
+        weak = np.load(d / "weak.npy")
+        state = np.where(weak == 1, capi.WEAK, np.where(weak == 2, capi.STRONG, capi.UNKNOWN)).astype(np.uint8)
+        maps.append(dict(depth=np.load(d / "depth.npy"), normal=np.load(d / "normal.npy"), state=state))
+        cols.append(cv2.imread(str(folder / "images" / f"{v:08d}.jpg"), cv2.IMREAD_COLOR))
+    grays = [cv2.cvtColor(c, cv2.COLOR_BGR2GRAY) for c in cols]
+    ctx = capi.Context(0)
+    capi.upload_scene(ctx, grays, [(c[0], c[1], c[2]) for c in cams], [(c[3], c[4]) for c in cams], [s for (_, s) in rp])
+    xyz_g, bgr_g = ctx.fuse(maps, cols)
+    ctx.close()
+    lib = C.CDLL(str(ROOT / "oracle" / "_ref" / "libfusion_oracle.so"))
+    lib.fusion_oracle_run.restype = C.c_long
+    P = H * W
+    dep = np.ascontiguousarray(np.stack([m["depth"] for m in maps]), np.float32)
+    nor = np.ascontiguousarray(np.stack([m["normal"] for m in maps]), np.float32)
+    sta = np.ascontiguousarray(np.stack([m["state"] for m in maps]), np.uint8)
+    col = np.ascontiguousarray(np.stack(cols), np.uint8)
+    K = np.ascontiguousarray(np.stack([c[0] for c in cams]), np.float32)
+    R = np.ascontiguousarray(np.stack([c[1] for c in cams]), np.float32)
+    t = np.ascontiguousarray(np.stack([c[2] for c in cams]), np.float32)
+    ms = max(len(s) for (_, s) in rp)
+    src = np.full((V, ms), -1, np.int32)
+    for v, (_, s) in enumerate(rp):
+        src[v, :len(s)] = s
+    cap = V * P
+    xyz_c = np.empty((cap, 3), np.float32); bgr_c = np.empty((cap, 3), np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = lib.fusion_oracle_run(V, W, H, vp(dep), vp(nor), vp(sta), vp(col), vp(K), vp(R), vp(t), vp(src), ms, vp(xyz_c), vp(bgr_c), C.c_long(cap))
+    xyz_c, bgr_c = xyz_c[:n], bgr_c[:n]
+    # point counts within 2 %, and almost every oracle point is in the device cloud (to 1e-4 scene units)
+    assert abs(len(xyz_g) - n) <= 0.02 * n, (len(xyz_g), n)
+    key = lambda a: set(map(tuple, np.round(a.astype(np.float64) * 1e4).astype(np.int64)))
+    kg, kc = key(xyz_g), key(xyz_c)
+    assert len(kg & kc) >= 0.97 * len(kc), (len(kg & kc), len(kc), len(kg))
+    # the pipeline's own cloud: it fuses the maps before depth.npy zeroes the UNKNOWN pixels (the reference
+    # fuses depths.dmb, DPE.cpp:1242-1270), so it is a little larger
+    assert len(xyz_g) <= len(xyz_p) <= 1.03 * len(xyz_g), (len(xyz_p), len(xyz_g))
+    # the points lie on the scene: floor z = 0 or the slanted panel, both within the scene's extent
+    assert np.isfinite(xyz_g).all() and np.abs(xyz_g).max() < 10.0
+    assert (np.abs(xyz_g[:, 2]) < 0.02).mean() > 0.5
+
+
 def test_pipeline_rejects_bad_input(tmp_path):
     import DPE_MVS
     (tmp_path / "pair.txt").write_text("1\n0\n0\n")
