@@ -41,7 +41,7 @@ struct ViewData {
   uint8_t* state = nullptr;
   uint32_t* selected = nullptr;
   int cur_scale = -1;  // scale index of planes/state/selected
-  uint8_t* gray_full = nullptr;  // uploaded u8 image (device), freed after commit
+  uint8_t* gray_full = nullptr;  // uploaded u8 image: this view's part of dpe_ctx::gray_slab
 };
 
 struct FuseData {
@@ -72,6 +72,10 @@ struct dpe_ctx {
   // one layered array + texture object per scale: layer v = image of view v (float, linear filter)
   std::vector<cudaArray_t> scale_arr;
   std::vector<cudaTextureObject_t> scale_tex;
+  // slabs: one allocation for all uploaded u8 images, one per scale for all float copies (a cudaMalloc /
+  // cudaFree per view serialises on the driver lock and synchronises the device)
+  uint8_t* gray_slab = nullptr;
+  std::vector<float*> lin_slab;
   bool committed = false;
   // shard
   int first_view = 0, n_local = 0, slots_per_rank = 0, n_ranks = 1;
@@ -126,10 +130,13 @@ static LaunchCfg cfg_of(dpe_ctx* ctx) { return LaunchCfg{ctx->num_sms, &ctx->lau
 
 static void free_scene(dpe_ctx* ctx) {
   for (auto& v : ctx->views) {
-    for (auto& s : v.scales) { cudaFree(s.lin); cudaFree(s.edge); cudaFree(s.label); }
-    cudaFree(v.planes); cudaFree(v.state); cudaFree(v.selected); cudaFree(v.gray_full);
+    for (auto& s : v.scales) { cudaFree(s.edge); cudaFree(s.label); }
+    cudaFree(v.planes); cudaFree(v.state); cudaFree(v.selected);
   }
   ctx->views.clear();
+  cudaFree(ctx->gray_slab); ctx->gray_slab = nullptr;
+  for (auto p : ctx->lin_slab) cudaFree(p);
+  ctx->lin_slab.clear();
   for (auto t : ctx->scale_tex) if (t) cudaDestroyTextureObject(t);
   for (auto a : ctx->scale_arr) if (a) cudaFreeArray(a);
   ctx->scale_tex.clear(); ctx->scale_arr.clear();
@@ -220,7 +227,8 @@ int dpe_scene_set_view(dpe_ctx* ctx, int view, const uint8_t* gray, const float 
   ViewData& v = ctx->views[view];
   host_cam_set(&v.cam, K, R, t, depth_min, depth_max);
   const size_t n = (size_t)ctx->W * ctx->H;
-  if (!v.gray_full) CK(cudaMalloc(&v.gray_full, n));
+  if (!ctx->gray_slab) CK(cudaMalloc(&ctx->gray_slab, n * ctx->n_views));
+  v.gray_full = ctx->gray_slab + n * view;
   CK(cudaMemcpy(v.gray_full, gray, n, cudaMemcpyHostToDevice));
   v.have_img = true;
   return DPE_OK;
@@ -279,14 +287,13 @@ int dpe_scene_commit(dpe_ctx* ctx) {
     td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
     CK(cudaCreateTextureObject(&ctx->scale_tex[k], &rd, &td, nullptr));
   }
+  ctx->lin_slab.assign(ctx->n_scales, nullptr);
+  for (int k = 0; k < ctx->n_scales; ++k)
+    CK(cudaMalloc(&ctx->lin_slab[k], (size_t)ctx->n_views * ctx->sw[k] * ctx->sh[k] * sizeof(float)));
   for (int vi = 0; vi < ctx->n_views; ++vi) {
     ViewData& v = ctx->views[vi];
     if (!v.have_img) FAIL(DPE_ERR_STATE, "view without image");
-    for (int k = 0; k < ctx->n_scales; ++k) {
-      ScaleImg& s = v.scales[k];
-      const int w = ctx->sw[k], h = ctx->sh[k];
-      CK(cudaMalloc(&s.lin, (size_t)w * h * sizeof(float)));
-    }
+    for (int k = 0; k < ctx->n_scales; ++k) v.scales[k].lin = ctx->lin_slab[k] + (size_t)vi * ctx->sw[k] * ctx->sh[k];
     launch_u8_to_f32(v.gray_full, v.scales[top].lin, ctx->W * ctx->H, cfg, 0);
     // every level is resized from the full-resolution image (DPE.cpp:798-820)
     for (int k = 0; k < top; ++k)
@@ -301,7 +308,7 @@ int dpe_scene_commit(dpe_ctx* ctx) {
       cp.kind = cudaMemcpyDeviceToDevice;
       CK(cudaMemcpy3DAsync(&cp, 0));
     }
-    CK(cudaFree(v.gray_full)); v.gray_full = nullptr;
+    v.gray_full = nullptr;
   }
   // depth atlases
   const int slots = ctx->slots_per_rank * ctx->n_ranks;
@@ -450,6 +457,9 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
     cudaStream_t st = s.stream;
     // every (view, stage) starts from curand_init(seed, y, x) like the reference (DPE.cu:1020-1033)
     CK(cudaMemcpyAsync(s.rng, ctx->rng_table[k], P * sizeof(Xorwow), cudaMemcpyDeviceToDevice, st));
+    // radius_cuda is a fresh allocation per view-stage in the reference and only written for WEAK pixels with
+    // >= 3 anchors (DPE.cu:2945-2948 returns before): start every view-stage from zeros, not from the last view's
+    if (p->use_apd) CK(cudaMemsetAsync(s.radius, 0, P * sizeof(int), st));
     // in profile mode every launch is bracketed by CUDA events on its own stream and the
     // eval-unit counter is read back after it
     auto L = [&](int cls, void (*fn)(const KernelParams&, const LaunchCfg&, cudaStream_t)) {
