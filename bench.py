@@ -238,9 +238,12 @@ def run_ours(args):
         tt = torch.tensor([dev_ms, wall * 1e3, float(launches), gather_ms_acc[0]], dtype=torch.float64, device="cuda")
         mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms, wall_ms, launches, gather_ms = float(mx[0]), float(mx[1]), int(sm[2]), float(mx[3])
+        mn = tt.clone(); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        # the all-gather time of a rank includes waiting for slower ranks; the minimum over ranks (the rank
+        # that arrives last) is what the collective itself costs, the maximum is the load imbalance
+        dev_ms, wall_ms, launches, gather_ms, gather_wait_ms = float(mx[0]), float(mx[1]), int(sm[2]), float(mn[3]), float(mx[3])
     else:
-        wall_ms, gather_ms = wall * 1e3, 0.0
+        wall_ms, gather_ms, gather_wait_ms = wall * 1e3, 0.0, 0.0
     ms_per_step = dev_ms / args.steps
     value = V / (ms_per_step * 1e-3)
 
@@ -318,6 +321,7 @@ def run_ours(args):
                        "rng_seed": SEED},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "wall_ms_per_step": wall_ms / args.steps, "allgather_ms_per_step": gather_ms / args.steps,
+            "allgather_wait_ms_per_step_slowest_rank": gather_wait_ms / args.steps,
         }
         if prof is not None:
             tot_units = sum(c["units"] for c in prof.values())
