@@ -267,8 +267,21 @@ def run_ours(args):
         dom = max(prof, key=lambda k: prof[k]["ms"])
         d = prof[dom]
         taps_per_s = d["units"] * 36.0 / (d["ms"] * 1e-3)
+        traffic = None
+        try:
+            traffic = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text()).get(dom, {}).get("bytes_per_launch")
+        except Exception:
+            pass
+        hbm_peak = None
+        try:
+            hbm_peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("hbm_gbs")
+        except Exception:
+            pass
         roof = {"bound": "texture", "kernel": dom, "achieved": taps_per_s / 1e9, "peak": tex_peak / 1e9, "unit": "Gtap/s",
-                "frac": taps_per_s / tex_peak, "traffic": None,
+                "frac": taps_per_s / tex_peak, "traffic": traffic,
+                "traffic_note": "DRAM bytes per full-resolution launch of this kernel class from the committed ncu --set full capture (profiles/ncu_traffic.json); the kernel is bound by the texture pipe, not HBM",
+                "hbm_gbs_of_dominant_kernel": (traffic / (d["ms"] / max(d["launches"], 1) * 1e-3) / 1e9) if traffic else None,
+                "hbm_peak_gbs_measured": hbm_peak,
                 "peak_source": "dpe_probe_tex_rate (filtered tex2D<float> microbenchmark, this run); MEASURED_PEAKS.json has no texture figure",
                 "avg_launch_ms": d["ms"] / max(d["launches"], 1), "units_per_launch": d["units"] / max(d["launches"], 1),
                 "share_of_step": d["ms"] / tot_ms,

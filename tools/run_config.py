@@ -1,0 +1,38 @@
+"""Runs DPE_MVS.dpe_mvs() on one of the BASELINE.json scene shapes (optionally reduced) and reports timing and
+accuracy against the analytic ground truth.  usage: run_config.py <c1|c2|c4|c5> [--views N] [--scale S] [--fusion] [--gpus K]"""
+import argparse, json, os, shutil, sys, time
+from pathlib import Path
+import numpy as np
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "dpe-mvs_b200"))
+import synth, DPE_MVS
+ap = argparse.ArgumentParser()
+ap.add_argument("config"); ap.add_argument("--views", type=int, default=None); ap.add_argument("--scale", type=float, default=1.0)
+ap.add_argument("--fusion", action="store_true"); ap.add_argument("--gpus", type=int, default=1)
+args = ap.parse_args()
+tag = f"{args.config}_v{args.views}_s{args.scale}"
+folder = Path("/tmp") / f"cfg_{tag}"
+shutil.rmtree(folder, ignore_errors=True)
+spec = synth.make_scene(args.config, scale=args.scale, n_views=args.views)
+t0 = time.time(); synth.write_scene(spec, folder, save_gt="depth"); t_gen = time.time() - t0
+if args.gpus > 1:
+    os.environ["DPE_GPUS"] = ",".join(str(i) for i in range(args.gpus))
+tj = folder / "timing.json"; os.environ["DPE_TIMING_JSON"] = str(tj)
+weak = args.config == "c4"
+t0 = time.perf_counter()
+DPE_MVS.dpe_mvs(str(folder), 0 if args.gpus == 1 else -1, False, args.fusion, False, True, True, weak, weak)
+dt = time.perf_counter() - t0
+out = dict(config=args.config, views=spec.n_views, width=spec.width, height=spec.height, n_src=spec.n_src, gpus=args.gpus,
+           fusion=args.fusion, scene_gen_s=t_gen, seconds=dt, depth_maps_per_s=spec.n_views / dt, breakdown=json.loads(tj.read_text()))
+acc = []
+for v in range(0, spec.n_views, max(1, spec.n_views // 8)):
+    d = np.load(folder / "DPE" / f"{v:08d}" / "depth.npy"); g = np.load(folder / "gt" / f"{v:08d}_depth.npy")
+    m = (g > 0) & (d > 0); rel = np.abs(d - g) / np.maximum(g, 1e-9)
+    acc.append(dict(view=v, cover=float((d > 0).mean()), depth_1pct=float((rel[m] < 0.01).mean())))
+out["accuracy"] = acc
+if args.fusion:
+    ply = folder / "DPE" / "DPE.ply"
+    head = ply.read_bytes()[:200].decode(errors="ignore")
+    out["ply_points"] = int([l for l in head.split("\n") if l.startswith("element vertex")][0].split()[-1])
+print(json.dumps(out))
+(ROOT / "gpurun_out" / f"cfg_{tag}.json").write_text(json.dumps(out, indent=1))
