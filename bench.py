@@ -280,7 +280,6 @@ def run_ours(args):
         roof = {"bound": "texture", "kernel": dom, "achieved": taps_per_s / 1e9, "peak": tex_peak / 1e9, "unit": "Gtap/s",
                 "frac": taps_per_s / tex_peak, "traffic": traffic,
                 "traffic_note": "DRAM bytes per full-resolution launch of this kernel class from the committed ncu --set full capture (profiles/ncu_traffic.json); the kernel is bound by the texture pipe, not HBM",
-                "hbm_gbs_of_dominant_kernel": (traffic / (d["ms"] / max(d["launches"], 1) * 1e-3) / 1e9) if traffic else None,
                 "hbm_peak_gbs_measured": hbm_peak,
                 "peak_source": "dpe_probe_tex_rate (filtered tex2D<float> microbenchmark, this run); MEASURED_PEAKS.json has no texture figure",
                 "avg_launch_ms": d["ms"] / max(d["launches"], 1), "units_per_launch": d["units"] / max(d["launches"], 1),
