@@ -278,6 +278,40 @@ def test_results_do_not_depend_on_sharding():
         c.close()
 
 
+def test_edge_cases_sizes_and_source_counts():
+    """Ragged image sizes (not multiples of the 32x8 tile), the maximum of 31 source views, a view without any
+    source, a source that is not itself a reference view: the whole schedule runs, maps have the
+    right shapes and sane values."""
+    spec, grays, cams, drs, pairs, gt = small_scene("c1", 0.25)
+    # ragged crop: 157 x 83
+    g2 = [np.ascontiguousarray(g[:83, :157]) for g in grays]
+    V = len(g2)
+    ctx = capi.Context(0)
+    ns = capi.compute_round_num(157, 83)
+    ctx.scene_begin(V, 157, 83, ns)
+    for v in range(V):
+        ctx.set_view(v, g2[v], *cams[v], *drs[v])
+    ctx.set_pairs(0, [1, 2, 3, 4] * 7 + [1, 2, 3])      # 31 sources (MAX_IMAGES - 1)
+    ctx.set_pairs(1, [])                                   # no source at all
+    ctx.set_pairs(2, [0, 4])
+    ctx.set_pairs(3, [2])
+    ctx.set_pairs(4, [0])
+    ctx.commit()
+    for (k, p) in capi.stage_schedule(ns):
+        ctx.run_stage(k, p, 5)
+        ctx.stage_commit()
+    m0 = ctx.get_maps(0, ns - 1)
+    assert m0["depth"].shape == (83, 157) and m0["normal"].shape == (83, 157, 3)
+    assert np.isfinite(m0["depth"]).all() and set(np.unique(m0["state"])) <= {0, 1, 2}
+    valid = m0["depth"] > 0
+    assert valid.mean() > 0.5
+    nn = np.linalg.norm(m0["normal"][valid], axis=-1)
+    assert np.abs(nn - 1).max() < 1e-3
+    m1 = ctx.get_maps(1, ns - 1)                            # nothing to match against: every pixel UNKNOWN, depth kept finite
+    assert (m1["state"] == capi.UNKNOWN).all()
+    ctx.close()
+
+
 def test_error_paths():
     spec, grays, cams, drs, pairs, gt = small_scene("c1", 0.25)
     ctx = capi.Context(0)

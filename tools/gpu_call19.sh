@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu19.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu19.log
+echo done
