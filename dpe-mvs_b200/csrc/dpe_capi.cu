@@ -28,6 +28,7 @@ namespace {
 struct ScaleImg {
   float* lin = nullptr;          // W*H float
   uint8_t* edge = nullptr;       // edges_k (optional)
+  uint32_t* edge_bits = nullptr; // coarsest scale only: the same map, one bit per pixel (rows of (w+31)/32 words)
   int32_t* label = nullptr;      // labels_k (optional)
 };
 
@@ -130,7 +131,7 @@ static LaunchCfg cfg_of(dpe_ctx* ctx) { return LaunchCfg{ctx->num_sms, &ctx->lau
 
 static void free_scene(dpe_ctx* ctx) {
   for (auto& v : ctx->views) {
-    for (auto& s : v.scales) { cudaFree(s.edge); cudaFree(s.label); }
+    for (auto& s : v.scales) { cudaFree(s.edge); cudaFree(s.edge_bits); cudaFree(s.label); }
     cudaFree(v.planes); cudaFree(v.state); cudaFree(v.selected);
   }
   ctx->views.clear();
@@ -251,6 +252,15 @@ int dpe_scene_set_prep(dpe_ctx* ctx, int view, int scale, const uint8_t* edge, c
   if (edge) {
     if (!s.edge) CK(cudaMalloc(&s.edge, n));
     CK(cudaMemcpy(s.edge, edge, n, cudaMemcpyHostToDevice));
+    if (scale == 0) {  // edge_low_res of every stage of this view: bit-packed copy for the Bresenham walks
+      const int w = ctx->sw[0], h = ctx->sh[0], words = (w + 31) / 32;
+      std::vector<uint32_t> bits((size_t)words * h, 0u);
+      for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+          if (edge[(size_t)y * w + x]) bits[(size_t)y * words + (x >> 5)] |= 1u << (x & 31);
+      if (!s.edge_bits) CK(cudaMalloc(&s.edge_bits, bits.size() * sizeof(uint32_t)));
+      CK(cudaMemcpy(s.edge_bits, bits.data(), bits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
   }
   if (label) {
     if (!s.label) CK(cudaMalloc(&s.label, n * sizeof(int32_t)));
@@ -392,6 +402,7 @@ static void fill_args(dpe_ctx* ctx, int view, int k, const dpe_stage_params* p, 
   a.edge = v.scales[k].edge ? v.scales[k].edge : ctx->zero_edge;
   a.edge_low = v.scales[0].edge ? v.scales[0].edge : ctx->zero_edge;  // coarsest scale (DPE.cpp:1036-1045)
   a.low_w = ctx->sw[0]; a.low_h = ctx->sh[0];
+  a.edge_low_bits = v.scales[0].edge ? v.scales[0].edge_bits : nullptr; a.low_words = (ctx->sw[0] + 31) / 32;
   a.edge_neigh = s.edge_neigh; a.complexity = s.complexity;
   a.label = v.scales[k].label ? v.scales[k].label : ctx->zero_label;
   a.label_boundary = s.label_boundary; a.weak_reliable = s.weak_reliable; a.nearest_strong = s.nearest_strong;

@@ -55,6 +55,8 @@ struct StageArgs {
   int* radius;
   const uint8_t* edge;      // edges_k
   const uint8_t* edge_low;  // edges of the coarsest scale (edge_low_res_cuda)
+  const uint32_t* edge_low_bits;  // the same map, one bit per pixel, rows of low_words 32-bit words (nullptr: use edge_low)
+  int low_words;
   int low_w, low_h;
   short2* edge_neigh;       // 8 per pixel
   float* complexity;        // complex_cuda

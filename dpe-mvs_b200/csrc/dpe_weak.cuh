@@ -28,7 +28,14 @@ DPE_HD bool point_in_triangle(short2 A, short2 B, short2 C, int px, int py) {  /
   return t1 * t2 >= 0 && t1 * t3 >= 0;
 }
 
-DPE_HD bool bresenham_walk(const uint8_t* edge, int lw, int lh, int x0, int y0, int x1, int y1, int max_step) {
+// coarse edge map lookup: the bit-packed copy when there is one (48 KB instead of 381 KB for a 756x504 map,
+// so the Bresenham walks of the anchor search stay in L1)
+DPE_HD bool edge_low_at(const StageArgs& a, const int x, const int y) {
+  if (a.edge_low_bits) return (a.edge_low_bits[y * a.low_words + (x >> 5)] >> (x & 31)) & 1u;
+  return a.edge_low[x + y * a.low_w] != 0;
+}
+
+DPE_HD bool bresenham_walk(const StageArgs& a, int lw, int lh, int x0, int y0, int x1, int y1, int max_step) {
   const int dx = x1 > x0 ? x1 - x0 : x0 - x1, sx = x0 < x1 ? 1 : -1;
   const int dy = y1 > y0 ? y1 - y0 : y0 - y1, sy = y0 < y1 ? 1 : -1;
   int err = (dx > dy ? dx : dy) / 2, step = 0;
@@ -41,7 +48,7 @@ DPE_HD bool bresenham_walk(const uint8_t* edge, int lw, int lh, int x0, int y0, 
     if (e2 < dy) { err += dx; y0 += sy; }
     // the reference indexes the coarse edge map unchecked; the walk can step one pixel past
     // the end point, so guard the read
-    if (x0 >= 0 && y0 >= 0 && x0 < lw && y0 < lh && edge[x0 + y0 * lw]) return true;
+    if (x0 >= 0 && y0 >= 0 && x0 < lw && y0 < lh && edge_low_at(a, x0, y0)) return true;
     if (++step >= max_step) break;
   }
   return false;
@@ -55,10 +62,26 @@ DPE_HD bool bresenham_line(const StageArgs& a, int ax, int ay, int bx, int by) {
   const int max_step = (int)round(imax(lh, lw) / 60.0);
   const int bx0 = (int)fminf(roundf(bx * scale_x), (float)(lw - 1)), by0 = (int)fminf(roundf(by * scale_y), (float)(lh - 1));
   const int ax0 = (int)fminf(roundf(ax * scale_x), (float)(lw - 1)), ay0 = (int)fminf(roundf(ay * scale_y), (float)(lh - 1));
-  if (bresenham_walk(a.edge_low, lw, lh, bx0, by0, ax0, ay0, max_step)) return true;
-  if (bresenham_walk(a.edge_low, lw, lh, ax0, ay0, bx0, by0, max_step)) return true;
+  if (bresenham_walk(a, lw, lh, bx0, by0, ax0, ay0, max_step)) return true;
+  if (bresenham_walk(a, lw, lh, ax0, ay0, bx0, by0, max_step)) return true;
   return false;
 }
+
+// "does the segment between anchors i and j cross an edge" cache of the RANSAC loops: one tested bit and
+// one result bit per pair (the reference keeps a byte per pair, DPE.cu:2289, 2957)
+template <int N>
+struct PairCache {
+  unsigned long long tested[N], crossed[N];
+  DPE_HD void clear() { for (int i = 0; i < N; ++i) { tested[i] = 0ull; crossed[i] = 0ull; } }
+  DPE_HD bool crosses(const StageArgs& a, const short2* pts, const int i, const int j) {
+    if (!((tested[i] >> j) & 1ull)) {
+      const bool c = bresenham_line(a, pts[i].x, pts[i].y, pts[j].x, pts[j].y);
+      tested[i] |= 1ull << j; tested[j] |= 1ull << i;
+      if (c) { crossed[i] |= 1ull << j; crossed[j] |= 1ull << i; }
+    }
+    return (crossed[i] >> j) & 1ull;
+  }
+};
 
 // ---- GenEdgeInform, DPE.cu:2483-2591 -------------------------------------------------------
 DPE_HDN void edge_info_pixel(const StageArgs& a, const int x, const int y) {
@@ -286,8 +309,16 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
     float residuals[MAXP];
     for (int i = 0; i < MAXP; ++i) residuals[i] = 0.f;
     float temp_thr = ransac_threshold;
-    uint8_t edge_test[MAXP * MAXP];
-    for (int i = 0; i < MAXP * MAXP; ++i) edge_test[i] = 0;
+    PairCache<MAXP> edge_test;
+    edge_test.clear();
+    // pixel -> normalised image coordinates of every anchor, once (the reference recomputes the two
+    // divisions for every anchor of every RANSAC draw, DPE.cu:2383-2385)
+    float fxs[MAXP], fys[MAXP];
+    for (int si = 0; si < valid_count; ++si) {
+      fxs[si] = fast_div(spv[si].x - rc.cx, rc.fx);
+      fys[si] = fast_div(spv[si].y - rc.cy, rc.fy);
+    }
+    const float fx_c = fast_div(x - rc.cx, rc.fx), fy_c = fast_div(y - rc.cy, rc.fy);
     bool has_consist_normal_plane = false;
     bool must_in_triangle = !(center_label > 0 && edge_limit);
     while (iteration > 0 && max_iter > 0) {
@@ -298,13 +329,8 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
       if (ai == bi || bi == ci || ai == ci) continue;
       if (must_in_triangle && !point_in_triangle(spv[ai], spv[bi], spv[ci], x, y)) continue;
       if (edge_limit) {
-        if (edge_test[ai * MAXP + bi] == 0)
-          edge_test[ai * MAXP + bi] = edge_test[bi * MAXP + ai] = bresenham_line(a, spv[ai].x, spv[ai].y, spv[bi].x, spv[bi].y) ? 1 : 2;
-        if (edge_test[bi * MAXP + ci] == 0)
-          edge_test[bi * MAXP + ci] = edge_test[ci * MAXP + bi] = bresenham_line(a, spv[bi].x, spv[bi].y, spv[ci].x, spv[ci].y) ? 1 : 2;
-        if (edge_test[ci * MAXP + ai] == 0)
-          edge_test[ci * MAXP + ai] = edge_test[ai * MAXP + ci] = bresenham_line(a, spv[ci].x, spv[ci].y, spv[ai].x, spv[ai].y) ? 1 : 2;
-        if (edge_test[ai * MAXP + bi] == 1 || edge_test[bi * MAXP + ci] == 1 || edge_test[ci * MAXP + ai] == 1) continue;
+        const bool c0 = edge_test.crosses(a, spv, ai, bi), c1 = edge_test.crosses(a, spv, bi, ci), c2 = edge_test.crosses(a, spv, ci, ai);
+        if (c0 || c1 || c2) continue;
       }
       bool normal_consistency = false;
       if (a.geom && edge_limit) {
@@ -328,8 +354,7 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
       cv.w = -(cv.x * A.x + cv.y * A.y + cv.z * A.z);
       int temp_count = 0;
       for (int si = 0; si < valid_count; ++si) {
-        const float fxx = (spv[si].x - rc.cx) / rc.fx, fyy = (spv[si].y - rc.cy) / rc.fy;
-        const float fit_depth = -cv.w / (cv.x * fxx + cv.y * fyy + cv.z);
+        const float fit_depth = fast_div(-cv.w, cv.x * fxs[si] + cv.y * fys[si] + cv.z);
         const float distance = fabsf(fit_depth - spv3d[si].z);
         residuals[si] = distance;
         if (distance < temp_thr) temp_count++;
@@ -338,8 +363,7 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
       if (temp_count > max_count) {
         if (!must_in_triangle && point_in_triangle(spv[ai], spv[bi], spv[ci], x, y)) must_in_triangle = true;
         if (!has_consist_normal_plane && normal_consistency) has_consist_normal_plane = true;
-        const float fxx = (x - rc.cx) / rc.fx, fyy = (y - rc.cy) / rc.fy;
-        const float fit_depth = -cv.w / (cv.x * fxx + cv.y * fyy + cv.z);
+        const float fit_depth = fast_div(-cv.w, cv.x * fx_c + cv.y * fy_c + cv.z);
         best_plane = cv;
         max_count = temp_count;
         min_cost = fabsf(fit_depth - center_z);
@@ -357,8 +381,7 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
         }
       } else if (temp_count == max_count) {
         if (!must_in_triangle && point_in_triangle(spv[ai], spv[bi], spv[ci], x, y)) must_in_triangle = true;
-        const float fxx = (x - rc.cx) / rc.fx, fyy = (y - rc.cy) / rc.fy;
-        const float fit_depth = -cv.w / (cv.x * fxx + cv.y * fyy + cv.z);
+        const float fit_depth = fast_div(-cv.w, cv.x * fx_c + cv.y * fy_c + cv.z);
         const float cd = fabsf(fit_depth - center_z);
         if (cd < min_cost) { best_plane = cv; max_count = temp_count; min_cost = cd; }
       }
@@ -370,8 +393,8 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
 
   float weight[MAXP];
   for (int i = 0; i < valid_count; ++i) {
-    const float fxx = (spv[i].x - rc.cx) / rc.fx, fyy = (spv[i].y - rc.cy) / rc.fy;
-    const float fit_depth = -best_plane.w / (best_plane.x * fxx + best_plane.y * fyy + best_plane.z);
+    const float fxx = fast_div(spv[i].x - rc.cx, rc.fx), fyy = fast_div(spv[i].y - rc.cy, rc.fy);
+    const float fit_depth = fast_div(-best_plane.w, best_plane.x * fxx + best_plane.y * fyy + best_plane.z);
     const float distance = fabsf(fit_depth - spv3d[i].z);
     if (distance >= ransac_threshold) { spv[i] = make_short2(-1, -1); weight[i] = FLT_MAX; continue; }
     weight[i] = distance;
@@ -426,8 +449,13 @@ DPE_HDN void fit_plane_pixel(const StageArgs& a, const int x, const int y) {
   bool has_best = false, has_strong_plane = false;
   const int center_label = a.label[center];
   bool must_in_triangle = !(center_label > 0 && edge_limit);
-  uint8_t edge_test[NB * NB];
-  for (int i = 0; i < NB * NB; ++i) edge_test[i] = 0;
+  PairCache<NB> edge_test;
+  edge_test.clear();
+  float fxs[NB], fys[NB];
+  for (int si = 0; si < sc; ++si) {
+    fxs[si] = fast_div(sp[si].x - rc.cx, rc.fx);
+    fys[si] = fast_div(sp[si].y - rc.cy, rc.fy);
+  }
   while (iteration--) {
     const int ai = (int)(rng.next() % (uint32_t)sc), bi = (int)(rng.next() % (uint32_t)sc), ci = (int)(rng.next() % (uint32_t)sc);
     if (ai == bi || bi == ci || ai == ci) continue;
@@ -442,13 +470,8 @@ DPE_HDN void fit_plane_pixel(const StageArgs& a, const int x, const int y) {
     }
     if (must_in_triangle && !point_in_triangle(sp[ai], sp[bi], sp[ci], x, y)) continue;
     if (edge_limit) {
-      if (edge_test[ai * NB + bi] == 0)
-        edge_test[ai * NB + bi] = edge_test[bi * NB + ai] = bresenham_line(a, sp[ai].x, sp[ai].y, sp[bi].x, sp[bi].y) ? 1 : 2;
-      if (edge_test[bi * NB + ci] == 0)
-        edge_test[bi * NB + ci] = edge_test[ci * NB + bi] = bresenham_line(a, sp[bi].x, sp[bi].y, sp[ci].x, sp[ci].y) ? 1 : 2;
-      if (edge_test[ci * NB + ai] == 0)
-        edge_test[ci * NB + ai] = edge_test[ai * NB + ci] = bresenham_line(a, sp[ci].x, sp[ci].y, sp[ai].x, sp[ai].y) ? 1 : 2;
-      if (edge_test[ai * NB + bi] == 1 || edge_test[bi * NB + ci] == 1 || edge_test[ci * NB + ai] == 1) continue;
+      const bool c0 = edge_test.crosses(a, sp, ai, bi), c1 = edge_test.crosses(a, sp, bi, ci), c2 = edge_test.crosses(a, sp, ci, ai);
+      if (c0 || c1 || c2) continue;
     }
     const float3 A = sp3[ai], B = sp3[bi], C = sp3[ci];
     const float3 AC = make_float3(A.x - C.x, A.y - C.y, A.z - C.z), BC = make_float3(B.x - C.x, B.y - C.y, B.z - C.z);
@@ -464,8 +487,7 @@ DPE_HDN void fit_plane_pixel(const StageArgs& a, const int x, const int y) {
     float temp_cost = 0.f;
     for (int si = 0; si < sc; ++si) {
       if (si == ai || si == bi || si == ci) continue;
-      const float fxx = (sp[si].x - rc.cx) / rc.fx, fyy = (sp[si].y - rc.cy) / rc.fy;
-      const float fit_depth = -cv.w / (cv.x * fxx + cv.y * fyy + cv.z);
+      const float fit_depth = fast_div(-cv.w, cv.x * fxs[si] + cv.y * fys[si] + cv.z);
       temp_cost += fabsf(fit_depth - sp3[si].z);
     }
     if (temp_cost < min_cost) {

@@ -10,7 +10,9 @@ import capi
 from bench import ensure_scene, load_scene_arrays, product_prep
 
 n_prof = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-folder = ensure_scene("c2", 12, "c2v12")
+cfg = sys.argv[2] if len(sys.argv) > 2 else "c2"
+n_views = int(sys.argv[3]) if len(sys.argv) > 3 else 12
+folder = ensure_scene(cfg, n_views, f"{cfg}v{n_views}")
 grays, cams, drs, pairs = load_scene_arrays(folder)
 V = len(grays); H, W = grays[0].shape
 lib = capi.load()
