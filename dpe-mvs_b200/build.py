@@ -58,6 +58,11 @@ def build_lib(verbose=False, force=False) -> Path:
         o = OBJ / (src.stem + ".o")
         if force or _newer(o, [src] + hdrs):
             extra = ["-Xptxas", "-v"] if (verbose and src.suffix == ".cu") else []
+            if src.name == "dpe_kernels.cu":
+                # the reference is built with --use_fast_math (csrc/DPE-MVS/CMakeLists.txt:16): approximate
+                # division / sqrt / exp / sin / cos and flush-to-zero.  The kernels follow the reference's
+                # expressions, so the same flag gives the same kind of rounding in the same places.
+                extra = extra + ["--use_fast_math"]
             _run([NVCC, *ARCH, *COMMON, *extra, "-I", CSRC, "-I", HERE.parent / "include", "-c", src, "-o", o], verbose)
         objs.append(o)
     so = LIB / "libdpe_b200.so"

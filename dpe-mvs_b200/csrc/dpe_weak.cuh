@@ -651,7 +651,7 @@ __noinline__ DPE_HDN float ncc_new(const Env& env, const float c0, const WeakTab
   h[6] = sc.A[6] - sc.b[2] * m.x; h[7] = sc.A[7] - sc.b[2] * m.y; h[8] = sc.A[8] - sc.b[2] * m.z;
   {
     const float Z = h[6] * x + h[7] * y + h[8];
-    const float px = (h[0] * x + h[1] * y + h[2]) / Z, py = (h[3] * x + h[4] * y + h[5]) / Z;
+    const float px = fast_div(h[0] * x + h[1] * y + h[2], Z), py = fast_div(h[3] * x + h[4] * y + h[5], Z);
     if (px >= sc.width || px < 0.0f || py >= sc.height || py < 0.0f) return 2.0f;
   }
   float center_cost = 0.f, strong_cost = 0.f;
@@ -663,7 +663,7 @@ __noinline__ DPE_HDN float ncc_new(const Env& env, const float c0, const WeakTab
     const short2 np = T.anchor[k];
     {
       const float Z = h[6] * np.x + h[7] * np.y + h[8];
-      const float qx = (h[0] * np.x + h[1] * np.y + h[2]) / Z, qy = (h[3] * np.x + h[4] * np.y + h[5]) / Z;
+      const float qx = fast_div(h[0] * np.x + h[1] * np.y + h[2], Z), qy = fast_div(h[3] * np.x + h[4] * np.y + h[5], Z);
       if (qx < 0 || qy < 0 || qx >= W || qy >= H) {  // sic: reference-image size (DPE.cu:596)
         if (k != 0) {
           if ((T.asel[k] >> v) & 1u) { strong_cost += 2.0f; strong_count++; }

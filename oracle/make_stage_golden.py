@@ -132,9 +132,26 @@ def main():
     np.savez_compressed(ROOT / "tests" / "golden" / "ref_stage_weak.npz", **rec)
     nweak = int((pv["state"] == 0).sum())
     print("weak: steps", sorted(dumps), "weak pixels in", nweak, "of", pv["state"].size)
+    # ---- the reference against itself: the same probe once more (its direction-4 race is the only difference)
+    import json
+    again = run_probe("weak2", imgs1, [cams[i] for i in ids], (W, H), drs[v], p, planes, pv["state"], pv["selected"], src_d,
+                      prep[v][1][0], prep[v][0][0], prep[v][1][1])
+    wm0 = pv["state"] == 0
+    rr = {}
+    for s_ in (2, 4, 10, 11):
+        dn_ = np.abs(again[s_]["planes"][..., :3] - dumps[s_]["planes"][..., :3]).max(-1)
+        rr[f"step{s_}_normal_identical"] = float((dn_ < 1e-4).mean())
+    rr["anchor_sets_equal_incl_order"] = float((again[0]["neighbours"][wm0] == dumps[0]["neighbours"][wm0]).all(-1).all(-1).mean())
+    rr["final_state_equal"] = float((again[11]["state"] == dumps[11]["state"]).mean())
+    a11, b11 = again[11]["planes"], dumps[11]["planes"]
+    ang_ = np.degrees(np.arccos(np.clip((a11[..., :3] * b11[..., :3]).sum(-1), -1, 1)))
+    ok_ = (a11[..., 3] > 0) & (b11[..., 3] > 0)
+    rr["final_normal_1deg"] = float((ang_[ok_] < 1).mean())
+    rr["final_depth_1pct"] = float((np.abs(a11[..., 3] - b11[..., 3])[ok_] / b11[..., 3][ok_] < 1e-2).mean())
+    report["ref_vs_ref_stage6"] = rr
+    print("reference kernels vs themselves (second run), stage 6:", json.dumps(rr))
     # ---- the same stage on the GPU (this implementation), all views on the first stream so that the last
     # view's scratch arrays survive; compared with the reference's dumps
-    import json
     for race in (0, 1):
         c2 = capi.Context(0)
         capi.upload_scene(c2, grays, cams, drs, pairs, 2)
