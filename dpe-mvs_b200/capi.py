@@ -263,7 +263,8 @@ class Context:
         return xyz, bgr
 
     def set_cost_arithmetic(self, mode):
-        """0 = centred (precise), 1 = the reference's raw fp32 accumulation (default)."""
+        """0 = centred (precise), 1 = the reference's raw fp32 accumulation (default), 2 = 1 plus homography /
+        source coordinates / geometric consistency in the reference's own operation order."""
         self._ck(self.lib.dpe_set_cost_arithmetic(self.h, int(mode)))
 
     def set_reference_race(self, on):

@@ -87,6 +87,7 @@ struct dpe_ctx {
   bool gauss_seidel = false;  // dpe_set_view_order
   bool ref_race = false;      // dpe_set_reference_race
   bool cost_raw = true;       // dpe_set_cost_arithmetic
+  bool exact = false;         // dpe_set_cost_arithmetic(DPE_COST_REFERENCE_EXACT)
   // scratch
   std::vector<Scratch> scratch;
   // device fusion (dpe_fuse_*): per-view maps at full resolution + the fused cloud (host)
@@ -410,6 +411,7 @@ static void fill_args(dpe_ctx* ctx, int view, int k, const dpe_stage_params* p, 
   a.rng = s.rng;
   a.ref_race = ctx->ref_race ? 1 : 0;
   a.cost_raw = ctx->cost_raw ? 1 : 0;
+  a.exact = ctx->exact ? 1 : 0;
   a.weak_list = s.weak_list; a.weak_count = s.weak_count; a.list_stride = ctx->W * ctx->H;
   a.eval_units = ctx->count_evals ? ctx->d_eval_units : nullptr;
   if (p) {
@@ -639,8 +641,9 @@ int dpe_fuse_get(dpe_ctx* ctx, float* xyz, uint8_t* bgr) {
 }
 
 int dpe_set_cost_arithmetic(dpe_ctx* ctx, int mode) {
-  if (!ctx || mode < 0 || mode > 1) return DPE_ERR_ARG;
-  ctx->cost_raw = mode == DPE_COST_REFERENCE;
+  if (!ctx || mode < 0 || mode > 2) return DPE_ERR_ARG;
+  ctx->cost_raw = mode != DPE_COST_CENTRED;
+  ctx->exact = mode == DPE_COST_REFERENCE_EXACT;
   return DPE_OK;
 }
 

@@ -48,6 +48,28 @@ inline void scaled_K(const HostCam& c, int w, int h, int full_w, int full_h, dou
   *fx = f0; *cx = f2; *fy = f4; *cy = f5; *k8 = c.K[8];
 }
 
+// Relative pose in fp32 exactly as the reference's ComputeHomography forms it for every evaluation
+// (DPE.cu:455-481): camera centres from R, t, then R_rel = Rs Rr^T and t_rel = Rs (Cr - Cs).  Host version;
+// the CUDA side recomputes it on the device with the same expressions (k_relative_pose) so that the values
+// carry the device compiler's fused multiply-adds.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline void relative_pose_ref(const float* rR, const float* rt, const float* sR, const float* st, float* Rrel, float* trel) {
+  float ref_C[3], src_C[3];
+  ref_C[0] = -(rR[0] * rt[0] + rR[3] * rt[1] + rR[6] * rt[2]);
+  ref_C[1] = -(rR[1] * rt[0] + rR[4] * rt[1] + rR[7] * rt[2]);
+  ref_C[2] = -(rR[2] * rt[0] + rR[5] * rt[1] + rR[8] * rt[2]);
+  src_C[0] = -(sR[0] * st[0] + sR[3] * st[1] + sR[6] * st[2]);
+  src_C[1] = -(sR[1] * st[0] + sR[4] * st[1] + sR[7] * st[2]);
+  src_C[2] = -(sR[2] * st[0] + sR[5] * st[1] + sR[8] * st[2]);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      Rrel[i * 3 + j] = sR[i * 3 + 0] * rR[j * 3 + 0] + sR[i * 3 + 1] * rR[j * 3 + 1] + sR[i * 3 + 2] * rR[j * 3 + 2];
+  const float C_relative[3] = {ref_C[0] - src_C[0], ref_C[1] - src_C[1], ref_C[2] - src_C[2]};
+  for (int i = 0; i < 3; ++i) trel[i] = sR[i * 3 + 0] * C_relative[0] + sR[i * 3 + 1] * C_relative[1] + sR[i * 3 + 2] * C_relative[2];
+}
+
 inline void fold_ref(const HostCam& r, int w, int h, int full_w, int full_h, int view, RefConst* rc) {
   memset(rc, 0, sizeof(*rc));
   double fx, cx, fy, cy, k8;
@@ -56,6 +78,9 @@ inline void fold_ref(const HostCam& r, int w, int h, int full_w, int full_h, int
   rc->fx = (float)fx; rc->cx = (float)cx; rc->fy = (float)fy; rc->cy = (float)cy;
   for (int i = 0; i < 9; ++i) rc->R[i] = (float)r.R[i];
   for (int i = 0; i < 3; ++i) rc->t[i] = (float)r.t[i];
+  for (int i = 0; i < 3; ++i) rc->c[i] = (float)r.C[i];
+  for (int i = 0; i < 9; ++i) rc->K9[i] = (float)r.K[i];
+  rc->K9[0] = (float)fx; rc->K9[2] = (float)cx; rc->K9[4] = (float)fy; rc->K9[5] = (float)cy;
   rc->depth_min = r.depth_min * 0.6f;  // DPE.cpp:788-789
   rc->depth_max = r.depth_max * 1.2f;
   rc->view = view;
@@ -85,6 +110,15 @@ inline void fold_pair(const HostCam& r, const HostCam& s, int w, int h, int full
   const float c0 = (float)r.C[0] - (float)s.C[0], c1 = (float)r.C[1] - (float)s.C[1], c2 = (float)r.C[2] - (float)s.C[2];
   sc->baseline = sqrtf((float)((double)(c0 * c0 + c1 * c1 + c2 * c2)));  // DPE.cu:2640-2645
   sc->width = (float)w; sc->height = (float)h;
+  // fp32 data of the reference-order arithmetic
+  for (int i = 0; i < 9; ++i) sc->sR[i] = (float)s.R[i];
+  for (int i = 0; i < 3; ++i) { sc->st[i] = (float)s.t[i]; sc->sc3[i] = (float)s.C[i]; }
+  for (int i = 0; i < 9; ++i) sc->sK[i] = (float)s.K[i];
+  sc->sK[0] = (float)sfx; sc->sK[2] = (float)scx; sc->sK[4] = (float)sfy; sc->sK[5] = (float)scy;
+  float rR[9], rt[3];
+  for (int i = 0; i < 9; ++i) rR[i] = (float)r.R[i];
+  for (int i = 0; i < 3; ++i) rt[i] = (float)r.t[i];
+  relative_pose_ref(rR, rt, sc->sR, sc->st, sc->Rrel, sc->trel);
 }
 
 }  // namespace dpe

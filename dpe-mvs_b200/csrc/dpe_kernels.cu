@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_full(const __grid_constant_
     __syncthreads();
     const int x = tx0 + (threadIdx.x & 31), y = ty0 + (threadIdx.x >> 5);
     if (x < a.W && y < a.H) {
-      const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0);
+      const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact != 0);
       if (OP == OP_INIT) init_pixel(env, ps, a, x, y, evals);
       else classify_refine_pixel(env, ps, a, x, y, evals);
     }
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_half(const __grid_constant_
     const int x = tx0 + lx, y = ty0 + 2 * (threadIdx.x >> 5) + ((lx + a.colour) & 1);
     if (x < a.W && y < a.H) {
       if (a.state[y * a.W + x] != DPE_WEAK) {
-        const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0);
+        const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact != 0);
         strong_update_pixel<OP == OP_STRONG_EDGE>(env, ps, a, x, y, cost_arr, evals);
       }
     }
@@ -246,6 +246,7 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
   PatchStats ps;
   ps.r0 = ref(x, y);
   ps.c0 = a.cost_raw ? 0.0f : ps.r0;
+  ps.exact = a.exact;
   for (int t = lane; t < 36; t += 32) {
     const int ixx = t / 6, jy = t - ixx * 6;
     const int i = 2 * ixx - 5, j = 2 * jy - 5;
@@ -339,7 +340,7 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
       const int w = vw.get(v);
       if (w > 0) {
         float c = S.cost[lane * DPE_MAX_IMAGES + v];
-        if (a.geom) c += a.geom_factor * (fl ? geom_cost(rc, rc.src[v], cand, x, y) : 3.0f);
+        if (a.geom) c += a.geom_factor * (fl ? geom_cost(a, rc, rc.src[v], cand, x, y) : 3.0f);
         f += w * c;
       }
     }
@@ -375,7 +376,7 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
       const float4 pl = S.hplane[h0 + hi];
       const float3 m = plane_to_m(rc, pl);
       float cv = ncc_new(env, ps.c0, T, rc.src[v], v, m, x, y, W, H, taps);
-      if (a.geom) cv += a.geom_factor * geom_cost(rc, rc.src[v], pl, x, y);
+      if (a.geom) cv += a.geom_factor * geom_cost(a, rc, rc.src[v], pl, x, y);
       S.hcost[(h0 + hi) * DPE_MAX_IMAGES + v] = cv;
     }
     __syncwarp();
@@ -447,7 +448,7 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
     const float3 m = plane_to_m(rc, final_plane);
     if (lane < nv) {
       const int v = vlist_lo;
-      S.hcost[v] = ncc_old(env, ps, rc.src[v], m, x, y);
+      S.hcost[v] = ncc_old(env, ps, rc, rc.src[v], final_plane, m, x, y);
       taps += 36;
     }
     __syncwarp();
@@ -641,14 +642,14 @@ __global__ void __launch_bounds__(NT) k_cost_eval(const __grid_constant__ Kernel
   const int x = xy[2 * i], y = xy[2 * i + 1];
   GlobalRef ref{P.a.ref_img, P.a.W, P.a.H};
   TblStore st{s_tbl + threadIdx.x};
-  const PatchStats ps = build_patch(ref, x, y, st, P.a.cost_raw != 0);
+  const PatchStats ps = build_patch(ref, x, y, st, P.a.cost_raw != 0, P.a.exact != 0);
   const float3 m = plane_to_m(rc, planes[i]);
   if (mode == 0) {
     DevEnv env{s_tbl + threadIdx.x, P.a.ref_img, P.a.W, P.a.H};
-    for (int v = 0; v < rc.n_src; ++v) out[(size_t)i * rc.n_src + v] = ncc_old(env, ps, rc.src[v], m, x, y);
+    for (int v = 0; v < rc.n_src; ++v) out[(size_t)i * rc.n_src + v] = ncc_old(env, ps, rc, rc.src[v], planes[i], m, x, y);
   } else {
     DevEnvExact env{s_tbl + threadIdx.x};
-    for (int v = 0; v < rc.n_src; ++v) out[(size_t)i * rc.n_src + v] = ncc_old(env, ps, rc.src[v], m, x, y);
+    for (int v = 0; v < rc.n_src; ++v) out[(size_t)i * rc.n_src + v] = ncc_old(env, ps, rc, rc.src[v], planes[i], m, x, y);
   }
 }
 void launch_cost_eval(const KernelParams& P, int n_pix, const int* xy, const float4* planes, int mode,
@@ -663,7 +664,7 @@ __global__ void k_geom_eval(const __grid_constant__ KernelParams P, int n_pix, c
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pix) return;
   for (int v = 0; v < rc.n_src; ++v)
-    out[(size_t)i * rc.n_src + v] = geom_cost(rc, rc.src[v], planes[i], xy[2 * i], xy[2 * i + 1]);
+    out[(size_t)i * rc.n_src + v] = geom_cost(P.a, rc, rc.src[v], planes[i], xy[2 * i], xy[2 * i + 1]);
 }
 void launch_geom_eval(const KernelParams& P, int n_pix, const int* xy, const float4* planes, float* out,
                       const LaunchCfg& cfg, cudaStream_t stream) {
@@ -701,7 +702,7 @@ __global__ void __launch_bounds__(NT, MINB) k_ncc_bench(const __grid_constant__ 
     const int lx = threadIdx.x & 31;
     const int x = tx0 + lx, y = ty0 + 2 * (threadIdx.x >> 5) + (lx & 1);
     if (x < a.W && y < a.H) {
-      const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0);
+      const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact != 0);
       float acc = 0.f;
       for (int c = 0; c < n_cand; ++c) {
         const int nx = iclamp(x + offx[c & 7], 0, a.W - 1), ny = iclamp(y + offy[c & 7], 0, a.H - 1);
@@ -710,7 +711,7 @@ __global__ void __launch_bounds__(NT, MINB) k_ncc_bench(const __grid_constant__ 
         pl.w = dist2origin(rc, nx, ny, pw.w > 0.f ? pw.w : 1.0f, pl);
         const float3 m = plane_to_m(rc, pl);
         for (int v = 0; v < rc.n_src; ++v) {
-          acc += ncc_old(env, ps, rc.src[v], m, x, y);
+          acc += ncc_old(env, ps, rc, rc.src[v], pl, m, x, y);
         }
       }
       out[y * a.W + x] = acc;

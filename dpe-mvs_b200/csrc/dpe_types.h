@@ -22,6 +22,11 @@ struct SrcConst {
   float Ai[9];
   float bi[3];
   float baseline;        // |C_ref - C_src|  (DPE.cu:2640-2645)
+  // fp32 camera data for the reference-order arithmetic (StageArgs::exact): relative pose as the reference's
+  // ComputeHomography forms it (DPE.cu:455-481), and the source camera itself (geometric consistency)
+  float Rrel[9], trel[3];
+  float sR[9], st[3], sc3[3];
+  float sK[9];           // source intrinsics at this scale, all nine entries as the reference multiplies by them
   float width, height;   // source image size at this scale
   int src_view;          // index of the source view in the scene = its layer in the scale's layered texture
   unsigned long long tex;  // host simulator: HostImage* of the source image (unused on the GPU)
@@ -33,6 +38,8 @@ struct RefConst {
   float fx, cx, fy, cy;
   float R[9];
   float t[3];
+  float c[3];   // camera centre as ReadCamera stores it (DPE.cpp:362-367)
+  float K9[9];  // intrinsics at this scale, all nine entries
   float depth_min, depth_max;  // PatchMatch range: cam file min*0.6, max*1.2 (DPE.cpp:788-789)
   int n_src;
   int view;
@@ -84,6 +91,7 @@ struct StageArgs {
   int run_state, geom, use_apd, top_k, weak_peak_radius, rotate_time;
   float ransac_threshold, geom_factor;
   int iter, colour;
+  int exact;     // 1: homography, source coordinates and geometric consistency in the reference's fp32 operation order
   int cost_raw;  // cost arithmetic: 1 = moments on raw intensities like the reference, 0 = centred (dpe_core.cuh)
   int ref_race;  // 1: edge-mode direction 4 samples its own colour like the reference, racy
   Xorwow* rng;  // per-pixel XORWOW state of this stage (dpe_rng.h), starts as curand_init(seed, y, x)

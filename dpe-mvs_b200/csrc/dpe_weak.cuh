@@ -698,7 +698,7 @@ DPE_HD float weighted_cost_weak(const Env& env, const PatchStats& ps, const Weak
     const int w = vw.get(v);
     if (w > 0) {
       float cv = ncc_new(env, ps.c0, T, rc.src[v], v, m, x, y, a.W, a.H, taps);
-      if (a.geom) cv += a.geom_factor * geom_cost(rc, rc.src[v], pl, x, y);
+      if (a.geom) cv += a.geom_factor * geom_cost(a, rc, rc.src[v], pl, x, y);
       c += w * cv;
     }
   }
@@ -759,7 +759,7 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
       const int w = vw.get(v);
       if (w > 0) {
         float c = cost_arr[j * DPE_MAX_IMAGES + v];
-        if (a.geom) c += a.geom_factor * (flag[j] ? geom_cost(rc, rc.src[v], cand, x, y) : 3.0f);
+        if (a.geom) c += a.geom_factor * (flag[j] ? geom_cost(a, rc, rc.src[v], cand, x, y) : 3.0f);
         f += w * c;
       }
     }
@@ -826,7 +826,7 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
     float c = 0.f;
     for (int v = 0; v < N; ++v) {
       const int w = vw.get(v);
-      if (w > 0) { c += w * ncc_old(env, ps, rc.src[v], m, x, y); taps += 36; }
+      if (w > 0) { c += w * ncc_old(env, ps, rc, rc.src[v], final_plane, m, x, y); taps += 36; }
     }
     a.costs[center] = c / weight_norm;
   }

@@ -117,8 +117,12 @@ DPE_API int dpe_set_view_order(dpe_ctx* ctx, int sequential);
 /* fp32 arithmetic of the NCC moments.  DPE_COST_REFERENCE (default): accumulated on the raw intensities in
  * the reference's operation order (DPE.cu:716-775), costs within ~1e-6 of the reference's own;
  * DPE_COST_CENTRED: intensities centred on the centre pixel first, costs within 1e-4 of the float64
- * formula also on low-contrast patches (where the reference's E[x^2]-E[x]^2 loses ~3 digits). */
-enum { DPE_COST_CENTRED = 0, DPE_COST_REFERENCE = 1 };
+ * formula also on low-contrast patches (where the reference's E[x^2]-E[x]^2 loses ~3 digits);
+ * DPE_COST_REFERENCE_EXACT: as DPE_COST_REFERENCE, and the homography, the source coordinates of every
+ * tap and the geometric-consistency projections are formed in the reference's own fp32 operation order
+ * (ComputeHomography / ComputeCorrespondingPoint / ComputeGeomConsistencyCost, DPE.cu:453-522, 881-953)
+ * instead of the constant-folded A - b m^T form: ~1.3x the instructions per tap, for parity runs. */
+enum { DPE_COST_CENTRED = 0, DPE_COST_REFERENCE = 1, DPE_COST_REFERENCE_EXACT = 2 };
 DPE_API int dpe_set_cost_arithmetic(dpe_ctx* ctx, int mode);
 /* Edge-mode propagation, direction 4: 0 (default) samples the other colour like directions 5-7, which
  * makes a sweep race-free and bit-reproducible; 1 samples the reference's positions (own colour, read while

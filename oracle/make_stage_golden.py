@@ -68,6 +68,23 @@ def run_probe(tag, imgs, cams, full_wh, drange, p, planes, state, selected, src_
     return out
 
 
+def final_compare(fin, ref_fin, drange):
+    """final maps of a stage (dpe_get_maps) against the reference kernels' last dump + the host tail of
+    ProcessProblem (main.cpp:427-437: depths outside the PatchMatch range -> 0 / UNKNOWN)."""
+    rd = ref_fin["planes"][..., 3].copy()
+    rst = ref_fin["state"].copy()
+    dmin, dmax = np.float32(drange[0]) * np.float32(0.6), np.float32(drange[1]) * np.float32(1.2)
+    oob = (rd < dmin) | (rd > dmax)
+    rd[oob] = 0; rst[oob] = 2
+    both = (fin["depth"] > 0) & (rd > 0)
+    rel_d = np.abs(fin["depth"] - rd) / np.maximum(rd, 1e-9)
+    dn = np.abs(fin["normal"] - ref_fin["planes"][..., :3]).max(-1)
+    ang = np.degrees(np.arccos(np.clip((fin["normal"] * ref_fin["planes"][..., :3]).sum(-1), -1, 1)))
+    return {"final_state_equal": float((fin["state"] == rst).mean()),
+            "final_depth_1e-3": float((rel_d[both] < 1e-3).mean()), "final_depth_1pct": float((rel_d[both] < 1e-2).mean()),
+            "final_normal_identical": float((dn[both] < 1e-4).mean()), "final_normal_1deg": float((ang[both] < 1).mean())}
+
+
 def main():
     spec, grays, cams, drs, pairs, gt = small_scene("c4", 0.05, 5)      # 151 x 101, low-texture planes
     lib = capi.load()
@@ -101,6 +118,19 @@ def main():
             rec[f"s{s}_{name}"] = dumps[s][name]
     np.savez_compressed(ROOT / "tests" / "golden" / "ref_stage_first.npz", **rec)
     print("first: steps", sorted(dumps))
+    import json
+    # the same stage on the GPU (this implementation) in the three cost arithmetics' reference variants
+    for arith in (1, 2):
+        c0 = capi.Context(0)
+        capi.upload_scene(c0, grays, cams, drs, pairs, 2)
+        c0.set_profile(len(grays))
+        c0.set_cost_arithmetic(arith)
+        c0.run_stage(*sched[0], SEED); c0.stage_commit()
+        fin = c0.get_maps(v, 0)
+        c0.close()
+        r = final_compare(fin, dumps[11], drs[v])
+        report[f"gpu_vs_ref_stage0_arith{arith}"] = r
+        print(f"GPU vs reference kernels, stage 0, view {v}, arithmetic={arith}:", json.dumps(r))
     # ---- case "weak": stage 6, inputs = this implementation's maps after stages 0..5 (GPU)
     ctx = capi.Context(0)
     capi.upload_scene(ctx, grays, cams, drs, pairs, 2)
@@ -133,7 +163,6 @@ def main():
     nweak = int((pv["state"] == 0).sum())
     print("weak: steps", sorted(dumps), "weak pixels in", nweak, "of", pv["state"].size)
     # ---- the reference against itself: the same probe once more (its direction-4 race is the only difference)
-    import json
     again = run_probe("weak2", imgs1, [cams[i] for i in ids], (W, H), drs[v], p, planes, pv["state"], pv["selected"], src_d,
                       prep[v][1][0], prep[v][0][0], prep[v][1][1])
     wm0 = pv["state"] == 0
@@ -152,7 +181,7 @@ def main():
     print("reference kernels vs themselves (second run), stage 6:", json.dumps(rr))
     # ---- the same stage on the GPU (this implementation), all views on the first stream so that the last
     # view's scratch arrays survive; compared with the reference's dumps
-    for race in (0, 1):
+    for race, arith in ((0, 1), (1, 1), (1, 2)):
         c2 = capi.Context(0)
         capi.upload_scene(c2, grays, cams, drs, pairs, 2)
         for vv in range(len(grays)):
@@ -162,6 +191,7 @@ def main():
             c2.run_stage(*sched[si], SEED); c2.stage_commit()
         c2.set_profile(len(grays))
         c2.set_reference_race(race)
+        c2.set_cost_arithmetic(arith)
         c2.run_stage(*sched[6], SEED); c2.stage_commit()
         nb = c2.debug_read(0, (H, W, 9, 2), np.int16)
         fit = c2.debug_read(1, (H, W, 4), np.float32)
@@ -177,23 +207,13 @@ def main():
         r["radius_equal_weak"] = float((rad[wm] == dumps[9]["radius"][wm]).mean())
         dn = np.abs(fit[..., :3] - dumps[9]["fit"][..., :3]).max(-1)
         r["fit_normal_equal_weak"] = float((dn[wm] < 1e-4).mean())
-        ref_fin = dumps[11]
-        rd = ref_fin["planes"][..., 3].copy()
-        rst = ref_fin["state"].copy()
-        dmin, dmax = np.float32(drs[v][0]) * np.float32(0.6), np.float32(drs[v][1]) * np.float32(1.2)
-        oob = (rd < dmin) | (rd > dmax)                       # host tail of ProcessProblem (main.cpp:427-437)
-        rd[oob] = 0; rst[oob] = 2
-        both = (fin["depth"] > 0) & (rd > 0)
-        rel_d = np.abs(fin["depth"] - rd) / np.maximum(rd, 1e-9)
-        dn = np.abs(fin["normal"] - ref_fin["planes"][..., :3]).max(-1)
-        r["final_state_equal"] = float((fin["state"] == rst).mean())
-        r["final_depth_1e-3"] = float((rel_d[both] < 1e-3).mean()); r["final_depth_1pct"] = float((rel_d[both] < 1e-2).mean())
-        r["final_normal_identical"] = float((dn[both] < 1e-4).mean())
-        ang = np.degrees(np.arccos(np.clip((fin["normal"] * ref_fin["planes"][..., :3]).sum(-1), -1, 1)))
-        r["final_normal_1deg"] = float((ang[both] < 1).mean())
+        r.update(final_compare(fin, dumps[11], drs[v]))
+        both = (fin["depth"] > 0) & (dumps[11]["planes"][..., 3] > 0)
+        rel_d = np.abs(fin["depth"] - dumps[11]["planes"][..., 3]) / np.maximum(dumps[11]["planes"][..., 3], 1e-9)
         r["final_weakpx_depth_1pct"] = float((rel_d[both & wm] < 1e-2).mean())
-        report[f"gpu_vs_ref_stage6_race{race}"] = r
-        print(f"GPU vs reference kernels, stage 6, view {v}, ref_race={race}:", json.dumps(r))
+        key = f"gpu_vs_ref_stage6_race{race}" + ("_exact" if arith == 2 else "")
+        report[key] = r
+        print(f"GPU vs reference kernels, stage 6, view {v}, ref_race={race}, arithmetic={arith}:", json.dumps(r))
     (ROOT / "gpurun_out" / "stage_diff.json").write_text(json.dumps(report, indent=1))
 
 

@@ -1,4 +1,4 @@
-"""GPU cost kernel vs the reference's own device outputs (tests/golden/ref_probe_c1.npz) in both cost
+"""GPU cost kernel vs the reference's own device outputs (tests/golden/ref_probe_c1.npz) in the three cost
 arithmetics."""
 import sys, json
 from pathlib import Path
@@ -10,7 +10,7 @@ fx = np.load(ROOT / "tests" / "golden" / "ref_probe_c1.npz")
 imgs = [fx["images"][i] for i in range(4)]
 cams = [(fx["K"][i], fx["R"][i], fx["t"][i]) for i in range(4)]
 out = {}
-for mode, name in ((1, "reference"), (0, "centred")):
+for mode, name in ((1, "reference"), (2, "reference_exact"), (0, "centred")):
     ctx = capi.Context(0)
     H, W = imgs[0].shape
     ctx.scene_begin(4, W, H, 1)
@@ -27,5 +27,23 @@ for mode, name in ((1, "reference"), (0, "centred")):
                      p90=float(np.percentile(d, 90)), p99=float(np.percentile(d, 99)), max=float(d.max()), exact=float((d == 0).mean()),
                      below_1e6=float((d < 1e-6).mean()), below_1e5=float((d < 1e-5).mean()))
     print(name, json.dumps(out[name]))
+    # geometric consistency against the reference's ComputeGeomConsistencyCost outputs (golden source depths
+    # written into the atlas)
+    import torch
+    ctx.run_stage(*capi.stage_schedule(1)[0], 5)
+    ptr, chunk, total = ctx.stage_atlas()
+
+    class _Raw:
+        __cuda_array_interface__ = {"shape": (4, H, W), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    torch.as_tensor(_Raw(), device="cuda:0").copy_(torch.from_numpy(np.ascontiguousarray(fx["depths"], np.float32)))
+    torch.cuda.synchronize()
+    ctx.stage_commit()
+    gg = ctx.geom_eval(0, 0, fx["xy"], fx["planes"], 3)
+    rg = fx["ref_geom"]
+    dg = np.abs(gg - rg)
+    near = dg < 1e-2
+    out[name + "_geom"] = dict(same_3=float(((gg == 3.0) == (rg == 3.0)).mean()), within_1e2=float(near.mean()), exact=float((dg == 0).mean()),
+                               median=float(np.median(dg[near])), p90=float(np.percentile(dg[near], 90)), p99=float(np.percentile(dg[near], 99)))
+    print(name + "_geom", json.dumps(out[name + "_geom"]))
     ctx.close()
 (ROOT / "gpurun_out" / "cost_diff.json").write_text(json.dumps(out, indent=1))

@@ -31,6 +31,9 @@ for (k, p) in sched:                      # warm pass: every view gets real dept
 # ncu --profile-from-start off: dpe_run_stage brackets the profiled views with
 # cudaProfilerStart/Stop, so only they are captured; the other views of each stage run after them
 ctx.set_profile(n_prof)
+import os
+if os.environ.get("DPE_ARITH"):
+    ctx.set_cost_arithmetic(int(os.environ["DPE_ARITH"]))
 t0 = time.time()
 for (k, p) in sched:
     ctx.run_stage(k, p, 20261018)
