@@ -573,7 +573,7 @@ DPE_HD int tab_offset(const int k) { return k == 0 ? 0 : 36 + (k - 1) * 9; }
 // reference side of patch k (tap order: x offset outer, y offset inner, as DPE.cu:619-621)
 template <class RefFetch>
 DPE_HD void build_weak_patch(const RefFetch& ref, const float r0, const float c0, WeakTab& T, const int k, const int first,
-                             const int inc) {
+                             const int inc, const StageArgs* ex = nullptr) {
   const int n = T.ntap[k];
   if (n == 0) return;
   const short2 np = T.anchor[k];
@@ -585,7 +585,7 @@ DPE_HD void build_weak_patch(const RefFetch& ref, const float r0, const float c0
       const int i = first + ti * inc, j = first + tj * inc;
       const int rx = np.x + i, ry = np.y + j;
       const float r = ref(rx, ry);
-      const float w = fast_exp(-sqrtf((float)(i * i + j * j)) * (1.0f / 50.0f) - fabsf(r - r0) * (1.0f / 18.0f));
+      const float w = bilateral_weight(i, j, r, r0, ex);
       const float rp = r - c0;
       const float wr = mul_rn(w, rp);
       T.ww[off + ti * n + tj] = make_float2(w, wr);
@@ -644,11 +644,16 @@ DPE_HD float patch_cost_tab(const Env& env, const float c0, const WeakTab& T, co
 // `taps` accumulates evaluated source taps
 template <class Env>
 __noinline__ DPE_HDN float ncc_new(const Env& env, const float c0, const WeakTab& T, const SrcConst& sc, const int v, const float3 m,
-                                   const int x, const int y, const int W, const int H, int& taps) {
+                                   const int x, const int y, const int W, const int H, int& taps,
+                                   const RefConst* rc_exact = nullptr, const float4 pl = float4{0.f, 0.f, 0.f, 1.f}) {
   float h[9];
-  h[0] = sc.A[0] - sc.b[0] * m.x; h[1] = sc.A[1] - sc.b[0] * m.y; h[2] = sc.A[2] - sc.b[0] * m.z;
-  h[3] = sc.A[3] - sc.b[1] * m.x; h[4] = sc.A[4] - sc.b[1] * m.y; h[5] = sc.A[5] - sc.b[1] * m.z;
-  h[6] = sc.A[6] - sc.b[2] * m.x; h[7] = sc.A[7] - sc.b[2] * m.y; h[8] = sc.A[8] - sc.b[2] * m.z;
+  if (rc_exact) {
+    homography_ref(*rc_exact, sc, pl, h);  // StageArgs::exact: the reference's operation order (dpe_core.cuh)
+  } else {
+    h[0] = sc.A[0] - sc.b[0] * m.x; h[1] = sc.A[1] - sc.b[0] * m.y; h[2] = sc.A[2] - sc.b[0] * m.z;
+    h[3] = sc.A[3] - sc.b[1] * m.x; h[4] = sc.A[4] - sc.b[1] * m.y; h[5] = sc.A[5] - sc.b[1] * m.z;
+    h[6] = sc.A[6] - sc.b[2] * m.x; h[7] = sc.A[7] - sc.b[2] * m.y; h[8] = sc.A[8] - sc.b[2] * m.z;
+  }
   {
     const float Z = h[6] * x + h[7] * y + h[8];
     const float px = fast_div(h[0] * x + h[1] * y + h[2], Z), py = fast_div(h[3] * x + h[4] * y + h[5], Z);
@@ -697,7 +702,7 @@ DPE_HD float weighted_cost_weak(const Env& env, const PatchStats& ps, const Weak
   for (int v = 0; v < rc.n_src; ++v) {
     const int w = vw.get(v);
     if (w > 0) {
-      float cv = ncc_new(env, ps.c0, T, rc.src[v], v, m, x, y, a.W, a.H, taps);
+      float cv = ncc_new(env, ps.c0, T, rc.src[v], v, m, x, y, a.W, a.H, taps, a.exact ? &rc : nullptr, pl);
       if (a.geom) cv += a.geom_factor * geom_cost(a, rc, rc.src[v], pl, x, y);
       c += w * cv;
     }
@@ -718,7 +723,7 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
     int first0 = 0, inc0 = 2;
     for (int k = 0; k < DPE_NEIGHBOUR_NUM; ++k) init_weak_tab_entry(a, center, T, k, first0, inc0);
     auto ref = [&](int rx, int ry) { return env.ref(rx, ry); };
-    for (int k = 0; k < DPE_NEIGHBOUR_NUM; ++k) build_weak_patch(ref, ps.r0, ps.c0, T, k, k == 0 ? first0 : -5, k == 0 ? inc0 : 5);
+    for (int k = 0; k < DPE_NEIGHBOUR_NUM; ++k) build_weak_patch(ref, ps.r0, ps.c0, T, k, k == 0 ? first0 : -5, k == 0 ? inc0 : 5, a.exact ? &a : nullptr);
   }
   for (int j = 0; j < 8; ++j)
     for (int v = 0; v < N; ++v) cost_arr[j * DPE_MAX_IMAGES + v] = 0.f;
@@ -738,8 +743,10 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
     for (int v = 0; v < N; ++v) priors[v] += ((sv >> v) & 1u) ? 0.9f : 0.1f;
     if (a.state[npc] != DPE_STRONG) continue;
     positions[i] = npc; flag[i] = true;
-    const float3 m = plane_to_m(rc, a.planes[npc]);
-    for (int v = 0; v < N; ++v) cost_arr[i * DPE_MAX_IMAGES + v] = ncc_new(env, ps.c0, T, rc.src[v], v, m, x, y, a.W, a.H, taps);
+    const float4 cpl = a.planes[npc];
+    const float3 m = plane_to_m(rc, cpl);
+    for (int v = 0; v < N; ++v)
+      cost_arr[i * DPE_MAX_IMAGES + v] = ncc_new(env, ps.c0, T, rc.src[v], v, m, x, y, a.W, a.H, taps, a.exact ? &rc : nullptr, cpl);
   }
   Rng rng;
   rng.load(a.rng + center);

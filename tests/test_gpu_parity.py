@@ -147,15 +147,17 @@ def test_geom_kernel_matches_reference_golden_vectors():
     torch.cuda.synchronize()
     ctx.stage_commit()
     ref = fx["ref_geom"]
-    for arith, tol90 in ((1, 1e-2), (2, 5e-3)):
+    for arith, tol90 in ((1, 2e-4), (2, 1e-5)):   # measured on B200: 1.8e-5 and 0 (96 % bit-identical)
         ctx.set_cost_arithmetic(arith)
         got = ctx.geom_eval(0, 0, fx["xy"], fx["planes"], 3)
         # 3.0 = source depth 0 or error clamped; a projection that lands within rounding of a texel border
         # reads the neighbouring depth sample in one implementation and not the other
         same = np.abs(got - ref) < 1e-2
-        assert same.mean() > 0.95, (arith, same.mean())
+        assert same.mean() > 0.99, (arith, same.mean())
         d = np.abs(got - ref)[same]
         assert np.percentile(d, 90) < tol90, (arith, np.percentile(d, 90))
+        if arith == 2:
+            assert (got == ref).mean() > 0.9
     ctx.set_cost_arithmetic(1)
     ctx.close()
 

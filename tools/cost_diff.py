@@ -27,6 +27,13 @@ for mode, name in ((1, "reference"), (2, "reference_exact"), (0, "centred")):
                      p90=float(np.percentile(d, 90)), p99=float(np.percentile(d, 99)), max=float(d.max()), exact=float((d == 0).mean()),
                      below_1e6=float((d < 1e-6).mean()), below_1e5=float((d < 1e-5).mean()))
     print(name, json.dumps(out[name]))
+    if mode == 2:
+        bad = np.argwhere(both & (got != ref))
+        print("differing evaluations (pixel index, view): ", len(bad))
+        for (i, v) in bad[:60]:
+            print(f"  i={i} v={v} xy={fx['xy'][i].tolist()} plane={fx['planes'][i].tolist()} got={got[i, v]:.9g} ref={ref[i, v]:.9g} d={got[i, v] - ref[i, v]:.3g}")
+        bad_px = sorted(set(int(b[0]) for b in bad))
+        print("pixels with a difference:", len(bad_px), "of", len(fx['xy']), "; views:", np.bincount(bad[:, 1], minlength=3).tolist())
     # geometric consistency against the reference's ComputeGeomConsistencyCost outputs (golden source depths
     # written into the atlas)
     import torch

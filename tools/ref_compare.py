@@ -61,6 +61,7 @@ def main():
     ap.add_argument("--no-hough", action="store_true")
     ap.add_argument("--match", action="store_true", help="run ours in the reference's view order (sequential) — the RNG stream is the reference's anyway")
     ap.add_argument("--ours-seed", type=int, default=20261018)
+    ap.add_argument("--exact", action="store_true", help="a second run of ours with DPE_COST_REFERENCE_EXACT")
     ap.add_argument("--seed2", action="store_true", help="one more reference run with a different pinned RNG seed")
     args = ap.parse_args()
     tag = args.out or args.config
@@ -118,37 +119,50 @@ def main():
         K, R, t, dmin, dmax = synth.read_cam(folder / "cams" / f"{v:08d}_cam.txt")
         cams.append((K, R, t)); drs.append((dmin, dmax))
     rp = synth.read_pairs(folder / "pair.txt")
-    ctx = capi.Context(0)
-    t_all = time.time()
-    capi.upload_scene(ctx, grays, cams, drs, [s for (_, s) in rp], n_scales)
-    for v in range(V):
-        for k in range(n_scales):
-            j = n_scales - 1 - k
-            ctx.set_prep(v, k, prep[v][j][0], prep[v][j][1])
-    t_up = time.time() - t_all
-    ctx.set_count_evals(True)
-    if args.match:
-        ctx.set_view_order(1)
-        ctx.set_reference_race(1)
-    stages = []
-    for (k, p) in capi.stage_schedule(n_scales):
-        m0, u0 = ctx.stage_gpu_ms(), ctx.eval_units()
-        ctx.run_stage(k, p, args.ours_seed)
-        ctx.stage_commit()
-        stages.append(dict(scale=k, state=p.state, geom=p.geom_consistency, gpu_ms=ctx.stage_gpu_ms() - m0, units=ctx.eval_units() - u0))
-        print("ours", stages[-1], flush=True)
-    ours = []
-    for v in range(V):
-        m = ctx.get_maps(v, n_scales - 1)
-        d = m["depth"].copy(); d[m["state"] == capi.UNKNOWN] = 0      # ZeroDepthForUnknown, main.cpp:36-46
-        w = np.zeros(m["state"].shape, np.int8); w[m["state"] == capi.WEAK] = 1; w[m["state"] == capi.STRONG] = 2
-        ours.append((d, m["normal"], w))
-    res["ours_wall_s"] = time.time() - t_all
-    res["ours_upload_s"] = t_up
-    res["ours_gpu_ms"] = ctx.stage_gpu_ms()
-    res["ours_units"] = ctx.eval_units()
-    res["ours_stages"] = stages
+    def run_ours(arith):
+        ctx = capi.Context(0)
+        t_all = time.time()
+        capi.upload_scene(ctx, grays, cams, drs, [s for (_, s) in rp], n_scales)
+        for v in range(V):
+            for k in range(n_scales):
+                j = n_scales - 1 - k
+                ctx.set_prep(v, k, prep[v][j][0], prep[v][j][1])
+        t_up = time.time() - t_all
+        ctx.set_count_evals(True)
+        ctx.set_cost_arithmetic(arith)
+        if args.match:
+            ctx.set_view_order(1)
+            ctx.set_reference_race(1)
+        stages = []
+        for (k, p) in capi.stage_schedule(n_scales):
+            m0, u0 = ctx.stage_gpu_ms(), ctx.eval_units()
+            ctx.run_stage(k, p, args.ours_seed)
+            ctx.stage_commit()
+            stages.append(dict(scale=k, state=p.state, geom=p.geom_consistency, gpu_ms=ctx.stage_gpu_ms() - m0, units=ctx.eval_units() - u0))
+            print("ours", arith, stages[-1], flush=True)
+        maps = []
+        for v in range(V):
+            m = ctx.get_maps(v, n_scales - 1)
+            d = m["depth"].copy(); d[m["state"] == capi.UNKNOWN] = 0      # ZeroDepthForUnknown, main.cpp:36-46
+            w = np.zeros(m["state"].shape, np.int8); w[m["state"] == capi.WEAK] = 1; w[m["state"] == capi.STRONG] = 2
+            maps.append((d, m["normal"], w))
+        info = dict(wall_s=time.time() - t_all, upload_s=t_up, gpu_ms=ctx.stage_gpu_ms(), units=ctx.eval_units(), stages=stages)
+        ctx.close()
+        return maps, info
+
+    ours, info = run_ours(1)
+    res["ours_wall_s"] = info["wall_s"]
+    res["ours_upload_s"] = info["upload_s"]
+    res["ours_gpu_ms"] = info["gpu_ms"]
+    res["ours_units"] = info["units"]
+    res["ours_stages"] = info["stages"]
     res["ours_depth_maps_per_s"] = V / res["ours_wall_s"]
+    if args.exact:
+        ours_x, info_x = run_ours(2)
+        res["ours_exact_gpu_ms"] = info_x["gpu_ms"]
+        if ref_out:
+            res["ours_exact_vs_ref"] = [compare(*ours_x[v], *ref_out[0][v]) for v in range(V)]
+        res["ours_exact_vs_gt"] = [vs_gt(ours_x[v][0], ours_x[v][1], *gt[v], ours_x[v][2]) for v in range(V)]
 
     # ---- comparisons
     if len(ref_out) >= 1:
@@ -167,7 +181,7 @@ def main():
     (OUT / f"cmp_{tag}.json").write_text(json.dumps(res, indent=1))
     short = {k: v for k, v in res.items() if not isinstance(v, list)}
     print(json.dumps(short, indent=1))
-    for key in ("ours_vs_ref", "ref_vs_ref", "refseed2_vs_ref", "ref_vs_gt", "refseed2_vs_gt", "ours_vs_gt"):
+    for key in ("ours_vs_ref", "ours_exact_vs_ref", "ours_exact_vs_gt", "ref_vs_ref", "refseed2_vs_ref", "ref_vs_gt", "refseed2_vs_gt", "ours_vs_gt"):
         if key in res:
             print(key, json.dumps(res[key][0]))
             print(key, "mean over views", json.dumps({k: round(float(np.mean([r[k] for r in res[key] if k in r])), 4) for k in res[key][0]}))
