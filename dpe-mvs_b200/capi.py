@@ -30,7 +30,7 @@ SYMBOLS = [
     "dpe_scene_set_view", "dpe_scene_set_pairs", "dpe_scene_set_prep", "dpe_scene_set_shard", "dpe_scene_commit",
     "dpe_run_stage", "dpe_stage_atlas", "dpe_stage_commit", "dpe_cost_eval", "dpe_geom_eval", "dpe_get_size",
     "dpe_get_maps", "dpe_set_count_evals", "dpe_eval_units", "dpe_stage_gpu_ms", "dpe_probe_tex_rate",
-    "dpe_probe_fma_rate", "dpe_probe_tex_pattern", "dpe_probe_tex_weights", "dpe_run_pipeline", "dpe_set_profile", "dpe_get_profile", "dpe_set_view_order", "dpe_bench_ncc", "dpe_set_reference_race", "dpe_debug_read", "dpe_set_cost_arithmetic", "dpe_fuse_set_view", "dpe_fuse_run", "dpe_fuse_get",
+    "dpe_probe_fma_rate", "dpe_probe_tex_pattern", "dpe_probe_tex_weights", "dpe_run_pipeline", "dpe_set_profile", "dpe_get_profile", "dpe_set_view_order", "dpe_bench_ncc", "dpe_set_reference_race", "dpe_debug_read", "dpe_debug_stop_after", "dpe_debug_set_maps", "dpe_set_cost_arithmetic", "dpe_fuse_set_view", "dpe_fuse_run", "dpe_fuse_get",
 ]
 
 _lib = None
@@ -88,6 +88,8 @@ def load(build=True):
     lib.dpe_fuse_run.argtypes = [vp, C.POINTER(C.c_size_t)]
     lib.dpe_fuse_get.argtypes = [vp, vp, vp]
     lib.dpe_debug_read.argtypes = [vp, ci, vp, C.c_size_t]
+    lib.dpe_debug_stop_after.argtypes = [vp, ci]
+    lib.dpe_debug_set_maps.argtypes = [vp, ci, ci, vp, vp, vp, vp]
     lib.dpe_bench_ncc.argtypes = [vp, ci, ci, ci, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.dpe_get_profile.argtypes = [vp, vp, vp, vp]
     lib.dpe_run_pipeline.argtypes = [C.c_char_p, ci, ci, ci, ci, ci, ci, ci, ci]
@@ -269,6 +271,16 @@ class Context:
 
     def set_reference_race(self, on):
         self._ck(self.lib.dpe_set_reference_race(self.h, int(on)))
+
+    def debug_set_maps(self, view, scale_idx, planes4=None, state=None, selected=None, atlas_depth=None):
+        keep = [np.ascontiguousarray(planes4, np.float32) if planes4 is not None else None,
+                np.ascontiguousarray(state, np.uint8) if state is not None else None,
+                np.ascontiguousarray(selected, np.uint32) if selected is not None else None,
+                np.ascontiguousarray(atlas_depth, np.float32) if atlas_depth is not None else None]
+        self._ck(self.lib.dpe_debug_set_maps(self.h, view, scale_idx, *[a.ctypes.data if a is not None else None for a in keep]))
+
+    def debug_stop_after(self, step):
+        self._ck(self.lib.dpe_debug_stop_after(self.h, int(step)))
 
     def debug_read(self, what, shape, dtype):
         out = np.empty(shape, dtype)

@@ -107,6 +107,7 @@ struct dpe_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // per-kernel-class profile (dpe_set_profile): single stream, CUDA events around each launch
   bool profile = false;
+  int debug_stop_after = -1;  // dpe_debug_stop_after: last step of a view-stage that still runs (-1: all)
   int profile_views = 0;  // profile only the first n local views (the others run normally)
   double prof_ms[DPE_N_KERNEL_CLASSES] = {0};
   double prof_units[DPE_N_KERNEL_CLASSES] = {0};
@@ -489,6 +490,11 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
       cudaEventElapsedTime(&ms, ctx->pa, ctx->pb);
       ctx->prof_ms[cls] += ms; ctx->prof_units[cls] += (double)(u1 - u0); ctx->prof_launches[cls]++;
     };
+    // steps as oracle/ref_stage_probe.cu numbers them: 0 anchors, 1 init, 2+3i strong sweeps of iteration i,
+    // 3+3i fit plane, 4+3i weak sweeps, 11 the tail; dpe_debug_stop_after(n) leaves the scratch arrays as they
+    // are after step n (test hook for the per-kernel differential comparison)
+    const int stop = ctx->debug_stop_after;
+    auto on = [&](int step) { return stop < 0 || step <= stop; };
     if (p->state != DPE_FIRST_INIT) L(DPE_K_LOAD, launch_load);
     if (p->use_apd) {
       L(DPE_K_EDGE_INFO, launch_edge_info);
@@ -496,22 +502,28 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
       L(DPE_K_NEIGHBOURS, launch_gen_neighbours);
       L(DPE_K_NEIGHBOURS, launch_compact_weak);
     }
-    L(DPE_K_INIT, launch_init);
+    if (on(1)) L(DPE_K_INIT, launch_init);
     for (int it = 0; it < p->max_iterations; ++it) {
       a.iter = it;
-      a.colour = 0; L(DPE_K_STRONG, launch_strong);
-      a.colour = 1; L(DPE_K_STRONG, launch_strong);
+      if (on(2 + 3 * it)) {
+        a.colour = 0; L(DPE_K_STRONG, launch_strong);
+        a.colour = 1; L(DPE_K_STRONG, launch_strong);
+      }
       if (p->use_apd) {
-        L(DPE_K_FIT, launch_fit_plane);
-        a.colour = 0; L(DPE_K_WEAK, launch_weak);
-        a.colour = 1; L(DPE_K_WEAK, launch_weak);
+        if (on(3 + 3 * it)) L(DPE_K_FIT, launch_fit_plane);
+        if (on(4 + 3 * it)) {
+          a.colour = 0; L(DPE_K_WEAK, launch_weak);
+          a.colour = 1; L(DPE_K_WEAK, launch_weak);
+        }
       }
     }
-    L(DPE_K_EXTRACT, launch_extract);
-    a.colour = 0; L(DPE_K_MEDIAN, launch_median);
-    a.colour = 1; L(DPE_K_MEDIAN, launch_median);
-    L(DPE_K_CLASSIFY, launch_classify_refine);
-    L(DPE_K_FINISH, launch_finish);
+    if (on(11)) {
+      L(DPE_K_EXTRACT, launch_extract);
+      a.colour = 0; L(DPE_K_MEDIAN, launch_median);
+      a.colour = 1; L(DPE_K_MEDIAN, launch_median);
+      L(DPE_K_CLASSIFY, launch_classify_refine);
+      L(DPE_K_FINISH, launch_finish);
+    }
     if (realloc) {
       to_free.push_back(v.planes); to_free.push_back(v.state); to_free.push_back(v.selected);
       v.planes = new_planes; v.state = new_state; v.selected = new_sel; v.cur_scale = k;
@@ -656,6 +668,34 @@ int dpe_set_reference_race(dpe_ctx* ctx, int on) {
 
 // scratch buffers of the last stage run for `view` (test hook; only meaningful when the view ran on the
 // first stream: sequential view order, or a shard of one view)
+int dpe_debug_stop_after(dpe_ctx* ctx, int step) {
+  if (!ctx || step < -1 || step > 11) return DPE_ERR_ARG;
+  ctx->debug_stop_after = step;
+  return DPE_OK;
+}
+
+int dpe_debug_set_maps(dpe_ctx* ctx, int view, int k, const float* planes4, const uint8_t* state, const uint32_t* selected,
+                       const float* atlas_depth) {
+  if (!ctx || view < 0 || view >= ctx->n_views || k < 0 || k >= ctx->n_scales) return DPE_ERR_ARG;
+  if (!ctx->committed) FAIL(DPE_ERR_STATE, "scene not committed");
+  if (planes4 && (!state || !selected)) return DPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const size_t P = (size_t)ctx->sw[k] * ctx->sh[k];
+  ViewData& v = ctx->views[view];
+  if (planes4) {
+    if (v.cur_scale != k) {
+      cudaFree(v.planes); cudaFree(v.state); cudaFree(v.selected);
+      CK(cudaMalloc(&v.planes, P * sizeof(float4))); CK(cudaMalloc(&v.state, P)); CK(cudaMalloc(&v.selected, P * sizeof(uint32_t)));
+      v.cur_scale = k;
+    }
+    CK(cudaMemcpy(v.planes, planes4, P * sizeof(float4), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(v.state, state, P, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(v.selected, selected, P * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
+  if (atlas_depth) CK(cudaMemcpy(ctx->atlas_front[k] + (size_t)view * P, atlas_depth, P * sizeof(float), cudaMemcpyHostToDevice));
+  return DPE_OK;
+}
+
 int dpe_debug_read(dpe_ctx* ctx, int what, void* out, size_t bytes) {
   if (!ctx || !out || ctx->scratch.empty() || ctx->last_stage_scale < 0) return DPE_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
@@ -670,6 +710,9 @@ int dpe_debug_read(dpe_ctx* ctx, int what, void* out, size_t bytes) {
     case 4: src = s.weak_reliable; n = P; break;
     case 5: src = s.nearest_strong; n = P * sizeof(short2); break;
     case 6: src = s.complexity; n = P * sizeof(float); break;
+    case 7: src = s.planes; n = P * sizeof(float4); break;
+    case 8: src = s.selected; n = P * sizeof(uint32_t); break;
+    case 9: src = s.state; n = P; break;
     default: return DPE_ERR_ARG;
   }
   if (bytes < n) return DPE_ERR_ARG;

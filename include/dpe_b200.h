@@ -130,8 +130,21 @@ DPE_API int dpe_set_cost_arithmetic(dpe_ctx* ctx, int mode);
 DPE_API int dpe_set_reference_race(dpe_ctx* ctx, int on);
 /* test hook: scratch arrays of the view that ran last on the first stream.  what: 0 anchors (P x 9 short2),
  * 1 fit planes (P float4), 2 radius (P int32), 3 costs (P float), 4 weak_reliable (P u8), 5 nearest strong
- * (P short2), 6 complexity (P float). */
+ * (P short2), 6 complexity (P float), 7 plane hypotheses in reference-camera coordinates (P float4), 8 selected
+ * views (P uint32), 9 pixel state (P u8). */
 DPE_API int dpe_debug_read(dpe_ctx* ctx, int what, void* out, size_t bytes);
+/* test hook: the following stages stop after `step` of every view-stage, in the numbering of
+ * DPE::RunPatchMatch's launch sequence (DPE.cu:3126-3249) used by oracle/ref_stage_probe.cu: 0 anchor search,
+ * 1 initialisation, 2+3i strong sweeps of iteration i, 3+3i plane fit, 4+3i weak sweeps, 11 the tail;
+ * -1 (default) runs everything.  The scratch arrays then hold the state after that step (dpe_debug_read);
+ * the carried maps of the view are not valid until a full stage has run. */
+DPE_API int dpe_debug_stop_after(dpe_ctx* ctx, int step);
+/* test hook: replaces the carried maps of `view` at scale k (planes4: P x (world normal, depth); state; selected
+ * views) and / or its slot of the committed depth atlas, i.e. what the reference reads back from depths.dmb,
+ * normals.dmb, weak.bin and selected_views.bin at the start of a view-stage (DPE.cpp:826-914).  Lets a stage
+ * be replayed from stored inputs (tests/golden/ref_stage_weak.npz). */
+DPE_API int dpe_debug_set_maps(dpe_ctx* ctx, int view, int scale_idx, const float* planes4, const uint8_t* state,
+                               const uint32_t* selected, const float* atlas_depth);
 
 /* --- gate-1 hook: bilateral NCC of fixed plane hypotheses ------------------
  * planes: n_pix x (nx,ny,nz,d) in reference-camera coordinates (n.X + d = 0,

@@ -68,6 +68,15 @@ def run_probe(tag, imgs, cams, full_wh, drange, p, planes, state, selected, src_
     return out
 
 
+def step_compare(planes, sel, ref):
+    """per-pixel state after one step (camera-coordinate plane hypotheses, selected views) against the
+    reference kernels' dump of the same step"""
+    dn = np.abs(planes[..., :3] - ref["planes"][..., :3]).max(-1)
+    dd = np.abs(planes[..., 3] - ref["planes"][..., 3]) / np.maximum(np.abs(ref["planes"][..., 3]), 1e-9)
+    return {"plane_identical": float(((dn < 1e-4) & (dd < 1e-4)).mean()), "plane_bitwise": float((planes == ref["planes"]).all(-1).mean()),
+            "selected_equal": float((sel == ref["selected"]).mean())}
+
+
 def final_compare(fin, ref_fin, drange):
     """final maps of a stage (dpe_get_maps) against the reference kernels' last dump + the host tail of
     ProcessProblem (main.cpp:427-437: depths outside the PatchMatch range -> 0 / UNKNOWN)."""
@@ -129,6 +138,14 @@ def main():
         fin = c0.get_maps(v, 0)
         c0.close()
         r = final_compare(fin, dumps[11], drs[v])
+        for step in (1, 2, 5, 8):
+            c0 = capi.Context(0)
+            capi.upload_scene(c0, grays, cams, drs, pairs, 2, shard=(v, 1, len(grays), 1))
+            c0.set_cost_arithmetic(arith)
+            c0.debug_stop_after(step)
+            c0.run_stage(*sched[0], SEED)
+            r[f"step{step}"] = step_compare(c0.debug_read(7, (ch, cw, 4), np.float32), c0.debug_read(8, (ch, cw), np.uint32), dumps[step])
+            c0.close()
         report[f"gpu_vs_ref_stage0_arith{arith}"] = r
         print(f"GPU vs reference kernels, stage 0, view {v}, arithmetic={arith}:", json.dumps(r))
     # ---- case "weak": stage 6, inputs = this implementation's maps after stages 0..5 (GPU)
@@ -208,6 +225,26 @@ def main():
         dn = np.abs(fit[..., :3] - dumps[9]["fit"][..., :3]).max(-1)
         r["fit_normal_equal_weak"] = float((dn[wm] < 1e-4).mean())
         r.update(final_compare(fin, dumps[11], drs[v]))
+        if race == 1:
+            for step in (1, 2, 4, 7, 10):
+                c3 = capi.Context(0)
+                capi.upload_scene(c3, grays, cams, drs, pairs, 2)
+                for vv in range(len(grays)):
+                    for kk in range(2):
+                        c3.set_prep(vv, kk, *prep[vv][kk])
+                for si in range(6):
+                    c3.run_stage(*sched[si], SEED); c3.stage_commit()
+                c3.set_profile(len(grays))
+                c3.set_reference_race(race)
+                c3.set_cost_arithmetic(arith)
+                c3.debug_stop_after(step)
+                c3.run_stage(*sched[6], SEED)
+                sc_ = step_compare(c3.debug_read(7, (H, W, 4), np.float32), c3.debug_read(8, (H, W), np.uint32), dumps[step])
+                pl3 = c3.debug_read(7, (H, W, 4), np.float32)
+                dn3 = np.abs(pl3[..., :3] - dumps[step]["planes"][..., :3]).max(-1)
+                sc_["plane_identical_weakpx"] = float((dn3[wm] < 1e-4).mean())
+                r[f"step{step}"] = sc_
+                c3.close()
         both = (fin["depth"] > 0) & (dumps[11]["planes"][..., 3] > 0)
         rel_d = np.abs(fin["depth"] - dumps[11]["planes"][..., 3]) / np.maximum(dumps[11]["planes"][..., 3], 1e-9)
         r["final_weakpx_depth_1pct"] = float((rel_d[both & wm] < 1e-2).mean())
