@@ -617,7 +617,8 @@ DPE_HD void init_weak_tab_entry(const StageArgs& a, const int center, WeakTab& T
 
 // source side of one patch: NTAP x NTAP independent fetches
 template <int NTAP, class Env>
-DPE_HD float patch_cost_tab(const Env& env, const float c0, const WeakTab& T, const int k, const SrcConst& sc, const float* h) {
+DPE_HD float patch_cost_tab(const Env& env, const float c0, const WeakTab& T, const int k, const SrcConst& sc, const float* h,
+                            const bool exact = false) {
   const int off = tab_offset(k);
   float ss = 0.f, sss = 0.f, srs = 0.f;
   // one column of taps (NTAP independent fetches) per iteration: the code stays small enough for the
@@ -629,9 +630,18 @@ DPE_HD float patch_cost_tab(const Env& env, const float c0, const WeakTab& T, co
     for (int tc = 0; tc < NTAP; ++tc) {
       const int t = tr * NTAP + tc;
       const short2 q = T.xy[off + t];
-      const float Z = h[6] * q.x + h[7] * q.y + h[8];
-      const float iz = fast_rcp(Z);
-      const float s = env.tex(sc, (h[0] * q.x + h[1] * q.y + h[2]) * iz + 0.5f, (h[3] * q.x + h[4] * q.y + h[5]) * iz + 0.5f) - c0;
+      float u, v;
+      if (exact) {  // the reference's association (ncc_old_exact, dpe_core.cuh)
+        const float qx = (float)q.x, qy = (float)q.y;
+        const float iz = fast_rcp(add_rn(h[8], fmaf(h[7], qy, mul_rn(h[6], qx))));
+        u = fmaf(add_rn(h[2], fmaf(h[1], qy, mul_rn(h[0], qx))), iz, 0.5f);
+        v = fmaf(add_rn(h[5], fmaf(h[4], qy, mul_rn(h[3], qx))), iz, 0.5f);
+      } else {
+        const float iz = fast_rcp(h[6] * q.x + h[7] * q.y + h[8]);
+        u = (h[0] * q.x + h[1] * q.y + h[2]) * iz + 0.5f;
+        v = (h[3] * q.x + h[4] * q.y + h[5]) * iz + 0.5f;
+      }
+      const float s = env.tex(sc, u, v) - c0;
       const float2 ww = T.ww[off + t];
       const float ws = mul_rn(ww.x, s);
       ss_c += ws; sss_c = fmaf(ws, s, sss_c); srs_c = fmaf(ww.y, s, srs_c);
@@ -654,9 +664,22 @@ __noinline__ DPE_HDN float ncc_new(const Env& env, const float c0, const WeakTab
     h[3] = sc.A[3] - sc.b[1] * m.x; h[4] = sc.A[4] - sc.b[1] * m.y; h[5] = sc.A[5] - sc.b[1] * m.z;
     h[6] = sc.A[6] - sc.b[2] * m.x; h[7] = sc.A[7] - sc.b[2] * m.y; h[8] = sc.A[8] - sc.b[2] * m.z;
   }
+  const bool exact = rc_exact != nullptr;
+  // H (x, y, 1) dehomogenised: ComputeCorrespondingPoint (DPE.cu:515-522)
+  auto corr = [&](const int qx_, const int qy_, float& ox, float& oy) {
+    if (exact) {
+      const float qx = (float)qx_, qy = (float)qy_;
+      const float iz = fast_rcp(add_rn(h[8], fmaf(h[7], qy, mul_rn(h[6], qx))));
+      ox = mul_rn(add_rn(h[2], fmaf(h[1], qy, mul_rn(h[0], qx))), iz);
+      oy = mul_rn(add_rn(h[5], fmaf(h[4], qy, mul_rn(h[3], qx))), iz);
+    } else {
+      const float Z = h[6] * qx_ + h[7] * qy_ + h[8];
+      ox = fast_div(h[0] * qx_ + h[1] * qy_ + h[2], Z); oy = fast_div(h[3] * qx_ + h[4] * qy_ + h[5], Z);
+    }
+  };
   {
-    const float Z = h[6] * x + h[7] * y + h[8];
-    const float px = fast_div(h[0] * x + h[1] * y + h[2], Z), py = fast_div(h[3] * x + h[4] * y + h[5], Z);
+    float px, py;
+    corr(x, y, px, py);
     if (px >= sc.width || px < 0.0f || py >= sc.height || py < 0.0f) return 2.0f;
   }
   float center_cost = 0.f, strong_cost = 0.f;
@@ -667,8 +690,8 @@ __noinline__ DPE_HDN float ncc_new(const Env& env, const float c0, const WeakTab
     if (n == 0) continue;
     const short2 np = T.anchor[k];
     {
-      const float Z = h[6] * np.x + h[7] * np.y + h[8];
-      const float qx = fast_div(h[0] * np.x + h[1] * np.y + h[2], Z), qy = fast_div(h[3] * np.x + h[4] * np.y + h[5], Z);
+      float qx, qy;
+      corr(np.x, np.y, qx, qy);
       if (qx < 0 || qy < 0 || qx >= W || qy >= H) {  // sic: reference-image size (DPE.cu:596)
         if (k != 0) {
           if ((T.asel[k] >> v) & 1u) { strong_cost += 2.0f; strong_count++; }
@@ -678,10 +701,10 @@ __noinline__ DPE_HDN float ncc_new(const Env& env, const float c0, const WeakTab
       }
     }
     if (k == 0) {
-      center_cost = (n == 1) ? patch_cost_tab<1>(env, c0, T, 0, sc, h) : patch_cost_tab<6>(env, c0, T, 0, sc, h);
+      center_cost = (n == 1) ? patch_cost_tab<1>(env, c0, T, 0, sc, h, exact) : patch_cost_tab<6>(env, c0, T, 0, sc, h, exact);
       taps += n * n;
     } else {
-      strong_cost += patch_cost_tab<3>(env, c0, T, k, sc, h);
+      strong_cost += patch_cost_tab<3>(env, c0, T, k, sc, h, exact);
       strong_count++;
       taps += 9;
     }
