@@ -188,6 +188,10 @@ def run_ours(args):
             ctx.set_prep(v, k, e, l)
     ctx.set_shard(first, count, spr, world)
     ctx.commit()
+    # cost arithmetic: the product default (the reference's own, operation by operation) unless DPE_ARITH=fast|centred,
+    # which dpe_mvs() honours too (host/pipeline.cpp)
+    arith = {"fast": 1, "centred": 0}.get(os.environ.get("DPE_ARITH", ""), 2)
+    ctx.set_cost_arithmetic(arith)
     sched = capi.stage_schedule(n_scales)
 
     def atlas_tensor():
@@ -330,7 +334,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "views": V, "width": W, "height": H, "src_per_view": len(pairs[0]),
                        "view_stages_per_step": V * len(sched), "parallelism": f"views sharded over {world} GPU(s), NCCL all-gather of the depth atlas per stage",
                        "l2": "inputs larger than L2 (per view-stage ~0.5 GB of state + 11 images; 49 views cycle through)",
-                       "rng_seed": SEED},
+                       "rng_seed": SEED,
+                       "cost_arithmetic": {2: "reference, operation by operation (default)", 1: "reference moments, constant-folded homography (DPE_ARITH=fast)", 0: "centred (DPE_ARITH=centred)"}[arith]},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "wall_ms_per_step": wall_ms / args.steps, "allgather_ms_per_step": gather_ms / args.steps,
             "allgather_wait_ms_per_step_slowest_rank": gather_wait_ms / args.steps,

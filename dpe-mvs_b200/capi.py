@@ -265,8 +265,8 @@ class Context:
         return xyz, bgr
 
     def set_cost_arithmetic(self, mode):
-        """0 = centred (precise), 1 = the reference's raw fp32 accumulation (default), 2 = 1 plus homography /
-        source coordinates / geometric consistency in the reference's own operation order."""
+        """0 = centred (precise against float64), 1 = the reference's raw fp32 moments on a constant-folded
+        homography (fast), 2 = the reference's arithmetic operation by operation (default; include/dpe_b200.h)."""
         self._ck(self.lib.dpe_set_cost_arithmetic(self.h, int(mode)))
 
     def set_reference_race(self, on):

@@ -87,7 +87,7 @@ struct dpe_ctx {
   bool gauss_seidel = false;  // dpe_set_view_order
   bool ref_race = false;      // dpe_set_reference_race
   bool cost_raw = true;       // dpe_set_cost_arithmetic
-  bool exact = false;         // dpe_set_cost_arithmetic(DPE_COST_REFERENCE_EXACT)
+  bool exact = true;          // dpe_set_cost_arithmetic: DPE_COST_REFERENCE_EXACT is the default
   // scratch
   std::vector<Scratch> scratch;
   // device fusion (dpe_fuse_*): per-view maps at full resolution + the fused cloud (host)
@@ -713,6 +713,7 @@ int dpe_debug_read(dpe_ctx* ctx, int what, void* out, size_t bytes) {
     case 7: src = s.planes; n = P * sizeof(float4); break;
     case 8: src = s.selected; n = P * sizeof(uint32_t); break;
     case 9: src = s.state; n = P; break;
+    case 10: src = ctx->views[ctx->first_view].scales[ctx->last_stage_scale].lin; n = P * sizeof(float); break;
     default: return DPE_ERR_ARG;
   }
   if (bytes < n) return DPE_ERR_ARG;

@@ -600,9 +600,12 @@ __global__ void k_resize_linear(const float* __restrict__ src, int sw, int sh, f
     if (sy >= sh - 1) { fy = 0.f; sy = sh - 1; }
     const int sx1 = imin(sx + 1, sw - 1), sy1 = imin(sy + 1, sh - 1);
     const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
-    const float r0 = src[(size_t)sy * sw + sx] * a0 + src[(size_t)sy * sw + sx1] * a1;
-    const float r1 = src[(size_t)sy1 * sw + sx] * a0 + src[(size_t)sy1 * sw + sx1] * a1;
-    dst[i] = r0 * b0 + r1 * b1;
+    // products and sums rounded separately, like the host code this restates (cv::resize on the CPU in the
+    // reference, DPE.cpp:808): a fused multiply-add here changes the last bit of the coarse images whenever
+    // the scale is not exactly 2, and the raw-moment NCC turns that into 1e-4 of cost
+    const float r0 = __fadd_rn(__fmul_rn(src[(size_t)sy * sw + sx], a0), __fmul_rn(src[(size_t)sy * sw + sx1], a1));
+    const float r1 = __fadd_rn(__fmul_rn(src[(size_t)sy1 * sw + sx], a0), __fmul_rn(src[(size_t)sy1 * sw + sx1], a1));
+    dst[i] = __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, b1));
   }
 }
 void launch_resize_linear(const float* src, int sw, int sh, float* dst, int dw, int dh, const LaunchCfg& cfg,

@@ -114,14 +114,18 @@ DPE_API int dpe_stage_commit(dpe_ctx* ctx);
  * problems serially through depths.dmb files (main.cpp:509-558, DPE.cpp:826-844).  Single GPU only. */
 DPE_API int dpe_set_view_order(dpe_ctx* ctx, int sequential);
 
-/* fp32 arithmetic of the NCC moments.  DPE_COST_REFERENCE (default): accumulated on the raw intensities in
- * the reference's operation order (DPE.cu:716-775), costs within ~1e-6 of the reference's own;
- * DPE_COST_CENTRED: intensities centred on the centre pixel first, costs within 1e-4 of the float64
- * formula also on low-contrast patches (where the reference's E[x^2]-E[x]^2 loses ~3 digits);
- * DPE_COST_REFERENCE_EXACT: as DPE_COST_REFERENCE, and the homography, the source coordinates of every
- * tap and the geometric-consistency projections are formed in the reference's own fp32 operation order
- * (ComputeHomography / ComputeCorrespondingPoint / ComputeGeomConsistencyCost, DPE.cu:453-522, 881-953)
- * instead of the constant-folded A - b m^T form: ~1.3x the instructions per tap, for parity runs. */
+/* fp32 arithmetic of the matching cost.
+ * DPE_COST_REFERENCE_EXACT (default): every cost is computed operation by operation as the reference's
+ * --use_fast_math build computes it — homography from R, t, K per evaluation (ComputeHomography, DPE.cu:453-513),
+ * tap coordinates associated as its SASS does (ComputeCorrespondingPoint, DPE.cu:515-522), bilateral weights from
+ * run-time sigmas (DPE.cu:550-555), raw-intensity moments in its summation order (DPE.cu:716-775), geometric
+ * consistency through world coordinates (DPE.cu:881-953): the NCC costs are bit-identical to the reference's
+ * device outputs on the golden vectors (tests/golden/ref_probe_c1.npz), the geometric costs on 96 % of them.
+ * DPE_COST_REFERENCE: the same moments, but the homography constant-folded per view pair (A - b m^T), taps
+ * stepped incrementally, one reciprocal per tap: ~8 % faster over a whole scene, 82 % of the costs bit-identical,
+ * the rest within ~2e-5 (a tap crossing a 1/256 filter-weight bin).
+ * DPE_COST_CENTRED: intensities centred on the centre pixel before the moment sums, costs within 1e-4 of the
+ * float64 formula also on low-contrast patches (where the reference's E[x^2]-E[x]^2 loses ~3 digits). */
 enum { DPE_COST_CENTRED = 0, DPE_COST_REFERENCE = 1, DPE_COST_REFERENCE_EXACT = 2 };
 DPE_API int dpe_set_cost_arithmetic(dpe_ctx* ctx, int mode);
 /* Edge-mode propagation, direction 4: 0 (default) samples the other colour like directions 5-7, which
@@ -131,7 +135,7 @@ DPE_API int dpe_set_reference_race(dpe_ctx* ctx, int on);
 /* test hook: scratch arrays of the view that ran last on the first stream.  what: 0 anchors (P x 9 short2),
  * 1 fit planes (P float4), 2 radius (P int32), 3 costs (P float), 4 weak_reliable (P u8), 5 nearest strong
  * (P short2), 6 complexity (P float), 7 plane hypotheses in reference-camera coordinates (P float4), 8 selected
- * views (P uint32), 9 pixel state (P u8). */
+ * views (P uint32), 9 pixel state (P u8), 10 the image of the shard's first view at that scale (P float). */
 DPE_API int dpe_debug_read(dpe_ctx* ctx, int what, void* out, size_t bytes);
 /* test hook: the following stages stop after `step` of every view-stage, in the numbering of
  * DPE::RunPatchMatch's launch sequence (DPE.cu:3126-3249) used by oracle/ref_stage_probe.cu: 0 anchor search,

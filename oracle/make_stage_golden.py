@@ -68,13 +68,16 @@ def run_probe(tag, imgs, cams, full_wh, drange, p, planes, state, selected, src_
     return out
 
 
-def step_compare(planes, sel, ref):
+def step_compare(planes, sel, ref, costs=None):
     """per-pixel state after one step (camera-coordinate plane hypotheses, selected views) against the
     reference kernels' dump of the same step"""
     dn = np.abs(planes[..., :3] - ref["planes"][..., :3]).max(-1)
     dd = np.abs(planes[..., 3] - ref["planes"][..., 3]) / np.maximum(np.abs(ref["planes"][..., 3]), 1e-9)
-    return {"plane_identical": float(((dn < 1e-4) & (dd < 1e-4)).mean()), "plane_bitwise": float((planes == ref["planes"]).all(-1).mean()),
-            "selected_equal": float((sel == ref["selected"]).mean())}
+    out = {"plane_identical": float(((dn < 1e-4) & (dd < 1e-4)).mean()), "plane_bitwise": float((planes == ref["planes"]).all(-1).mean()),
+           "selected_equal": float((sel == ref["selected"]).mean())}
+    if costs is not None:
+        out["cost_bitwise"] = float(((costs == ref["costs"]) | (np.isnan(costs) & np.isnan(ref["costs"]))).mean())
+    return out
 
 
 def final_compare(fin, ref_fin, drange):
@@ -144,7 +147,7 @@ def main():
             c0.set_cost_arithmetic(arith)
             c0.debug_stop_after(step)
             c0.run_stage(*sched[0], SEED)
-            r[f"step{step}"] = step_compare(c0.debug_read(7, (ch, cw, 4), np.float32), c0.debug_read(8, (ch, cw), np.uint32), dumps[step])
+            r[f"step{step}"] = step_compare(c0.debug_read(7, (ch, cw, 4), np.float32), c0.debug_read(8, (ch, cw), np.uint32), dumps[step], c0.debug_read(3, (ch, cw), np.float32))
             c0.close()
         report[f"gpu_vs_ref_stage0_arith{arith}"] = r
         print(f"GPU vs reference kernels, stage 0, view {v}, arithmetic={arith}:", json.dumps(r))
@@ -239,7 +242,7 @@ def main():
                 c3.set_cost_arithmetic(arith)
                 c3.debug_stop_after(step)
                 c3.run_stage(*sched[6], SEED)
-                sc_ = step_compare(c3.debug_read(7, (H, W, 4), np.float32), c3.debug_read(8, (H, W), np.uint32), dumps[step])
+                sc_ = step_compare(c3.debug_read(7, (H, W, 4), np.float32), c3.debug_read(8, (H, W), np.uint32), dumps[step], c3.debug_read(3, (H, W), np.float32))
                 pl3 = c3.debug_read(7, (H, W, 4), np.float32)
                 dn3 = np.abs(pl3[..., :3] - dumps[step]["planes"][..., :3]).max(-1)
                 sc_["plane_identical_weakpx"] = float((dn3[wm] < 1e-4).mean())
