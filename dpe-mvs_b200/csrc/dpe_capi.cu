@@ -413,7 +413,6 @@ static void fill_args(dpe_ctx* ctx, int view, int k, const dpe_stage_params* p, 
   a.ref_race = ctx->ref_race ? 1 : 0;
   a.cost_raw = ctx->cost_raw ? 1 : 0;
   a.exact = ctx->exact ? 1 : 0;
-  a.sigma_spatial = 5.0f; a.sigma_color = 3.0f; a.izero = 0;  // main.h:81-82
   a.weak_list = s.weak_list; a.weak_count = s.weak_count; a.list_stride = ctx->W * ctx->H;
   a.eval_units = ctx->count_evals ? ctx->d_eval_units : nullptr;
   if (p) {

@@ -83,7 +83,7 @@ int dpe_hostsim_cost_eval(int W, int H, int full_w, int full_h, const float* ref
     HostRef ref{ref_img, W, H};
     HostStore st{env.tbl};
     const int x = xy[2 * i], y = xy[2 * i + 1];
-    const PatchStats ps = build_patch(ref, x, y, st, getenv("DPE_HOSTSIM_CENTRED") == nullptr, nullptr);
+    const PatchStats ps = build_patch(ref, x, y, st, getenv("DPE_HOSTSIM_CENTRED") == nullptr, getenv("DPE_HOSTSIM_EXACT") != nullptr);
     const float4 pl = make_float4(planes[4 * i], planes[4 * i + 1], planes[4 * i + 2], planes[4 * i + 3]);
     const float3 m = plane_to_m(*rc, pl);
     for (int v = 0; v < n_src; ++v) out[(size_t)i * n_src + v] = ncc_old(env, ps, *rc, rc->src[v], pl, m, x, y);
@@ -157,7 +157,6 @@ static int hostsim_stage_impl(int W, int H, int full_w, int full_h, int n_src, c
   a.ref_race = getenv("DPE_HOSTSIM_REF_RACE") ? 1 : 0;
   a.cost_raw = getenv("DPE_HOSTSIM_CENTRED") ? 0 : 1;
   a.exact = getenv("DPE_HOSTSIM_EXACT") ? 1 : 0;
-  a.sigma_spatial = 5.0f; a.sigma_color = 3.0f; a.izero = 0;
   (void)stage_counter;
   std::vector<Xorwow> rng_states(P);
   xorwow_init_table(seed, W, H, rng_states.data());
@@ -190,7 +189,7 @@ static int hostsim_stage_impl(int W, int H, int full_w, int full_h, int n_src, c
   auto with_patch = [&](int x, int y, auto&& fn) {
     HostEnv env; env.img = images[0]; env.W = W; env.H = H;
     HostStore st{env.tbl};
-    const PatchStats ps = build_patch(ref, x, y, st, a.cost_raw != 0, a.exact ? &a : nullptr);
+    const PatchStats ps = build_patch(ref, x, y, st, a.cost_raw != 0, a.exact != 0);
     unsigned ev = 0;
     fn(env, ps, ev);
     if (ev) {

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_full(const __grid_constant_
     __syncthreads();
     const int x = tx0 + (threadIdx.x & 31), y = ty0 + (threadIdx.x >> 5);
     if (x < a.W && y < a.H) {
-      const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact ? &a : nullptr);
+      const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact != 0);
       if (OP == OP_INIT) init_pixel(env, ps, a, x, y, evals);
       else classify_refine_pixel(env, ps, a, x, y, evals);
     }
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_half(const __grid_constant_
     const int x = tx0 + lx, y = ty0 + 2 * (threadIdx.x >> 5) + ((lx + a.colour) & 1);
     if (x < a.W && y < a.H) {
       if (a.state[y * a.W + x] != DPE_WEAK) {
-        const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact ? &a : nullptr);
+        const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact != 0);
         strong_update_pixel<OP == OP_STRONG_EDGE>(env, ps, a, x, y, cost_arr, evals);
       }
     }
@@ -251,7 +251,7 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
     const int ixx = t / 6, jy = t - ixx * 6;
     const int i = 2 * ixx - 5, j = 2 * jy - 5;
     const float r = ref(x + i, y + j);
-    const float w = bilateral_weight(i, j, r, ps.r0, a.exact ? &a : nullptr);
+    const float w = bilateral_weight(i, j, r, ps.r0);
     const float rp = r - ps.c0;
     S.tbl36[t] = make_float2(w, mul_rn(w, rp));
     S.hcost[t] = rp;
@@ -275,7 +275,7 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
     ps.var_r = fmaf(ps.inv_sw, swrr, -mul_rn(ps.mean_r, ps.mean_r));
   }
   __syncwarp();
-  if (lane < DPE_NEIGHBOUR_NUM) build_weak_patch(ref, ps.r0, ps.c0, T, lane, lane == 0 ? first0 : -5, lane == 0 ? inc0 : 5, a.exact ? &a : nullptr);
+  if (lane < DPE_NEIGHBOUR_NUM) build_weak_patch(ref, ps.r0, ps.c0, T, lane, lane == 0 ? first0 : -5, lane == 0 ? inc0 : 5);
   for (int i = lane; i < 8 * DPE_MAX_IMAGES; i += 32) S.cost[i] = 0.f;
   __syncwarp();
   if (lane == 0) S.cost[0] = 2.0f;
@@ -416,7 +416,7 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
       const float4 n_rand = random_normal(rc, x, y, rng, depth_now);
       const float lo = (1 - 0.02f) * depth_now, hi = (1 + 0.02f) * depth_now;
       const float depth_pert = rng.uniform() * (hi - lo) + lo;
-      const float4 n_pert = perturbed_normal(rc, x, y, plane_now, rng, 0.02f * 3.14159265358979323846f);
+      const float4 n_pert = perturbed_normal(rc, x, y, plane_now, rng, (float)(0.02f * 3.14159265358979323846));
       for (int i = 0; i < 5; ++i) {
         const float d = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : depth_now);
         float4 n = (i == 1 || i == 2) ? n_rand : (i == 3 ? n_pert : plane_now);
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(NT) k_cost_eval(const __grid_constant__ Kernel
   const int x = xy[2 * i], y = xy[2 * i + 1];
   GlobalRef ref{P.a.ref_img, P.a.W, P.a.H};
   TblStore st{s_tbl + threadIdx.x};
-  const PatchStats ps = build_patch(ref, x, y, st, P.a.cost_raw != 0, P.a.exact ? &P.a : nullptr);
+  const PatchStats ps = build_patch(ref, x, y, st, P.a.cost_raw != 0, P.a.exact != 0);
   const float3 m = plane_to_m(rc, planes[i]);
   if (mode == 0) {
     DevEnv env{s_tbl + threadIdx.x, P.a.ref_img, P.a.W, P.a.H};
@@ -705,7 +705,7 @@ __global__ void __launch_bounds__(NT, MINB) k_ncc_bench(const __grid_constant__ 
     const int lx = threadIdx.x & 31;
     const int x = tx0 + lx, y = ty0 + 2 * (threadIdx.x >> 5) + (lx & 1);
     if (x < a.W && y < a.H) {
-      const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact ? &a : nullptr);
+      const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact != 0);
       float acc = 0.f;
       for (int c = 0; c < n_cand; ++c) {
         const int nx = iclamp(x + offx[c & 7], 0, a.W - 1), ny = iclamp(y + offy[c & 7], 0, a.H - 1);

@@ -92,8 +92,6 @@ struct StageArgs {
   float ransac_threshold, geom_factor;
   int iter, colour;
   int exact;     // 1: homography, source coordinates, bilateral weights and geometric consistency in the reference's fp32 operation order
-  float sigma_spatial, sigma_color;  // 5, 3 (main.h:81-82); run-time values so that the exact path divides by them like the reference
-  int izero;     // 0 at run time: keeps the tap offsets of the exact weight path out of constant folding
   int cost_raw;  // cost arithmetic: 1 = moments on raw intensities like the reference, 0 = centred (dpe_core.cuh)
   int ref_race;  // 1: edge-mode direction 4 samples its own colour like the reference, racy
   Xorwow* rng;  // per-pixel XORWOW state of this stage (dpe_rng.h), starts as curand_init(seed, y, x)

@@ -172,10 +172,12 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
 
   const int rotate_time = a.rotate_time;
   const float angle = 45.0f / rotate_time;
-  const float kPi = 3.14159265358979323846f;
-  const float cos_a = cosf(angle * kPi / 180.f), sin_a = sinf(angle * kPi / 180.f);
-  const float threshold = cosf((angle / 2.0f) * kPi / 180.0f);
-  const int shift_range = imax((int)(tanf((angle / 2.0f) * kPi / 180.0f) * 20), 1);
+  // in double like the reference (angle * M_PI is a double expression there, DPE.cu:2149-2152), so that
+  // --use_fast_math does not turn these into the approximate single-precision intrinsics
+  const double kPi = 3.14159265358979323846;
+  const float cos_a = (float)cos(angle * kPi / 180.f), sin_a = (float)sin(angle * kPi / 180.f);
+  const float threshold = (float)cos((angle / 2.0f) * kPi / 180.0f);
+  const int shift_range = imax((int)(tan((angle / 2.0f) * kPi / 180.0f) * 20), 1);
   const float ransac_threshold = a.ransac_threshold * depth_diff;
 
   bool edge_limit = true;  // use_limit
@@ -573,7 +575,7 @@ DPE_HD int tab_offset(const int k) { return k == 0 ? 0 : 36 + (k - 1) * 9; }
 // reference side of patch k (tap order: x offset outer, y offset inner, as DPE.cu:619-621)
 template <class RefFetch>
 DPE_HD void build_weak_patch(const RefFetch& ref, const float r0, const float c0, WeakTab& T, const int k, const int first,
-                             const int inc, const StageArgs* ex = nullptr) {
+                             const int inc) {
   const int n = T.ntap[k];
   if (n == 0) return;
   const short2 np = T.anchor[k];
@@ -585,7 +587,7 @@ DPE_HD void build_weak_patch(const RefFetch& ref, const float r0, const float c0
       const int i = first + ti * inc, j = first + tj * inc;
       const int rx = np.x + i, ry = np.y + j;
       const float r = ref(rx, ry);
-      const float w = bilateral_weight(i, j, r, r0, ex);
+      const float w = bilateral_weight(i, j, r, r0);
       const float rp = r - c0;
       const float wr = mul_rn(w, rp);
       T.ww[off + ti * n + tj] = make_float2(w, wr);
@@ -616,9 +618,8 @@ DPE_HD void init_weak_tab_entry(const StageArgs& a, const int center, WeakTab& T
 }
 
 // source side of one patch: NTAP x NTAP independent fetches
-template <int NTAP, class Env>
-DPE_HD float patch_cost_tab(const Env& env, const float c0, const WeakTab& T, const int k, const SrcConst& sc, const float* h,
-                            const bool exact = false) {
+template <int NTAP, bool EXACT, class Env>
+DPE_HD float patch_cost_tab(const Env& env, const float c0, const WeakTab& T, const int k, const SrcConst& sc, const float* h) {
   const int off = tab_offset(k);
   float ss = 0.f, sss = 0.f, srs = 0.f;
   // one column of taps (NTAP independent fetches) per iteration: the code stays small enough for the
@@ -631,7 +632,7 @@ DPE_HD float patch_cost_tab(const Env& env, const float c0, const WeakTab& T, co
       const int t = tr * NTAP + tc;
       const short2 q = T.xy[off + t];
       float u, v;
-      if (exact) {  // the reference's association (ncc_old_exact, dpe_core.cuh)
+      if (EXACT) {  // the reference's association (ncc_old_exact, dpe_core.cuh)
         const float qx = (float)q.x, qy = (float)q.y;
         const float iz = fast_rcp(add_rn(h[8], fmaf(h[7], qy, mul_rn(h[6], qx))));
         u = fmaf(add_rn(h[2], fmaf(h[1], qy, mul_rn(h[0], qx))), iz, 0.5f);
@@ -652,22 +653,23 @@ DPE_HD float patch_cost_tab(const Env& env, const float c0, const WeakTab& T, co
 }
 
 // `taps` accumulates evaluated source taps
-template <class Env>
-__noinline__ DPE_HDN float ncc_new(const Env& env, const float c0, const WeakTab& T, const SrcConst& sc, const int v, const float3 m,
-                                   const int x, const int y, const int W, const int H, int& taps,
-                                   const RefConst* rc_exact = nullptr, const float4 pl = float4{0.f, 0.f, 0.f, 1.f}) {
+// EXACT is a template flag: a run-time test per tap would put both variants into the tap loops, and the weak
+// sweep is sensitive to its code size (instruction cache, see patch_cost_tab)
+template <bool EXACT, class Env>
+__noinline__ DPE_HDN float ncc_new_t(const Env& env, const float c0, const WeakTab& T, const SrcConst& sc, const int v, const float3 m,
+                                     const int x, const int y, const int W, const int H, int& taps,
+                                     const RefConst* rc_exact, const float4 pl) {
   float h[9];
-  if (rc_exact) {
+  if (EXACT) {
     homography_ref(*rc_exact, sc, pl, h);  // StageArgs::exact: the reference's operation order (dpe_core.cuh)
   } else {
     h[0] = sc.A[0] - sc.b[0] * m.x; h[1] = sc.A[1] - sc.b[0] * m.y; h[2] = sc.A[2] - sc.b[0] * m.z;
     h[3] = sc.A[3] - sc.b[1] * m.x; h[4] = sc.A[4] - sc.b[1] * m.y; h[5] = sc.A[5] - sc.b[1] * m.z;
     h[6] = sc.A[6] - sc.b[2] * m.x; h[7] = sc.A[7] - sc.b[2] * m.y; h[8] = sc.A[8] - sc.b[2] * m.z;
   }
-  const bool exact = rc_exact != nullptr;
   // H (x, y, 1) dehomogenised: ComputeCorrespondingPoint (DPE.cu:515-522)
   auto corr = [&](const int qx_, const int qy_, float& ox, float& oy) {
-    if (exact) {
+    if (EXACT) {
       const float qx = (float)qx_, qy = (float)qy_;
       const float iz = fast_rcp(add_rn(h[8], fmaf(h[7], qy, mul_rn(h[6], qx))));
       ox = mul_rn(add_rn(h[2], fmaf(h[1], qy, mul_rn(h[0], qx))), iz);
@@ -701,10 +703,10 @@ __noinline__ DPE_HDN float ncc_new(const Env& env, const float c0, const WeakTab
       }
     }
     if (k == 0) {
-      center_cost = (n == 1) ? patch_cost_tab<1>(env, c0, T, 0, sc, h, exact) : patch_cost_tab<6>(env, c0, T, 0, sc, h, exact);
+      center_cost = (n == 1) ? patch_cost_tab<1, EXACT>(env, c0, T, 0, sc, h) : patch_cost_tab<6, EXACT>(env, c0, T, 0, sc, h);
       taps += n * n;
     } else {
-      strong_cost += patch_cost_tab<3>(env, c0, T, k, sc, h, exact);
+      strong_cost += patch_cost_tab<3, EXACT>(env, c0, T, k, sc, h);
       strong_count++;
       taps += 9;
     }
@@ -713,6 +715,14 @@ __noinline__ DPE_HDN float ncc_new(const Env& env, const float c0, const WeakTab
   strong_cost /= strong_count;
   strong_cost = fminf(strong_cost, 2.0f);
   return (float)(0.25 * center_cost + 0.75 * strong_cost);
+}
+
+template <class Env>
+DPE_HD float ncc_new(const Env& env, const float c0, const WeakTab& T, const SrcConst& sc, const int v, const float3 m,
+                     const int x, const int y, const int W, const int H, int& taps,
+                     const RefConst* rc_exact = nullptr, const float4 pl = float4{0.f, 0.f, 0.f, 1.f}) {
+  return rc_exact ? ncc_new_t<true>(env, c0, T, sc, v, m, x, y, W, H, taps, rc_exact, pl)
+                  : ncc_new_t<false>(env, c0, T, sc, v, m, x, y, W, H, taps, nullptr, pl);
 }
 
 // weighted (photometric + geometric) cost of one hypothesis over the sampled views
@@ -746,7 +756,7 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
     int first0 = 0, inc0 = 2;
     for (int k = 0; k < DPE_NEIGHBOUR_NUM; ++k) init_weak_tab_entry(a, center, T, k, first0, inc0);
     auto ref = [&](int rx, int ry) { return env.ref(rx, ry); };
-    for (int k = 0; k < DPE_NEIGHBOUR_NUM; ++k) build_weak_patch(ref, ps.r0, ps.c0, T, k, k == 0 ? first0 : -5, k == 0 ? inc0 : 5, a.exact ? &a : nullptr);
+    for (int k = 0; k < DPE_NEIGHBOUR_NUM; ++k) build_weak_patch(ref, ps.r0, ps.c0, T, k, k == 0 ? first0 : -5, k == 0 ? inc0 : 5);
   }
   for (int j = 0; j < 8; ++j)
     for (int v = 0; v < N; ++v) cost_arr[j * DPE_MAX_IMAGES + v] = 0.f;
@@ -828,7 +838,7 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
       const float4 n_rand = random_normal(rc, x, y, rng, depth_now);
       const float lo = (1 - 0.02f) * depth_now, hi = (1 + 0.02f) * depth_now;
       const float depth_pert = rng.uniform() * (hi - lo) + lo;
-      const float4 n_pert = perturbed_normal(rc, x, y, plane_now, rng, 0.02f * 3.14159265358979323846f);
+      const float4 n_pert = perturbed_normal(rc, x, y, plane_now, rng, (float)(0.02f * 3.14159265358979323846));
       const float4 plane_in = plane_now;
       const float depth_in = depth_now;
 #pragma unroll 1
