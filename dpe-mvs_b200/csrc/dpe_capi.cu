@@ -36,6 +36,7 @@ struct ViewData {
   HostCam cam;
   bool have_img = false;
   std::vector<int> src;
+  std::vector<float> relpose;  // per source: R_rel[9], t_rel[3] as the device computes them (k_relative_pose)
   std::vector<ScaleImg> scales;
   // state carried between stages (owner only)
   float4* planes = nullptr;  // (world normal, depth)
@@ -351,6 +352,38 @@ int dpe_scene_commit(dpe_ctx* ctx) {
   }
   CK(cudaMalloc(&ctx->zero_edge, P)); CK(cudaMemset(ctx->zero_edge, 0, P));
   CK(cudaMalloc(&ctx->zero_label, P * sizeof(int32_t))); CK(cudaMemset(ctx->zero_label, 0xFF, P * sizeof(int32_t)));
+  // relative poses of all (reference, source) pairs of this context's views, from the device (see k_relative_pose)
+  {
+    std::vector<float> in;
+    size_t n_pairs = 0;
+    for (int v = 0; v < ctx->n_views; ++v) {
+      const ViewData& rv = ctx->views[v];
+      for (int sv : rv.src) {
+        const HostCam& r = rv.cam; const HostCam& sc = ctx->views[sv].cam;
+        for (int i = 0; i < 9; ++i) in.push_back((float)r.R[i]);
+        for (int i = 0; i < 3; ++i) in.push_back((float)r.t[i]);
+        for (int i = 0; i < 9; ++i) in.push_back((float)sc.R[i]);
+        for (int i = 0; i < 3; ++i) in.push_back((float)sc.t[i]);
+        ++n_pairs;
+      }
+    }
+    if (n_pairs) {
+      float *d_in = nullptr, *d_out = nullptr;
+      std::vector<float> out(n_pairs * 12);
+      CK(cudaMalloc(&d_in, in.size() * sizeof(float))); CK(cudaMalloc(&d_out, out.size() * sizeof(float)));
+      CK(cudaMemcpy(d_in, in.data(), in.size() * sizeof(float), cudaMemcpyHostToDevice));
+      launch_relative_pose(d_in, d_out, (int)n_pairs, 0);
+      CK(cudaGetLastError());
+      CK(cudaMemcpy(out.data(), d_out, out.size() * sizeof(float), cudaMemcpyDeviceToHost));
+      cudaFree(d_in); cudaFree(d_out);
+      size_t o = 0;
+      for (int v = 0; v < ctx->n_views; ++v) {
+        ViewData& rv = ctx->views[v];
+        rv.relpose.assign(out.begin() + o, out.begin() + o + rv.src.size() * 12);
+        o += rv.src.size() * 12;
+      }
+    }
+  }
   CK(cudaDeviceSynchronize());
   ctx->committed = true;
   return DPE_OK;
@@ -368,6 +401,10 @@ static void build_ref_const(const dpe_ctx* ctx, int view, int k, bool geom, RefC
     const int sv = rv.src[si];
     SrcConst& sc = rc->src[si];
     fold_pair(rv.cam, ctx->views[sv].cam, w, h, ctx->W, ctx->H, &sc);
+    if (rv.relpose.size() >= (size_t)(si + 1) * 12) {
+      memcpy(sc.Rrel, &rv.relpose[(size_t)si * 12], 9 * sizeof(float));
+      memcpy(sc.trel, &rv.relpose[(size_t)si * 12 + 9], 3 * sizeof(float));
+    }
     sc.src_view = sv;
     sc.tex = 0;
     sc.depth = geom ? ctx->atlas_front[k] + (size_t)sv * P : nullptr;

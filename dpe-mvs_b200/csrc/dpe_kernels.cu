@@ -15,6 +15,7 @@
 //    deterministic.
 #include <cuda_pipeline.h>
 #include "dpe_core.cuh"
+#include "dpe_consts.h"
 #include "dpe_weak.cuh"
 #include "dpe_kernels.cuh"
 
@@ -608,6 +609,20 @@ __global__ void k_resize_linear(const float* __restrict__ src, int sw, int sh, f
     dst[i] = __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, b1));
   }
 }
+// Relative pose of every (reference, source) pair of the scene, computed by the DEVICE compiler from the same
+// expressions ComputeHomography evaluates per call (DPE.cu:455-481): the reference's nvcc contracts these
+// multiply-adds, a host compiler would not, and the last bit of R_rel / t_rel is enough to move a tap across a
+// 1/256 filter-weight bin.  in: n x (ref R[9], ref t[3], src R[9], src t[3]); out: n x (R_rel[9], t_rel[3]).
+__global__ void k_relative_pose(const float* __restrict__ in, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* c = in + (size_t)i * 24;
+  relative_pose_ref(c, c + 9, c + 12, c + 21, out + (size_t)i * 12, out + (size_t)i * 12 + 9);
+}
+void launch_relative_pose(const float* in, float* out, int n, cudaStream_t stream) {
+  k_relative_pose<<<(n + 127) / 128, 128, 0, stream>>>(in, out, n);
+}
+
 void launch_resize_linear(const float* src, int sw, int sh, float* dst, int dw, int dh, const LaunchCfg& cfg,
                           cudaStream_t stream) {
   k_resize_linear<<<cfg.num_sms * 8, 256, 0, stream>>>(src, sw, sh, dst, dw, dh);

@@ -38,6 +38,7 @@ void launch_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t strea
 // scene preparation
 void launch_u8_to_f32(const uint8_t* src, float* dst, int n, const LaunchCfg& cfg, cudaStream_t stream);
 // cv::resize(INTER_LINEAR) of a float image (DPE.cpp:808)
+void launch_relative_pose(const float* in, float* out, int n, cudaStream_t stream);
 void launch_resize_linear(const float* src, int sw, int sh, float* dst, int dw, int dh,
                           const LaunchCfg& cfg, cudaStream_t stream);
 
