@@ -561,8 +561,12 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
       L(DPE_K_FINISH, launch_finish);
     }
     if (realloc) {
-      to_free.push_back(v.planes); to_free.push_back(v.state); to_free.push_back(v.selected);
-      v.planes = new_planes; v.state = new_state; v.selected = new_sel; v.cur_scale = k;
+      if (stop >= 0 && stop < 11) {  // truncated stage (test hook): the carried maps stay as they were
+        to_free.push_back(new_planes); to_free.push_back(new_state); to_free.push_back(new_sel);
+      } else {
+        to_free.push_back(v.planes); to_free.push_back(v.state); to_free.push_back(v.selected);
+        v.planes = new_planes; v.state = new_state; v.selected = new_sel; v.cur_scale = k;
+      }
     }
   }
   if (ctx->profile && ctx->n_local <= ctx->profile_views) cudaProfilerStop();
@@ -707,6 +711,8 @@ int dpe_set_reference_race(dpe_ctx* ctx, int on) {
 int dpe_debug_stop_after(dpe_ctx* ctx, int step) {
   if (!ctx || step < -1 || step > 11) return DPE_ERR_ARG;
   ctx->debug_stop_after = step;
+  // a truncated stage has written neither the carried maps nor the atlas: it may be run again without a commit
+  ctx->stage_pending = false;
   return DPE_OK;
 }
 

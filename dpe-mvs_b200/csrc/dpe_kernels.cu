@@ -438,7 +438,7 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
   if (writer) rng.store(a.rng + center);
   float4 final_plane = a.planes[center];
   if (a.run_state == DPE_REFINE_INIT) {
-    if (cost_now < cost_before - 0.1f) { final_plane = plane_now; if (writer) a.planes[center] = plane_now; }
+    if (cost_now < cost_before - 0.1) { final_plane = plane_now; if (writer) a.planes[center] = plane_now; }  // double, DPE.cu:1835
   } else {
     final_plane = plane_now;
     if (writer) a.planes[center] = plane_now;

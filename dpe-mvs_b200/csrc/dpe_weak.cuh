@@ -111,7 +111,7 @@ DPE_HDN void edge_info_pixel(const StageArgs& a, const int x, const int y) {
     }
     float density = 1.0f * edge_pix / tot_pix;
     density = fmaxf(density, (float)(bound_pix / tot_pix));  // integer division
-    a.complexity[center] = 1.0f / (1.0f + expf(-25.0f * (density - 0.35f)));
+    a.complexity[center] = (float)(1.0f / (1.0f + exp(-25.0 * (density - 0.35))));  // double arithmetic, DPE.cu:2554
   }
   if (a.state[center] == DPE_WEAK) {  // use_label
     const int center_label = a.label[center];
@@ -249,7 +249,7 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
       float dist = 0.0f;
       if (bp.x != -1 && bp.y != -1) {
         dist = sqrtf((float)((x - bp.x) * (x - bp.x) + (y - bp.y) * (y - bp.y)));
-        if (i >= 4) dist /= 1.41421356237309515f;
+        if (i >= 4) dist = (float)(dist / 1.4142135623730951);  // dist /= std::sqrt(2.0): a double division
       }
       bound_dist[i] = dist;
       if (i % 2 == 1) {
@@ -338,8 +338,9 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
       if (a.geom && edge_limit) {
         const float3 AN = spvn[ai], BN = spvn[bi], CN = spvn[ci];
         normal_consistency = true;
-        if (AN.x * BN.x + AN.y * BN.y + AN.z * BN.z < 0.8660254f || AN.x * CN.x + AN.y * CN.y + AN.z * CN.z < 0.8660254f ||
-            BN.x * CN.x + BN.y * CN.y + BN.z * CN.z < 0.8660254f)
+        // the threshold is a double literal in the reference (DPE.cu:2347)
+        if (AN.x * BN.x + AN.y * BN.y + AN.z * BN.z < 0.8660254 || AN.x * CN.x + AN.y * CN.y + AN.z * CN.z < 0.8660254 ||
+            BN.x * CN.x + BN.y * CN.y + BN.z * CN.z < 0.8660254)
           normal_consistency = false;
         if (has_consist_normal_plane && !normal_consistency) continue;
       }
@@ -370,10 +371,10 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
         max_count = temp_count;
         min_cost = fabsf(fit_depth - center_z);
         has_valid_plane = true;
-        if (temp_thr > 0.05f) {
+        if (temp_thr > 0.05) {  // high_res_img (main.h:97); double literals, DPE.cu:2403-2406
           sort_small(residuals, valid_count);
           if (temp_thr < residuals[DPE_NEIGHBOUR_NUM]) continue;
-          temp_thr = residuals[DPE_NEIGHBOUR_NUM] - 1e-6f;
+          temp_thr = (float)(residuals[DPE_NEIGHBOUR_NUM] - 1e-6);
           temp_count = 0;
           for (int i = 0; i < valid_count; ++i) {
             if (residuals[i] < temp_thr) temp_count++;
@@ -465,8 +466,8 @@ DPE_HDN void fit_plane_pixel(const StageArgs& a, const int x, const int y) {
     if (a.geom && edge_limit) {
       const float3 AN = spn[ai], BN = spn[bi], CN = spn[ci];
       is_strong_plane = true;
-      if (AN.x * BN.x + AN.y * BN.y + AN.z * BN.z < 0.8660254f || AN.x * CN.x + AN.y * CN.y + AN.z * CN.z < 0.8660254f ||
-          BN.x * CN.x + BN.y * CN.y + BN.z * CN.z < 0.8660254f)
+      if (AN.x * BN.x + AN.y * BN.y + AN.z * BN.z < 0.8660254 || AN.x * CN.x + AN.y * CN.y + AN.z * CN.z < 0.8660254 ||
+          BN.x * CN.x + BN.y * CN.y + BN.z * CN.z < 0.8660254)
         is_strong_plane = false;
       if (has_strong_plane && !is_strong_plane) continue;
     }
@@ -855,7 +856,7 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
   rng.store(a.rng + center);
   float4 final_plane = a.planes[center];
   if (a.run_state == DPE_REFINE_INIT) {
-    if (cost_now < cost_before - 0.1f) { final_plane = plane_now; a.planes[center] = plane_now; }
+    if (cost_now < cost_before - 0.1) { final_plane = plane_now; a.planes[center] = plane_now; }  // double, DPE.cu:1835
   } else {
     final_plane = plane_now;
     a.planes[center] = plane_now;

@@ -141,7 +141,8 @@ DPE_API int dpe_debug_read(dpe_ctx* ctx, int what, void* out, size_t bytes);
  * DPE::RunPatchMatch's launch sequence (DPE.cu:3126-3249) used by oracle/ref_stage_probe.cu: 0 anchor search,
  * 1 initialisation, 2+3i strong sweeps of iteration i, 3+3i plane fit, 4+3i weak sweeps, 11 the tail;
  * -1 (default) runs everything.  The scratch arrays then hold the state after that step (dpe_debug_read);
- * the carried maps of the view are not valid until a full stage has run. */
+ * the carried maps of the view are not valid until a full stage has run.  Calling it also discards a pending
+ * (truncated) stage, so that the same stage can be run again from the same inputs without dpe_stage_commit. */
 DPE_API int dpe_debug_stop_after(dpe_ctx* ctx, int step);
 /* test hook: replaces the carried maps of `view` at scale k (planes4: P x (world normal, depth); state; selected
  * views) and / or its slot of the committed depth atlas, i.e. what the reference reads back from depths.dmb,

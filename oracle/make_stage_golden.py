@@ -97,6 +97,70 @@ def final_compare(fin, ref_fin, drange):
             "final_normal_identical": float((dn[both] < 1e-4).mean()), "final_normal_1deg": float((ang[both] < 1).mean())}
 
 
+def all_stages(report, grays, cams, drs, pairs, prep, sizes, sched, v):
+    """Every stage of the schedule for view v: the reference's kernels (probe) run on the maps THIS implementation
+    holds after the previous stage, and the stage's final maps are compared.  Tells which stage type still
+    differs (FIRST_INIT / coarse REFINE_ITER with geometric consistency / REFINE_INIT across the scale change /
+    fine REFINE_ITER with the weak path)."""
+    import json
+    W, H = sizes[-1]
+    ids = [v] + list(pairs[v])
+    ctx = capi.Context(0)
+    capi.upload_scene(ctx, grays, cams, drs, pairs, 2)
+    for vv in range(len(grays)):
+        for kk in range(2):
+            ctx.set_prep(vv, kk, *prep[vv][kk])
+    ctx.set_reference_race(1)
+    ctx.set_profile(len(grays))
+    out = {}
+    prev_k = None
+    maps = None
+    for si, (k, p) in enumerate(sched):
+        w, h = sizes[k]
+        imgs = [grays[i].astype(np.float32) if (w, h) == (W, H) else hostsim.resize_linear(grays[i].astype(np.float32), w, h) for i in ids]
+        if si == 0:
+            planes = np.zeros((h, w, 4), np.float32); state = np.ones((h, w), np.uint8); sel = np.zeros((h, w), np.uint32)
+        else:
+            pm = maps[v]
+            planes = np.concatenate([pm["normal"], pm["depth"][..., None]], -1).astype(np.float32)
+            state, sel = pm["state"], pm["selected"]
+            if prev_k != k:      # RescaleMatToTargetSize (DPE.cpp:1147-1168): nearest neighbour, factors swapped
+                ph, pw_ = state.shape
+                sx, sy = np.float32(w) / np.float32(pw_), np.float32(h) / np.float32(ph)
+                oy = (np.arange(h, dtype=np.float32) / sx).astype(np.int64); ox = (np.arange(w, dtype=np.float32) / sy).astype(np.int64)
+                ok = (oy[:, None] < ph) & (ox[None, :] < pw_)
+                oyc, oxc = np.minimum(oy, ph - 1), np.minimum(ox, pw_ - 1)
+                planes = np.where(ok[..., None], planes[oyc][:, oxc], 0).astype(np.float32)
+                state = np.where(ok, state[oyc][:, oxc], 1).astype(np.uint8)
+                sel = np.where(ok, sel[oyc][:, oxc], 0).astype(np.uint32)
+        src_d = [maps[i]["depth"] for i in pairs[v]] if p.geom_consistency else None
+        if p.use_apd:
+            edge, edge_low, label = prep[v][k][0], prep[v][0][0], prep[v][k][1]
+        else:
+            edge = np.zeros((h, w), np.uint8); edge_low = np.zeros(sizes[0][::-1], np.uint8); label = np.full((h, w), -1, np.int32)
+        dumps = run_probe(f"all{si}", imgs, [cams[i] for i in ids], (W, H), drs[v], p, planes, state, sel, src_d, edge, edge_low, label)
+        steps = {}
+        if si > 0:               # per step (a truncated stage leaves the carried maps and the atlas untouched)
+            for step in ((1, 2, 5, 8) if not p.use_apd else (1, 2, 4, 7, 10)):
+                ctx.debug_stop_after(step)
+                ctx.run_stage(k, p, SEED)
+                steps[f"step{step}"] = step_compare(ctx.debug_read(7, (h, w, 4), np.float32), ctx.debug_read(8, (h, w), np.uint32), dumps[step],
+                                                    ctx.debug_read(3, (h, w), np.float32))
+            ctx.debug_stop_after(-1)
+        ctx.run_stage(k, p, SEED); ctx.stage_commit()
+        maps = [ctx.get_maps(i, k) for i in range(len(grays))]
+        prev_k = k
+        r = final_compare(maps[v], dumps[11], drs[v])
+        r.update(steps)
+        r["selected_equal"] = float((maps[v]["selected"] == dumps[11]["selected"]).mean())
+        r["weak_frac"] = float((maps[v]["state"] == 0).mean())
+        out[f"stage{si}"] = r
+        print(f"stage {si} (scale {k}, state {p.state}, geom {p.geom_consistency}, apd {p.use_apd}):",
+              json.dumps({a: (round(b, 4) if not isinstance(b, dict) else {c: round(d, 4) for c, d in b.items()}) for a, b in r.items()}), flush=True)
+    ctx.close()
+    report["gpu_vs_ref_every_stage"] = out
+
+
 def main():
     spec, grays, cams, drs, pairs, gt = small_scene("c4", 0.05, 5)      # 151 x 101, low-texture planes
     lib = capi.load()
@@ -254,6 +318,7 @@ def main():
         key = f"gpu_vs_ref_stage6_race{race}" + ("_exact" if arith == 2 else "")
         report[key] = r
         print(f"GPU vs reference kernels, stage 6, view {v}, ref_race={race}, arithmetic={arith}:", json.dumps(r))
+    all_stages(report, grays, cams, drs, pairs, prep, sizes, sched, len(grays) - 1)
     (ROOT / "gpurun_out" / "stage_diff.json").write_text(json.dumps(report, indent=1))
 
 
