@@ -20,7 +20,7 @@ pl, co, se = run(1)
 img = ctx.debug_read(10, (ch, cw), np.float32)
 print("coarse image of view 0 bitwise equal to the fixture's:", (img == fx["images"][0]).mean(), "max |d|", np.abs(img - fx["images"][0]).max())
 d1 = np.abs(co - fx["s1_costs"]); d1 = d1[np.isfinite(d1) & (d1 > 0)]
-print("step1 nonzero |dcost| percentiles 10/50/90:", np.percentile(d1, [10, 50, 90]))
+print("step1 nonzero |dcost|:", len(d1), np.percentile(d1, [10, 50, 90]) if len(d1) else "")
 print("step1: planes bitwise", (pl == fx["s1_planes"]).all(-1).mean(), "costs bitwise", (co == fx["s1_costs"]).mean(),
       "max |dcost|", np.nanmax(np.abs(co - fx["s1_costs"])), "selected", (se == fx["s1_selected"]).mean())
 bad = np.argwhere(co != fx["s1_costs"])
@@ -31,6 +31,28 @@ rp, rc, rs = fx["s2_planes"], fx["s2_costs"], fx["s2_selected"]
 same = (pl == rp).all(-1)
 print("step2: planes bitwise", same.mean(), "costs bitwise", ((co == rc) | (np.isnan(co) & np.isnan(rc))).mean(), "selected", (se == rs).mean())
 print("  among pixels with the same plane: costs bitwise", ((co == rc) | (np.isnan(co) & np.isnan(rc)))[same].mean(), "selected equal", (se == rs)[same].mean())
+cd = same & ~((co == rc) | (np.isnan(co) & np.isnan(rc)))
+print("  same plane, different cost:", int(cd.sum()), "pixels; |dcost| / cost percentiles 10/50/90:", np.percentile(np.abs(co - rc)[cd] / np.abs(rc)[cd], [10, 50, 90]))
+for (y, x) in np.argwhere(cd)[:12]:
+    print(f"    ({x},{y}) colour {(x+y)%2} ours {co[y,x]:.9g} ref {rc[y,x]:.9g} rel {abs(co[y,x]-rc[y,x])/abs(rc[y,x]):.3g} sel {se[y,x]:x}/{rs[y,x]:x} plane changed in sweep: {not (pl[y,x] == fx['s1_planes'][y,x]).all()}")
+# which integer view weights (15 draws) reproduce each stored cost from the per-view costs of the stored plane?
+import itertools
+pts = np.argwhere(cd)[:8]
+if len(pts):
+    xy = np.array([[x, y] for (y, x) in pts], np.int32)
+    pv = ctx.cost_eval(0, 0, xy, np.stack([pl[y, x] for (y, x) in pts]), len(pairs[0]))
+    for (y, x), c in zip(pts, pv):
+        best = {}
+        for w in itertools.product(range(16), repeat=len(c)):
+            if sum(w) != 15: continue
+            acc = np.float32(0)
+            for wi, ci in zip(w, c):
+                if wi > 0: acc = np.float32(np.float32(wi) * ci + acc)
+            val = np.float32(acc / np.float32(15))
+            for name, tgt in (("ours", co[y, x]), ("ref", rc[y, x])):
+                d = abs(float(val) - float(tgt))
+                if name not in best or d < best[name][0]: best[name] = (d, w)
+        print(f"    ({x},{y}) per-view costs {c.tolist()} -> ours weights {best['ours'][1]} (|d| {best['ours'][0]:.2g}), ref weights {best['ref'][1]} (|d| {best['ref'][0]:.2g})")
 bad = np.argwhere(~same)
 dn = np.abs(pl[..., :3] - rp[..., :3]).max(-1)
 tiny = (~same) & (dn < 1e-4) & (np.abs(pl[..., 3] - rp[..., 3]) < 1e-4 * np.abs(rp[..., 3]))
