@@ -27,12 +27,15 @@ bad = np.argwhere(co != fx["s1_costs"])
 for (y, x) in bad[:10]:
     print("  s1 cost differs", x, y, co[y, x], fx["s1_costs"][y, x], hex(se[y, x]), hex(fx["s1_selected"][y, x]))
 pl, co, se = run(2)
+acc = ctx.debug_read(4, (ch, cw), np.uint8)
 rp, rc, rs = fx["s2_planes"], fx["s2_costs"], fx["s2_selected"]
 same = (pl == rp).all(-1)
 print("step2: planes bitwise", same.mean(), "costs bitwise", ((co == rc) | (np.isnan(co) & np.isnan(rc))).mean(), "selected", (se == rs).mean())
 print("  among pixels with the same plane: costs bitwise", ((co == rc) | (np.isnan(co) & np.isnan(rc)))[same].mean(), "selected equal", (se == rs)[same].mean())
 cd = same & ~((co == rc) | (np.isnan(co) & np.isnan(rc)))
 print("  same plane, different cost:", int(cd.sum()), "pixels; |dcost| / cost percentiles 10/50/90:", np.percentile(np.abs(co - rc)[cd] / np.abs(rc)[cd], [10, 50, 90]))
+print("  accepted-candidate histogram, all pixels:", np.bincount(acc.ravel(), minlength=15).tolist())
+print("  accepted-candidate histogram, same plane / different cost:", np.bincount(acc[cd], minlength=15).tolist())
 for (y, x) in np.argwhere(cd)[:12]:
     print(f"    ({x},{y}) colour {(x+y)%2} ours {co[y,x]:.9g} ref {rc[y,x]:.9g} rel {abs(co[y,x]-rc[y,x])/abs(rc[y,x]):.3g} sel {se[y,x]:x}/{rs[y,x]:x} plane changed in sweep: {not (pl[y,x] == fx['s1_planes'][y,x]).all()}")
 # which integer view weights (15 draws) reproduce each stored cost from the per-view costs of the stored plane?
