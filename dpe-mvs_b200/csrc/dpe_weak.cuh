@@ -248,7 +248,7 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
       const short2 bp = lb[i];
       float dist = 0.0f;
       if (bp.x != -1 && bp.y != -1) {
-        dist = sqrtf((float)((x - bp.x) * (x - bp.x) + (y - bp.y) * (y - bp.y)));
+        dist = (float)sqrt((double)((x - bp.x) * (x - bp.x) + (y - bp.y) * (y - bp.y)));  // double in the reference (DPE.cu:2235)
         if (i >= 4) dist = (float)(dist / 1.4142135623730951);  // dist /= std::sqrt(2.0): a double division
       }
       bound_dist[i] = dist;
@@ -542,7 +542,7 @@ DPE_HDN void fit_plane_pixel(const StageArgs& a, const int x, const int y) {
       for (int d = 0; d < 8; ++d) {
         const short2 b = lbp[d];
         if (b.x == -1 || b.y == -1) continue;
-        mbd = fminf(mbd, sqrtf((float)((x - b.x) * (x - b.x) + (y - b.y) * (y - b.y))));
+        mbd = fminf(mbd, (float)sqrt((double)((x - b.x) * (x - b.x) + (y - b.y) * (y - b.y))));  // double in the reference (DPE.cu:3097)
       }
       if (mbd < radius) radius = (int)mbd;
     }
