@@ -163,6 +163,9 @@ def main():
         if ref_out:
             res["ours_exact_vs_ref"] = [compare(*ours_x[v], *ref_out[0][v]) for v in range(V)]
         res["ours_exact_vs_gt"] = [vs_gt(ours_x[v][0], ours_x[v][1], *gt[v], ours_x[v][2]) for v in range(V)]
+        if args.match:   # with the reference's direction-4 positions a sweep is racy here too: our own run-to-run noise
+            ours_y, _ = run_ours(2)
+            res["ours_exact_vs_ours_exact"] = [compare(*ours_y[v], *ours_x[v]) for v in range(V)]
 
     # ---- comparisons
     if len(ref_out) >= 1:
@@ -181,7 +184,7 @@ def main():
     (OUT / f"cmp_{tag}.json").write_text(json.dumps(res, indent=1))
     short = {k: v for k, v in res.items() if not isinstance(v, list)}
     print(json.dumps(short, indent=1))
-    for key in ("ours_vs_ref", "ours_exact_vs_ref", "ours_exact_vs_gt", "ref_vs_ref", "refseed2_vs_ref", "ref_vs_gt", "refseed2_vs_gt", "ours_vs_gt"):
+    for key in ("ours_vs_ref", "ours_exact_vs_ref", "ours_exact_vs_ours_exact", "ours_exact_vs_gt", "ref_vs_ref", "refseed2_vs_ref", "ref_vs_gt", "refseed2_vs_gt", "ours_vs_gt"):
         if key in res:
             print(key, json.dumps(res[key][0]))
             print(key, "mean over views", json.dumps({k: round(float(np.mean([r[k] for r in res[key] if k in r])), 4) for k in res[key][0]}))
