@@ -113,3 +113,26 @@ def test_full_schedule_with_weak_path():
     assert valid.mean() > 0.5
     assert (rel[valid] < 0.05).mean() > 0.6
     assert set(np.unique(st[0]["state"])) <= {0, 1, 2}
+
+
+def test_reference_arithmetic_restatement_agrees_with_the_folded_one(monkeypatch):
+    """The operation-by-operation restatement of the reference's cost arithmetic (ncc_old_exact: homography
+    from R_rel / t_rel / K per evaluation, taps in its association) and the constant-folded fast path are two
+    roundings of one formula: on the CPU build they agree to ~1e-4 (a tap crossing a 1/256 bin), and both to
+    ~1e-3 with float64 (raw moments).  The bit-level claim is tested on the GPU against the reference's own
+    device outputs (tests/test_gpu_parity.py)."""
+    spec, grays, cams, drs, pairs, gt = small_scene()
+    xy, planes = seeded_hypotheses(spec, cams, gt, 120, seed=5)
+    ids = [0] + pairs[0]
+    imgs = [grays[i].astype(np.float32) for i in ids]
+    cc = [cams[i] for i in ids]
+    fast = hostsim.cost_eval(imgs, cc, (spec.width, spec.height), xy, planes, quant=1, centred=False)
+    monkeypatch.setenv("DPE_HOSTSIM_EXACT", "1")
+    exact = hostsim.cost_eval(imgs, cc, (spec.width, spec.height), xy, planes, quant=1, centred=False)
+    assert np.array_equal(fast >= 2.0, exact >= 2.0)
+    d = np.abs(fast - exact)
+    assert np.median(d) < 2e-5 and np.percentile(d, 99) < 2e-3, (np.median(d), np.percentile(d, 99))
+    assert (d > 0).any()          # it really is a different code path
+    want = np.array([[O.bilateral_ncc_old(imgs[0], imgs[v + 1], cc[0], cc[v + 1], int(x), int(y), planes[i].astype(np.float64), quant=1)
+                      for v in range(len(ids) - 1)] for i, (x, y) in enumerate(xy)])
+    assert np.median(np.abs(exact - want)) < 3e-4 and np.percentile(np.abs(exact - want), 99) < 1e-2
