@@ -450,6 +450,10 @@ static void fill_args(dpe_ctx* ctx, int view, int k, const dpe_stage_params* p, 
   a.ref_race = ctx->ref_race ? 1 : 0;
   a.cost_raw = ctx->cost_raw ? 1 : 0;
   a.exact = ctx->exact ? 1 : 0;
+  {  // a stage truncated after a strong sweep leaves the fit-plane scratch free for the accepted-candidate codes
+    const int st = ctx->debug_stop_after;
+    a.debug_accept = (st == 2 || st == 5 || st == 8) ? reinterpret_cast<unsigned char*>(s.fit_planes) : nullptr;
+  }
   a.weak_list = s.weak_list; a.weak_count = s.weak_count; a.list_stride = ctx->W * ctx->H;
   a.eval_units = ctx->count_evals ? ctx->d_eval_units : nullptr;
   if (p) {
@@ -755,6 +759,7 @@ int dpe_debug_read(dpe_ctx* ctx, int what, void* out, size_t bytes) {
     case 7: src = s.planes; n = P * sizeof(float4); break;
     case 8: src = s.selected; n = P * sizeof(uint32_t); break;
     case 9: src = s.state; n = P; break;
+    case 11: src = s.fit_planes; n = P; break;  // accepted-candidate codes of a stage truncated after a strong sweep
     case 10: src = ctx->views[ctx->first_view].scales[ctx->last_stage_scale].lin; n = P * sizeof(float); break;
     default: return DPE_ERR_ARG;
   }

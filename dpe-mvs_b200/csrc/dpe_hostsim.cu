@@ -157,6 +157,7 @@ static int hostsim_stage_impl(int W, int H, int full_w, int full_h, int n_src, c
   a.ref_race = getenv("DPE_HOSTSIM_REF_RACE") ? 1 : 0;
   a.cost_raw = getenv("DPE_HOSTSIM_CENTRED") ? 0 : 1;
   a.exact = getenv("DPE_HOSTSIM_EXACT") ? 1 : 0;
+  a.debug_accept = nullptr;
   (void)stage_counter;
   std::vector<Xorwow> rng_states(P);
   xorwow_init_table(seed, W, H, rng_states.data());

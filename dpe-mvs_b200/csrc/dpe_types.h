@@ -91,6 +91,7 @@ struct StageArgs {
   int run_state, geom, use_apd, top_k, weak_peak_radius, rotate_time;
   float ransac_threshold, geom_factor;
   int iter, colour;
+  unsigned char* debug_accept;  // test hook (dpe_debug_stop_after at a strong-sweep step): per pixel, which candidate the sweep took
   int exact;     // 1: homography, source coordinates, bilateral weights and geometric consistency in the reference's fp32 operation order
   int cost_raw;  // cost arithmetic: 1 = moments on raw intensities like the reference, 0 = centred (dpe_core.cuh)
   int ref_race;  // 1: edge-mode direction 4 samples its own colour like the reference, racy

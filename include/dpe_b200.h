@@ -135,7 +135,8 @@ DPE_API int dpe_set_reference_race(dpe_ctx* ctx, int on);
 /* test hook: scratch arrays of the view that ran last on the first stream.  what: 0 anchors (P x 9 short2),
  * 1 fit planes (P float4), 2 radius (P int32), 3 costs (P float), 4 weak_reliable (P u8), 5 nearest strong
  * (P short2), 6 complexity (P float), 7 plane hypotheses in reference-camera coordinates (P float4), 8 selected
- * views (P uint32), 9 pixel state (P u8), 10 the image of the shard's first view at that scale (P float). */
+ * views (P uint32), 9 pixel state (P u8), 10 the image of the shard's first view at that scale (P float), 11 after a stage truncated at a strong sweep (step 2, 5, 8):
+ * which candidate each pixel took in it (P u8: 0 kept, 1..8 propagation slot + 1, 10..14 refinement hypothesis). */
 DPE_API int dpe_debug_read(dpe_ctx* ctx, int what, void* out, size_t bytes);
 /* test hook: the following stages stop after `step` of every view-stage, in the numbering of
  * DPE::RunPatchMatch's launch sequence (DPE.cu:3126-3249) used by oracle/ref_stage_probe.cu: 0 anchor search,

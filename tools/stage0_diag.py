@@ -27,7 +27,7 @@ bad = np.argwhere(co != fx["s1_costs"])
 for (y, x) in bad[:10]:
     print("  s1 cost differs", x, y, co[y, x], fx["s1_costs"][y, x], hex(se[y, x]), hex(fx["s1_selected"][y, x]))
 pl, co, se = run(2)
-acc = ctx.debug_read(4, (ch, cw), np.uint8)
+acc = ctx.debug_read(11, (ch, cw), np.uint8)
 rp, rc, rs = fx["s2_planes"], fx["s2_costs"], fx["s2_selected"]
 same = (pl == rp).all(-1)
 print("step2: planes bitwise", same.mean(), "costs bitwise", ((co == rc) | (np.isnan(co) & np.isnan(rc))).mean(), "selected", (se == rs).mean())
