@@ -174,19 +174,27 @@ def run_ours(args):
     V = len(grays)
     H, W = grays[0].shape
     n_scales = capi.compute_round_num(W, H)
-    spr = (V + world - 1) // world
-    first = min(rank * spr, V)
-    count = max(0, min(spr, V - first))
+    first, count = capi.shard_range(V, world, rank)
 
     ctx = capi.Context(local)
+    if use_dist:
+        # the library's own NCCL communicator (the all-gather of the depth atlas and the image broadcast run inside
+        # libdpe_b200.so); torch.distributed only carries the id and, below, the barrier + max-over-ranks of the timings
+        ids = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0, group=cpu_group)
+        ctx.comm_init_rank(ids[0], world, rank)
     ctx.scene_begin(V, W, H, n_scales)
     for v in range(V):
-        ctx.set_view(v, grays[v], *cams[v], *drs[v])
+        if rank == 0:
+            ctx.set_view(v, grays[v], *cams[v], *drs[v])
+        else:
+            ctx.set_cams(v, *cams[v], *drs[v])          # images arrive by the broadcast
         ctx.set_pairs(v, pairs[v])
     for v in range(first, first + count):
         for k, (e, l) in enumerate(product_prep(lib, grays[v], n_scales)):
             ctx.set_prep(v, k, e, l)
-    ctx.set_shard(first, count, spr, world)
+    ctx.set_shard(V, rank, world)
+    ctx.broadcast_images(0)
     ctx.commit()
     # cost arithmetic: the product default (the reference's own, operation by operation) unless DPE_ARITH=fast|centred,
     # which dpe_mvs() honours too (host/pipeline.cpp)
@@ -194,26 +202,9 @@ def run_ours(args):
     ctx.set_cost_arithmetic(arith)
     sched = capi.stage_schedule(n_scales)
 
-    def atlas_tensor():
-        ptr, chunk, total = ctx.stage_atlas()
-
-        class _Raw:
-            __cuda_array_interface__ = {"shape": (total // 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-        return torch.as_tensor(_Raw(), device=torch.device("cuda", local)), chunk // 4
-
-    gather_ms_acc = [0.0]
-
     def one_step():
         for (k, p) in sched:
-            ctx.run_stage(k, p, SEED)
-            if use_dist:
-                full, chunk = atlas_tensor()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                dist.all_gather_into_tensor(full, full[rank * chunk:(rank + 1) * chunk])
-                e1.record()
-                e1.synchronize()
-                gather_ms_acc[0] += e0.elapsed_time(e1)
+            ctx.run_stage(k, p, SEED)      # every kernel of every owned view + the NCCL all-gathers, one sync
             ctx.stage_commit()
 
     def sync_all():
@@ -228,23 +219,23 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0, m0 = ctx.kernel_launches(), ctx.stage_gpu_ms()
-    gather_ms_acc[0] = 0.0
+    l0, m0, c0 = ctx.kernel_launches(), ctx.stage_gpu_ms(), ctx.stage_comm_ms()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         one_step()
     sync_all()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
-    dev_ms = (ctx.stage_gpu_ms() - m0) + gather_ms_acc[0]        # CUDA-event time on this rank
+    dev_ms = ctx.stage_gpu_ms() - m0        # CUDA events around every stage (kernels + exchange) on this rank
+    comm_ms = ctx.stage_comm_ms() - c0      # of which: after this rank's last view, until the exchange is complete
     launches = ctx.kernel_launches() - l0
     if use_dist:
-        tt = torch.tensor([dev_ms, wall * 1e3, float(launches), gather_ms_acc[0]], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([dev_ms, wall * 1e3, float(launches), comm_ms], dtype=torch.float64, device="cuda")
         mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         mn = tt.clone(); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
-        # the all-gather time of a rank includes waiting for slower ranks; the minimum over ranks (the rank
-        # that arrives last) is what the collective itself costs, the maximum is the load imbalance
+        # the rank that finishes its views last sees only the exposed tail of the exchange (minimum over ranks);
+        # the maximum over ranks is the load imbalance (a rank with one view fewer waits a view's time)
         dev_ms, wall_ms, launches, gather_ms, gather_wait_ms = float(mx[0]), float(mx[1]), int(sm[2]), float(mn[3]), float(mx[3])
     else:
         wall_ms, gather_ms, gather_wait_ms = wall * 1e3, 0.0, 0.0
@@ -257,10 +248,10 @@ def run_ours(args):
     if arith == 2:
         ctx.set_cost_arithmetic(1)
         sync_all()
-        mf, gf = ctx.stage_gpu_ms(), gather_ms_acc[0]
+        mf = ctx.stage_gpu_ms()
         one_step()
         sync_all()
-        fast_ms = (ctx.stage_gpu_ms() - mf) + (gather_ms_acc[0] - gf)
+        fast_ms = ctx.stage_gpu_ms() - mf
         if use_dist:
             tf = torch.tensor([fast_ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(tf, op=dist.ReduceOp.MAX)
@@ -338,18 +329,25 @@ def run_ours(args):
             os.environ["DPE_GPUS"] = ",".join(str(i) for i in range(world))
         tj = folder / "timing.json"
         os.environ["DPE_TIMING_JSON"] = str(tj)
-        t0 = time.perf_counter()
-        DPE_MVS.dpe_mvs(str(folder), local if world == 1 else -1, False, False, False, True, False, False, False)
-        e2e_s = time.perf_counter() - t0
+        runs = []
+        for rep in range(3):        # the first call also brings up CUDA contexts (and, N > 1, the NCCL communicator) on the GPUs
+            shutil.rmtree(folder / "DPE", ignore_errors=True)
+            t0 = time.perf_counter()
+            DPE_MVS.dpe_mvs(str(folder), local if world == 1 else -1, False, False, False, True, False, False, False)
+            dt = time.perf_counter() - t0
+            try:
+                bd = json.loads(tj.read_text())
+            except Exception:
+                bd = None
+            runs.append((dt, bd))
+        order = sorted(range(3), key=lambda i: runs[i][0])
+        e2e_s, bd = runs[order[1]]
         px = [(int(np.floor(W / (1 << (n_scales - 1 - k)) + 0.5)) * int(np.floor(H / (1 << (n_scales - 1 - k)) + 0.5))) for k in range(n_scales)]
-        h2d = V * W * H * world + V * sum(5 * p for p in px)        # images on every GPU + edge(1)+label(4) per scale
-        d2h = V * W * H + V * W * H * (16 + 1)                       # nvJPEG luma back to host + planes(16)+state(1)
+        h2d = V * W * H + V * sum(5 * p for p in px)                 # images once (broadcast over NVLink) + edge(1)+label(4) per scale
+        d2h = V * W * H + V * W * H * 4                              # nvJPEG luma back to host + depth.npy payload
         e2e = {"value": V / e2e_s, "unit": "depth maps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "seconds": e2e_s, "api": "DPE_MVS.dpe_mvs(dense_folder, depth=True)"}
-        try:
-            e2e["breakdown"] = json.loads(tj.read_text())
-        except Exception:
-            pass
+               "seconds": e2e_s, "seconds_all_runs": [r[0] for r in runs], "statistic": "median of 3 calls",
+               "api": "DPE_MVS.dpe_mvs(dense_folder, depth=True)", "breakdown": bd}
     if use_dist:
         dist.barrier(group=cpu_group)
 
@@ -364,7 +362,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "views": V, "width": W, "height": H, "src_per_view": len(pairs[0]),
-                       "view_stages_per_step": V * len(sched), "parallelism": f"views sharded over {world} GPU(s), NCCL all-gather of the depth atlas per stage",
+                       "view_stages_per_step": V * len(sched), "parallelism": f"reference views sharded over {world} GPU(s); per stage one in-place ncclAllGather per view slot of the depth atlas, issued by libdpe_b200.so behind each view's last kernel",
                        "l2": "inputs larger than L2 (per view-stage ~0.5 GB of state + 11 images; 49 views cycle through)",
                        "rng_seed": SEED,
                        "cost_arithmetic": {2: "reference, operation by operation (default)", 1: "reference moments, constant-folded homography (DPE_ARITH=fast)", 0: "centred (DPE_ARITH=centred)"}[arith]},

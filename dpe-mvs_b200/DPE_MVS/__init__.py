@@ -12,6 +12,28 @@ from ._dpe import dpe_mvs as _native  # type: ignore
 __all__ = ["dpe_mvs"]
 
 
+def _nccl_hint():
+    """Multi-GPU runs bind NCCL at run time (csrc/dpe_capi.cu: NcclApi).  When this interpreter has a pip-installed
+    NCCL (PyTorch's, newer than the system's, same soname), point the library at that file so that a later
+    `import torch` in the same process finds the NCCL it was built against already loaded."""
+    import importlib.util
+    import os
+    if os.environ.get("DPE_NCCL_LIB"):
+        return
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["DPE_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
+_nccl_hint()
+
+
 def dpe_mvs(
     dense_folder: str,
     gpu_index: int = 0,

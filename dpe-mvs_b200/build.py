@@ -4,7 +4,6 @@ Artifacts (all git-ignored, all travel to the GPU box with the snapshot):
   dpe-mvs_b200/lib/libdpe_b200.so       CUDA kernels (sm_100a) + C ABI + C++ host pipeline
   dpe-mvs_b200/DPE_MVS/_dpe.*.so         pybind11 module (drop-in for the reference's _dpe)
   dpe-mvs_b200/bin/DPE                   CLI (drop-in for the reference's ./DPE)
-  dpe-mvs_b200/lib/libdpe_hostsim.so    TEST-ONLY CPU simulator of the kernel logic
 """
 from __future__ import annotations
 
@@ -67,17 +66,7 @@ def build_lib(verbose=False, force=False) -> Path:
         objs.append(o)
     so = LIB / "libdpe_b200.so"
     if force or _newer(so, objs):
-        _run([NVCC, *ARCH, "-shared", "-o", so, *objs, "-lnvjpeg", "-lcudart", "-lpthread"], verbose)
-    return so
-
-
-def build_hostsim(verbose=False, force=False) -> Path:
-    LIB.mkdir(exist_ok=True)
-    so = LIB / "libdpe_hostsim.so"
-    src = CSRC / "dpe_hostsim.cu"
-    if force or _newer(so, [src] + _headers()):
-        _run([NVCC, "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared", "-I", CSRC,
-              "-I", HERE.parent / "include", src, "-o", so, "-lgomp"], verbose)
+        _run([NVCC, *ARCH, "-shared", "-o", so, *objs, "-lnvjpeg", "-lcudart", "-lpthread", "-ldl"], verbose)
     return so
 
 
@@ -107,7 +96,6 @@ def build_cli(verbose=False, force=False) -> Path:
 
 def build_all(verbose=False, force=False):
     build_lib(verbose, force)
-    build_hostsim(verbose, force)
     if (CSRC / "bindings.cpp").exists():
         build_pybind(verbose, force)
     if (CSRC / "main.cpp").exists():

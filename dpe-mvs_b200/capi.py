@@ -28,12 +28,33 @@ class StageParams(C.Structure):
 SYMBOLS = [
     "dpe_ctx_create", "dpe_ctx_destroy", "dpe_last_error", "dpe_kernel_launches", "dpe_scene_begin",
     "dpe_scene_set_view", "dpe_scene_set_pairs", "dpe_scene_set_prep", "dpe_scene_set_shard", "dpe_scene_commit",
-    "dpe_run_stage", "dpe_stage_atlas", "dpe_stage_commit", "dpe_cost_eval", "dpe_geom_eval", "dpe_get_size",
+    "dpe_run_stage", "dpe_stage_begin", "dpe_stage_wait_view", "dpe_stage_end", "dpe_stage_atlas", "dpe_view_slot", "dpe_stage_commit",
+    "dpe_shard_range", "dpe_comm_get_unique_id", "dpe_comm_init_rank", "dpe_comm_init_all", "dpe_comm_reset_all",
+    "dpe_scene_broadcast_images", "dpe_export_view", "dpe_scene_set_active", "dpe_stage_comm_ms", "dpe_cost_eval", "dpe_geom_eval", "dpe_get_size",
     "dpe_get_maps", "dpe_set_count_evals", "dpe_eval_units", "dpe_stage_gpu_ms", "dpe_probe_tex_rate",
     "dpe_probe_fma_rate", "dpe_probe_tex_pattern", "dpe_probe_tex_weights", "dpe_run_pipeline", "dpe_set_profile", "dpe_get_profile", "dpe_set_view_order", "dpe_bench_ncc", "dpe_set_reference_race", "dpe_debug_read", "dpe_debug_stop_after", "dpe_debug_set_maps", "dpe_set_cost_arithmetic", "dpe_fuse_set_view", "dpe_fuse_run", "dpe_fuse_get",
 ]
 
 _lib = None
+
+
+def _nccl_hint():
+    """Multi-GPU runs bind NCCL at run time (csrc/dpe_capi.cu: NcclApi).  When this interpreter has a pip-installed
+    NCCL (PyTorch's, newer than the system's, same soname), point the library at that file so that a later
+    `import torch` in the same process finds the NCCL it was built against already loaded."""
+    import importlib.util
+    import os
+    if os.environ.get("DPE_NCCL_LIB"):
+        return
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["DPE_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
 
 
 def load(build=True):
@@ -49,6 +70,7 @@ def load(build=True):
         b.build_lib()
     if not LIB_PATH.exists():
         raise RuntimeError(f"{LIB_PATH} is missing: build the CUDA extension first (python dpe-mvs_b200/build.py)")
+    _nccl_hint()
     lib = C.CDLL(str(LIB_PATH))
     vp, ci, cf = C.c_void_p, C.c_int, C.c_float
     lib.dpe_ctx_create.argtypes = [C.POINTER(vp), ci]
@@ -61,8 +83,21 @@ def load(build=True):
     lib.dpe_scene_begin.argtypes = [vp, ci, ci, ci, ci]
     lib.dpe_scene_set_view.argtypes = [vp, ci, vp, vp, vp, vp, cf, cf]
     lib.dpe_scene_set_pairs.argtypes = [vp, ci, vp, ci]
-    lib.dpe_scene_set_prep.argtypes = [vp, ci, ci, vp, vp]
-    lib.dpe_scene_set_shard.argtypes = [vp, ci, ci, ci, ci]
+    lib.dpe_scene_set_prep.argtypes = [vp, ci, ci, vp, vp, C.c_size_t]
+    lib.dpe_scene_set_shard.argtypes = [vp, ci, ci, ci]
+    lib.dpe_scene_broadcast_images.argtypes = [vp, ci]
+    lib.dpe_scene_set_active.argtypes = [vp, ci, ci]
+    lib.dpe_shard_range.argtypes = [ci, ci, ci, C.POINTER(ci), C.POINTER(ci)]
+    lib.dpe_comm_get_unique_id.argtypes = [vp, C.c_size_t]
+    lib.dpe_comm_init_rank.argtypes = [vp, vp, ci, ci]
+    lib.dpe_comm_init_all.argtypes = [C.POINTER(vp), ci]
+    lib.dpe_comm_reset_all.argtypes = []
+    lib.dpe_comm_reset_all.restype = None
+    lib.dpe_stage_begin.argtypes = [vp, ci, C.POINTER(StageParams), C.c_uint64]
+    lib.dpe_stage_wait_view.argtypes = [vp, ci]
+    lib.dpe_stage_end.argtypes = [vp]
+    lib.dpe_view_slot.argtypes = [vp, ci, C.POINTER(ci)]
+    lib.dpe_export_view.argtypes = [vp, ci, vp, vp, vp]
     lib.dpe_scene_commit.argtypes = [vp]
     lib.dpe_run_stage.argtypes = [vp, ci, C.POINTER(StageParams), C.c_uint64]
     lib.dpe_stage_atlas.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
@@ -76,6 +111,8 @@ def load(build=True):
     lib.dpe_eval_units.restype = C.c_double
     lib.dpe_stage_gpu_ms.argtypes = [vp]
     lib.dpe_stage_gpu_ms.restype = C.c_double
+    lib.dpe_stage_comm_ms.argtypes = [vp]
+    lib.dpe_stage_comm_ms.restype = C.c_double
     lib.dpe_probe_tex_rate.argtypes = [vp, ci, ci, ci, C.POINTER(C.c_double)]
     lib.dpe_probe_fma_rate.argtypes = [vp, ci, C.POINTER(C.c_double)]
     lib.dpe_probe_tex_pattern.argtypes = [vp, ci, ci, ci, ci, ci, vp, ci, ci, C.POINTER(C.c_double)]
@@ -95,6 +132,26 @@ def load(build=True):
     lib.dpe_run_pipeline.argtypes = [C.c_char_p, ci, ci, ci, ci, ci, ci, ci, ci]
     _lib = lib
     return lib
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library (rank 0 calls it; the launcher hands the bytes to every rank)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = load().dpe_comm_get_unique_id(buf, COMM_ID_BYTES)
+    if rc != 0:
+        raise DpeError(f"dpe_comm_get_unique_id failed with code {rc}")
+    return buf.raw
+
+
+def shard_range(n_problems, n_ranks, rank):
+    """(first, count) of the block of reference views rank `rank` owns (dpe_shard_range)."""
+    f, c = C.c_int(), C.c_int()
+    if load().dpe_shard_range(n_problems, n_ranks, rank, C.byref(f), C.byref(c)) != 0:
+        raise DpeError("dpe_shard_range: bad arguments")
+    return f.value, c.value
 
 
 def stage_schedule(n_scales):
@@ -171,11 +228,33 @@ class Context:
     def set_prep(self, view, scale, edge=None, label=None):
         e = np.ascontiguousarray(edge, np.uint8) if edge is not None else None
         l = np.ascontiguousarray(label, np.int32) if label is not None else None
+        n = e.size if e is not None else (l.size if l is not None else 0)
+        if e is not None and l is not None and e.size != l.size:
+            raise DpeError("edge and label arrays differ in size")
         self._ck(self.lib.dpe_scene_set_prep(self.h, view, scale, e.ctypes.data if e is not None else None,
-                                             l.ctypes.data if l is not None else None))
+                                             l.ctypes.data if l is not None else None, n))
 
-    def set_shard(self, first, count, slots_per_rank, n_ranks):
-        self._ck(self.lib.dpe_scene_set_shard(self.h, first, count, slots_per_rank, n_ranks))
+    def set_shard(self, n_problems, rank, n_ranks):
+        """This context is rank `rank` of n_ranks; it owns the block shard_range(n_problems, n_ranks, rank)."""
+        self._ck(self.lib.dpe_scene_set_shard(self.h, n_problems, rank, n_ranks))
+
+    def set_active(self, first, count):
+        """Test / profiling hook: run stages over views [first, first + count) only."""
+        self._ck(self.lib.dpe_scene_set_active(self.h, first, count))
+
+    def comm_init_rank(self, unique_id: bytes, n_ranks, rank):
+        buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        self._ck(self.lib.dpe_comm_init_rank(self.h, buf, n_ranks, rank))
+
+    def broadcast_images(self, root=0):
+        self._ck(self.lib.dpe_scene_broadcast_images(self.h, root))
+
+    def set_cams(self, view, K, R, t, dmin, dmax):
+        """Camera only; the image arrives by broadcast_images()."""
+        K = np.ascontiguousarray(K, np.float32).reshape(9)
+        R = np.ascontiguousarray(R, np.float32).reshape(9)
+        t = np.ascontiguousarray(t, np.float32).reshape(3)
+        self._ck(self.lib.dpe_scene_set_view(self.h, view, None, K.ctypes.data, R.ctypes.data, t.ctypes.data, dmin, dmax))
 
     def commit(self):
         self._ck(self.lib.dpe_scene_commit(self.h))
@@ -184,10 +263,35 @@ class Context:
     def run_stage(self, scale_idx, params, seed):
         self._ck(self.lib.dpe_run_stage(self.h, scale_idx, C.byref(params), C.c_uint64(seed)))
 
+    def stage_begin(self, scale_idx, params, seed):
+        self._ck(self.lib.dpe_stage_begin(self.h, scale_idx, C.byref(params), C.c_uint64(seed)))
+
+    def stage_wait_view(self, view):
+        self._ck(self.lib.dpe_stage_wait_view(self.h, view))
+
+    def stage_end(self):
+        self._ck(self.lib.dpe_stage_end(self.h))
+
+    def view_slot(self, view):
+        s = C.c_int()
+        self._ck(self.lib.dpe_view_slot(self.h, view, C.byref(s)))
+        return s.value
+
+    def export_view(self, view, scale_idx, depth=True, normal=True, weak=True):
+        """The payloads of depth.npy / normal.npy / weak.npy of a view."""
+        w, h = self.size(scale_idx)
+        d = np.empty((h, w), np.float32) if depth else None
+        n = np.empty((h, w, 3), np.float32) if normal else None
+        k = np.empty((h, w), np.int8) if weak else None
+        self._ck(self.lib.dpe_export_view(self.h, view, d.ctypes.data if depth else None, n.ctypes.data if normal else None,
+                                          k.ctypes.data if weak else None))
+        return dict(depth=d, normal=n, weak=k)
+
     def stage_atlas(self):
-        p, chunk, total = C.c_void_p(), C.c_size_t(), C.c_size_t()
-        self._ck(self.lib.dpe_stage_atlas(self.h, C.byref(p), C.byref(chunk), C.byref(total)))
-        return p.value, chunk.value, total.value
+        """(device pointer, bytes per slot, total bytes) of the atlas the last stage wrote."""
+        p, slot, total = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        self._ck(self.lib.dpe_stage_atlas(self.h, C.byref(p), C.byref(slot), C.byref(total)))
+        return p.value, slot.value, total.value
 
     def stage_commit(self):
         self._ck(self.lib.dpe_stage_commit(self.h))
@@ -233,6 +337,9 @@ class Context:
 
     def stage_gpu_ms(self):
         return self.lib.dpe_stage_gpu_ms(self.h)
+
+    def stage_comm_ms(self):
+        return self.lib.dpe_stage_comm_ms(self.h)
 
     def kernel_launches(self):
         return self.lib.dpe_kernel_launches(self.h)
@@ -318,8 +425,9 @@ class Context:
         return w
 
 
-def upload_scene(ctx: Context, images, cams, depth_ranges, pairs, n_scales=None, shard=None):
-    """images: list of HxW uint8; cams: list of (K,R,t); pairs: list of source-id lists."""
+def upload_scene(ctx: Context, images, cams, depth_ranges, pairs, n_scales=None, shard=None, active=None):
+    """images: list of HxW uint8; cams: list of (K,R,t); pairs: list of source-id lists;
+    shard = (n_problems, rank, n_ranks); active = (first, count)."""
     H, W = images[0].shape
     if n_scales is None:
         n_scales = compute_round_num(W, H)
@@ -329,5 +437,7 @@ def upload_scene(ctx: Context, images, cams, depth_ranges, pairs, n_scales=None,
         ctx.set_pairs(v, pairs[v])
     if shard is not None:
         ctx.set_shard(*shard)
+    if active is not None:
+        ctx.set_active(*active)
     ctx.commit()
     return n_scales

@@ -1,5 +1,5 @@
 // dpe_capi.cu — C-ABI layer (include/dpe_b200.h) over the sm_100a kernels: context,
-// scene-resident device state, per-stage orchestration.
+// scene-resident device state, per-stage orchestration, the NCCL exchange between GPUs.
 //
 // Where the reference rebuilds everything per (view, stage) — N+1 JPEG decodes, cv::resize,
 // 2(N+1) cudaMallocArray + texture objects, ~20 cudaMallocs, .dmb round trips
@@ -7,15 +7,24 @@
 // levels of all images as float textures + linear copies, cameras folded to per-pair
 // constants in double precision, prep arrays, and per-view PatchMatch state that never
 // leaves HBM between stages.  Source depth maps for geometric consistency live in one
-// "depth atlas" per scale ([slot][pixel] floats) so that a multi-GPU driver can all-gather
-// it in place.
+// "depth atlas" per scale ([slot][pixel] floats); with several GPUs each rank owns a block of
+// reference views and the atlas is all-gathered in place with NCCL, one collective per view
+// slot, issued on a side stream as soon as that view's last kernel has written its slot.
+// Nothing is allocated or freed while a stage is in flight (an implicit device synchronisation
+// under an NCCL kernel that waits for a peer is how multi-GPU processes deadlock).
 #include <cuda_runtime.h>
 #include <cuda_profiler_api.h>
 #include <cuda_fp16.h>
+#include <nccl.h>  // types and prototypes only: the library itself is bound at run time (NcclApi below)
+#include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <map>
+#include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 #include "dpe_kernels.cuh"
 #include "dpe_fusion.cuh"
@@ -27,23 +36,28 @@ namespace {
 
 struct ScaleImg {
   float* lin = nullptr;          // W*H float
-  uint8_t* edge = nullptr;       // edges_k (optional)
+  // prep arrays (optional): pointers into dpe_ctx::edge_slab / label_slab / bits_slab once supplied
+  uint8_t* edge = nullptr;       // edges_k
   uint32_t* edge_bits = nullptr; // coarsest scale only: the same map, one bit per pixel (rows of (w+31)/32 words)
-  int32_t* label = nullptr;      // labels_k (optional)
+  int32_t* label = nullptr;      // labels_k
+  // prep handed in before dpe_scene_commit waits here until the slabs exist
+  std::vector<uint8_t> pending_edge;
+  std::vector<int32_t> pending_label;
 };
 
 struct ViewData {
   HostCam cam;
+  bool have_cam = false;
   bool have_img = false;
   std::vector<int> src;
   std::vector<float> relpose;  // per source: R_rel[9], t_rel[3] as the device computes them (k_relative_pose)
   std::vector<ScaleImg> scales;
-  // state carried between stages (owner only)
+  // state carried between stages (owner only): pointers into dpe_ctx::maps_*[cur_buf]
   float4* planes = nullptr;  // (world normal, depth)
   uint8_t* state = nullptr;
   uint32_t* selected = nullptr;
   int cur_scale = -1;  // scale index of planes/state/selected
-  uint8_t* gray_full = nullptr;  // uploaded u8 image: this view's part of dpe_ctx::gray_slab
+  int cur_buf = 0;     // which of the two map buffers holds them (a stage at a new scale writes the other one)
 };
 
 struct FuseData {
@@ -59,6 +73,50 @@ struct Scratch {
   int* weak_list = nullptr; int* weak_count = nullptr;
   cudaStream_t stream = nullptr;
 };
+
+// NCCL is bound at run time, on the first call that needs a communicator, not linked: a process that never
+// leaves one GPU never loads it, and a process that already holds an NCCL (PyTorch ships its own, newer than
+// the system's, under the same soname) keeps using that one instead of getting a second copy or the wrong one.
+// Search order: the libnccl.so.2 already in the process, $DPE_NCCL_LIB, the loader's libnccl.so.2.
+struct NcclApi {
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommInitAll) CommInitAll = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclCommAbort) CommAbort = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok = false;
+  std::string why;
+};
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+const NcclApi& nccl_api() {
+  std::call_once(g_nccl_once, []() {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) if (const char* e = getenv("DPE_NCCL_LIB")) h = dlopen(e, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { g_nccl.why = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+    bool all = true;
+    auto bind = [&](auto& fn, const char* name) {
+      fn = reinterpret_cast<typename std::remove_reference<decltype(fn)>::type>(dlsym(h, name));
+      if (!fn) { all = false; g_nccl.why = std::string("libnccl.so.2 lacks ") + name; }
+    };
+    bind(g_nccl.GetUniqueId, "ncclGetUniqueId"); bind(g_nccl.CommInitRank, "ncclCommInitRank");
+    bind(g_nccl.CommInitAll, "ncclCommInitAll"); bind(g_nccl.CommDestroy, "ncclCommDestroy");
+    bind(g_nccl.CommAbort, "ncclCommAbort"); bind(g_nccl.AllGather, "ncclAllGather");
+    bind(g_nccl.Broadcast, "ncclBroadcast"); bind(g_nccl.GetErrorString, "ncclGetErrorString");
+    g_nccl.ok = all;
+  });
+  return g_nccl;
+}
+
+// NCCL communicators of single-process multi-GPU runs (dpe_comm_init_all), kept for the life of the
+// process: creating one costs far more than a stage, a second dpe_run_pipeline call reuses it.
+struct CommSet { std::vector<ncclComm_t> comms; };
+std::mutex g_comm_mutex;
+std::map<std::vector<int>, CommSet> g_comm_cache;
 
 }  // namespace
 
@@ -78,13 +136,33 @@ struct dpe_ctx {
   // cudaFree per view serialises on the driver lock and synchronises the device)
   uint8_t* gray_slab = nullptr;
   std::vector<float*> lin_slab;
+  // prep arrays of the owned views: per scale [n_local][P_k]; bit-packed coarsest edges [n_local][words*h]
+  std::vector<uint8_t*> edge_slab;
+  std::vector<int32_t*> label_slab;
+  uint32_t* bits_slab = nullptr;
+  // carried maps of the owned views, double-buffered, sized for the finest scale: [2][n_local][P_full]
+  float4* maps_planes[2] = {nullptr, nullptr};
+  uint8_t* maps_state[2] = {nullptr, nullptr};
+  uint32_t* maps_selected[2] = {nullptr, nullptr};
   bool committed = false;
-  // shard
-  int first_view = 0, n_local = 0, slots_per_rank = 0, n_ranks = 1;
+  // shard: problems [0, n_problems) split into n_ranks contiguous balanced blocks (dpe_shard_range); atlas slot of
+  // a problem view = local index * n_ranks + owner rank, so that the views with local index i of all ranks form
+  // one contiguous chunk — the in-place ncclAllGather of view slot i
+  int n_problems = 0, rank = 0, n_ranks = 1;
+  int first_view = 0, n_local = 0, slots_per_rank = 0;
+  ncclComm_t comm = nullptr;
+  bool comm_owned = false;  // created by dpe_comm_init_rank (destroyed with the context); cached ones are not
+  cudaStream_t comm_stream = nullptr, upload_stream = nullptr, copy_stream = nullptr;
+  std::vector<cudaEvent_t> view_done;  // per local view: its last kernel of the running stage
+  cudaEvent_t comm_done = nullptr;
+  bool comm_queued = false;  // the running stage has all-gathers in flight
+  // device staging of dpe_export_view (depth, normal3, weak as the .npy files hold them)
+  float* exp_depth = nullptr; float* exp_normal = nullptr; int8_t* exp_weak = nullptr;
   // depth atlas per scale: front = committed (read by geom stages), back = being written
   std::vector<float*> atlas_front, atlas_back;
   int last_stage_scale = -1;
   bool stage_pending = false;
+  bool stage_open = false;    // between dpe_stage_begin and dpe_stage_end
   bool gauss_seidel = false;  // dpe_set_view_order
   bool ref_race = false;      // dpe_set_reference_race
   bool cost_raw = true;       // dpe_set_cost_arithmetic
@@ -104,8 +182,9 @@ struct dpe_ctx {
   bool count_evals = false;
   double eval_units_total = 0.0;
   double stage_ms = 0.0;
+  double comm_ms = 0.0;
   uint32_t stage_counter = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_views = nullptr;
   // per-kernel-class profile (dpe_set_profile): single stream, CUDA events around each launch
   bool profile = false;
   int debug_stop_after = -1;  // dpe_debug_stop_after: last step of a view-stage that still runs (-1: all)
@@ -127,20 +206,47 @@ struct dpe_ctx {
     }                                                                                    \
   } while (0)
 
+#define NCK(call)                                                                        \
+  do {                                                                                   \
+    ncclResult_t r_ = (call);                                                            \
+    if (r_ != ncclSuccess) {                                                             \
+      char buf_[512];                                                                    \
+      snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #call, nccl_api().GetErrorString(r_), __FILE__, __LINE__); \
+      ctx->err = buf_;                                                                   \
+      return DPE_ERR_COMM;                                                               \
+    }                                                                                    \
+  } while (0)
+
 #define FAIL(code, msg) \
   do { ctx->err = (msg); return (code); } while (0)
 
 static LaunchCfg cfg_of(dpe_ctx* ctx) { return LaunchCfg{ctx->num_sms, &ctx->launches}; }
 
-static void free_scene(dpe_ctx* ctx) {
-  for (auto& v : ctx->views) {
-    for (auto& s : v.scales) { cudaFree(s.edge); cudaFree(s.edge_bits); cudaFree(s.label); }
-    cudaFree(v.planes); cudaFree(v.state); cudaFree(v.selected);
+// atlas slot of a view (see dpe_ctx::n_problems)
+static int slot_of(const dpe_ctx* ctx, int view) {
+  if (view >= ctx->n_problems) return ctx->slots_per_rank * ctx->n_ranks + (view - ctx->n_problems);
+  int first = 0, count = 0, r = 0;
+  for (; r < ctx->n_ranks; ++r) {
+    dpe_shard_range(ctx->n_problems, ctx->n_ranks, r, &first, &count);
+    if (view < first + count) break;
   }
+  return (view - first) * ctx->n_ranks + r;
+}
+static int total_slots(const dpe_ctx* ctx) { return ctx->slots_per_rank * ctx->n_ranks + (ctx->n_views - ctx->n_problems); }
+
+static void free_scene(dpe_ctx* ctx) {
   ctx->views.clear();
   cudaFree(ctx->gray_slab); ctx->gray_slab = nullptr;
   for (auto p : ctx->lin_slab) cudaFree(p);
   ctx->lin_slab.clear();
+  for (auto p : ctx->edge_slab) cudaFree(p);
+  for (auto p : ctx->label_slab) cudaFree(p);
+  ctx->edge_slab.clear(); ctx->label_slab.clear();
+  cudaFree(ctx->bits_slab); ctx->bits_slab = nullptr;
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(ctx->maps_planes[b]); cudaFree(ctx->maps_state[b]); cudaFree(ctx->maps_selected[b]);
+    ctx->maps_planes[b] = nullptr; ctx->maps_state[b] = nullptr; ctx->maps_selected[b] = nullptr;
+  }
   for (auto t : ctx->scale_tex) if (t) cudaDestroyTextureObject(t);
   for (auto a : ctx->scale_arr) if (a) cudaFreeArray(a);
   ctx->scale_tex.clear(); ctx->scale_arr.clear();
@@ -155,6 +261,10 @@ static void free_scene(dpe_ctx* ctx) {
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   ctx->scratch.clear();
+  for (auto e : ctx->view_done) cudaEventDestroy(e);
+  ctx->view_done.clear();
+  cudaFree(ctx->exp_depth); cudaFree(ctx->exp_normal); cudaFree(ctx->exp_weak);
+  ctx->exp_depth = nullptr; ctx->exp_normal = nullptr; ctx->exp_weak = nullptr;
   for (auto& f : ctx->fuse) { cudaFree(f.depth); cudaFree(f.normal); cudaFree(f.state); cudaFree(f.bgr); cudaFree(f.mask); }
   ctx->fuse.clear(); ctx->cloud.clear();
   for (auto p : ctx->rng_table) cudaFree(p);
@@ -162,6 +272,7 @@ static void free_scene(dpe_ctx* ctx) {
   cudaFree(ctx->zero_edge); ctx->zero_edge = nullptr;
   cudaFree(ctx->zero_label); ctx->zero_label = nullptr;
   ctx->committed = false;
+  ctx->stage_open = false; ctx->stage_pending = false;
 }
 
 extern "C" {
@@ -179,8 +290,17 @@ int dpe_ctx_create(dpe_ctx** out, int gpu_index) {
   if (cudaGetDeviceProperties(&prop, gpu_index) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
   cudaEventCreate(&ctx->ev0);
   cudaEventCreate(&ctx->ev1);
+  cudaEventCreate(&ctx->ev_views);
   cudaEventCreate(&ctx->pa);
   cudaEventCreate(&ctx->pb);
+  cudaEventCreateWithFlags(&ctx->comm_done, cudaEventDisableTiming);
+  // the exchange runs beside the view kernels: highest priority, so that its few CTAs are placed as soon as a
+  // persistent view kernel retires
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_hi);
+  cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   cudaMalloc(&ctx->d_eval_units, sizeof(unsigned long long));
   cudaMemset(ctx->d_eval_units, 0, sizeof(unsigned long long));
   *out = ctx;
@@ -191,22 +311,90 @@ void dpe_ctx_destroy(dpe_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  if (ctx->comm && ctx->comm_owned) nccl_api().CommDestroy(ctx->comm);
+  ctx->comm = nullptr;
   free_scene(ctx);
   cudaFree(ctx->d_eval_units);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev_views) cudaEventDestroy(ctx->ev_views);
   if (ctx->pa) cudaEventDestroy(ctx->pa);
   if (ctx->pb) cudaEventDestroy(ctx->pb);
+  if (ctx->comm_done) cudaEventDestroy(ctx->comm_done);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
 }
 
 const char* dpe_last_error(const dpe_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 long long dpe_kernel_launches(const dpe_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+// ---- multi-GPU: shard arithmetic + NCCL communicator -------------------------------------------
+int dpe_shard_range(int n_problems, int n_ranks, int rank, int* first, int* count) {
+  if (n_problems < 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return DPE_ERR_ARG;
+  const int q = n_problems / n_ranks, rem = n_problems % n_ranks;
+  if (first) *first = rank * q + (rank < rem ? rank : rem);
+  if (count) *count = q + (rank < rem ? 1 : 0);
+  return DPE_OK;
+}
+
+int dpe_comm_get_unique_id(void* id, size_t bytes) {
+  if (!id || bytes < sizeof(ncclUniqueId)) return DPE_ERR_ARG;
+  ncclUniqueId u;
+  if (!nccl_api().ok || nccl_api().GetUniqueId(&u) != ncclSuccess) return DPE_ERR_COMM;
+  memset(id, 0, bytes);
+  memcpy(id, &u, sizeof(u));
+  return DPE_OK;
+}
+
+int dpe_comm_init_rank(dpe_ctx* ctx, const void* id, int n_ranks, int rank) {
+  if (!ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return DPE_ERR_ARG;
+  if (ctx->comm) FAIL(DPE_ERR_STATE, "context already has a communicator");
+  CK(cudaSetDevice(ctx->device));
+  if (!nccl_api().ok) FAIL(DPE_ERR_COMM, nccl_api().why);
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof(u));
+  NCK(nccl_api().CommInitRank(&ctx->comm, n_ranks, u, rank));
+  ctx->comm_owned = true;
+  return DPE_OK;
+}
+
+int dpe_comm_init_all(dpe_ctx** ctxs, int n) {
+  if (!ctxs || n < 1) return DPE_ERR_ARG;
+  std::vector<int> devs(n);
+  for (int i = 0; i < n; ++i) {
+    if (!ctxs[i]) return DPE_ERR_ARG;
+    devs[i] = ctxs[i]->device;
+  }
+  dpe_ctx* ctx = ctxs[0];
+  for (int i = 0; i < n; ++i)
+    if (ctxs[i]->comm) FAIL(DPE_ERR_STATE, "context already has a communicator");
+  if (!nccl_api().ok) FAIL(DPE_ERR_COMM, nccl_api().why);
+  std::lock_guard<std::mutex> lock(g_comm_mutex);
+  auto it = g_comm_cache.find(devs);
+  if (it == g_comm_cache.end()) {
+    CommSet cs;
+    cs.comms.assign(n, nullptr);
+    NCK(nccl_api().CommInitAll(cs.comms.data(), n, devs.data()));
+    it = g_comm_cache.emplace(devs, cs).first;
+  }
+  for (int i = 0; i < n; ++i) { ctxs[i]->comm = it->second.comms[i]; ctxs[i]->comm_owned = false; }
+  return DPE_OK;
+}
+
+void dpe_comm_reset_all(void) {
+  std::lock_guard<std::mutex> lock(g_comm_mutex);
+  for (auto& kv : g_comm_cache)
+    for (ncclComm_t c : kv.second.comms) if (c) nccl_api().CommAbort(c);
+  g_comm_cache.clear();
+}
+
 int dpe_scene_begin(dpe_ctx* ctx, int n_views, int width, int height, int n_scales) {
   if (!ctx) return DPE_ERR_ARG;
   if (n_views <= 0 || width <= 0 || height <= 0 || n_scales <= 0 || n_scales > 8) FAIL(DPE_ERR_ARG, "bad scene dimensions");
   CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
   free_scene(ctx);
   ctx->n_views = n_views; ctx->W = width; ctx->H = height; ctx->n_scales = n_scales;
   ctx->sw.assign(n_scales, 0); ctx->sh.assign(n_scales, 0);
@@ -218,23 +406,43 @@ int dpe_scene_begin(dpe_ctx* ctx, int n_views, int width, int height, int n_scal
   }
   ctx->views.assign(n_views, ViewData());
   for (auto& v : ctx->views) v.scales.assign(n_scales, ScaleImg());
-  ctx->first_view = 0; ctx->n_local = n_views; ctx->slots_per_rank = n_views; ctx->n_ranks = 1;
-  ctx->stage_counter = 0; ctx->last_stage_scale = -1; ctx->stage_pending = false;
+  ctx->n_problems = n_views; ctx->rank = 0; ctx->n_ranks = 1;
+  ctx->first_view = 0; ctx->n_local = n_views; ctx->slots_per_rank = n_views;
+  ctx->stage_counter = 0; ctx->last_stage_scale = -1; ctx->stage_pending = false; ctx->stage_open = false;
+  CK(cudaMalloc(&ctx->gray_slab, (size_t)width * height * n_views));
   return DPE_OK;
 }
 
 int dpe_scene_set_view(dpe_ctx* ctx, int view, const uint8_t* gray, const float K[9], const float R[9],
                        const float t[3], float depth_min, float depth_max) {
-  if (!ctx || view < 0 || view >= ctx->n_views || !gray || !K || !R || !t) return DPE_ERR_ARG;
+  if (!ctx || view < 0 || view >= ctx->n_views || !K || !R || !t) return DPE_ERR_ARG;
   if (ctx->committed) FAIL(DPE_ERR_STATE, "scene already committed");
   CK(cudaSetDevice(ctx->device));
   ViewData& v = ctx->views[view];
   host_cam_set(&v.cam, K, R, t, depth_min, depth_max);
-  const size_t n = (size_t)ctx->W * ctx->H;
-  if (!ctx->gray_slab) CK(cudaMalloc(&ctx->gray_slab, n * ctx->n_views));
-  v.gray_full = ctx->gray_slab + n * view;
-  CK(cudaMemcpy(v.gray_full, gray, n, cudaMemcpyHostToDevice));
-  v.have_img = true;
+  v.have_cam = true;
+  if (gray) {
+    // asynchronous on the upload stream (truly so from pinned memory); dpe_scene_commit / dpe_scene_broadcast_images
+    // order themselves behind it
+    const size_t n = (size_t)ctx->W * ctx->H;
+    CK(cudaMemcpyAsync(ctx->gray_slab + n * view, gray, n, cudaMemcpyHostToDevice, ctx->upload_stream));
+    v.have_img = true;
+  }
+  return DPE_OK;
+}
+
+int dpe_scene_broadcast_images(dpe_ctx* ctx, int root) {
+  if (!ctx || root < 0 || root >= ctx->n_ranks) return DPE_ERR_ARG;
+  if (ctx->committed) FAIL(DPE_ERR_STATE, "scene already committed");
+  if (ctx->n_ranks > 1 && !ctx->comm) FAIL(DPE_ERR_STATE, "no communicator (dpe_comm_init_rank / dpe_comm_init_all)");
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->rank == root)
+    for (const auto& v : ctx->views) if (!v.have_img) FAIL(DPE_ERR_STATE, "the broadcasting rank lacks an image");
+  if (ctx->n_ranks > 1) {
+    const size_t n = (size_t)ctx->W * ctx->H * ctx->n_views;
+    NCK(nccl_api().Broadcast(ctx->gray_slab, ctx->gray_slab, n, ncclUint8, root, ctx->comm, ctx->upload_stream));
+  }
+  for (auto& v : ctx->views) v.have_img = true;
   return DPE_OK;
 }
 
@@ -247,37 +455,71 @@ int dpe_scene_set_pairs(dpe_ctx* ctx, int view, const int* src_ids, int n_src) {
   return DPE_OK;
 }
 
-int dpe_scene_set_prep(dpe_ctx* ctx, int view, int scale, const uint8_t* edge, const int32_t* label) {
-  if (!ctx || view < 0 || view >= ctx->n_views || scale < 0 || scale >= ctx->n_scales) return DPE_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
+// uploads prep arrays of an owned view into its slab slots (after commit)
+static int upload_prep(dpe_ctx* ctx, int view, int scale, const uint8_t* edge, const int32_t* label) {
+  const int li = view - ctx->first_view;
   ScaleImg& s = ctx->views[view].scales[scale];
   const size_t n = (size_t)ctx->sw[scale] * ctx->sh[scale];
   if (edge) {
-    if (!s.edge) CK(cudaMalloc(&s.edge, n));
-    CK(cudaMemcpy(s.edge, edge, n, cudaMemcpyHostToDevice));
+    uint8_t* dst = ctx->edge_slab[scale] + (size_t)li * n;
+    CK(cudaMemcpyAsync(dst, edge, n, cudaMemcpyHostToDevice, ctx->upload_stream));
     if (scale == 0) {  // edge_low_res of every stage of this view: bit-packed copy for the Bresenham walks
       const int w = ctx->sw[0], h = ctx->sh[0], words = (w + 31) / 32;
       std::vector<uint32_t> bits((size_t)words * h, 0u);
       for (int y = 0; y < h; ++y)
         for (int x = 0; x < w; ++x)
           if (edge[(size_t)y * w + x]) bits[(size_t)y * words + (x >> 5)] |= 1u << (x & 31);
-      if (!s.edge_bits) CK(cudaMalloc(&s.edge_bits, bits.size() * sizeof(uint32_t)));
-      CK(cudaMemcpy(s.edge_bits, bits.data(), bits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+      uint32_t* bdst = ctx->bits_slab + (size_t)li * words * h;
+      CK(cudaMemcpyAsync(bdst, bits.data(), bits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->upload_stream));
+      CK(cudaStreamSynchronize(ctx->upload_stream));  // `bits` is a local
+      s.edge_bits = bdst;
     }
+    s.edge = dst;
   }
   if (label) {
-    if (!s.label) CK(cudaMalloc(&s.label, n * sizeof(int32_t)));
-    CK(cudaMemcpy(s.label, label, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    int32_t* dst = ctx->label_slab[scale] + (size_t)li * n;
+    CK(cudaMemcpyAsync(dst, label, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->upload_stream));
+    s.label = dst;
   }
+  CK(cudaStreamSynchronize(ctx->upload_stream));
   return DPE_OK;
 }
 
-int dpe_scene_set_shard(dpe_ctx* ctx, int first_view, int count, int slots_per_rank, int n_ranks) {
-  if (!ctx || first_view < 0 || count < 0 || first_view + count > ctx->n_views || n_ranks < 1 ||
-      slots_per_rank * n_ranks < ctx->n_views)
-    return DPE_ERR_ARG;
+int dpe_scene_set_prep(dpe_ctx* ctx, int view, int scale, const uint8_t* edge, const int32_t* label, size_t n_elems) {
+  if (!ctx || view < 0 || view >= ctx->n_views || scale < 0 || scale >= ctx->n_scales) return DPE_ERR_ARG;
+  const size_t n = (size_t)ctx->sw[scale] * ctx->sh[scale];
+  if (n_elems != n) FAIL(DPE_ERR_ARG, "prep array size does not match the scale (dpe_get_size)");
+  if (!ctx->committed) {  // kept on the host until the slabs exist
+    ScaleImg& s = ctx->views[view].scales[scale];
+    if (edge) s.pending_edge.assign(edge, edge + n);
+    if (label) s.pending_label.assign(label, label + n);
+    return DPE_OK;
+  }
+  if (view < ctx->first_view || view >= ctx->first_view + ctx->n_local) return DPE_OK;  // not this rank's view
+  CK(cudaSetDevice(ctx->device));
+  return upload_prep(ctx, view, scale, edge, label);
+}
+
+int dpe_scene_set_shard(dpe_ctx* ctx, int n_problems, int rank, int n_ranks) {
+  if (!ctx || n_problems < 1 || n_problems > ctx->n_views || n_ranks < 1 || rank < 0 || rank >= n_ranks) return DPE_ERR_ARG;
   if (ctx->committed) FAIL(DPE_ERR_STATE, "scene already committed");
-  ctx->first_view = first_view; ctx->n_local = count; ctx->slots_per_rank = slots_per_rank; ctx->n_ranks = n_ranks;
+  ctx->n_problems = n_problems; ctx->rank = rank; ctx->n_ranks = n_ranks;
+  dpe_shard_range(n_problems, n_ranks, rank, &ctx->first_view, &ctx->n_local);
+  ctx->slots_per_rank = (n_problems + n_ranks - 1) / n_ranks;
+  return DPE_OK;
+}
+
+int dpe_scene_set_active(dpe_ctx* ctx, int first_view, int count) {
+  if (!ctx || first_view < 0 || count < 1) return DPE_ERR_ARG;
+  if (ctx->committed) FAIL(DPE_ERR_STATE, "scene already committed");
+  if (ctx->n_ranks != 1 || first_view + count > ctx->n_problems) FAIL(DPE_ERR_ARG, "an active sub-range needs an unsharded context and views inside it");
+  ctx->first_view = first_view; ctx->n_local = count;
+  return DPE_OK;
+}
+
+int dpe_view_slot(dpe_ctx* ctx, int view, int* slot) {
+  if (!ctx || view < 0 || view >= ctx->n_views || !slot) return DPE_ERR_ARG;
+  *slot = slot_of(ctx, view);
   return DPE_OK;
 }
 
@@ -287,6 +529,11 @@ int dpe_scene_commit(dpe_ctx* ctx) {
   CK(cudaSetDevice(ctx->device));
   const LaunchCfg cfg = cfg_of(ctx);
   const int top = ctx->n_scales - 1;
+  for (const auto& v : ctx->views) {
+    if (!v.have_cam) FAIL(DPE_ERR_STATE, "view without camera");
+    if (!v.have_img) FAIL(DPE_ERR_STATE, "view without image");
+  }
+  CK(cudaStreamSynchronize(ctx->upload_stream));  // images (uploads and / or the broadcast)
   ctx->scale_arr.assign(ctx->n_scales, nullptr); ctx->scale_tex.assign(ctx->n_scales, 0);
   for (int k = 0; k < ctx->n_scales; ++k) {
     cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
@@ -303,11 +550,11 @@ int dpe_scene_commit(dpe_ctx* ctx) {
   ctx->lin_slab.assign(ctx->n_scales, nullptr);
   for (int k = 0; k < ctx->n_scales; ++k)
     CK(cudaMalloc(&ctx->lin_slab[k], (size_t)ctx->n_views * ctx->sw[k] * ctx->sh[k] * sizeof(float)));
+  const size_t P = (size_t)ctx->W * ctx->H;
   for (int vi = 0; vi < ctx->n_views; ++vi) {
     ViewData& v = ctx->views[vi];
-    if (!v.have_img) FAIL(DPE_ERR_STATE, "view without image");
     for (int k = 0; k < ctx->n_scales; ++k) v.scales[k].lin = ctx->lin_slab[k] + (size_t)vi * ctx->sw[k] * ctx->sh[k];
-    launch_u8_to_f32(v.gray_full, v.scales[top].lin, ctx->W * ctx->H, cfg, 0);
+    launch_u8_to_f32(ctx->gray_slab + P * vi, v.scales[top].lin, ctx->W * ctx->H, cfg, 0);
     // every level is resized from the full-resolution image (DPE.cpp:798-820)
     for (int k = 0; k < top; ++k)
       launch_resize_linear(v.scales[top].lin, ctx->W, ctx->H, v.scales[k].lin, ctx->sw[k], ctx->sh[k], cfg, 0);
@@ -321,18 +568,34 @@ int dpe_scene_commit(dpe_ctx* ctx) {
       cp.kind = cudaMemcpyDeviceToDevice;
       CK(cudaMemcpy3DAsync(&cp, 0));
     }
-    v.gray_full = nullptr;
   }
   // depth atlases
-  const int slots = ctx->slots_per_rank * ctx->n_ranks;
+  const int slots = total_slots(ctx);
   ctx->atlas_front.assign(ctx->n_scales, nullptr); ctx->atlas_back.assign(ctx->n_scales, nullptr);
   for (int k = 0; k < ctx->n_scales; ++k) {
     const size_t bytes = (size_t)slots * ctx->sw[k] * ctx->sh[k] * sizeof(float);
     CK(cudaMalloc(&ctx->atlas_front[k], bytes)); CK(cudaMemset(ctx->atlas_front[k], 0, bytes));
     CK(cudaMalloc(&ctx->atlas_back[k], bytes)); CK(cudaMemset(ctx->atlas_back[k], 0, bytes));
   }
+  // owned views: prep slabs, carried maps (two buffers), completion events
+  const int nl = ctx->n_local > 0 ? ctx->n_local : 1;
+  ctx->edge_slab.assign(ctx->n_scales, nullptr); ctx->label_slab.assign(ctx->n_scales, nullptr);
+  for (int k = 0; k < ctx->n_scales; ++k) {
+    const size_t n = (size_t)ctx->sw[k] * ctx->sh[k];
+    CK(cudaMalloc(&ctx->edge_slab[k], (size_t)nl * n));
+    CK(cudaMalloc(&ctx->label_slab[k], (size_t)nl * n * sizeof(int32_t)));
+  }
+  CK(cudaMalloc(&ctx->bits_slab, (size_t)nl * ((ctx->sw[0] + 31) / 32) * ctx->sh[0] * sizeof(uint32_t)));
+  for (int b = 0; b < 2; ++b) {
+    CK(cudaMalloc(&ctx->maps_planes[b], (size_t)nl * P * sizeof(float4)));
+    CK(cudaMalloc(&ctx->maps_state[b], (size_t)nl * P));
+    CK(cudaMalloc(&ctx->maps_selected[b], (size_t)nl * P * sizeof(uint32_t)));
+  }
+  ctx->view_done.assign(ctx->n_local, nullptr);
+  for (auto& e : ctx->view_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CK(cudaMalloc(&ctx->exp_depth, P * sizeof(float))); CK(cudaMalloc(&ctx->exp_normal, P * 3 * sizeof(float)));
+  CK(cudaMalloc(&ctx->exp_weak, P));
   // scratch: one set per stream, sized for the finest scale
-  const size_t P = (size_t)ctx->W * ctx->H;
   const int n_streams = 4;
   ctx->scratch.assign(n_streams, Scratch());
   for (auto& s : ctx->scratch) {
@@ -345,8 +608,8 @@ int dpe_scene_commit(dpe_ctx* ctx) {
     CK(cudaMalloc(&s.weak_reliable, P)); CK(cudaMalloc(&s.nearest_strong, P * sizeof(short2)));
     CK(cudaMalloc(&s.neighbours, P * DPE_NEIGHBOUR_NUM * sizeof(short2)));
     CK(cudaMalloc(&s.rng, P * sizeof(Xorwow)));
-    CK(cudaMalloc(&s.weak_list, 2 * P * sizeof(int))); CK(cudaMalloc(&s.weak_count, 2 * sizeof(int)));
-    CK(cudaMemset(s.weak_count, 0, 2 * sizeof(int)));
+    CK(cudaMalloc(&s.weak_list, 2 * P * sizeof(int))); CK(cudaMalloc(&s.weak_count, 4 * sizeof(int)));
+    CK(cudaMemset(s.weak_count, 0, 4 * sizeof(int)));
     CK(cudaMemset(s.view_w, 0, P * sizeof(uint4)));
     CK(cudaMemset(s.radius, 0, P * sizeof(int)));
   }
@@ -386,6 +649,17 @@ int dpe_scene_commit(dpe_ctx* ctx) {
   }
   CK(cudaDeviceSynchronize());
   ctx->committed = true;
+  // prep that arrived before the slabs existed
+  for (int vi = ctx->first_view; vi < ctx->first_view + ctx->n_local; ++vi)
+    for (int k = 0; k < ctx->n_scales; ++k) {
+      ScaleImg& s = ctx->views[vi].scales[k];
+      if (s.pending_edge.empty() && s.pending_label.empty()) continue;
+      if (int rc = upload_prep(ctx, vi, k, s.pending_edge.empty() ? nullptr : s.pending_edge.data(),
+                               s.pending_label.empty() ? nullptr : s.pending_label.data()))
+        return rc;
+    }
+  for (auto& v : ctx->views)
+    for (auto& s : v.scales) { std::vector<uint8_t>().swap(s.pending_edge); std::vector<int32_t>().swap(s.pending_label); }
   return DPE_OK;
 }
 
@@ -407,7 +681,7 @@ static void build_ref_const(const dpe_ctx* ctx, int view, int k, bool geom, RefC
     }
     sc.src_view = sv;
     sc.tex = 0;
-    sc.depth = geom ? ctx->atlas_front[k] + (size_t)sv * P : nullptr;
+    sc.depth = geom ? ctx->atlas_front[k] + (size_t)slot_of(ctx, sv) * P : nullptr;
   }
 }
 
@@ -464,24 +738,33 @@ static void fill_args(dpe_ctx* ctx, int view, int k, const dpe_stage_params* p, 
   (void)seed;
 }
 
+// the carried-map buffers of local view li in buffer b
+static void map_buffers(dpe_ctx* ctx, int li, int b, float4** planes, uint8_t** state, uint32_t** sel) {
+  const size_t P = (size_t)ctx->W * ctx->H;
+  *planes = ctx->maps_planes[b] + (size_t)li * P;
+  *state = ctx->maps_state[b] + (size_t)li * P;
+  *sel = ctx->maps_selected[b] + (size_t)li * P;
+}
+
 extern "C" {
 
-int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed) {
+int dpe_stage_begin(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed) {
   if (!ctx || !p || k < 0 || k >= ctx->n_scales) return DPE_ERR_ARG;
   if (!ctx->committed) FAIL(DPE_ERR_STATE, "scene not committed");
+  if (ctx->stage_open) FAIL(DPE_ERR_STATE, "a stage is already running (dpe_stage_end)");
   if (ctx->stage_pending) FAIL(DPE_ERR_STATE, "previous stage not committed (dpe_stage_commit)");
   CK(cudaSetDevice(ctx->device));
   const LaunchCfg cfg = cfg_of(ctx);
   const size_t P = (size_t)ctx->sw[k] * ctx->sh[k];
   const int ns = (int)ctx->scratch.size();
   if (int rc = ensure_rng_tables(ctx, seed)) return rc;
-  // all views of a scale are layers of one texture (layer = view, linear filter, clamp)
-  CK(cudaDeviceSynchronize());
+  // all views of a scale are layers of one texture (layer = view, linear filter, clamp); the handle sits in a
+  // device-wide constant, so nothing of another scale may be in flight (it is not: dpe_stage_end drained it)
   launch_set_scale_tex((unsigned long long)ctx->scale_tex[k], 0);
   CK(cudaEventRecord(ctx->ev0, 0));
   for (auto& s : ctx->scratch) CK(cudaStreamWaitEvent(s.stream, ctx->ev0, 0));
-  std::vector<cudaEvent_t> done(ns, nullptr);
-  std::vector<void*> to_free;  // previous-scale maps, released once the stage has drained
+  const int stop = ctx->debug_stop_after;
+  const bool truncated = stop >= 0 && stop < 11;
   for (int li = 0; li < ctx->n_local; ++li) {
     const int view = ctx->first_view + li;
     ViewData& v = ctx->views[view];
@@ -494,20 +777,18 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
     KernelParams KP;
     fill_args(ctx, view, k, p, seed, s, &KP);
     StageArgs& a = KP.a;
-    // outputs: new buffers when the scale changes, in place otherwise
-    float4* new_planes = v.planes; uint8_t* new_state = v.state; uint32_t* new_sel = v.selected;
-    const bool realloc = (v.cur_scale != k);
-    if (realloc) {
-      CK(cudaMalloc(&new_planes, P * sizeof(float4))); CK(cudaMalloc(&new_state, P));
-      CK(cudaMalloc(&new_sel, P * sizeof(uint32_t)));
-    }
+    // outputs: the other map buffer when the scale changes, in place otherwise
+    const bool flip = (v.cur_scale != k);
+    const int out_buf = flip ? (v.cur_scale < 0 ? 0 : 1 - v.cur_buf) : v.cur_buf;
+    float4* new_planes; uint8_t* new_state; uint32_t* new_sel;
+    map_buffers(ctx, li, out_buf, &new_planes, &new_state, &new_sel);
     a.prev_planes = v.planes; a.prev_state = v.state; a.prev_selected = v.selected;
     a.prev_W = v.cur_scale >= 0 ? ctx->sw[v.cur_scale] : a.W;
     a.prev_H = v.cur_scale >= 0 ? ctx->sh[v.cur_scale] : a.H;
     a.out_planes = new_planes; a.out_state = new_state; a.out_selected = new_sel;
     // sequential order: publish straight into the committed atlas, so that later views of this stage
     // read it (the reference's depths.dmb files)
-    a.atlas_out = (ctx->gauss_seidel ? ctx->atlas_front[k] : ctx->atlas_back[k]) + (size_t)view * P;
+    a.atlas_out = (ctx->gauss_seidel ? ctx->atlas_front[k] : ctx->atlas_back[k]) + (size_t)slot_of(ctx, view) * P;
 
     cudaStream_t st = s.stream;
     // every (view, stage) starts from curand_init(seed, y, x) like the reference (DPE.cu:1020-1033)
@@ -533,7 +814,6 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
     // steps as oracle/ref_stage_probe.cu numbers them: 0 anchors, 1 init, 2+3i strong sweeps of iteration i,
     // 3+3i fit plane, 4+3i weak sweeps, 11 the tail; dpe_debug_stop_after(n) leaves the scratch arrays as they
     // are after step n (test hook for the per-kernel differential comparison)
-    const int stop = ctx->debug_stop_after;
     auto on = [&](int step) { return stop < 0 || step <= stop; };
     if (p->state != DPE_FIRST_INIT) L(DPE_K_LOAD, launch_load);
     if (p->use_apd) {
@@ -564,48 +844,80 @@ int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed)
       L(DPE_K_CLASSIFY, launch_classify_refine);
       L(DPE_K_FINISH, launch_finish);
     }
-    if (realloc) {
-      if (stop >= 0 && stop < 11) {  // truncated stage (test hook): the carried maps stay as they were
-        to_free.push_back(new_planes); to_free.push_back(new_state); to_free.push_back(new_sel);
-      } else {
-        to_free.push_back(v.planes); to_free.push_back(v.state); to_free.push_back(v.selected);
-        v.planes = new_planes; v.state = new_state; v.selected = new_sel; v.cur_scale = k;
-      }
+    CK(cudaEventRecord(ctx->view_done[li], st));
+    if (!truncated) {  // a truncated stage (test hook) leaves the carried maps as they were
+      v.planes = new_planes; v.state = new_state; v.selected = new_sel; v.cur_scale = k; v.cur_buf = out_buf;
     }
   }
   if (ctx->profile && ctx->n_local <= ctx->profile_views) cudaProfilerStop();
   CK(cudaGetLastError());
-  for (int i = 0; i < ns; ++i) {
-    CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-    CK(cudaEventRecord(done[i], ctx->scratch[i].stream));
-    CK(cudaStreamWaitEvent(0, done[i], 0));
+  // the exchange: view slot i of every rank forms one contiguous chunk of the atlas (slot = i * n_ranks + rank);
+  // its in-place all-gather waits only for this rank's view i, so all but the last slot travel under the kernels
+  // of the views behind them.  Every rank issues slots_per_rank collectives in the same order; a rank that owns
+  // fewer views contributes a slot nobody reads.
+  ctx->comm_queued = false;
+  if (ctx->n_ranks > 1 && ctx->comm && !truncated) {
+    float* atlas = ctx->atlas_back[k];
+    for (int i = 0; i < ctx->slots_per_rank; ++i) {
+      if (i < ctx->n_local) CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->view_done[i], 0));
+      float* chunk = atlas + (size_t)i * ctx->n_ranks * P;
+      NCK(nccl_api().AllGather(chunk + (size_t)ctx->rank * P, chunk, P, ncclFloat, ctx->comm, ctx->comm_stream));
+    }
+    CK(cudaEventRecord(ctx->comm_done, ctx->comm_stream));
+    ctx->comm_queued = true;
   }
+  ctx->last_stage_scale = k;
+  ctx->stage_open = true;
+  return DPE_OK;
+}
+
+int dpe_stage_wait_view(dpe_ctx* ctx, int view) {
+  if (!ctx || view < ctx->first_view || view >= ctx->first_view + ctx->n_local) return DPE_ERR_ARG;
+  if (!ctx->stage_open) return DPE_OK;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventSynchronize(ctx->view_done[view - ctx->first_view]));
+  return DPE_OK;
+}
+
+int dpe_stage_end(dpe_ctx* ctx) {
+  if (!ctx) return DPE_ERR_ARG;
+  if (!ctx->stage_open) return DPE_OK;
+  CK(cudaSetDevice(ctx->device));
+  for (int li = 0; li < ctx->n_local; ++li) CK(cudaStreamWaitEvent(0, ctx->view_done[li], 0));
+  CK(cudaEventRecord(ctx->ev_views, 0));  // all of this rank's views done; what follows is the exposed part of the exchange
+  if (ctx->comm_queued) CK(cudaStreamWaitEvent(0, ctx->comm_done, 0));
   CK(cudaEventRecord(ctx->ev1, 0));
   CK(cudaEventSynchronize(ctx->ev1));
-  for (int i = 0; i < ns; ++i) cudaEventDestroy(done[i]);
-  for (void* p_ : to_free) cudaFree(p_);
   CK(cudaGetLastError());
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->stage_ms += ms;
+  CK(cudaEventElapsedTime(&ms, ctx->ev_views, ctx->ev1));
+  ctx->comm_ms += ms;
   ctx->stage_counter++;
-  ctx->last_stage_scale = k;
+  ctx->stage_open = false;
   ctx->stage_pending = true;
   return DPE_OK;
 }
 
-int dpe_stage_atlas(dpe_ctx* ctx, void** dev_ptr, size_t* chunk_bytes, size_t* total_bytes) {
+int dpe_run_stage(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t seed) {
+  if (int rc = dpe_stage_begin(ctx, k, p, seed)) return rc;
+  return dpe_stage_end(ctx);
+}
+
+int dpe_stage_atlas(dpe_ctx* ctx, void** dev_ptr, size_t* slot_bytes, size_t* total_bytes) {
   if (!ctx || ctx->last_stage_scale < 0) return DPE_ERR_ARG;
   const int k = ctx->last_stage_scale;
   const size_t P = (size_t)ctx->sw[k] * ctx->sh[k];
   if (dev_ptr) *dev_ptr = ctx->gauss_seidel ? ctx->atlas_front[k] : ctx->atlas_back[k];
-  if (chunk_bytes) *chunk_bytes = (size_t)ctx->slots_per_rank * P * sizeof(float);
-  if (total_bytes) *total_bytes = (size_t)ctx->slots_per_rank * ctx->n_ranks * P * sizeof(float);
+  if (slot_bytes) *slot_bytes = P * sizeof(float);
+  if (total_bytes) *total_bytes = (size_t)total_slots(ctx) * P * sizeof(float);
   return DPE_OK;
 }
 
 int dpe_stage_commit(dpe_ctx* ctx) {
   if (!ctx) return DPE_ERR_ARG;
+  if (ctx->stage_open) if (int rc = dpe_stage_end(ctx)) return rc;
   if (!ctx->stage_pending) return DPE_OK;
   const int k = ctx->last_stage_scale;
   if (!ctx->gauss_seidel) std::swap(ctx->atlas_front[k], ctx->atlas_back[k]);
@@ -615,7 +927,7 @@ int dpe_stage_commit(dpe_ctx* ctx) {
 
 int dpe_set_view_order(dpe_ctx* ctx, int sequential) {
   if (!ctx) return DPE_ERR_ARG;
-  if (ctx->stage_pending) FAIL(DPE_ERR_STATE, "stage not committed");
+  if (ctx->stage_pending || ctx->stage_open) FAIL(DPE_ERR_STATE, "stage not committed");
   if (sequential && ctx->n_ranks > 1) FAIL(DPE_ERR_ARG, "sequential view order needs all views on one GPU");
   ctx->gauss_seidel = sequential != 0;
   return DPE_OK;
@@ -729,16 +1041,15 @@ int dpe_debug_set_maps(dpe_ctx* ctx, int view, int k, const float* planes4, cons
   const size_t P = (size_t)ctx->sw[k] * ctx->sh[k];
   ViewData& v = ctx->views[view];
   if (planes4) {
-    if (v.cur_scale != k) {
-      cudaFree(v.planes); cudaFree(v.state); cudaFree(v.selected);
-      CK(cudaMalloc(&v.planes, P * sizeof(float4))); CK(cudaMalloc(&v.state, P)); CK(cudaMalloc(&v.selected, P * sizeof(uint32_t)));
-      v.cur_scale = k;
-    }
+    if (view < ctx->first_view || view >= ctx->first_view + ctx->n_local) FAIL(DPE_ERR_ARG, "not a view of this context");
+    if (v.cur_scale < 0) v.cur_buf = 0;
+    map_buffers(ctx, view - ctx->first_view, v.cur_buf, &v.planes, &v.state, &v.selected);
+    v.cur_scale = k;
     CK(cudaMemcpy(v.planes, planes4, P * sizeof(float4), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(v.state, state, P, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(v.selected, selected, P * sizeof(uint32_t), cudaMemcpyHostToDevice));
   }
-  if (atlas_depth) CK(cudaMemcpy(ctx->atlas_front[k] + (size_t)view * P, atlas_depth, P * sizeof(float), cudaMemcpyHostToDevice));
+  if (atlas_depth) CK(cudaMemcpy(ctx->atlas_front[k] + (size_t)slot_of(ctx, view) * P, atlas_depth, P * sizeof(float), cudaMemcpyHostToDevice));
   return DPE_OK;
 }
 
@@ -837,6 +1148,24 @@ int dpe_get_maps(dpe_ctx* ctx, int view, float* depth, float* normal3, uint8_t* 
   return DPE_OK;
 }
 
+// the arrays the .npy writers hold, packed on the device and copied out on the copy stream (beside running stages)
+int dpe_export_view(dpe_ctx* ctx, int view, float* depth, float* normal3, int8_t* weak) {
+  if (!ctx || view < 0 || view >= ctx->n_views) return DPE_ERR_ARG;
+  ViewData& v = ctx->views[view];
+  if (v.cur_scale < 0 || !v.planes) FAIL(DPE_ERR_STATE, "view has no result on this context");
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->stage_open) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->view_done[view - ctx->first_view], 0));
+  const size_t P = (size_t)ctx->sw[v.cur_scale] * ctx->sh[v.cur_scale];
+  launch_export(v.planes, v.state, depth ? ctx->exp_depth : nullptr, normal3 ? ctx->exp_normal : nullptr,
+                weak ? ctx->exp_weak : nullptr, (int)P, cfg_of(ctx), ctx->copy_stream);
+  if (depth) CK(cudaMemcpyAsync(depth, ctx->exp_depth, P * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
+  if (normal3) CK(cudaMemcpyAsync(normal3, ctx->exp_normal, P * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
+  if (weak) CK(cudaMemcpyAsync(weak, ctx->exp_weak, P, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  CK(cudaStreamSynchronize(ctx->copy_stream));
+  CK(cudaGetLastError());
+  return DPE_OK;
+}
+
 int dpe_set_count_evals(dpe_ctx* ctx, int on) {
   if (!ctx) return DPE_ERR_ARG;
   ctx->count_evals = on != 0;
@@ -852,6 +1181,7 @@ double dpe_eval_units(dpe_ctx* ctx) {
 }
 
 double dpe_stage_gpu_ms(dpe_ctx* ctx) { return ctx ? ctx->stage_ms : 0.0; }
+double dpe_stage_comm_ms(dpe_ctx* ctx) { return ctx ? ctx->comm_ms : 0.0; }
 
 int dpe_set_profile(dpe_ctx* ctx, int on) {
   if (!ctx) return DPE_ERR_ARG;

@@ -572,6 +572,27 @@ void launch_gen_neighbours(const KernelParams& P, const LaunchCfg& cfg, cudaStre
 void launch_fit_plane(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_FIT>(P, cfg, s); }
 void launch_load(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_LOAD>(P, cfg, s); }
 
+// ---- result export ---------------------------------------------------------------------------
+// The arrays of the .npy files, from a view's carried maps (world normal, depth) + state: depth zeroed where the
+// pixel is UNKNOWN (ZeroDepthForUnknown, main.cpp:36-46), normals packed to 3 floats, the state remapped
+// {UNKNOWN 0, WEAK 1, STRONG 2} (main.cpp:190-197).  Pure streaming: 17 B read, up to 17 B written per pixel.
+__global__ void __launch_bounds__(256) k_export(const float4* __restrict__ planes, const uint8_t* __restrict__ state,
+                                                float* __restrict__ depth, float* __restrict__ normal3,
+                                                int8_t* __restrict__ weak, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = planes[i];
+    const uint8_t st = state[i];
+    if (depth) depth[i] = st == DPE_UNKNOWN ? 0.0f : p.w;
+    if (normal3) { normal3[3 * i] = p.x; normal3[3 * i + 1] = p.y; normal3[3 * i + 2] = p.z; }
+    if (weak) weak[i] = st == DPE_WEAK ? 1 : (st == DPE_STRONG ? 2 : 0);
+  }
+}
+void launch_export(const float4* planes, const uint8_t* state, float* depth, float* normal3, int8_t* weak, int n,
+                   const LaunchCfg& cfg, cudaStream_t stream) {
+  k_export<<<cfg.num_sms * 8, 256, 0, stream>>>(planes, state, depth, normal3, weak, n);
+  count(cfg);
+}
+
 // ---- scene preparation ---------------------------------------------------------------------
 __global__ void k_u8_to_f32(const uint8_t* __restrict__ src, float* __restrict__ dst, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = (float)src[i];

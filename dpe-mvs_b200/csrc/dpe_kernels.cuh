@@ -35,6 +35,10 @@ void launch_compact_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream
 void launch_fit_plane(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
 void launch_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);  // one colour, one iter
 
+// .npy payloads of a view from its carried maps (any output may be nullptr)
+void launch_export(const float4* planes, const uint8_t* state, float* depth, float* normal3, int8_t* weak, int n,
+                   const LaunchCfg& cfg, cudaStream_t stream);
+
 // scene preparation
 void launch_u8_to_f32(const uint8_t* src, float* dst, int n, const LaunchCfg& cfg, cudaStream_t stream);
 // cv::resize(INTER_LINEAR) of a float image (DPE.cpp:808)

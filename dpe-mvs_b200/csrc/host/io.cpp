@@ -158,8 +158,9 @@ void jpeg_decoder_destroy(JpegDecoder* d) {
   delete d;
 }
 
-static bool jpeg_decode(JpegDecoder* d, const std::string& path, nvjpegOutputFormat_t fmt, int ch, std::vector<uint8_t>* out,
-                        int* width, int* height, std::string* err) {
+// decodes into `dst` (host memory of `cap` bytes; pinned memory makes the copy back asynchronous to other streams)
+static bool jpeg_decode_to(JpegDecoder* d, const std::string& path, nvjpegOutputFormat_t fmt, int ch, uint8_t* dst, size_t cap,
+                           std::vector<uint8_t>* grow, int* width, int* height, std::string* err) {
   std::ifstream in(path, std::ios::binary | std::ios::ate);
   if (!in.good()) { if (err) *err = "cannot open " + path; return false; }
   const std::streamsize n = in.tellg();
@@ -187,14 +188,24 @@ static bool jpeg_decode(JpegDecoder* d, const std::string& path, nvjpegOutputFor
     if (err) *err = "nvjpegDecode failed: " + path;
     return false;
   }
-  out->resize(need);
-  if (cudaMemcpyAsync(out->data(), d->dev, need, cudaMemcpyDeviceToHost, d->stream) != cudaSuccess ||
+  if (grow) { grow->resize(need); dst = grow->data(); cap = need; }
+  if (need > cap) { if (err) *err = "image larger than expected: " + path; return false; }
+  if (cudaMemcpyAsync(dst, d->dev, need, cudaMemcpyDeviceToHost, d->stream) != cudaSuccess ||
       cudaStreamSynchronize(d->stream) != cudaSuccess) {
     if (err) *err = "copy after jpeg decode failed";
     return false;
   }
   *width = w; *height = h;
   return true;
+}
+
+static bool jpeg_decode(JpegDecoder* d, const std::string& path, nvjpegOutputFormat_t fmt, int ch, std::vector<uint8_t>* out,
+                        int* width, int* height, std::string* err) {
+  return jpeg_decode_to(d, path, fmt, ch, nullptr, 0, out, width, height, err);
+}
+
+bool jpeg_decode_gray_into(JpegDecoder* d, const std::string& path, uint8_t* dst, size_t cap, int* width, int* height, std::string* err) {
+  return jpeg_decode_to(d, path, NVJPEG_OUTPUT_Y, 1, dst, cap, nullptr, width, height, err);
 }
 
 bool jpeg_decode_gray(JpegDecoder* d, const std::string& path, std::vector<uint8_t>* gray, int* width, int* height, std::string* err) {

@@ -39,6 +39,9 @@ JpegDecoder* jpeg_decoder_create(std::string* err);
 void jpeg_decoder_destroy(JpegDecoder* d);
 bool jpeg_decode_gray(JpegDecoder* d, const std::string& path, std::vector<uint8_t>* gray, int* width, int* height,
                       std::string* err);
+// the same into caller-provided host memory of `cap` bytes (e.g. a slot of a pinned slab)
+bool jpeg_decode_gray_into(JpegDecoder* d, const std::string& path, uint8_t* dst, size_t cap, int* width, int* height,
+                           std::string* err);
 // BGR interleaved (cv::IMREAD_COLOR), used by fusion only
 bool jpeg_decode_bgr(JpegDecoder* d, const std::string& path, std::vector<uint8_t>* bgr, int* width, int* height,
                      std::string* err);

@@ -6,14 +6,20 @@
 //  * the scene is loaded once (one JPEG decode per image instead of (N+1) x 4R decodes) and
 //    stays in HBM; per-view state never touches the disk between stages (the reference
 //    round-trips depths.dmb / normals.dmb / weak.bin / selected_views.bin per view-stage);
-//  * all views of a stage read the previous stage's depth maps (Jacobi) instead of a mix of
-//    this stage's and the previous stage's (Gauss-Seidel through files), which
-//    makes the result independent of how views are spread over streams and GPUs;
 //  * gpu_index >= 0 selects that GPU; gpu_index < 0 (or env DPE_GPUS=0,1,..) shards the
-//    views over several GPUs of the box, exchanging depth atlases with peer copies;
+//    reference views over several GPUs of the box: one worker thread and one context per GPU, the
+//    images uploaded to the first GPU and broadcast with NCCL, the depth atlas all-gathered with NCCL
+//    behind every stage (include/dpe_b200.h, "several GPUs").  With several GPUs all views of a
+//    stage read the previous stage's depth maps (Jacobi) instead of a mix of this stage's and the
+//    previous stage's (Gauss-Seidel through files);
+//  * the host work around the path overlaps it: contexts and the communicator come up while the
+//    JPEGs decode, edge / label preparation (needed from the first fine stage on) runs on the host
+//    cores under the coarse stages, and every view's .npy files are written while the views behind
+//    it are still in their last stage;
 //  * errors are returned (never exit()).
 // Kept: the verbose lines, the stage schedule and parameters, the edges_k/labels_k .dmb
-// cache (used if present, deleted at the end), the .npy outputs, DPE.ply when fusion is on.
+// cache (used if present and of the right size, deleted at the end), the .npy outputs, DPE.ply
+// when fusion is on.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -22,10 +28,15 @@
 
 #include <algorithm>
 #include <atomic>
-#include <functional>
 #include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <iostream>
 #include <map>
+#include <mutex>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -66,8 +77,89 @@ void parallel_for(int n, int n_threads, const std::function<void(int)>& fn) {
 
 struct Timing {
   double load = 0, prep = 0, upload = 0, stages = 0, output = 0, fusion = 0, total = 0, gpu_ms = 0;
-  double up_create = 0, up_views = 0, up_commit = 0;  // parts of `upload` on the first GPU
+  double ctx = 0, comm = 0, prep_wait = 0;
   long long launches = 0;
+};
+
+// the stage schedule of RunDPEPipeline (main.cpp:507-567)
+struct Stage { int scale; dpe_stage_params p; bool resolution_up; };
+std::vector<Stage> make_schedule(int round_num) {
+  std::vector<Stage> out;
+  for (int i = 0; i < round_num; ++i) {
+    dpe_stage_params p;
+    memset(&p, 0, sizeof(p));
+    p.max_iterations = 3; p.top_k = 4; p.geom_factor = 0.2f;
+    p.ransac_threshold = 0.005f; p.rotate_time = 4;
+    if (i == 0) { p.state = DPE_FIRST_INIT; p.use_apd = 0; }
+    else {
+      p.state = DPE_REFINE_INIT; p.use_apd = 1;
+      p.ransac_threshold = (float)(0.01 - i * 0.00125);
+      p.rotate_time = std::min((int)(1 << i), 4);
+    }
+    p.geom_consistency = 0; p.weak_peak_radius = 6;
+    out.push_back({i, p, false});
+    for (int j = 0; j < 3; ++j) {
+      p.state = DPE_REFINE_ITER; p.use_apd = i == 0 ? 0 : 1;
+      p.ransac_threshold = (float)(0.01 - i * 0.00125);
+      p.rotate_time = std::min((int)(1 << i), 4);
+      p.geom_consistency = 1; p.weak_peak_radius = std::max(4 - 2 * j, 2);
+      out.push_back({i, p, j == 2});
+    }
+  }
+  return out;
+}
+
+// pinned host buffers for the export of one view, recycled through a small pool
+struct ExportBuf {
+  float* depth = nullptr; float* normal = nullptr; int8_t* weak = nullptr;
+  int view = -1;
+};
+
+// bounded pool + queue between the GPU workers (producers) and the .npy writer threads
+class ExportQueue {
+ public:
+  ExportQueue(size_t P, bool want_normal, bool want_weak, int n_bufs) {
+    for (int i = 0; i < n_bufs; ++i) {
+      ExportBuf* b = new ExportBuf();
+      bool ok = cudaHostAlloc((void**)&b->depth, P * sizeof(float), cudaHostAllocPortable) == cudaSuccess;
+      if (want_normal) ok = ok && cudaHostAlloc((void**)&b->normal, P * 3 * sizeof(float), cudaHostAllocPortable) == cudaSuccess;
+      if (want_weak) ok = ok && cudaHostAlloc((void**)&b->weak, P, cudaHostAllocPortable) == cudaSuccess;
+      if (!ok) { release(b); continue; }
+      all_.push_back(b); free_.push_back(b);
+    }
+  }
+  ~ExportQueue() { for (auto* b : all_) release(b); }
+  bool usable() const { return !all_.empty(); }
+  ExportBuf* acquire() {
+    std::unique_lock<std::mutex> l(m_);
+    cv_.wait(l, [&]() { return !free_.empty(); });
+    ExportBuf* b = free_.back(); free_.pop_back();
+    return b;
+  }
+  void submit(ExportBuf* b) { { std::lock_guard<std::mutex> l(m_); ready_.push_back(b); } cv_.notify_all(); }
+  void recycle(ExportBuf* b) { { std::lock_guard<std::mutex> l(m_); free_.push_back(b); } cv_.notify_all(); }
+  // nullptr once close() was called and the queue is drained
+  ExportBuf* take() {
+    std::unique_lock<std::mutex> l(m_);
+    cv_.wait(l, [&]() { return !ready_.empty() || closed_; });
+    if (ready_.empty()) return nullptr;
+    ExportBuf* b = ready_.front(); ready_.pop_front();
+    return b;
+  }
+  void close() { { std::lock_guard<std::mutex> l(m_); closed_ = true; } cv_.notify_all(); }
+
+ private:
+  static void release(ExportBuf* b) {
+    if (b->depth) cudaFreeHost(b->depth);
+    if (b->normal) cudaFreeHost(b->normal);
+    if (b->weak) cudaFreeHost(b->weak);
+    delete b;
+  }
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::vector<ExportBuf*> all_, free_;
+  std::deque<ExportBuf*> ready_;
+  bool closed_ = false;
 };
 
 }  // namespace
@@ -107,6 +199,8 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
 
   // ---- devices --------------------------------------------------------------------------------
   std::vector<int> gpus;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess) n_dev = 0;
   if (const char* env = getenv("DPE_GPUS")) {
     std::string s(env);
     size_t pos = 0;
@@ -116,35 +210,64 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
       if (c > pos) gpus.push_back(atoi(s.substr(pos, c - pos).c_str()));
       pos = c + 1;
     }
+    std::set<int> seen;
+    for (int g : gpus)
+      if (g < 0 || g >= n_dev || !seen.insert(g).second) {
+        std::cerr << "DPE-MVS: DPE_GPUS names GPU " << g << " twice or out of range (" << n_dev << " visible)\n";
+        return 1;
+      }
   }
   if (gpus.empty()) {
     if (gpu_index >= 0) gpus.push_back(gpu_index);
-    else {
-      int n = 0;
-      cudaGetDeviceCount(&n);
-      for (int i = 0; i < n; ++i) gpus.push_back(i);
-    }
+    else for (int i = 0; i < n_dev; ++i) gpus.push_back(i);
   }
-  if (gpus.empty()) { std::cerr << "DPE-MVS: no CUDA device\n"; return 1; }
+  if (gpus.empty() || n_dev == 0) { std::cerr << "DPE-MVS: no CUDA device\n"; return 1; }
   if ((int)gpus.size() > n_problems) gpus.resize(n_problems);
   const int G = (int)gpus.size();
   if (cudaSetDevice(gpus[0]) != cudaSuccess) { std::cerr << "DPE-MVS: cannot select GPU " << gpus[0] << "\n"; return 1; }
+
+  // ---- contexts come up on their own threads while the images decode ----------------------------------
+  std::vector<dpe_ctx*> ctxs(G, nullptr);
+  std::vector<std::string> errs(G);
+  std::vector<std::thread> ctx_threads;
+  const double t_ctx0 = now_s();
+  for (int g = 0; g < G; ++g) ctx_threads.emplace_back([&, g]() {
+    if (dpe_ctx_create(&ctxs[g], gpus[g]) != DPE_OK) errs[g] = "cannot create a context on GPU " + std::to_string(gpus[g]);
+  });
+  auto destroy_all = [&]() {
+    for (auto*& x : ctxs) { dpe_ctx_destroy(x); x = nullptr; }
+  };
 
   // ---- images + cameras (CheckImages: all the same size) --------------------------------------
   double t0 = now_s();
   std::string err;
   JpegDecoder* dec = jpeg_decoder_create(&err);
-  if (!dec) { std::cerr << "DPE-MVS: " << err << "\n"; return 1; }
-  std::vector<ImageU8> grays(n_views);
+  uint8_t* gray_slab = nullptr;  // pinned: all images, view-major (uploads overlap, prep reads it)
+  auto bail = [&](const std::string& msg) {
+    for (auto& t : ctx_threads) if (t.joinable()) t.join();
+    destroy_all();
+    jpeg_decoder_destroy(dec);
+    if (gray_slab) cudaFreeHost(gray_slab);
+    std::cerr << msg << "\n";
+    return 1;
+  };
+  if (!dec) return bail("DPE-MVS: " + err);
   std::vector<CamFile> cams(n_views);
   int width = 0, height = 0;
+  auto image_path = [&](int v) { return dense + "/images/" + format_index(view_ids[v]) + ".jpg"; };
+  size_t P = 0;
   {
-    // one nvJPEG decoder per loader thread (Huffman decoding is host work, the rest runs on gpus[0])
+    // the first image gives the size (and pays nvJPEG's start-up); the rest decode on a few threads, one nvJPEG
+    // decoder each (Huffman decoding is host work, the rest runs on gpus[0]), straight into the pinned slab
+    std::vector<uint8_t> first;
+    if (!jpeg_decode_gray(dec, image_path(0), &first, &width, &height, &err)) return bail("Images may error, check it!");
+    P = (size_t)width * height;
+    if (cudaHostAlloc((void**)&gray_slab, P * n_views, cudaHostAllocPortable) != cudaSuccess) return bail("DPE-MVS: cannot allocate pinned memory");
+    memcpy(gray_slab, first.data(), P);
     const int n_load = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 8, n_views}));
     std::vector<JpegDecoder*> decs(n_load, nullptr);
     decs[0] = dec;
-    std::vector<int> ws(n_views, 0), hs(n_views, 0);
-    std::atomic<int> bad(0), next_dec(0);
+    std::atomic<int> bad(0), bad_cam(0), next_dec(0);
     parallel_for(n_views, n_load, [&](int v) {
       thread_local int my = -1;
       thread_local const void* owner = nullptr;
@@ -153,128 +276,104 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
         cudaSetDevice(gpus[0]);
         if (my > 0) { std::string e; decs[my] = jpeg_decoder_create(&e); }
       }
+      if (!read_cam(dense + "/cams/" + format_index(view_ids[v]) + "_cam.txt", &cams[v])) bad_cam++;
+      if (v == 0) return;
       std::string e;
-      const std::string ip = dense + "/images/" + format_index(view_ids[v]) + ".jpg";
-      if (!decs[my] || !jpeg_decode_gray(decs[my], ip, &grays[v].d, &ws[v], &hs[v], &e)) { bad++; return; }
-      grays[v].cols = ws[v]; grays[v].rows = hs[v];
-      if (!read_cam(dense + "/cams/" + format_index(view_ids[v]) + "_cam.txt", &cams[v])) bad += 1000;
+      int w = 0, h = 0;
+      if (!decs[my] || !jpeg_decode_gray_into(decs[my], image_path(v), gray_slab + P * v, P, &w, &h, &e) || w != width || h != height) bad++;
     });
     for (int i = 1; i < n_load; ++i) jpeg_decoder_destroy(decs[i]);
-    width = ws[0]; height = hs[0];
-    bool same = bad.load() % 1000 == 0;
-    for (int v = 0; v < n_views && same; ++v) same = (ws[v] == width && hs[v] == height);
-    if (!same) {  // CheckImages (main.cpp:310-329)
-      std::cerr << "Images may error, check it!\n";
-      jpeg_decoder_destroy(dec);
-      return 1;
-    }
-    if (bad.load() >= 1000) {
-      std::cerr << "DPE-MVS: cannot read a camera file\n";
-      jpeg_decoder_destroy(dec);
-      return 1;
-    }
+    if (bad.load()) return bail("Images may error, check it!");  // CheckImages (main.cpp:310-329)
+    if (bad_cam.load()) return bail("DPE-MVS: cannot read a camera file");
   }
   tm.load = now_s() - t0;
   if (verbose) std::cout << "There are " << n_problems << " images to be processed!" << std::endl;
   const int round_num = compute_round_num(width, height);
   const int iteration_num = round_num * 4;
 
-  // ---- edge / label preparation (GetProblemEdges), cached .dmb files honoured -----------------
-  t0 = now_s();
+  // ---- edge / label preparation (GetProblemEdges) in the background: the first fine stage needs it, the
+  //      coarse stages do not.  Cached .dmb files are honoured (main.cpp:351-355, 370-374).
   std::vector<ViewPrep> prep(n_problems);
-  {
+  for (int v = 0; v < n_problems; ++v) { prep[v].edge.resize(round_num); prep[v].label.resize(round_num); }
+  std::mutex prep_m;
+  std::condition_variable prep_cv;
+  std::vector<int> prep_left(n_problems, round_num);  // jobs outstanding per view
+  const double t_prep0 = now_s();
+  std::atomic<double> prep_done_at(0.0);
+  std::thread prep_thread([&]() {
     const int hw = (int)std::thread::hardware_concurrency();
-    for (int v = 0; v < n_problems; ++v) { prep[v].edge.resize(round_num); prep[v].label.resize(round_num); }
-    parallel_for(n_problems * round_num, hw > 0 ? hw : 4, [&](int job) {
-      const int v = job / round_num, j = job % round_num;
+    // full-resolution jobs first (they take longest), views in order
+    std::vector<std::pair<int, int>> jobs;
+    for (int j = 0; j < round_num; ++j)
+      for (int v = 0; v < n_problems; ++v) jobs.push_back({v, j});
+    parallel_for((int)jobs.size(), std::max(1, (hw > 0 ? hw : 4) - 1), [&](int job) {
+      const int v = jobs[job].first, j = jobs[job].second;
       const std::string dir = out_root + "/" + format_index(view_ids[v]);
       const std::string ep = dir + "/edges_" + std::to_string(j) + ".dmb";
       const std::string lp = dir + "/labels_" + std::to_string(j) + ".dmb";
       bool have_e = false, have_l = false;
       int r, c, t;
       std::vector<uint8_t> buf;
-      if (file_exists(ep) && read_dmb(ep, &r, &c, &t, &buf) && t == DMB_8UC1) {
+      // a cached file is honoured only if it has the size this scale needs (round(W/2^j) x round(H/2^j), the
+      // reference's cv::resize target, main.cpp:343-345) and carries that many elements; a stale or foreign
+      // file is ignored and the arrays recomputed
+      const int want_c = (int)std::round(width * (1.0f / (float)(1 << j))), want_r = (int)std::round(height * (1.0f / (float)(1 << j)));
+      if (file_exists(ep) && read_dmb(ep, &r, &c, &t, &buf) && t == DMB_8UC1 && r == want_r && c == want_c &&
+          buf.size() == (size_t)r * c) {
         prep[v].edge[j].rows = r; prep[v].edge[j].cols = c; prep[v].edge[j].d = buf;
         have_e = true;
       }
-      if (file_exists(lp) && read_dmb(lp, &r, &c, &t, &buf) && t == DMB_32SC1) {
+      if (file_exists(lp) && read_dmb(lp, &r, &c, &t, &buf) && t == DMB_32SC1 && r == want_r && c == want_c &&
+          buf.size() == (size_t)r * c * sizeof(int32_t)) {
         prep[v].label[j].resize((size_t)r * c);
         memcpy(prep[v].label[j].data(), buf.data(), buf.size());
         have_l = true;
       }
       if (!have_e || !have_l) {
+        ImageU8 gimg;
+        gimg.rows = height; gimg.cols = width;
+        gimg.d.assign(gray_slab + P * v, gray_slab + P * (v + 1));
         ImageU8 e;
         std::vector<int32_t> l;
         int oc, orr;
-        problem_edges(grays[v], 1 << j, &e, &l, &oc, &orr);
+        problem_edges(gimg, 1 << j, &e, &l, &oc, &orr);
         if (!have_e) prep[v].edge[j] = e;
         if (!have_l) prep[v].label[j] = l;
       }
+      { std::lock_guard<std::mutex> lk(prep_m); prep_left[v]--; }
+      prep_cv.notify_all();
     });
-  }
-  tm.prep = now_s() - t0;
+    prep_done_at = now_s();
+  });
+  auto wait_prep = [&](int v) {
+    std::unique_lock<std::mutex> lk(prep_m);
+    prep_cv.wait(lk, [&]() { return prep_left[v] == 0; });
+  };
 
-  // ---- contexts + scene upload ------------------------------------------------------------------
-  t0 = now_s();
-  // views are split into G contiguous blocks of spr = ceil(V/G); atlas slot = view index, so the
-  // block of rank g is also its chunk of the all-gather
-  const int slots = (n_views + G - 1) / G;
-  std::vector<dpe_ctx*> ctxs(G, nullptr);
-  auto fail = [&](const char* what, dpe_ctx* c) {
-    std::cerr << "DPE-MVS: " << what << ": " << (c ? dpe_last_error(c) : "") << "\n";
-    for (auto* x : ctxs) dpe_ctx_destroy(x);
+  // ---- contexts ready?  communicator -----------------------------------------------------------------
+  for (auto& t : ctx_threads) t.join();
+  tm.ctx = now_s() - t_ctx0;
+  auto fail = [&](const std::string& what) {
+    if (prep_thread.joinable()) prep_thread.join();
+    if (G > 1) dpe_comm_reset_all();
+    destroy_all();
     jpeg_decoder_destroy(dec);
+    cudaFreeHost(gray_slab);
+    std::cerr << "DPE-MVS: " << what << "\n";
     return 1;
   };
-  const int slots_per_rank = slots;
-  {
-    std::vector<std::string> errs(G);
-    std::vector<std::thread> th;
-    for (int g = 0; g < G; ++g) th.emplace_back([&, g]() {
-      auto bad = [&](const char* what) { errs[g] = std::string(what) + ": " + (ctxs[g] ? dpe_last_error(ctxs[g]) : ""); };
-      const double tu0 = now_s();
-      if (dpe_ctx_create(&ctxs[g], gpus[g]) != DPE_OK) { errs[g] = "cannot create context"; return; }
-      dpe_ctx* c = ctxs[g];
-      const double tu1 = now_s();
-      if (dpe_scene_begin(c, n_views, width, height, round_num)) return bad("scene_begin");
-      for (int v = 0; v < n_views; ++v)
-        if (dpe_scene_set_view(c, v, grays[v].d.data(), cams[v].K, cams[v].R, cams[v].t, cams[v].depth_min, cams[v].depth_max))
-          return bad("set_view");
-      for (int v = 0; v < n_problems; ++v) {
-        std::vector<int> src;
-        for (int s : problems[v].src_image_ids) src.push_back(id_to_view[s]);
-        if (dpe_scene_set_pairs(c, v, src.data(), (int)src.size())) return bad("set_pairs");
-      }
-      const int first = std::min(g * slots, n_problems), count = std::max(0, std::min(slots, n_problems - first));
-      for (int v = first; v < first + count; ++v)
-        for (int k = 0; k < round_num; ++k) {
-          const int j = round_num - 1 - k;
-          if (dpe_scene_set_prep(c, v, k, prep[v].edge[j].d.data(), prep[v].label[j].data())) return bad("set_prep");
-        }
-      if (dpe_scene_set_shard(c, first, count, slots_per_rank, G)) return bad("set_shard");
-      const double tu2 = now_s();
-      if (dpe_scene_commit(c)) return bad("commit");
-      if (g == 0) { tm.up_create = tu1 - tu0; tm.up_views = tu2 - tu1; tm.up_commit = now_s() - tu2; }
-    });
-    for (auto& t : th) t.join();
-    for (int g = 0; g < G; ++g)
-      if (!errs[g].empty()) {
-        std::cerr << "DPE-MVS: " << errs[g] << "\n";
-        for (auto* x : ctxs) dpe_ctx_destroy(x);
-        jpeg_decoder_destroy(dec);
-        return 1;
-      }
-    cudaSetDevice(gpus[0]);
+  for (int g = 0; g < G; ++g) if (!errs[g].empty()) return fail(errs[g]);
+  if (G > 1) {
+    const double tc = now_s();
+    if (dpe_comm_init_all(ctxs.data(), G) != DPE_OK) return fail(std::string("communicator: ") + dpe_last_error(ctxs[0]));
+    tm.comm = now_s() - tc;
   }
-  tm.upload = now_s() - t0;
 
   if (verbose) {
     std::cout << "There are " << round_num << " resolution stages for coarse-to-fine processing!" << std::endl;
     std::cout << "Iteration nums: " << iteration_num << std::endl;
   }
 
-  // ---- stage loop (main.cpp:507-567) ------------------------------------------------------------
-  t0 = now_s();
   // RNG seed: the reference seeds cuRAND with clock64() (DPE.cu:1032); any value is "the reference's";
   // a fixed default makes runs reproducible, DPE_SEED overrides it.
   uint64_t seed = 20261018ull;
@@ -282,162 +381,165 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
   // view order inside a stage: single GPU defaults to the reference's sequential order (view k reads
   // this stage's depth maps of views < k); several GPUs need the order-independent one.
   // DPE_VIEW_ORDER=parallel|sequential overrides.
-  {
-    bool sequential = (G == 1);
-    if (const char* e = getenv("DPE_VIEW_ORDER")) sequential = (std::string(e) == "sequential") && G == 1;
-    if (sequential) dpe_set_view_order(ctxs[0], 1);
-  }
+  bool sequential = (G == 1);
+  if (const char* e = getenv("DPE_VIEW_ORDER")) sequential = (std::string(e) == "sequential") && G == 1;
   // cost arithmetic (include/dpe_b200.h): the reference's own, operation by operation, unless DPE_ARITH says
   // fast (constant-folded homography, ~8 % faster) or centred
+  int arith = -1;
   if (const char* e = getenv("DPE_ARITH")) {
     const std::string m(e);
-    const int mode = m == "fast" ? DPE_COST_REFERENCE : (m == "centred" ? DPE_COST_CENTRED : DPE_COST_REFERENCE_EXACT);
-    for (auto* c : ctxs) dpe_set_cost_arithmetic(c, mode);
+    arith = m == "fast" ? DPE_COST_REFERENCE : (m == "centred" ? DPE_COST_CENTRED : DPE_COST_REFERENCE_EXACT);
   }
-  int iteration_index = 0;
-  auto run_stage_all = [&](int k, const dpe_stage_params& p) -> int {
-    std::vector<int> rcs(G, 0);
-    if (G == 1) {
-      rcs[0] = dpe_run_stage(ctxs[0], k, &p, seed);
-    } else {
-      std::vector<std::thread> th;
-      for (int g = 0; g < G; ++g) th.emplace_back([&, g]() { rcs[g] = dpe_run_stage(ctxs[g], k, &p, seed); });
-      for (auto& t : th) t.join();
-    }
-    for (int g = 0; g < G; ++g) if (rcs[g]) return fail("run_stage", ctxs[g]);
-    if (G > 1) {
-      // all-gather of the depth atlas: every rank's chunk is copied to every peer
-      std::vector<void*> ptr(G);
-      size_t chunk = 0, total = 0;
-      for (int g = 0; g < G; ++g) dpe_stage_atlas(ctxs[g], &ptr[g], &chunk, &total);
-      for (int dst = 0; dst < G; ++dst) {
-        cudaSetDevice(gpus[dst]);
-        for (int src = 0; src < G; ++src)
-          if (src != dst)
-            cudaMemcpyPeerAsync((char*)ptr[dst] + (size_t)src * chunk, gpus[dst], (char*)ptr[src] + (size_t)src * chunk, gpus[src], chunk, 0);
-      }
-      for (int g = 0; g < G; ++g) { cudaSetDevice(gpus[g]); cudaDeviceSynchronize(); }
-      cudaSetDevice(gpus[0]);
-    }
-    for (int g = 0; g < G; ++g) if (dpe_stage_commit(ctxs[g])) return fail("stage_commit", ctxs[g]);
-    return 0;
-  };
-  for (int i = 0; i < round_num; ++i) {
-    dpe_stage_params p;
-    memset(&p, 0, sizeof(p));
-    p.max_iterations = 3; p.top_k = 4; p.geom_factor = 0.2f;
-    p.ransac_threshold = 0.005f; p.rotate_time = 4;
-    if (i == 0) { p.state = DPE_FIRST_INIT; p.use_apd = 0; }
-    else {
-      p.state = DPE_REFINE_INIT; p.use_apd = 1;
-      p.ransac_threshold = (float)(0.01 - i * 0.00125);
-      p.rotate_time = std::min((int)(1 << i), 4);
-    }
-    p.geom_consistency = 0; p.weak_peak_radius = 6;
-    if (int rc = run_stage_all(i, p)) return rc;
-    if (verbose) std::cout << "Iteration " << iteration_index + 1 << " / " << iteration_num << " done" << std::endl;
-    iteration_index++;
-    for (int j = 0; j < 3; ++j) {
-      p.state = DPE_REFINE_ITER; p.use_apd = i == 0 ? 0 : 1;
-      p.ransac_threshold = (float)(0.01 - i * 0.00125);
-      p.rotate_time = std::min((int)(1 << i), 4);
-      p.geom_consistency = 1; p.weak_peak_radius = std::max(4 - 2 * j, 2);
-      if (int rc = run_stage_all(i, p)) return rc;
-      if (verbose) std::cout << "Iteration " << iteration_index + 1 << " / " << iteration_num << " done" << std::endl;
-      iteration_index++;
-    }
-    if (verbose) std::cout << "Resolution up" << std::endl;
-  }
-  tm.stages = now_s() - t0;
-  for (int g = 0; g < G; ++g) { tm.gpu_ms = std::max(tm.gpu_ms, dpe_stage_gpu_ms(ctxs[g])); tm.launches += dpe_kernel_launches(ctxs[g]); }
+  const std::vector<Stage> schedule = make_schedule(round_num);
 
-  // ---- results: .npy export (main.cpp:570-575), optional fusion ---------------------------------
-  t0 = now_s();
-  const size_t P = (size_t)width * height;
-  std::vector<std::vector<float>> all_depth, all_normal;
-  std::vector<std::vector<uint8_t>> all_state;
-  if (fusion) { all_depth.resize(n_problems); all_normal.resize(n_problems); all_state.resize(n_problems); }
-  {
-    // one reader thread per GPU pulls its views' maps off the device; the .npy files are written by
-    // a few writer tasks behind it
-    struct Job { int v; std::vector<float> d, n3; std::vector<uint8_t> st; };
-    std::vector<std::string> errs(G);
-    std::atomic<int> write_fail(0);
-    auto write_view = [&](Job* job) {
-      const int v = job->v;
+  // ---- .npy writers (main.cpp:570-575) run behind the GPU workers -------------------------------------
+  const bool any_output = depth || normal || weak || edge;
+  ExportQueue queue(P, normal != 0, weak != 0, any_output ? 2 * G + 2 : 0);
+  if (any_output && !queue.usable()) return fail("cannot allocate pinned export buffers");
+  std::atomic<int> write_fail(0);
+  std::vector<std::thread> writers;
+  const int n_writers = any_output ? std::min(4 + G, 12) : 0;
+  for (int w = 0; w < n_writers; ++w) writers.emplace_back([&]() {
+    std::vector<int8_t> i8;
+    while (ExportBuf* b = queue.take()) {
+      const int v = b->view;
       const std::string dir = out_root + "/" + format_index(view_ids[v]);
-      std::vector<int8_t> i8;
       bool ok = true;
-      if (depth) {
-        std::vector<float> dz(job->d);
-        for (size_t i = 0; i < P; ++i) if (job->st[i] == DPE_UNKNOWN) dz[i] = 0.0f;  // ZeroDepthForUnknown
-        ok &= write_npy(dir + "/depth.npy", dz.data(), "<f4", 4, height, width, 1);
-      }
-      if (normal) ok &= write_npy(dir + "/normal.npy", job->n3.data(), "<f4", 4, height, width, 3);
-      if (weak) {
-        i8.resize(P);
-        for (size_t i = 0; i < P; ++i) { const uint8_t st = job->st[i]; i8[i] = st == DPE_WEAK ? 1 : (st == DPE_STRONG ? 2 : 0); }
-        ok &= write_npy(dir + "/weak.npy", i8.data(), "|i1", 1, height, width, 1);
-      }
-      if (edge) {
+      if (depth) ok &= write_npy(dir + "/depth.npy", b->depth, "<f4", 4, height, width, 1);
+      if (normal) ok &= write_npy(dir + "/normal.npy", b->normal, "<f4", 4, height, width, 3);
+      if (weak) ok &= write_npy(dir + "/weak.npy", b->weak, "|i1", 1, height, width, 1);
+      queue.recycle(b);
+      if (edge) {  // edges_0 > 0 (main.cpp:226-260)
+        wait_prep(v);
         i8.resize(P);
         const ImageU8& e = prep[v].edge[0];
         for (size_t i = 0; i < P; ++i) i8[i] = e.d[i] > 0 ? 1 : 0;
         ok &= write_npy(dir + "/edge.npy", i8.data(), "|i1", 1, height, width, 1);
       }
       if (!ok) write_fail++;
-      if (fusion) { all_depth[v].swap(job->d); all_normal[v].swap(job->n3); all_state[v].swap(job->st); }
-      delete job;
+    }
+  });
+
+  // ---- one worker per GPU: scene upload, the whole schedule, export of its views ----------------------
+  std::atomic<bool> abort_flag(false);
+  std::vector<double> t_upload(G, 0.0), t_stages(G, 0.0), t_prep_wait(G, 0.0);
+  auto worker = [&](int g) {
+    dpe_ctx* c = ctxs[g];
+    auto bad = [&](const char* what) {
+      errs[g] = std::string(what) + ": " + dpe_last_error(c);
+      if (!abort_flag.exchange(true) && G > 1) dpe_comm_reset_all();  // peers blocked in a collective return
     };
-    std::vector<std::thread> readers;
-    for (int g = 0; g < G; ++g) readers.emplace_back([&, g]() {
-      cudaSetDevice(gpus[g]);
-      const int first = std::min(g * slots, n_problems), count = std::max(0, std::min(slots, n_problems - first));
-      std::vector<std::thread> writers;
-      for (int v = first; v < first + count; ++v) {
-        Job* job = new Job{v, std::vector<float>(P), std::vector<float>((normal || fusion) ? P * 3 : 0), std::vector<uint8_t>(P)};
-        if (dpe_get_maps(ctxs[g], v, job->d.data(), job->n3.empty() ? nullptr : job->n3.data(), job->st.data(), nullptr)) {
-          errs[g] = dpe_last_error(ctxs[g]);
-          delete job;
-          break;
+    const double tu0 = now_s();
+    if (dpe_scene_begin(c, n_views, width, height, round_num)) return bad("scene_begin");
+    for (int v = 0; v < n_views; ++v)
+      if (dpe_scene_set_view(c, v, g == 0 ? gray_slab + P * v : nullptr, cams[v].K, cams[v].R, cams[v].t, cams[v].depth_min, cams[v].depth_max))
+        return bad("set_view");
+    for (int v = 0; v < n_problems; ++v) {
+      std::vector<int> src;
+      for (int s : problems[v].src_image_ids) src.push_back(id_to_view[s]);
+      if (dpe_scene_set_pairs(c, v, src.data(), (int)src.size())) return bad("set_pairs");
+    }
+    if (dpe_scene_set_shard(c, n_problems, g, G)) return bad("set_shard");
+    if (dpe_scene_broadcast_images(c, 0)) return bad("broadcast_images");
+    if (dpe_scene_commit(c)) return bad("commit");
+    if (sequential) dpe_set_view_order(c, 1);
+    if (arith >= 0) dpe_set_cost_arithmetic(c, arith);
+    t_upload[g] = now_s() - tu0;
+    int first = 0, count = 0;
+    dpe_shard_range(n_problems, G, g, &first, &count);
+    const double ts0 = now_s();
+    bool prep_up = false;
+    for (size_t si = 0; si < schedule.size(); ++si) {
+      if (abort_flag.load()) return;
+      const Stage& st = schedule[si];
+      if (st.p.use_apd && !prep_up) {
+        const double tw = now_s();
+        for (int v = first; v < first + count; ++v) {
+          wait_prep(v);
+          for (int k = 0; k < round_num; ++k) {
+            const int j = round_num - 1 - k;
+            if (dpe_scene_set_prep(c, v, k, prep[v].edge[j].d.data(), prep[v].label[j].data(), prep[v].edge[j].d.size())) return bad("set_prep");
+          }
         }
-        if (writers.size() >= 4) { writers.front().join(); writers.erase(writers.begin()); }
-        writers.emplace_back(write_view, job);
+        t_prep_wait[g] = now_s() - tw;
+        prep_up = true;
       }
-      for (auto& w : writers) w.join();
-    });
-    for (auto& r : readers) r.join();
-    cudaSetDevice(gpus[0]);
-    for (int g = 0; g < G; ++g) if (!errs[g].empty()) { std::cerr << "DPE-MVS: get_maps: " << errs[g] << "\n"; return fail("get_maps", nullptr); }
-    if (write_fail.load()) { std::cerr << "DPE-MVS: cannot write the .npy outputs\n"; return fail("write", nullptr); }
+      const bool last = si + 1 == schedule.size();
+      if (dpe_stage_begin(c, st.scale, &st.p, seed)) return bad("stage_begin");
+      if (last && (depth || normal || weak)) {
+        for (int v = first; v < first + count; ++v) {
+          if (dpe_stage_wait_view(c, v)) return bad("stage_wait_view");
+          ExportBuf* b = queue.acquire();
+          b->view = v;
+          if (dpe_export_view(c, v, depth ? b->depth : nullptr, normal ? b->normal : nullptr, weak ? b->weak : nullptr)) {
+            queue.recycle(b);
+            return bad("export_view");
+          }
+          queue.submit(b);
+        }
+      } else if (last && edge) {
+        for (int v = first; v < first + count; ++v) { ExportBuf* b = queue.acquire(); b->view = v; queue.submit(b); }
+      }
+      if (dpe_stage_end(c)) return bad("stage_end");
+      if (dpe_stage_commit(c)) return bad("stage_commit");
+      if (g == 0 && verbose) {
+        std::cout << "Iteration " << si + 1 << " / " << iteration_num << " done" << std::endl;
+        if (st.resolution_up) std::cout << "Resolution up" << std::endl;
+      }
+    }
+    t_stages[g] = now_s() - ts0;
+  };
+  t0 = now_s();
+  if (G == 1) worker(0);
+  else {
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) th.emplace_back(worker, g);
+    for (auto& t : th) t.join();
   }
-  tm.output = now_s() - t0;
+  queue.close();
+  for (auto& w : writers) w.join();
+  prep_thread.join();
+  tm.prep = prep_done_at.load() - t_prep0;
+  for (int g = 0; g < G; ++g) {
+    tm.upload = std::max(tm.upload, t_upload[g]); tm.stages = std::max(tm.stages, t_stages[g]);
+    tm.prep_wait = std::max(tm.prep_wait, t_prep_wait[g]);
+  }
+  tm.output = std::max(0.0, now_s() - t0 - tm.upload - tm.stages);  // what the writers needed beyond the last stage
+  for (int g = 0; g < G; ++g) if (!errs[g].empty()) return fail(errs[g]);
+  if (write_fail.load()) return fail("cannot write the .npy outputs");
+  for (int g = 0; g < G; ++g) { tm.gpu_ms = std::max(tm.gpu_ms, dpe_stage_gpu_ms(ctxs[g])); tm.launches += dpe_kernel_launches(ctxs[g]); }
+
   if (fusion) {
     // on the device of the first context: maps of every problem view + colour images go up, the cloud comes back
     t0 = now_s();
     dpe_ctx* fc = ctxs[0];
-    cudaSetDevice(gpus[0]);
     std::vector<uint8_t> color;
+    std::vector<float> fd(P), fn(P * 3);
+    std::vector<uint8_t> fs(P);
     for (int v = 0; v < n_problems; ++v) {
       int w, h;
-      if (!jpeg_decode_bgr(dec, dense + "/images/" + format_index(view_ids[v]) + ".jpg", &color, &w, &h, &err)) {
+      cudaSetDevice(gpus[0]);
+      if (!jpeg_decode_bgr(dec, image_path(v), &color, &w, &h, &err)) {
         color.resize(P * 3);  // grey-only JPEG: replicate luma
-        for (size_t i = 0; i < P; ++i) color[3 * i] = color[3 * i + 1] = color[3 * i + 2] = grays[v].d[i];
+        for (size_t i = 0; i < P; ++i) color[3 * i] = color[3 * i + 1] = color[3 * i + 2] = gray_slab[P * v + i];
       }
-      if (dpe_fuse_set_view(fc, v, all_depth[v].data(), all_normal[v].data(), all_state[v].data(), color.data())) return fail("fuse_set_view", fc);
-      std::vector<float>().swap(all_depth[v]); std::vector<float>().swap(all_normal[v]);
+      int owner = 0, first = 0, count = 0;
+      for (; owner < G; ++owner) { dpe_shard_range(n_problems, G, owner, &first, &count); if (v < first + count) break; }
+      if (dpe_get_maps(ctxs[owner], v, fd.data(), fn.data(), fs.data(), nullptr)) return fail(std::string("get_maps: ") + dpe_last_error(ctxs[owner]));
+      for (size_t i = 0; i < P; ++i) if (fs[i] == DPE_UNKNOWN) fd[i] = 0.0f;  // ZeroDepthForUnknown
+      if (dpe_fuse_set_view(fc, v, fd.data(), fn.data(), fs.data(), color.data())) return fail(std::string("fuse_set_view: ") + dpe_last_error(fc));
     }
     size_t n_points = 0;
-    if (dpe_fuse_run(fc, &n_points)) return fail("fuse_run", fc);
+    if (dpe_fuse_run(fc, &n_points)) return fail(std::string("fuse_run: ") + dpe_last_error(fc));
     std::vector<float> xyz(n_points * 3);
     std::vector<uint8_t> bgr(n_points * 3);
-    if (n_points && dpe_fuse_get(fc, xyz.data(), bgr.data())) return fail("fuse_get", fc);
-    if (!write_ply(dense + "/DPE/DPE.ply", xyz.data(), bgr.data(), n_points)) { std::cerr << "DPE-MVS: cannot write DPE.ply\n"; return fail("write_ply", nullptr); }
+    if (n_points && dpe_fuse_get(fc, xyz.data(), bgr.data())) return fail(std::string("fuse_get: ") + dpe_last_error(fc));
+    if (!write_ply(dense + "/DPE/DPE.ply", xyz.data(), bgr.data(), n_points)) return fail("cannot write DPE.ply");
     tm.fusion = now_s() - t0;
   }
-  for (auto* c : ctxs) dpe_ctx_destroy(c);
-  ctxs.assign(G, nullptr);
+  destroy_all();
   jpeg_decoder_destroy(dec);
+  cudaFreeHost(gray_slab);
 
   // ---- cleanup of intermediates the reference deletes (main.cpp:581-595) ------------------------
   for (int v = 0; v < n_problems; ++v) {
@@ -452,11 +554,11 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     FILE* f = fopen(tj, "w");
     if (f) {
       fprintf(f,
-              "{\"views\": %d, \"gpus\": %d, \"width\": %d, \"height\": %d, \"load_s\": %.6f, \"prep_s\": %.6f, "
-              "\"upload_s\": %.6f, \"upload_parts_s\": [%.6f, %.6f, %.6f], \"stages_s\": %.6f, \"output_s\": %.6f, \"fusion_s\": %.6f, \"total_s\": %.6f, "
-              "\"gpu_ms\": %.3f, \"kernel_launches\": %lld}\n",
-              n_problems, G, width, height, tm.load, tm.prep, tm.upload, tm.up_create, tm.up_views, tm.up_commit, tm.stages, tm.output, tm.fusion, tm.total,
-              tm.gpu_ms, tm.launches);
+              "{\"views\": %d, \"gpus\": %d, \"width\": %d, \"height\": %d, \"load_s\": %.6f, \"ctx_s\": %.6f, \"comm_init_s\": %.6f, "
+              "\"prep_background_s\": %.6f, \"prep_wait_s\": %.6f, \"upload_s\": %.6f, \"stages_s\": %.6f, \"output_tail_s\": %.6f, "
+              "\"fusion_s\": %.6f, \"total_s\": %.6f, \"gpu_ms\": %.3f, \"kernel_launches\": %lld}\n",
+              n_problems, G, width, height, tm.load, tm.ctx, tm.comm, tm.prep, tm.prep_wait, tm.upload, tm.stages, tm.output, tm.fusion,
+              tm.total, tm.gpu_ms, tm.launches);
       fclose(f);
     }
   }

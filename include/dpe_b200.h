@@ -41,7 +41,8 @@ typedef enum dpe_status {
   DPE_ERR_STATE = -3,
   DPE_ERR_IO = -4,
   DPE_ERR_TOO_MANY_IMAGES = -5, /* DPE.cpp:762-765 */
-  DPE_ERR_NO_DEVICE = -6
+  DPE_ERR_NO_DEVICE = -6,
+  DPE_ERR_COMM = -7             /* NCCL */
 } dpe_status;
 
 /* Per-stage parameters: the fields of PatchMatchParams (main.h:78-106) that
@@ -68,26 +69,53 @@ DPE_API const char* dpe_last_error(const dpe_ctx* ctx);
 /* how many CUDA kernels this context has launched so far */
 DPE_API long long dpe_kernel_launches(const dpe_ctx* ctx);
 
+/* --- several GPUs (no counterpart in the reference, which processes problems one after the other on one GPU,
+ *     main.cpp:509-558, and exchanges depth maps through depths.dmb files, DPE.cpp:826-844) -------------------
+ * The path shards by reference view: problems [0, n_problems) are split into n_ranks contiguous, balanced
+ * blocks, one context (= one GPU) per rank; images and cameras are replicated, per-view state lives on the
+ * owner.  The one exchange is the depth atlas: after every stage each rank's depth maps are all-gathered with
+ * NCCL, one in-place collective per view slot, queued on a side stream behind that view's last kernel.  A
+ * sharded context WITHOUT a communicator leaves the exchange to its driver (dpe_stage_atlas + dpe_view_slot
+ * between dpe_run_stage and dpe_stage_commit): what the single-GPU sharding test does. */
+/* block of rank `rank`: first = rank*q + min(rank, r), count = q + (rank < r), q = n / n_ranks, r = n % n_ranks */
+DPE_API int dpe_shard_range(int n_problems, int n_ranks, int rank, int* first, int* count);
+/* one process per GPU (bench.py under torchrun): rank 0 makes the id, the launcher hands it to every rank */
+#define DPE_COMM_ID_BYTES 128
+DPE_API int dpe_comm_get_unique_id(void* id, size_t bytes);
+DPE_API int dpe_comm_init_rank(dpe_ctx* ctx, const void* id, int n_ranks, int rank);
+/* one process, n contexts on n GPUs (dpe_run_pipeline): context i becomes rank i.  The communicators are kept
+ * for the life of the process and reused by later calls with the same GPUs; dpe_comm_reset_all aborts them. */
+DPE_API int dpe_comm_init_all(dpe_ctx** ctxs, int n);
+DPE_API void dpe_comm_reset_all(void);
+
 /* --- scene upload (replaces DPE::InuputInitialization DPE.cpp:733-914,
  *     SupportInitialization :1025-1052, CudaSpaceInitialization :916-1023) -- */
 /* n_scales = ComputeRoundNum (main.cpp:390-408); scale index k has size
  * round(W/2^(n_scales-1-k)) x round(H/2^(n_scales-1-k)); k=0 is the coarsest. */
 DPE_API int dpe_scene_begin(dpe_ctx* ctx, int n_views, int width, int height, int n_scales);
-/* gray: H*W bytes (cv::IMREAD_GRAYSCALE image, DPE.cpp:745); K,R row-major;
- * depth_min/max are the cam-file values (the 0.6/1.2 factors of
+/* gray: H*W bytes (cv::IMREAD_GRAYSCALE image, DPE.cpp:745), copied asynchronously (keep it alive until
+ * dpe_scene_commit; pinned memory makes the copy overlap), or NULL when the image arrives by
+ * dpe_scene_broadcast_images; K,R row-major; depth_min/max are the cam-file values (the 0.6/1.2 factors of
  * DPE.cpp:788-789 are applied inside). */
 DPE_API int dpe_scene_set_view(dpe_ctx* ctx, int view, const uint8_t* gray, const float K[9],
                        const float R[9], const float t[3], float depth_min, float depth_max);
+/* collective (every rank calls it, after dpe_scene_set_shard): the images rank `root` uploaded are broadcast
+ * to all ranks over NVLink (ncclBroadcast), so a scene's images cross PCIe once */
+DPE_API int dpe_scene_broadcast_images(dpe_ctx* ctx, int root);
 /* src_ids index views of this scene (positions in pair.txt order), n_src<=31 */
 DPE_API int dpe_scene_set_pairs(dpe_ctx* ctx, int view, const int* src_ids, int n_src);
-/* edge: edges_k (uchar 0/255), label: labels_k (int32) of GetProblemEdges
- * (main.cpp:331-388) at scale index `scale` (0 = coarsest). */
+/* edge: edges_k (uchar 0/255), label: labels_k (int32) of GetProblemEdges (main.cpp:331-388) at scale index
+ * `scale` (0 = coarsest); n_elems = width x height of that scale (dpe_get_size), anything else is rejected.
+ * May be called before dpe_scene_commit or after it (then it uploads at once, also while a stage that does not
+ * use prep is running); a view this context does not own is ignored. */
 DPE_API int dpe_scene_set_prep(dpe_ctx* ctx, int view, int scale, const uint8_t* edge,
-                       const int32_t* label);
-/* multi-GPU: this context owns views [first, first+count); depth-atlas slots
- * are padded to slots_per_rank*n_ranks (NCCL all-gather needs equal chunks). */
-DPE_API int dpe_scene_set_shard(dpe_ctx* ctx, int first_view, int count, int slots_per_rank,
-                        int n_ranks);
+                       const int32_t* label, size_t n_elems);
+/* this context is rank `rank` of n_ranks and owns the block dpe_shard_range gives it; views >= n_problems are
+ * sources only.  Without this call the context owns every view. */
+DPE_API int dpe_scene_set_shard(dpe_ctx* ctx, int n_problems, int rank, int n_ranks);
+/* test / profiling hook: an unsharded context runs its stages over views [first_view, first_view + count) only
+ * (the other views still serve as sources) */
+DPE_API int dpe_scene_set_active(dpe_ctx* ctx, int first_view, int count);
 /* builds pyramids, textures, per-pair constants; after this the scene is
  * resident in HBM. */
 DPE_API int dpe_scene_commit(dpe_ctx* ctx);
@@ -98,10 +126,18 @@ DPE_API int dpe_scene_commit(dpe_ctx* ctx);
 /* seed: the reference's curand_init seed (clock64() there, DPE.cu:1032): every (view, stage) starts
  * pixel (x, y) from the cuRAND XORWOW state curand_init(seed, y, x). */
 DPE_API int dpe_run_stage(dpe_ctx* ctx, int scale_idx, const dpe_stage_params* params, uint64_t seed);
-/* device pointer + byte size of the depth atlas this stage wrote (slots x P
- * floats).  Between dpe_run_stage and dpe_stage_commit a multi-GPU driver
- * all-gathers it in place (chunk = slots_per_rank*P floats at rank offset). */
-DPE_API int dpe_stage_atlas(dpe_ctx* ctx, void** dev_ptr, size_t* chunk_bytes, size_t* total_bytes);
+/* the same in two halves: dpe_stage_begin queues every kernel of every owned view (and, with several ranks, the
+ * all-gathers) and returns; dpe_stage_wait_view blocks until `view` has finished the stage, after which its maps
+ * can be read (dpe_export_view, dpe_get_maps) while later views still run; dpe_stage_end waits for the rest.
+ * dpe_run_stage = begin + end. */
+DPE_API int dpe_stage_begin(dpe_ctx* ctx, int scale_idx, const dpe_stage_params* params, uint64_t seed);
+DPE_API int dpe_stage_wait_view(dpe_ctx* ctx, int view);
+DPE_API int dpe_stage_end(dpe_ctx* ctx);
+/* device pointer of the depth atlas the last stage wrote, bytes per slot (one depth map) and in total.  A view's
+ * map sits in slot dpe_view_slot: local index * n_ranks + owner rank for problems, behind them for source-only
+ * views (which stay zero). */
+DPE_API int dpe_stage_atlas(dpe_ctx* ctx, void** dev_ptr, size_t* slot_bytes, size_t* total_bytes);
+DPE_API int dpe_view_slot(dpe_ctx* ctx, int view, int* slot);
 /* publishes the atlas written by the last stage as the source depth maps of
  * the next geometric-consistency stage (the reference does this through
  * depths.dmb files, DPE.cpp:826-844). */
@@ -171,12 +207,20 @@ DPE_API int dpe_geom_eval(dpe_ctx* ctx, int view, int scale_idx, int n_pix, cons
 DPE_API int dpe_get_size(dpe_ctx* ctx, int scale_idx, int* width, int* height);
 DPE_API int dpe_get_maps(dpe_ctx* ctx, int view, float* depth, float* normal3, uint8_t* state,
                  uint32_t* selected);
+/* the payloads of depth.npy / normal.npy / weak.npy of `view` (Write*AsNpy, main.cpp:99-260): depth zeroed where
+ * the pixel is UNKNOWN (main.cpp:36-46), normal H*W*3, weak int8 {0 unknown, 1 weak, 2 strong} (main.cpp:190-197);
+ * packed on the device, copied on a stream of their own (pinned destinations overlap running stages).  Any pointer
+ * may be NULL. */
+DPE_API int dpe_export_view(dpe_ctx* ctx, int view, float* depth, float* normal3, int8_t* weak);
 /* number of (pixel,hypothesis,view) bilateral-NCC units evaluated so far
  * (NCCOld = 1 unit = 36 taps, NCCNew = taps/36); 0 unless counting is on. */
 DPE_API int dpe_set_count_evals(dpe_ctx* ctx, int on);
 DPE_API double dpe_eval_units(dpe_ctx* ctx);
 /* GPU milliseconds spent inside dpe_run_stage so far (CUDA events). */
 DPE_API double dpe_stage_gpu_ms(dpe_ctx* ctx);
+/* the part of it this rank spent after its own last view, waiting for the all-gathers to finish (the exposed
+ * exchange plus the wait for slower ranks); 0 on one GPU */
+DPE_API double dpe_stage_comm_ms(dpe_ctx* ctx);
 
 /* per-kernel-class profile: dpe_set_profile(ctx, n) with n > 0 makes dpe_run_stage bracket every
  * launch of its first n local views with CUDA events (those views run on one stream, the eval-unit

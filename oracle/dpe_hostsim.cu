@@ -1,4 +1,4 @@
-// dpe_hostsim.cu — TEST-ONLY CPU simulator of the kernel logic.
+// dpe_hostsim.cu — TEST INFRASTRUCTURE: CPU simulator of the kernel logic (built by oracle/Makefile).
 //
 // This is not a product path and not an oracle: it compiles the same per-pixel
 // __host__ __device__ code as the CUDA kernels (dpe_core.cuh / dpe_weak.cuh) for the host,

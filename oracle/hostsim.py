@@ -1,7 +1,7 @@
 """ctypes wrapper of the TEST-ONLY CPU logic simulator (libdpe_hostsim.so).
 
-Only tests/ import this.  See csrc/dpe_hostsim.cu for why it exists and why it is neither
-an oracle nor a fallback.
+TEST INFRASTRUCTURE: only tests/ and oracle/make_stage_golden.py import this.  See
+oracle/dpe_hostsim.cu for why it exists and why it is neither an oracle nor a fallback.
 """
 from __future__ import annotations
 
@@ -46,11 +46,12 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        import importlib.util
-        spec = importlib.util.spec_from_file_location("dpe_build", HERE / "build.py")
-        b = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(b)
-        _lib = C.CDLL(str(b.build_hostsim()))
+        import subprocess
+        so = HERE / "_ref" / "libdpe_hostsim.so"
+        rc = subprocess.call(["make", "-s", "-C", str(HERE), "_ref/libdpe_hostsim.so"])
+        if rc != 0 and not so.exists():
+            raise RuntimeError("cannot build oracle/_ref/libdpe_hostsim.so")
+        _lib = C.CDLL(str(so))
     return _lib
 
 

@@ -17,7 +17,7 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parents[1]
-sys.path.insert(0, str(ROOT / "dpe-mvs_b200")); sys.path.insert(0, str(ROOT / "tests"))
+sys.path.insert(0, str(ROOT / "dpe-mvs_b200")); sys.path.insert(0, str(ROOT / "tests")); sys.path.insert(0, str(ROOT / "oracle"))
 import capi, hostsim, synth  # noqa: E402
 from scenes import small_scene  # noqa: E402
 import simpipe  # noqa: E402
@@ -207,7 +207,7 @@ def main():
         r = final_compare(fin, dumps[11], drs[v])
         for step in (1, 2, 5, 8):
             c0 = capi.Context(0)
-            capi.upload_scene(c0, grays, cams, drs, pairs, 2, shard=(v, 1, len(grays), 1))
+            capi.upload_scene(c0, grays, cams, drs, pairs, 2, active=(v, 1))
             c0.set_cost_arithmetic(arith)
             c0.debug_stop_after(step)
             c0.run_stage(*sched[0], SEED)

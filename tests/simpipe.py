@@ -1,5 +1,5 @@
 """Test helper: the reference's stage schedule (main.cpp:508-567) driven over the TEST-ONLY CPU
-logic simulator (dpe-mvs_b200/hostsim.py), Jacobi order like the product (all views of a stage
+logic simulator (oracle/hostsim.py), Jacobi order like the product (all views of a stage
 read the previous stage's depth maps)."""
 import sys
 from pathlib import Path

@@ -136,8 +136,8 @@ def test_geom_kernel_matches_reference_golden_vectors():
     ctx.commit()
     sched = capi.stage_schedule(1)
     ctx.run_stage(*sched[0], 5)
-    ptr, chunk, total = ctx.stage_atlas()
-    assert total == 4 * W * H * 4
+    ptr, slot, total = ctx.stage_atlas()
+    assert total == 4 * W * H * 4 and slot == W * H * 4
 
     class _Raw:
         __cuda_array_interface__ = {"shape": (4, H, W), "typestr": "<f4", "data": (ptr, False), "version": 2}
@@ -294,32 +294,34 @@ def test_results_do_not_depend_on_sharding():
     _run_schedule(one, ns)
     want = [one.get_maps(v, ns - 1) for v in range(V)]
     one.close()
-    spr = (V + 1) // 2
     ctxs = []
     for r in range(2):
         c = capi.Context(0)
-        first = r * spr
-        capi.upload_scene(c, grays, cams, drs, pairs, ns, shard=(first, min(spr, V - first), spr, 2))
+        capi.upload_scene(c, grays, cams, drs, pairs, ns, shard=(V, r, 2))   # no communicator: the test moves the slots
         ctxs.append(c)
+    owner = lambda v: 0 if v < capi.shard_range(V, 2, 0)[1] else 1
+    assert capi.shard_range(V, 2, 0) == (0, (V + 1) // 2) and capi.shard_range(V, 2, 1) == ((V + 1) // 2, V // 2)
 
     def tensor(c):
-        ptr, chunk, total = c.stage_atlas()
+        ptr, slot, total = c.stage_atlas()
 
         class Raw:
-            __cuda_array_interface__ = {"shape": (total // 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-        return torch.as_tensor(Raw(), device="cuda:0"), chunk // 4
+            __cuda_array_interface__ = {"shape": (total // slot, slot // 4), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(Raw(), device="cuda:0")
 
     for (k, p) in capi.stage_schedule(ns):
         for c in ctxs:
             c.run_stage(k, p, 3)
-        (t0, ch), (t1, _) = tensor(ctxs[0]), tensor(ctxs[1])
-        t1[0:ch] = t0[0:ch]
-        t0[ch:2 * ch] = t1[ch:2 * ch]
+        t = [tensor(ctxs[0]), tensor(ctxs[1])]
+        for v in range(V):
+            s = ctxs[0].view_slot(v)
+            assert s == ctxs[1].view_slot(v)
+            t[1 - owner(v)][s] = t[owner(v)][s]
         torch.cuda.synchronize()
         for c in ctxs:
             c.stage_commit()
     for v in range(V):
-        got = ctxs[v // spr].get_maps(v, ns - 1)
+        got = ctxs[owner(v)].get_maps(v, ns - 1)
         for key in ("depth", "normal", "state", "selected"):
             assert np.array_equal(got[key], want[v][key]), (v, key)
     for c in ctxs:

@@ -45,7 +45,7 @@ def test_first_stage_follows_the_reference_kernels(arith, thr):
         assert np.array_equal(hostsim.resize_linear(grays[i].astype(np.float32), cw, ch), fx["images"][j])
         assert np.array_equal(np.asarray(cams[i][0], np.float32), fx["K"][j])
     ctx = capi.Context(0)
-    capi.upload_scene(ctx, grays, cams, drs, pairs, 2, shard=(v, 1, len(grays), 1))
+    capi.upload_scene(ctx, grays, cams, drs, pairs, 2, active=(v, 1))
     ctx.set_cost_arithmetic(arith)
     ctx.set_view_order(1)            # commits do not flip the atlas: the same stage can be replayed
     k, p = capi.stage_schedule(2)[0]
@@ -83,7 +83,7 @@ def test_weak_stage_follows_the_reference_kernels(arith, thr):
         ctx.set_pairs(i, list(range(1, n)) if i == 0 else [])
     ctx.set_prep(0, 1, fx["edge"], fx["label"])
     ctx.set_prep(0, 0, fx["edge_low"], np.full(fx["edge_low"].shape, -1, np.int32))   # stage 6 reads the coarse EDGE map only
-    ctx.set_shard(0, 1, n, 1)
+    ctx.set_active(0, 1)
     ctx.commit()
     ctx.set_view_order(1)
     ctx.set_reference_race(1)

@@ -38,7 +38,7 @@ for mode, name in ((1, "reference"), (2, "reference_exact"), (0, "centred")):
     # written into the atlas)
     import torch
     ctx.run_stage(*capi.stage_schedule(1)[0], 5)
-    ptr, chunk, total = ctx.stage_atlas()
+    ptr, slot, total = ctx.stage_atlas()
 
     class _Raw:
         __cuda_array_interface__ = {"shape": (4, H, W), "typestr": "<f4", "data": (ptr, False), "version": 2}

@@ -23,7 +23,6 @@ for v in range(V):
     ctx.set_view(v, grays[v], *cams[v], *drs[v]); ctx.set_pairs(v, pairs[v])
     for k, (e, l) in enumerate(product_prep(lib, grays[v], ns)):
         ctx.set_prep(v, k, e, l)
-ctx.set_shard(0, V, V, 1)
 ctx.commit()
 sched = capi.stage_schedule(ns)
 for (k, p) in sched:                      # warm pass: every view gets real depth maps

@@ -22,7 +22,7 @@ def run(race, step):
         ctx.set_pairs(i, list(range(1, n)) if i == 0 else [])
     ctx.set_prep(0, 1, fx["edge"], fx["label"])
     ctx.set_prep(0, 0, fx["edge_low"], np.full(fx["edge_low"].shape, -1, np.int32))
-    ctx.set_shard(0, 1, n, 1)
+    ctx.set_active(0, 1)
     ctx.commit()
     ctx.set_view_order(1); ctx.set_reference_race(race)
     ctx.debug_set_maps(0, 1, fx["prev_planes"], fx["prev_state"], fx["prev_selected"])

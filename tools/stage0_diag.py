@@ -10,7 +10,7 @@ fx = np.load(ROOT / "tests" / "golden" / "ref_stage_first.npz")
 spec, grays, cams, drs, pairs, gt = small_scene("c4", 0.05, 5)
 ch, cw = fx["images"].shape[1:]
 ctx = capi.Context(0)
-capi.upload_scene(ctx, grays, cams, drs, pairs, 2, shard=(0, 1, len(grays), 1))
+capi.upload_scene(ctx, grays, cams, drs, pairs, 2, active=(0, 1))
 ctx.set_cost_arithmetic(2); ctx.set_view_order(1)
 k, p = capi.stage_schedule(2)[0]
 def run(step):
