@@ -217,10 +217,31 @@ struct dpe_ctx {
     }                                                                                    \
   } while (0)
 
+// DPE_TRACE=1: wall-clock of the set-up steps on stderr (where does an end-to-end call spend its time outside the stages)
+#include <chrono>
+struct Trace {
+  bool on; std::chrono::steady_clock::time_point t; int dev;
+  explicit Trace(int device) : on(getenv("DPE_TRACE") != nullptr), t(std::chrono::steady_clock::now()), dev(device) {}
+  void operator()(const char* what) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    const auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[dpe trace gpu %d] %-28s %8.2f ms\n", dev, what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 #define FAIL(code, msg) \
   do { ctx->err = (msg); return (code); } while (0)
 
 static LaunchCfg cfg_of(dpe_ctx* ctx) { return LaunchCfg{ctx->num_sms, &ctx->launches}; }
+
+// pixels per view in carried-map buffer b (see dpe_scene_commit)
+static size_t map_stride(const dpe_ctx* ctx, int b) {
+  const int k = ctx->n_scales - 1 - b;
+  return k >= 0 ? (size_t)ctx->sw[k] * ctx->sh[k] : 1;
+}
+static int map_buffer_of_scale(const dpe_ctx* ctx, int k) { return (ctx->n_scales - 1 - k) & 1; }
 
 // atlas slot of a view (see dpe_ctx::n_problems)
 static int slot_of(const dpe_ctx* ctx, int view) {
@@ -533,7 +554,9 @@ int dpe_scene_commit(dpe_ctx* ctx) {
     if (!v.have_cam) FAIL(DPE_ERR_STATE, "view without camera");
     if (!v.have_img) FAIL(DPE_ERR_STATE, "view without image");
   }
+  Trace trace(ctx->device);
   CK(cudaStreamSynchronize(ctx->upload_stream));  // images (uploads and / or the broadcast)
+  trace("images arrived");
   ctx->scale_arr.assign(ctx->n_scales, nullptr); ctx->scale_tex.assign(ctx->n_scales, 0);
   for (int k = 0; k < ctx->n_scales; ++k) {
     cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
@@ -569,6 +592,7 @@ int dpe_scene_commit(dpe_ctx* ctx) {
       CK(cudaMemcpy3DAsync(&cp, 0));
     }
   }
+  trace("pyramids + textures");
   // depth atlases
   const int slots = total_slots(ctx);
   ctx->atlas_front.assign(ctx->n_scales, nullptr); ctx->atlas_back.assign(ctx->n_scales, nullptr);
@@ -577,6 +601,7 @@ int dpe_scene_commit(dpe_ctx* ctx) {
     CK(cudaMalloc(&ctx->atlas_front[k], bytes)); CK(cudaMemset(ctx->atlas_front[k], 0, bytes));
     CK(cudaMalloc(&ctx->atlas_back[k], bytes)); CK(cudaMemset(ctx->atlas_back[k], 0, bytes));
   }
+  trace("atlases");
   // owned views: prep slabs, carried maps (two buffers), completion events
   const int nl = ctx->n_local > 0 ? ctx->n_local : 1;
   ctx->edge_slab.assign(ctx->n_scales, nullptr); ctx->label_slab.assign(ctx->n_scales, nullptr);
@@ -586,15 +611,19 @@ int dpe_scene_commit(dpe_ctx* ctx) {
     CK(cudaMalloc(&ctx->label_slab[k], (size_t)nl * n * sizeof(int32_t)));
   }
   CK(cudaMalloc(&ctx->bits_slab, (size_t)nl * ((ctx->sw[0] + 31) / 32) * ctx->sh[0] * sizeof(uint32_t)));
+  // buffer 0 holds the scales top, top-2, .. (sized for the finest), buffer 1 the scales top-1, top-3, .. (sized for
+  // the second finest): consecutive scales never share a buffer, which is all a stage at a new scale needs
   for (int b = 0; b < 2; ++b) {
-    CK(cudaMalloc(&ctx->maps_planes[b], (size_t)nl * P * sizeof(float4)));
-    CK(cudaMalloc(&ctx->maps_state[b], (size_t)nl * P));
-    CK(cudaMalloc(&ctx->maps_selected[b], (size_t)nl * P * sizeof(uint32_t)));
+    const size_t Pb = map_stride(ctx, b);
+    CK(cudaMalloc(&ctx->maps_planes[b], (size_t)nl * Pb * sizeof(float4)));
+    CK(cudaMalloc(&ctx->maps_state[b], (size_t)nl * Pb));
+    CK(cudaMalloc(&ctx->maps_selected[b], (size_t)nl * Pb * sizeof(uint32_t)));
   }
   ctx->view_done.assign(ctx->n_local, nullptr);
   for (auto& e : ctx->view_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CK(cudaMalloc(&ctx->exp_depth, P * sizeof(float))); CK(cudaMalloc(&ctx->exp_normal, P * 3 * sizeof(float)));
   CK(cudaMalloc(&ctx->exp_weak, P));
+  trace("prep + map slabs");
   // scratch: one set per stream, sized for the finest scale
   const int n_streams = 4;
   ctx->scratch.assign(n_streams, Scratch());
@@ -615,6 +644,7 @@ int dpe_scene_commit(dpe_ctx* ctx) {
   }
   CK(cudaMalloc(&ctx->zero_edge, P)); CK(cudaMemset(ctx->zero_edge, 0, P));
   CK(cudaMalloc(&ctx->zero_label, P * sizeof(int32_t))); CK(cudaMemset(ctx->zero_label, 0xFF, P * sizeof(int32_t)));
+  trace("scratch");
   // relative poses of all (reference, source) pairs of this context's views, from the device (see k_relative_pose)
   {
     std::vector<float> in;
@@ -648,6 +678,7 @@ int dpe_scene_commit(dpe_ctx* ctx) {
     }
   }
   CK(cudaDeviceSynchronize());
+  trace("relative poses");
   ctx->committed = true;
   // prep that arrived before the slabs existed
   for (int vi = ctx->first_view; vi < ctx->first_view + ctx->n_local; ++vi)
@@ -740,7 +771,7 @@ static void fill_args(dpe_ctx* ctx, int view, int k, const dpe_stage_params* p, 
 
 // the carried-map buffers of local view li in buffer b
 static void map_buffers(dpe_ctx* ctx, int li, int b, float4** planes, uint8_t** state, uint32_t** sel) {
-  const size_t P = (size_t)ctx->W * ctx->H;
+  const size_t P = map_stride(ctx, b);
   *planes = ctx->maps_planes[b] + (size_t)li * P;
   *state = ctx->maps_state[b] + (size_t)li * P;
   *sel = ctx->maps_selected[b] + (size_t)li * P;
@@ -757,7 +788,12 @@ int dpe_stage_begin(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t see
   const LaunchCfg cfg = cfg_of(ctx);
   const size_t P = (size_t)ctx->sw[k] * ctx->sh[k];
   const int ns = (int)ctx->scratch.size();
-  if (int rc = ensure_rng_tables(ctx, seed)) return rc;
+  {
+    Trace trace(ctx->device);
+    const bool had = ctx->rng_ready && ctx->rng_seed == seed;
+    if (int rc = ensure_rng_tables(ctx, seed)) return rc;
+    if (!had) trace("rng tables");
+  }
   // all views of a scale are layers of one texture (layer = view, linear filter, clamp); the handle sits in a
   // device-wide constant, so nothing of another scale may be in flight (it is not: dpe_stage_end drained it)
   launch_set_scale_tex((unsigned long long)ctx->scale_tex[k], 0);
@@ -778,8 +814,7 @@ int dpe_stage_begin(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t see
     fill_args(ctx, view, k, p, seed, s, &KP);
     StageArgs& a = KP.a;
     // outputs: the other map buffer when the scale changes, in place otherwise
-    const bool flip = (v.cur_scale != k);
-    const int out_buf = flip ? (v.cur_scale < 0 ? 0 : 1 - v.cur_buf) : v.cur_buf;
+    const int out_buf = map_buffer_of_scale(ctx, k);
     float4* new_planes; uint8_t* new_state; uint32_t* new_sel;
     map_buffers(ctx, li, out_buf, &new_planes, &new_state, &new_sel);
     a.prev_planes = v.planes; a.prev_state = v.state; a.prev_selected = v.selected;
@@ -1042,7 +1077,7 @@ int dpe_debug_set_maps(dpe_ctx* ctx, int view, int k, const float* planes4, cons
   ViewData& v = ctx->views[view];
   if (planes4) {
     if (view < ctx->first_view || view >= ctx->first_view + ctx->n_local) FAIL(DPE_ERR_ARG, "not a view of this context");
-    if (v.cur_scale < 0) v.cur_buf = 0;
+    v.cur_buf = map_buffer_of_scale(ctx, k);
     map_buffers(ctx, view - ctx->first_view, v.cur_buf, &v.planes, &v.state, &v.selected);
     v.cur_scale = k;
     CK(cudaMemcpy(v.planes, planes4, P * sizeof(float4), cudaMemcpyHostToDevice));

@@ -449,8 +449,9 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
     const float3 m = plane_to_m(rc, final_plane);
     if (lane < nv) {
       const int v = vlist_lo;
-      S.hcost[v] = ncc_old(env, ps, rc, rc.src[v], final_plane, m, x, y);
-      taps += 36;
+      const float cv = ncc_old(env, ps, rc, rc.src[v], final_plane, m, x, y);
+      S.hcost[v] = cv;
+      if (cv < 2.0f) taps += 36;
     }
     __syncwarp();
     if (writer) a.costs[center] = weighted(0);

@@ -867,7 +867,11 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
     float c = 0.f;
     for (int v = 0; v < N; ++v) {
       const int w = vw.get(v);
-      if (w > 0) { c += w * ncc_old(env, ps, rc, rc.src[v], final_plane, m, x, y); taps += 36; }
+      if (w > 0) {
+        const float cv = ncc_old(env, ps, rc, rc.src[v], final_plane, m, x, y);
+        c += w * cv;
+        if (cv < 2.0f) taps += 36;
+      }
     }
     a.costs[center] = c / weight_norm;
   }

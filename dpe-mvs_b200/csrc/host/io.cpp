@@ -204,6 +204,23 @@ static bool jpeg_decode(JpegDecoder* d, const std::string& path, nvjpegOutputFor
   return jpeg_decode_to(d, path, fmt, ch, nullptr, 0, out, width, height, err);
 }
 
+bool jpeg_image_size(JpegDecoder* d, const std::string& path, int* width, int* height, std::string* err) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in.good()) { if (err) *err = "cannot open " + path; return false; }
+  // the frame header sits in the first kilobytes; nvjpegGetImageInfo needs no entropy data
+  std::vector<unsigned char> head(65536);
+  in.read((char*)head.data(), (std::streamsize)head.size());
+  const size_t n = (size_t)in.gcount();
+  int comps = 0, ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
+  nvjpegChromaSubsampling_t ss;
+  if (nvjpegGetImageInfo(d->handle, head.data(), n, &comps, &ss, ws, hs) != NVJPEG_STATUS_SUCCESS) {
+    if (err) *err = "not a decodable JPEG: " + path;
+    return false;
+  }
+  *width = ws[0]; *height = hs[0];
+  return true;
+}
+
 bool jpeg_decode_gray_into(JpegDecoder* d, const std::string& path, uint8_t* dst, size_t cap, int* width, int* height, std::string* err) {
   return jpeg_decode_to(d, path, NVJPEG_OUTPUT_Y, 1, dst, cap, nullptr, width, height, err);
 }

@@ -39,6 +39,8 @@ JpegDecoder* jpeg_decoder_create(std::string* err);
 void jpeg_decoder_destroy(JpegDecoder* d);
 bool jpeg_decode_gray(JpegDecoder* d, const std::string& path, std::vector<uint8_t>* gray, int* width, int* height,
                       std::string* err);
+// image size from the JPEG header alone
+bool jpeg_image_size(JpegDecoder* d, const std::string& path, int* width, int* height, std::string* err);
 // the same into caller-provided host memory of `cap` bytes (e.g. a slot of a pinned slab)
 bool jpeg_decode_gray_into(JpegDecoder* d, const std::string& path, uint8_t* dst, size_t cap, int* width, int* height,
                            std::string* err);

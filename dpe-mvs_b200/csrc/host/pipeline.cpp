@@ -257,13 +257,11 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
   auto image_path = [&](int v) { return dense + "/images/" + format_index(view_ids[v]) + ".jpg"; };
   size_t P = 0;
   {
-    // the first image gives the size (and pays nvJPEG's start-up); the rest decode on a few threads, one nvJPEG
-    // decoder each (Huffman decoding is host work, the rest runs on gpus[0]), straight into the pinned slab
-    std::vector<uint8_t> first;
-    if (!jpeg_decode_gray(dec, image_path(0), &first, &width, &height, &err)) return bail("Images may error, check it!");
+    // the header of the first image gives the size; then all images decode on a few threads, one nvJPEG decoder each
+    // (Huffman decoding is host work, the rest runs on gpus[0]), straight into the pinned slab
+    if (!jpeg_image_size(dec, image_path(0), &width, &height, &err) || width <= 0 || height <= 0) return bail("Images may error, check it!");
     P = (size_t)width * height;
     if (cudaHostAlloc((void**)&gray_slab, P * n_views, cudaHostAllocPortable) != cudaSuccess) return bail("DPE-MVS: cannot allocate pinned memory");
-    memcpy(gray_slab, first.data(), P);
     const int n_load = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 8, n_views}));
     std::vector<JpegDecoder*> decs(n_load, nullptr);
     decs[0] = dec;
@@ -277,7 +275,6 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
         if (my > 0) { std::string e; decs[my] = jpeg_decoder_create(&e); }
       }
       if (!read_cam(dense + "/cams/" + format_index(view_ids[v]) + "_cam.txt", &cams[v])) bad_cam++;
-      if (v == 0) return;
       std::string e;
       int w = 0, h = 0;
       if (!decs[my] || !jpeg_decode_gray_into(decs[my], image_path(v), gray_slab + P * v, P, &w, &h, &e) || w != width || h != height) bad++;
@@ -422,7 +419,7 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
 
   // ---- one worker per GPU: scene upload, the whole schedule, export of its views ----------------------
   std::atomic<bool> abort_flag(false);
-  std::vector<double> t_upload(G, 0.0), t_stages(G, 0.0), t_prep_wait(G, 0.0);
+  std::vector<double> t_upload(G, 0.0), t_stages(G, 0.0), t_prep_wait(G, 0.0), t_up_views(G, 0.0), t_up_commit(G, 0.0);
   auto worker = [&](int g) {
     dpe_ctx* c = ctxs[g];
     auto bad = [&](const char* what) {
@@ -441,7 +438,9 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     }
     if (dpe_scene_set_shard(c, n_problems, g, G)) return bad("set_shard");
     if (dpe_scene_broadcast_images(c, 0)) return bad("broadcast_images");
+    t_up_views[g] = now_s() - tu0;
     if (dpe_scene_commit(c)) return bad("commit");
+    t_up_commit[g] = now_s() - tu0 - t_up_views[g];
     if (sequential) dpe_set_view_order(c, 1);
     if (arith >= 0) dpe_set_cost_arithmetic(c, arith);
     t_upload[g] = now_s() - tu0;
@@ -526,7 +525,6 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
       int owner = 0, first = 0, count = 0;
       for (; owner < G; ++owner) { dpe_shard_range(n_problems, G, owner, &first, &count); if (v < first + count) break; }
       if (dpe_get_maps(ctxs[owner], v, fd.data(), fn.data(), fs.data(), nullptr)) return fail(std::string("get_maps: ") + dpe_last_error(ctxs[owner]));
-      for (size_t i = 0; i < P; ++i) if (fs[i] == DPE_UNKNOWN) fd[i] = 0.0f;  // ZeroDepthForUnknown
       if (dpe_fuse_set_view(fc, v, fd.data(), fn.data(), fs.data(), color.data())) return fail(std::string("fuse_set_view: ") + dpe_last_error(fc));
     }
     size_t n_points = 0;
@@ -537,9 +535,16 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     if (!write_ply(dense + "/DPE/DPE.ply", xyz.data(), bgr.data(), n_points)) return fail("cannot write DPE.ply");
     tm.fusion = now_s() - t0;
   }
-  destroy_all();
+  const double t_destroy0 = now_s();
+  if (G == 1) destroy_all();
+  else {  // freeing a few GB per GPU takes a while: all GPUs at once
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) th.emplace_back([&, g]() { dpe_ctx_destroy(ctxs[g]); ctxs[g] = nullptr; });
+    for (auto& t : th) t.join();
+  }
   jpeg_decoder_destroy(dec);
   cudaFreeHost(gray_slab);
+  const double t_destroy = now_s() - t_destroy0;
 
   // ---- cleanup of intermediates the reference deletes (main.cpp:581-595) ------------------------
   for (int v = 0; v < n_problems; ++v) {
@@ -555,10 +560,10 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     if (f) {
       fprintf(f,
               "{\"views\": %d, \"gpus\": %d, \"width\": %d, \"height\": %d, \"load_s\": %.6f, \"ctx_s\": %.6f, \"comm_init_s\": %.6f, "
-              "\"prep_background_s\": %.6f, \"prep_wait_s\": %.6f, \"upload_s\": %.6f, \"stages_s\": %.6f, \"output_tail_s\": %.6f, "
-              "\"fusion_s\": %.6f, \"total_s\": %.6f, \"gpu_ms\": %.3f, \"kernel_launches\": %lld}\n",
-              n_problems, G, width, height, tm.load, tm.ctx, tm.comm, tm.prep, tm.prep_wait, tm.upload, tm.stages, tm.output, tm.fusion,
-              tm.total, tm.gpu_ms, tm.launches);
+              "\"prep_background_s\": %.6f, \"prep_wait_s\": %.6f, \"upload_s\": %.6f, \"upload_parts_s\": [%.6f, %.6f], \"stages_s\": %.6f, \"output_tail_s\": %.6f, "
+              "\"fusion_s\": %.6f, \"teardown_s\": %.6f, \"total_s\": %.6f, \"gpu_ms\": %.3f, \"kernel_launches\": %lld}\n",
+              n_problems, G, width, height, tm.load, tm.ctx, tm.comm, tm.prep, tm.prep_wait, tm.upload, t_up_views[0], t_up_commit[0], tm.stages, tm.output, tm.fusion,
+              t_destroy, tm.total, tm.gpu_ms, tm.launches);
       fclose(f);
     }
   }
