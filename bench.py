@@ -101,7 +101,7 @@ def scene_dir(tag):
     return Path(os.environ.get("DPE_BENCH_DIR", "/tmp")) / f"dpe_bench_{tag}"
 
 
-def ensure_scene(config, n_views, tag):
+def ensure_scene(config, n_views, tag, scale=1.0):
     """Renders and writes the scene once (idempotent marker file); GT depth is kept because the
     reference arm supplies it as the depth maps of source-only views."""
     import synth
@@ -110,7 +110,7 @@ def ensure_scene(config, n_views, tag):
     if marker.exists():
         return folder
     shutil.rmtree(folder, ignore_errors=True)
-    spec = synth.make_scene(config, n_views=n_views)
+    spec = synth.make_scene(config, scale=scale, n_views=n_views)
     synth.write_scene(spec, folder, save_gt="depth")
     marker.write_text("ok")
     return folder

@@ -30,7 +30,7 @@ SYMBOLS = [
     "dpe_scene_set_view", "dpe_scene_set_pairs", "dpe_scene_set_prep", "dpe_scene_set_shard", "dpe_scene_commit",
     "dpe_run_stage", "dpe_stage_begin", "dpe_stage_wait_view", "dpe_stage_end", "dpe_stage_atlas", "dpe_view_slot", "dpe_stage_commit",
     "dpe_shard_range", "dpe_comm_get_unique_id", "dpe_comm_init_rank", "dpe_comm_init_all", "dpe_comm_reset_all",
-    "dpe_scene_broadcast_images", "dpe_export_view", "dpe_scene_set_active", "dpe_stage_comm_ms", "dpe_cost_eval", "dpe_geom_eval", "dpe_get_size",
+    "dpe_scene_broadcast_images", "dpe_export_view", "dpe_scene_set_active", "dpe_stage_comm_ms", "dpe_debug_set_variants", "dpe_cost_eval", "dpe_geom_eval", "dpe_get_size",
     "dpe_get_maps", "dpe_set_count_evals", "dpe_eval_units", "dpe_stage_gpu_ms", "dpe_probe_tex_rate",
     "dpe_probe_fma_rate", "dpe_probe_tex_pattern", "dpe_probe_tex_weights", "dpe_run_pipeline", "dpe_set_profile", "dpe_get_profile", "dpe_set_view_order", "dpe_bench_ncc", "dpe_set_reference_race", "dpe_debug_read", "dpe_debug_stop_after", "dpe_debug_set_maps", "dpe_set_cost_arithmetic", "dpe_fuse_set_view", "dpe_fuse_run", "dpe_fuse_get",
 ]
@@ -120,6 +120,7 @@ def load(build=True):
     lib.dpe_set_profile.argtypes = [vp, ci]
     lib.dpe_set_view_order.argtypes = [vp, ci]
     lib.dpe_set_reference_race.argtypes = [vp, ci]
+    lib.dpe_debug_set_variants.argtypes = [vp, ci]
     lib.dpe_set_cost_arithmetic.argtypes = [vp, ci]
     lib.dpe_fuse_set_view.argtypes = [vp, ci, vp, vp, vp, vp]
     lib.dpe_fuse_run.argtypes = [vp, C.POINTER(C.c_size_t)]
@@ -375,6 +376,9 @@ class Context:
         """0 = centred (precise against float64), 1 = the reference's raw fp32 moments on a constant-folded
         homography (fast), 2 = the reference's arithmetic operation by operation (default; include/dpe_b200.h)."""
         self._ck(self.lib.dpe_set_cost_arithmetic(self.h, int(mode)))
+
+    def debug_set_variants(self, mask):
+        self._ck(self.lib.dpe_debug_set_variants(self.h, int(mask)))
 
     def set_reference_race(self, on):
         self._ck(self.lib.dpe_set_reference_race(self.h, int(on)))

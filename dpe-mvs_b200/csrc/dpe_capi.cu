@@ -70,7 +70,7 @@ struct Scratch {
   float* complexity = nullptr; short2* label_boundary = nullptr; uint8_t* weak_reliable = nullptr;
   short2* nearest_strong = nullptr; short2* neighbours = nullptr;
   Xorwow* rng = nullptr;
-  int* weak_list = nullptr; int* weak_count = nullptr;
+  int* weak_list = nullptr; int* weak_count = nullptr; int* weak_scan = nullptr;
   cudaStream_t stream = nullptr;
 };
 
@@ -167,6 +167,7 @@ struct dpe_ctx {
   bool ref_race = false;      // dpe_set_reference_race
   bool cost_raw = true;       // dpe_set_cost_arithmetic
   bool exact = true;          // dpe_set_cost_arithmetic: DPE_COST_REFERENCE_EXACT is the default
+  int variants = 0;           // dpe_debug_set_variants
   // scratch
   std::vector<Scratch> scratch;
   // device fusion (dpe_fuse_*): per-view maps at full resolution + the fused cloud (host)
@@ -231,6 +232,15 @@ struct Trace {
   }
 };
 
+// Device memory comes from the device's stream-ordered pool with the release threshold lifted: what a context
+// frees stays with the process, so the next scene (the next dpe_run_pipeline call) gets it back without a trip to
+// the driver — a plain cudaMalloc / cudaFree of the ~6 GB a scene holds costs 0.1-2 s per call, more with peer
+// mappings between several GPUs of one process.  DPE_RELEASE_MEMORY=1 hands everything back when a context is
+// destroyed.  All allocation and release happens with the device drained (dpe_scene_begin / commit / destroy).
+template <class T>
+static cudaError_t dmalloc(T** p, size_t bytes) { return cudaMallocAsync((void**)p, bytes ? bytes : 1, (cudaStream_t)0); }
+static cudaError_t dfree(void* p) { return p ? cudaFreeAsync(p, (cudaStream_t)0) : cudaSuccess; }
+
 #define FAIL(code, msg) \
   do { ctx->err = (msg); return (code); } while (0)
 
@@ -257,41 +267,41 @@ static int total_slots(const dpe_ctx* ctx) { return ctx->slots_per_rank * ctx->n
 
 static void free_scene(dpe_ctx* ctx) {
   ctx->views.clear();
-  cudaFree(ctx->gray_slab); ctx->gray_slab = nullptr;
-  for (auto p : ctx->lin_slab) cudaFree(p);
+  dfree(ctx->gray_slab); ctx->gray_slab = nullptr;
+  for (auto p : ctx->lin_slab) dfree(p);
   ctx->lin_slab.clear();
-  for (auto p : ctx->edge_slab) cudaFree(p);
-  for (auto p : ctx->label_slab) cudaFree(p);
+  for (auto p : ctx->edge_slab) dfree(p);
+  for (auto p : ctx->label_slab) dfree(p);
   ctx->edge_slab.clear(); ctx->label_slab.clear();
-  cudaFree(ctx->bits_slab); ctx->bits_slab = nullptr;
+  dfree(ctx->bits_slab); ctx->bits_slab = nullptr;
   for (int b = 0; b < 2; ++b) {
-    cudaFree(ctx->maps_planes[b]); cudaFree(ctx->maps_state[b]); cudaFree(ctx->maps_selected[b]);
+    dfree(ctx->maps_planes[b]); dfree(ctx->maps_state[b]); dfree(ctx->maps_selected[b]);
     ctx->maps_planes[b] = nullptr; ctx->maps_state[b] = nullptr; ctx->maps_selected[b] = nullptr;
   }
   for (auto t : ctx->scale_tex) if (t) cudaDestroyTextureObject(t);
   for (auto a : ctx->scale_arr) if (a) cudaFreeArray(a);
   ctx->scale_tex.clear(); ctx->scale_arr.clear();
-  for (auto p : ctx->atlas_front) cudaFree(p);
-  for (auto p : ctx->atlas_back) cudaFree(p);
+  for (auto p : ctx->atlas_front) dfree(p);
+  for (auto p : ctx->atlas_back) dfree(p);
   ctx->atlas_front.clear(); ctx->atlas_back.clear();
   for (auto& s : ctx->scratch) {
-    cudaFree(s.planes); cudaFree(s.costs); cudaFree(s.selected); cudaFree(s.view_w); cudaFree(s.state);
-    cudaFree(s.fit_planes); cudaFree(s.radius); cudaFree(s.edge_neigh); cudaFree(s.complexity);
-    cudaFree(s.label_boundary); cudaFree(s.weak_reliable); cudaFree(s.nearest_strong); cudaFree(s.neighbours);
-    cudaFree(s.rng); cudaFree(s.weak_list); cudaFree(s.weak_count);
+    dfree(s.planes); dfree(s.costs); dfree(s.selected); dfree(s.view_w); dfree(s.state);
+    dfree(s.fit_planes); dfree(s.radius); dfree(s.edge_neigh); dfree(s.complexity);
+    dfree(s.label_boundary); dfree(s.weak_reliable); dfree(s.nearest_strong); dfree(s.neighbours);
+    dfree(s.rng); dfree(s.weak_list); dfree(s.weak_count); dfree(s.weak_scan);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   ctx->scratch.clear();
   for (auto e : ctx->view_done) cudaEventDestroy(e);
   ctx->view_done.clear();
-  cudaFree(ctx->exp_depth); cudaFree(ctx->exp_normal); cudaFree(ctx->exp_weak);
+  dfree(ctx->exp_depth); dfree(ctx->exp_normal); dfree(ctx->exp_weak);
   ctx->exp_depth = nullptr; ctx->exp_normal = nullptr; ctx->exp_weak = nullptr;
-  for (auto& f : ctx->fuse) { cudaFree(f.depth); cudaFree(f.normal); cudaFree(f.state); cudaFree(f.bgr); cudaFree(f.mask); }
+  for (auto& f : ctx->fuse) { dfree(f.depth); dfree(f.normal); dfree(f.state); dfree(f.bgr); dfree(f.mask); }
   ctx->fuse.clear(); ctx->cloud.clear();
-  for (auto p : ctx->rng_table) cudaFree(p);
+  for (auto p : ctx->rng_table) dfree(p);
   ctx->rng_table.clear(); ctx->rng_ready = false;
-  cudaFree(ctx->zero_edge); ctx->zero_edge = nullptr;
-  cudaFree(ctx->zero_label); ctx->zero_label = nullptr;
+  dfree(ctx->zero_edge); ctx->zero_edge = nullptr;
+  dfree(ctx->zero_label); ctx->zero_label = nullptr;
   ctx->committed = false;
   ctx->stage_open = false; ctx->stage_pending = false;
 }
@@ -309,6 +319,13 @@ int dpe_ctx_create(dpe_ctx** out, int gpu_index) {
   ctx->device = gpu_index;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, gpu_index) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, gpu_index) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   cudaEventCreate(&ctx->ev0);
   cudaEventCreate(&ctx->ev1);
   cudaEventCreate(&ctx->ev_views);
@@ -322,7 +339,7 @@ int dpe_ctx_create(dpe_ctx** out, int gpu_index) {
   cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_hi);
   cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-  cudaMalloc(&ctx->d_eval_units, sizeof(unsigned long long));
+  dmalloc(&ctx->d_eval_units, sizeof(unsigned long long));
   cudaMemset(ctx->d_eval_units, 0, sizeof(unsigned long long));
   *out = ctx;
   return DPE_OK;
@@ -335,7 +352,7 @@ void dpe_ctx_destroy(dpe_ctx* ctx) {
   if (ctx->comm && ctx->comm_owned) nccl_api().CommDestroy(ctx->comm);
   ctx->comm = nullptr;
   free_scene(ctx);
-  cudaFree(ctx->d_eval_units);
+  dfree(ctx->d_eval_units);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev_views) cudaEventDestroy(ctx->ev_views);
@@ -345,6 +362,11 @@ void dpe_ctx_destroy(dpe_ctx* ctx) {
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
   if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  cudaDeviceSynchronize();
+  if (const char* e = getenv("DPE_RELEASE_MEMORY")) {
+    cudaMemPool_t pool;
+    if (atoi(e) != 0 && cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  }
   delete ctx;
 }
 
@@ -392,6 +414,22 @@ int dpe_comm_init_all(dpe_ctx** ctxs, int n) {
   for (int i = 0; i < n; ++i)
     if (ctxs[i]->comm) FAIL(DPE_ERR_STATE, "context already has a communicator");
   if (!nccl_api().ok) FAIL(DPE_ERR_COMM, nccl_api().why);
+  // within one process NCCL moves data straight between the ranks' buffers over NVLink: the memory pools the
+  // buffers come from must be mapped on the peers (the analogue of cudaDeviceEnablePeerAccess for pool memory)
+  for (int i = 0; i < n; ++i) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, devs[i]) != cudaSuccess) continue;
+    for (int j = 0; j < n; ++j) {
+      int can = 0;
+      if (j == i || cudaDeviceCanAccessPeer(&can, devs[j], devs[i]) != cudaSuccess || !can) continue;
+      cudaMemAccessDesc d;
+      memset(&d, 0, sizeof(d));
+      d.location.type = cudaMemLocationTypeDevice; d.location.id = devs[j];
+      d.flags = cudaMemAccessFlagsProtReadWrite;
+      cudaMemPoolSetAccess(pool, &d, 1);
+    }
+  }
+  cudaGetLastError();
   std::lock_guard<std::mutex> lock(g_comm_mutex);
   auto it = g_comm_cache.find(devs);
   if (it == g_comm_cache.end()) {
@@ -430,7 +468,7 @@ int dpe_scene_begin(dpe_ctx* ctx, int n_views, int width, int height, int n_scal
   ctx->n_problems = n_views; ctx->rank = 0; ctx->n_ranks = 1;
   ctx->first_view = 0; ctx->n_local = n_views; ctx->slots_per_rank = n_views;
   ctx->stage_counter = 0; ctx->last_stage_scale = -1; ctx->stage_pending = false; ctx->stage_open = false;
-  CK(cudaMalloc(&ctx->gray_slab, (size_t)width * height * n_views));
+  CK(dmalloc(&ctx->gray_slab, (size_t)width * height * n_views));
   return DPE_OK;
 }
 
@@ -572,7 +610,7 @@ int dpe_scene_commit(dpe_ctx* ctx) {
   }
   ctx->lin_slab.assign(ctx->n_scales, nullptr);
   for (int k = 0; k < ctx->n_scales; ++k)
-    CK(cudaMalloc(&ctx->lin_slab[k], (size_t)ctx->n_views * ctx->sw[k] * ctx->sh[k] * sizeof(float)));
+    CK(dmalloc(&ctx->lin_slab[k], (size_t)ctx->n_views * ctx->sw[k] * ctx->sh[k] * sizeof(float)));
   const size_t P = (size_t)ctx->W * ctx->H;
   for (int vi = 0; vi < ctx->n_views; ++vi) {
     ViewData& v = ctx->views[vi];
@@ -598,8 +636,8 @@ int dpe_scene_commit(dpe_ctx* ctx) {
   ctx->atlas_front.assign(ctx->n_scales, nullptr); ctx->atlas_back.assign(ctx->n_scales, nullptr);
   for (int k = 0; k < ctx->n_scales; ++k) {
     const size_t bytes = (size_t)slots * ctx->sw[k] * ctx->sh[k] * sizeof(float);
-    CK(cudaMalloc(&ctx->atlas_front[k], bytes)); CK(cudaMemset(ctx->atlas_front[k], 0, bytes));
-    CK(cudaMalloc(&ctx->atlas_back[k], bytes)); CK(cudaMemset(ctx->atlas_back[k], 0, bytes));
+    CK(dmalloc(&ctx->atlas_front[k], bytes)); CK(cudaMemset(ctx->atlas_front[k], 0, bytes));
+    CK(dmalloc(&ctx->atlas_back[k], bytes)); CK(cudaMemset(ctx->atlas_back[k], 0, bytes));
   }
   trace("atlases");
   // owned views: prep slabs, carried maps (two buffers), completion events
@@ -607,43 +645,44 @@ int dpe_scene_commit(dpe_ctx* ctx) {
   ctx->edge_slab.assign(ctx->n_scales, nullptr); ctx->label_slab.assign(ctx->n_scales, nullptr);
   for (int k = 0; k < ctx->n_scales; ++k) {
     const size_t n = (size_t)ctx->sw[k] * ctx->sh[k];
-    CK(cudaMalloc(&ctx->edge_slab[k], (size_t)nl * n));
-    CK(cudaMalloc(&ctx->label_slab[k], (size_t)nl * n * sizeof(int32_t)));
+    CK(dmalloc(&ctx->edge_slab[k], (size_t)nl * n));
+    CK(dmalloc(&ctx->label_slab[k], (size_t)nl * n * sizeof(int32_t)));
   }
-  CK(cudaMalloc(&ctx->bits_slab, (size_t)nl * ((ctx->sw[0] + 31) / 32) * ctx->sh[0] * sizeof(uint32_t)));
+  CK(dmalloc(&ctx->bits_slab, (size_t)nl * ((ctx->sw[0] + 31) / 32) * ctx->sh[0] * sizeof(uint32_t)));
   // buffer 0 holds the scales top, top-2, .. (sized for the finest), buffer 1 the scales top-1, top-3, .. (sized for
   // the second finest): consecutive scales never share a buffer, which is all a stage at a new scale needs
   for (int b = 0; b < 2; ++b) {
     const size_t Pb = map_stride(ctx, b);
-    CK(cudaMalloc(&ctx->maps_planes[b], (size_t)nl * Pb * sizeof(float4)));
-    CK(cudaMalloc(&ctx->maps_state[b], (size_t)nl * Pb));
-    CK(cudaMalloc(&ctx->maps_selected[b], (size_t)nl * Pb * sizeof(uint32_t)));
+    CK(dmalloc(&ctx->maps_planes[b], (size_t)nl * Pb * sizeof(float4)));
+    CK(dmalloc(&ctx->maps_state[b], (size_t)nl * Pb));
+    CK(dmalloc(&ctx->maps_selected[b], (size_t)nl * Pb * sizeof(uint32_t)));
   }
   ctx->view_done.assign(ctx->n_local, nullptr);
   for (auto& e : ctx->view_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  CK(cudaMalloc(&ctx->exp_depth, P * sizeof(float))); CK(cudaMalloc(&ctx->exp_normal, P * 3 * sizeof(float)));
-  CK(cudaMalloc(&ctx->exp_weak, P));
+  CK(dmalloc(&ctx->exp_depth, P * sizeof(float))); CK(dmalloc(&ctx->exp_normal, P * 3 * sizeof(float)));
+  CK(dmalloc(&ctx->exp_weak, P));
   trace("prep + map slabs");
   // scratch: one set per stream, sized for the finest scale
   const int n_streams = 4;
   ctx->scratch.assign(n_streams, Scratch());
   for (auto& s : ctx->scratch) {
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    CK(cudaMalloc(&s.planes, P * sizeof(float4))); CK(cudaMalloc(&s.costs, P * sizeof(float)));
-    CK(cudaMalloc(&s.selected, P * sizeof(uint32_t))); CK(cudaMalloc(&s.view_w, P * sizeof(uint4)));
-    CK(cudaMalloc(&s.state, P)); CK(cudaMalloc(&s.fit_planes, P * sizeof(float4)));
-    CK(cudaMalloc(&s.radius, P * sizeof(int))); CK(cudaMalloc(&s.edge_neigh, P * 8 * sizeof(short2)));
-    CK(cudaMalloc(&s.complexity, P * sizeof(float))); CK(cudaMalloc(&s.label_boundary, P * 8 * sizeof(short2)));
-    CK(cudaMalloc(&s.weak_reliable, P)); CK(cudaMalloc(&s.nearest_strong, P * sizeof(short2)));
-    CK(cudaMalloc(&s.neighbours, P * DPE_NEIGHBOUR_NUM * sizeof(short2)));
-    CK(cudaMalloc(&s.rng, P * sizeof(Xorwow)));
-    CK(cudaMalloc(&s.weak_list, 2 * P * sizeof(int))); CK(cudaMalloc(&s.weak_count, 4 * sizeof(int)));
+    CK(dmalloc(&s.planes, P * sizeof(float4))); CK(dmalloc(&s.costs, P * sizeof(float)));
+    CK(dmalloc(&s.selected, P * sizeof(uint32_t))); CK(dmalloc(&s.view_w, P * sizeof(uint4)));
+    CK(dmalloc(&s.state, P)); CK(dmalloc(&s.fit_planes, P * sizeof(float4)));
+    CK(dmalloc(&s.radius, P * sizeof(int))); CK(dmalloc(&s.edge_neigh, P * 8 * sizeof(short2)));
+    CK(dmalloc(&s.complexity, P * sizeof(float))); CK(dmalloc(&s.label_boundary, P * 8 * sizeof(short2)));
+    CK(dmalloc(&s.weak_reliable, P)); CK(dmalloc(&s.nearest_strong, P * sizeof(short2)));
+    CK(dmalloc(&s.neighbours, P * DPE_NEIGHBOUR_NUM * sizeof(short2)));
+    CK(dmalloc(&s.rng, P * sizeof(Xorwow)));
+    CK(dmalloc(&s.weak_list, 2 * P * sizeof(int))); CK(dmalloc(&s.weak_count, 4 * sizeof(int)));
     CK(cudaMemset(s.weak_count, 0, 4 * sizeof(int)));
+    CK(dmalloc(&s.weak_scan, (size_t)compact_scan_entries(ctx->num_sms) * sizeof(int)));
     CK(cudaMemset(s.view_w, 0, P * sizeof(uint4)));
     CK(cudaMemset(s.radius, 0, P * sizeof(int)));
   }
-  CK(cudaMalloc(&ctx->zero_edge, P)); CK(cudaMemset(ctx->zero_edge, 0, P));
-  CK(cudaMalloc(&ctx->zero_label, P * sizeof(int32_t))); CK(cudaMemset(ctx->zero_label, 0xFF, P * sizeof(int32_t)));
+  CK(dmalloc(&ctx->zero_edge, P)); CK(cudaMemset(ctx->zero_edge, 0, P));
+  CK(dmalloc(&ctx->zero_label, P * sizeof(int32_t))); CK(cudaMemset(ctx->zero_label, 0xFF, P * sizeof(int32_t)));
   trace("scratch");
   // relative poses of all (reference, source) pairs of this context's views, from the device (see k_relative_pose)
   {
@@ -663,12 +702,12 @@ int dpe_scene_commit(dpe_ctx* ctx) {
     if (n_pairs) {
       float *d_in = nullptr, *d_out = nullptr;
       std::vector<float> out(n_pairs * 12);
-      CK(cudaMalloc(&d_in, in.size() * sizeof(float))); CK(cudaMalloc(&d_out, out.size() * sizeof(float)));
+      CK(dmalloc(&d_in, in.size() * sizeof(float))); CK(dmalloc(&d_out, out.size() * sizeof(float)));
       CK(cudaMemcpy(d_in, in.data(), in.size() * sizeof(float), cudaMemcpyHostToDevice));
       launch_relative_pose(d_in, d_out, (int)n_pairs, 0);
       CK(cudaGetLastError());
       CK(cudaMemcpy(out.data(), d_out, out.size() * sizeof(float), cudaMemcpyDeviceToHost));
-      cudaFree(d_in); cudaFree(d_out);
+      dfree(d_in); dfree(d_out);
       size_t o = 0;
       for (int v = 0; v < ctx->n_views; ++v) {
         ViewData& rv = ctx->views[v];
@@ -725,7 +764,7 @@ static int ensure_rng_tables(dpe_ctx* ctx, uint64_t seed) {
     const size_t P = (size_t)ctx->sw[k] * ctx->sh[k];
     host.resize(P);
     xorwow_init_table(seed, ctx->sw[k], ctx->sh[k], host.data());
-    if (!ctx->rng_table[k]) CK(cudaMalloc(&ctx->rng_table[k], P * sizeof(Xorwow)));
+    if (!ctx->rng_table[k]) CK(dmalloc(&ctx->rng_table[k], P * sizeof(Xorwow)));
     CK(cudaMemcpy(ctx->rng_table[k], host.data(), P * sizeof(Xorwow), cudaMemcpyHostToDevice));
   }
   ctx->rng_seed = seed; ctx->rng_ready = true;
@@ -755,11 +794,12 @@ static void fill_args(dpe_ctx* ctx, int view, int k, const dpe_stage_params* p, 
   a.ref_race = ctx->ref_race ? 1 : 0;
   a.cost_raw = ctx->cost_raw ? 1 : 0;
   a.exact = ctx->exact ? 1 : 0;
+  a.variants = ctx->variants;
   {  // a stage truncated after a strong sweep leaves the fit-plane scratch free for the accepted-candidate codes
     const int st = ctx->debug_stop_after;
     a.debug_accept = (st == 2 || st == 5 || st == 8) ? reinterpret_cast<unsigned char*>(s.fit_planes) : nullptr;
   }
-  a.weak_list = s.weak_list; a.weak_count = s.weak_count; a.list_stride = ctx->W * ctx->H;
+  a.weak_list = s.weak_list; a.weak_count = s.weak_count; a.list_stride = ctx->W * ctx->H; a.weak_scan = s.weak_scan;
   a.eval_units = ctx->count_evals ? ctx->d_eval_units : nullptr;
   if (p) {
     a.run_state = p->state; a.geom = p->geom_consistency; a.use_apd = p->use_apd; a.top_k = p->top_k;
@@ -852,10 +892,11 @@ int dpe_stage_begin(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t see
     auto on = [&](int step) { return stop < 0 || step <= stop; };
     if (p->state != DPE_FIRST_INIT) L(DPE_K_LOAD, launch_load);
     if (p->use_apd) {
+      L(DPE_K_NEAREST, launch_compact_weak);       // the WEAK pixels the previous stage left: input of the next three
       L(DPE_K_EDGE_INFO, launch_edge_info);
       L(DPE_K_NEAREST, launch_nearest_strong);
       L(DPE_K_NEIGHBOURS, launch_gen_neighbours);
-      L(DPE_K_NEIGHBOURS, launch_compact_weak);
+      L(DPE_K_NEIGHBOURS, launch_compact_weak);    // again: the anchor search demoted the unreliable ones
     }
     if (on(1)) L(DPE_K_INIT, launch_init);
     for (int it = 0; it < p->max_iterations; ++it) {
@@ -976,8 +1017,8 @@ int dpe_fuse_set_view(dpe_ctx* ctx, int view, const float* depth, const float* n
   FuseData& f = ctx->fuse[view];
   const size_t P = (size_t)ctx->W * ctx->H;
   if (!f.depth) {
-    CK(cudaMalloc(&f.depth, P * 4)); CK(cudaMalloc(&f.normal, P * 12)); CK(cudaMalloc(&f.state, P)); CK(cudaMalloc(&f.bgr, P * 3));
-    CK(cudaMalloc(&f.mask, P));
+    CK(dmalloc(&f.depth, P * 4)); CK(dmalloc(&f.normal, P * 12)); CK(dmalloc(&f.state, P)); CK(dmalloc(&f.bgr, P * 3));
+    CK(dmalloc(&f.mask, P));
   }
   CK(cudaMemcpy(f.depth, depth, P * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(f.normal, normal3, P * 12, cudaMemcpyHostToDevice));
@@ -1005,13 +1046,13 @@ int dpe_fuse_run(dpe_ctx* ctx, size_t* n_points) {
     // camera centre as the reference's fusion computes it: float arithmetic (DPE.cpp:1170-1194)
     for (int j = 0; j < 3; ++j) fv.C[j] = -(fv.R[0 + j] * fv.t[0] + fv.R[3 + j] * fv.t[1] + fv.R[6 + j] * fv.t[2]);
   }
-  FuseView* dv; CK(cudaMalloc(&dv, V * sizeof(FuseView)));
+  FuseView* dv; CK(dmalloc(&dv, V * sizeof(FuseView)));
   CK(cudaMemcpy(dv, hv.data(), V * sizeof(FuseView), cudaMemcpyHostToDevice));
   FusedPointDev *pts, *sel; uint8_t* accept; int* d_n; void* temp;
-  CK(cudaMalloc(&pts, P * sizeof(FusedPointDev))); CK(cudaMalloc(&sel, P * sizeof(FusedPointDev)));
-  CK(cudaMalloc(&accept, P)); CK(cudaMalloc(&d_n, sizeof(int)));
+  CK(dmalloc(&pts, P * sizeof(FusedPointDev))); CK(dmalloc(&sel, P * sizeof(FusedPointDev)));
+  CK(dmalloc(&accept, P)); CK(dmalloc(&d_n, sizeof(int)));
   const size_t temp_bytes = fuse_select_temp_bytes((int)P);
-  CK(cudaMalloc(&temp, temp_bytes ? temp_bytes : 1));
+  CK(dmalloc(&temp, temp_bytes ? temp_bytes : 1));
   ctx->cloud.clear();
   for (int i = 0; i < V; ++i) {  // views in order: a view sees every mark of the views before it
     if (!hv[i].depth) continue;
@@ -1029,7 +1070,7 @@ int dpe_fuse_run(dpe_ctx* ctx, size_t* n_points) {
     if (n) CK(cudaMemcpy(ctx->cloud.data() + at, sel, (size_t)n * sizeof(FusedPointDev), cudaMemcpyDeviceToHost));
   }
   CK(cudaGetLastError());
-  cudaFree(dv); cudaFree(pts); cudaFree(sel); cudaFree(accept); cudaFree(d_n); cudaFree(temp);
+  dfree(dv); dfree(pts); dfree(sel); dfree(accept); dfree(d_n); dfree(temp);
   *n_points = ctx->cloud.size();
   return DPE_OK;
 }
@@ -1048,6 +1089,12 @@ int dpe_set_cost_arithmetic(dpe_ctx* ctx, int mode) {
   if (!ctx || mode < 0 || mode > 2) return DPE_ERR_ARG;
   ctx->cost_raw = mode != DPE_COST_CENTRED;
   ctx->exact = mode == DPE_COST_REFERENCE_EXACT;
+  return DPE_OK;
+}
+
+int dpe_debug_set_variants(dpe_ctx* ctx, int mask) {
+  if (!ctx) return DPE_ERR_ARG;
+  ctx->variants = mask;
   return DPE_OK;
 }
 
@@ -1123,8 +1170,8 @@ int dpe_cost_eval(dpe_ctx* ctx, int view, int k, int n_pix, const int* xy, const
   fill_args(ctx, view, k, nullptr, 0, ctx->scratch[0], &KP);
   const int N = KP.rc.n_src;
   int* d_xy; float4* d_pl; float* d_out;
-  CK(cudaMalloc(&d_xy, (size_t)n_pix * 2 * sizeof(int))); CK(cudaMalloc(&d_pl, (size_t)n_pix * sizeof(float4)));
-  CK(cudaMalloc(&d_out, (size_t)n_pix * N * sizeof(float)));
+  CK(dmalloc(&d_xy, (size_t)n_pix * 2 * sizeof(int))); CK(dmalloc(&d_pl, (size_t)n_pix * sizeof(float4)));
+  CK(dmalloc(&d_out, (size_t)n_pix * N * sizeof(float)));
   CK(cudaMemcpy(d_xy, xy, (size_t)n_pix * 2 * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_pl, planes, (size_t)n_pix * sizeof(float4), cudaMemcpyHostToDevice));
   CK(cudaDeviceSynchronize());
@@ -1132,7 +1179,7 @@ int dpe_cost_eval(dpe_ctx* ctx, int view, int k, int n_pix, const int* xy, const
   launch_cost_eval(KP, n_pix, d_xy, d_pl, mode, 0ull, d_out, cfg_of(ctx), 0);
   CK(cudaGetLastError());
   CK(cudaMemcpy(out, d_out, (size_t)n_pix * N * sizeof(float), cudaMemcpyDeviceToHost));
-  cudaFree(d_xy); cudaFree(d_pl); cudaFree(d_out);
+  dfree(d_xy); dfree(d_pl); dfree(d_out);
   return DPE_OK;
 }
 
@@ -1146,14 +1193,14 @@ int dpe_geom_eval(dpe_ctx* ctx, int view, int k, int n_pix, const int* xy, const
   fill_args(ctx, view, k, &p, 0, ctx->scratch[0], &KP);
   const int N = KP.rc.n_src;
   int* d_xy; float4* d_pl; float* d_out;
-  CK(cudaMalloc(&d_xy, (size_t)n_pix * 2 * sizeof(int))); CK(cudaMalloc(&d_pl, (size_t)n_pix * sizeof(float4)));
-  CK(cudaMalloc(&d_out, (size_t)n_pix * N * sizeof(float)));
+  CK(dmalloc(&d_xy, (size_t)n_pix * 2 * sizeof(int))); CK(dmalloc(&d_pl, (size_t)n_pix * sizeof(float4)));
+  CK(dmalloc(&d_out, (size_t)n_pix * N * sizeof(float)));
   CK(cudaMemcpy(d_xy, xy, (size_t)n_pix * 2 * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_pl, planes, (size_t)n_pix * sizeof(float4), cudaMemcpyHostToDevice));
   launch_geom_eval(KP, n_pix, d_xy, d_pl, d_out, cfg_of(ctx), 0);
   CK(cudaGetLastError());
   CK(cudaMemcpy(out, d_out, (size_t)n_pix * N * sizeof(float), cudaMemcpyDeviceToHost));
-  cudaFree(d_xy); cudaFree(d_pl); cudaFree(d_out);
+  dfree(d_xy); dfree(d_pl); dfree(d_out);
   return DPE_OK;
 }
 
@@ -1284,7 +1331,7 @@ int dpe_probe_tex_rate(dpe_ctx* ctx, int width, int height, int iters, double* t
   td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp; td.filterMode = cudaFilterModeLinear;
   td.readMode = cudaReadModeElementType;
   CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
-  float* sink; CK(cudaMalloc(&sink, 4));
+  float* sink; CK(dmalloc(&sink, 4));
   const int blocks = ctx->num_sms * 8, threads = 256;
   const LaunchCfg cfg = cfg_of(ctx);
   launch_probe_tex((unsigned long long)tex, width, height, iters / 4 + 1, sink, blocks, threads, cfg, 0);  // warm-up
@@ -1294,7 +1341,7 @@ int dpe_probe_tex_rate(dpe_ctx* ctx, int width, int height, int iters, double* t
   CK(cudaEventSynchronize(ctx->ev1));
   float ms = 0.f; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   *taps_per_s = (double)blocks * threads * (double)iters * 36.0 / (ms * 1e-3);
-  cudaFree(sink); cudaDestroyTextureObject(tex); cudaFreeArray(arr);
+  dfree(sink); cudaDestroyTextureObject(tex); cudaFreeArray(arr);
   return DPE_OK;
 }
 
@@ -1330,7 +1377,7 @@ int dpe_probe_tex_pattern(dpe_ctx* ctx, int fmt, int layout, int width, int heig
   }
   cudaResourceDesc rd; memset(&rd, 0, sizeof(rd)); rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
   CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
-  float* sink; CK(cudaMalloc(&sink, 4));
+  float* sink; CK(dmalloc(&sink, 4));
   const int blocks = ctx->num_sms * blocks_per_sm;
   const LaunchCfg cfg = cfg_of(ctx);
   launch_probe_tex_pattern((unsigned long long)tex, width, height, iters / 4 + 1, layout, m, sink, blocks, threads, cfg, 0);
@@ -1340,14 +1387,14 @@ int dpe_probe_tex_pattern(dpe_ctx* ctx, int fmt, int layout, int width, int heig
   CK(cudaEventSynchronize(ctx->ev1));
   float ms = 0.f; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   *taps_per_s = (double)blocks * threads * (double)iters * 36.0 / (ms * 1e-3);
-  cudaFree(sink); cudaDestroyTextureObject(tex); cudaFreeArray(arr);
+  dfree(sink); cudaDestroyTextureObject(tex); cudaFreeArray(arr);
   return DPE_OK;
 }
 
 int dpe_probe_fma_rate(dpe_ctx* ctx, int iters, double* fma_per_s) {
   if (!ctx || iters <= 0 || !fma_per_s) return DPE_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  float* sink; CK(cudaMalloc(&sink, 4));
+  float* sink; CK(dmalloc(&sink, 4));
   const int blocks = ctx->num_sms * 8, threads = 256;
   const LaunchCfg cfg = cfg_of(ctx);
   launch_probe_fma(iters / 4 + 1, sink, blocks, threads, cfg, 0);
@@ -1357,7 +1404,7 @@ int dpe_probe_fma_rate(dpe_ctx* ctx, int iters, double* fma_per_s) {
   CK(cudaEventSynchronize(ctx->ev1));
   float ms = 0.f; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   *fma_per_s = (double)blocks * threads * (double)iters * 128.0 / (ms * 1e-3);
-  cudaFree(sink);
+  dfree(sink);
   return DPE_OK;
 }
 
@@ -1374,10 +1421,10 @@ int dpe_probe_tex_weights(dpe_ctx* ctx, int n, float* weights) {
   td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp; td.filterMode = cudaFilterModeLinear;
   td.readMode = cudaReadModeElementType;
   CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
-  float* d; CK(cudaMalloc(&d, (size_t)(n + 1) * 4));
+  float* d; CK(dmalloc(&d, (size_t)(n + 1) * 4));
   launch_probe_weights((unsigned long long)tex, n, d, cfg_of(ctx), 0);
   CK(cudaMemcpy(weights, d, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost));
-  cudaFree(d); cudaDestroyTextureObject(tex); cudaFreeArray(arr);
+  dfree(d); cudaDestroyTextureObject(tex); cudaFreeArray(arr);
   return DPE_OK;
 }
 

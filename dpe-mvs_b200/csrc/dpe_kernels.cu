@@ -117,6 +117,203 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_full(const __grid_constant_
   flush_evals(a.eval_units, evals);
 }
 
+// ---- DepthToWeak + LocalRefine, warp-cooperative ----------------------------------------------
+// classify_refine_pixel (dpe_core.cuh) is the definition: per pixel, 61 disparity hypotheses x the pixel's
+// selected views.  One thread per pixel leaves the lanes of a warp idle whenever their pixel has not selected
+// the view the warp is walking (a warp walks the union of its 32 pixels' selections: 23-26 of 32 lanes
+// active, profiles/r01_ncu_v5_classify.txt).  Here a warp still owns 32 neighbouring pixels, but for each view
+// v the (pixel, hypothesis) pairs of the pixels that selected v are dealt round-robin to all 32 lanes: lane L
+// of round j scores pair i = 32 j + L = (pixel of rank i mod n among the n selecting pixels, hypothesis
+// i / n), so a round works on neighbouring pixels at the same or adjacent disparities (texture locality as
+// before) and every lane is busy.  Costs go back to the owning lane by shuffle; each owner adds them to its
+// 61-entry profile in ascending view order, which is the order of the per-pixel loop, so the sums are bit
+// for bit the same.
+struct ClsPix {
+  float nx, ny, nz;   // plane normal in reference-camera coordinates
+  float fxB, disp;    // fx * mean baseline, current disparity
+  float r0, c0, inv_sw, mean_r, var_r;  // PatchStats
+  int klo, khi;       // hypothesis range: -30..30, or -5..5 on the 6-pixel border (LocalRefine only)
+  int pad;            // 13 words: lanes reading different pixels' records hit different banks
+};
+
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) k_classify_warp(const __grid_constant__ KernelParams P) {
+  __shared__ float2 s_tbl[36 * NT];
+  __shared__ float s_tile[SMW * (4 + 2 * HALO)];
+  __shared__ ClsPix s_pix[NT];
+  StageArgs a = P.a;
+  a.rc = &P.rc;
+  const RefConst& rc = P.rc;
+  const int n_tiles = a.tiles_x * a.tiles_y;
+  const int W = a.W, H = a.H, N = rc.n_src;
+  unsigned evals = 0;
+  RefTile<4> tile;
+  tile.s = s_tile;
+  TblStore st;
+  st.tbl = s_tbl + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  ClsPix* wpix = s_pix + warp * 32;
+  const bool mul_add = (a.variants & DPE_VARIANT_CLASSIFY_MUL_ADD) != 0;
+  float prof[61];
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int tx0 = (t % a.tiles_x) * TILE_W, ty0 = (t / a.tiles_x) * 4;
+    __syncthreads();
+    tile.stage(a.ref_img, W, H, tx0, ty0);
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    const int x = tx0 + lane, y = ty0 + warp;
+    const int center = y * W + x;
+    // ---- per-pixel set-up (the head of classify_refine_pixel)
+    bool active = false, classify = false, refine = false;
+    uint8_t new_state = DPE_UNKNOWN;
+    uint32_t sel = 0u;
+    ViewW vw; vw.clear();
+    float origin_depth = 0.f, weight_normal = 0.f, fxB = 0.f, disp = 0.f;
+    float4 pl = make_float4(0.f, 0.f, 1.f, 0.f);
+    if (x < W && y < H) {
+      const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact != 0);
+      const bool border = (x < 6 || y < 6 || x >= W - 6 || y >= H - 6);
+      new_state = a.state[center];
+      classify = true;
+      if (border) { new_state = DPE_UNKNOWN; classify = false; }
+      const float4 pw = a.planes[center];
+      origin_depth = pw.w;
+      pl = world_to_cam_normal(rc, pw);
+      if (origin_depth == 0.f) {
+        if (classify) new_state = DPE_UNKNOWN;
+        a.state[center] = new_state;
+      } else {
+        sel = a.selected[center];
+        vw = ViewW::unpack(a.view_w[center]);
+        float base_line = 0.f;
+        int valid = 0;
+        for (int v = 0; v < N; ++v)
+          if ((sel >> v) & 1u) { base_line += rc.src[v].baseline; weight_normal += (float)vw.get(v); valid++; }
+        if (valid == 0) {
+          if (classify) new_state = DPE_UNKNOWN;
+          a.state[center] = new_state;
+        } else {
+          base_line /= valid;
+          disp = rc.fx * base_line / origin_depth;
+          fxB = rc.fx * base_line;
+          refine = !(weight_normal == 0.f);
+          active = true;
+          ClsPix& cp = wpix[lane];
+          cp.nx = pl.x; cp.ny = pl.y; cp.nz = pl.z; cp.fxB = fxB; cp.disp = disp;
+          cp.r0 = ps.r0; cp.c0 = ps.c0; cp.inv_sw = ps.inv_sw; cp.mean_r = ps.mean_r; cp.var_r = ps.var_r;
+          cp.klo = classify ? -30 : -5; cp.khi = classify ? 30 : 5;
+        }
+      }
+    }
+    if (!active) sel = 0u;
+#pragma unroll 1
+    for (int kk = 0; kk < 61; ++kk) prof[kk] = 0.f;
+    __syncwarp();
+    // ---- the profile, view by view
+#pragma unroll 1
+    for (int v = 0; v < N; ++v) {
+      const unsigned S = __ballot_sync(0xffffffffu, (sel >> v) & 1u);
+      if (S == 0u) continue;
+      const int n = __popc(S);
+      const int total = n * 61;
+      const bool mine = (S >> lane) & 1u;
+      const int my_rank = __popc(S & lt_mask);
+      const float wf = (float)vw.get(v);
+      const int per_round = (32 + n - 1) / n;  // at most this many pairs of one pixel in a round
+      const SrcConst& sc = rc.src[v];
+#pragma unroll 1
+      for (int base = 0; base < total; base += 32) {
+        const int i = base + lane;
+        float c = 0.f;
+        bool ok = false;
+        if (i < total) {
+          const int kk = i / n, r = i - kk * n;
+          const int pl_lane = __fns(S, 0, r + 1);
+          const ClsPix cp = wpix[pl_lane];
+          const int k = kk - 30;
+          if (k >= cp.klo && k <= cp.khi) {
+            const float p_depth = cp.fxB / (cp.disp + k);
+            if (!(p_depth < rc.depth_min || p_depth > rc.depth_max)) {
+              const int px = tx0 + pl_lane;
+              float4 hp = make_float4(cp.nx, cp.ny, cp.nz, 0.f);
+              hp.w = dist2origin(rc, px, y, p_depth, hp);
+              const float3 m = plane_to_m(rc, hp);
+              PatchStats ps;
+              ps.r0 = cp.r0; ps.c0 = cp.c0; ps.exact = a.exact; ps.inv_sw = cp.inv_sw; ps.mean_r = cp.mean_r; ps.var_r = cp.var_r;
+              DevEnv env;
+              env.tbl = s_tbl + warp * 32 + pl_lane;
+              env.img = a.ref_img; env.W = W; env.H = H;
+              const float g = a.geom ? a.geom_factor * geom_cost(a, rc, sc, hp, px, y) : 0.f;
+              c = ncc_old(env, ps, rc, sc, hp, m, px, y);
+              evals += c < 2.0f;
+              if (a.geom) c += g;
+              ok = true;
+            }
+          }
+        }
+        const unsigned okm = __ballot_sync(0xffffffffu, ok);
+        // hand the costs to their owners: pixel of rank r holds pairs i = r, r + n, r + 2n, ...
+        int mi = base + ((my_rank - base % n) + n) % n;  // this owner's first pair of the round
+#pragma unroll 1
+        for (int q = 0; q < per_round; ++q, mi += n) {
+          const int src = mi - base;
+          const float cv = __shfl_sync(0xffffffffu, c, src & 31);
+          if (mine && src < 32 && mi < total && ((okm >> src) & 1u)) {
+            const int kk = mi / n;
+            prof[kk] = mul_add ? add_rn(mul_rn(cv, wf), prof[kk]) : fmaf(cv, wf, prof[kk]);
+          }
+        }
+      }
+    }
+    // ---- per-pixel tail: LocalRefine's arg-min over k in [-5, 5], the classifier on the profile
+    if (active) {
+      float lr_min = 2.0f, lr_best_depth = origin_depth, lr_now = 0.f;
+      bool need_extra = false;
+      const int k_lo = classify ? -30 : -5, k_hi = classify ? 30 : 5;
+#pragma unroll 1
+      for (int k = k_lo; k <= k_hi; ++k) {
+        const float p_depth = fxB / (disp + k);
+        const bool in_range = !(p_depth < rc.depth_min || p_depth > rc.depth_max);
+        const float pc = in_range ? prof[k + 30] / weight_normal : 2.0f;
+        if (in_range && k >= -5 && k <= 5 && refine) {
+          if (pc < lr_min) { lr_min = pc; lr_best_depth = p_depth; }
+        }
+        if (k == 0) {
+          if (in_range) lr_now = pc;
+          else if (refine) need_extra = true;
+        }
+        if (classify) prof[k + 30] = (2.0f > pc) ? pc : 2.0f;
+      }
+      if (need_extra) {  // LocalRefine scores the current depth even when disparity 0 is out of range (rare)
+        float4 hp = pl;
+        hp.w = dist2origin(rc, x, y, origin_depth, hp);
+        const float3 m = plane_to_m(rc, hp);
+        PatchStats ps;
+        const ClsPix cp = wpix[lane];
+        ps.r0 = cp.r0; ps.c0 = cp.c0; ps.exact = a.exact; ps.inv_sw = cp.inv_sw; ps.mean_r = cp.mean_r; ps.var_r = cp.var_r;
+        DevEnv env;
+        env.tbl = s_tbl + threadIdx.x; env.img = a.ref_img; env.W = W; env.H = H;
+        float acc = 0.f;
+        for (int v = 0; v < N; ++v) {
+          if ((sel >> v) & 1u) {
+            const float g = a.geom ? a.geom_factor * geom_cost(a, rc, rc.src[v], hp, x, y) : 0.f;
+            float c = ncc_old(env, ps, rc, rc.src[v], hp, m, x, y);
+            evals += c < 2.0f;
+            if (a.geom) c += g;
+            acc = mul_add ? add_rn(mul_rn(c, (float)vw.get(v)), acc) : fmaf(c, (float)vw.get(v), acc);
+          }
+        }
+        lr_now = acc / weight_normal;
+      }
+      if (classify) new_state = classify_profile(prof, a.weak_peak_radius);
+      a.state[center] = new_state;
+      if (refine && (lr_now - lr_min > 0.1)) a.planes[center].w = lr_best_depth;  // double comparison, DPE.cu:2832
+    }
+    __syncwarp();
+  }
+  flush_evals(a.eval_units, evals);
+}
+
 // ---- red/black half sweeps: tile = 32 x 8 pixels, one thread per pixel of one colour ----
 enum HalfOp { OP_STRONG = 0, OP_STRONG_EDGE = 1 };
 
@@ -159,8 +356,8 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_half(const __grid_constant_
 // the image-tile kernel leaves most lanes idle behind a handful of long-running ones (the
 // reference does exactly that, DPE.cu:1864-1898).  The stage therefore compacts the WEAK pixels
 // of each colour once (after GenNeighbours has demoted the unreliable ones) and the weak sweep
-// runs over the dense list.  List order varies from run to run (warp-aggregated atomics); the
-// result does not depend on it, a sweep only reads the other colour.
+// runs over the dense list; so do the nearest-strong search, the label-boundary walk, the anchor search and the
+// plane fit, which only WEAK pixels take part in (k_list below).
 struct GlobalRef {
   const float* img;
   int W, H;
@@ -169,22 +366,93 @@ struct GlobalRef {
   }
 };
 
-__global__ void __launch_bounds__(256) k_compact_weak(const __grid_constant__ KernelParams P) {
-  const StageArgs& a = P.a;
+// Ordered compaction in three small passes (count per warp, scan, scatter): every warp owns a contiguous run
+// of pixels, so each colour's list comes out in raster order — neighbouring list entries are neighbouring WEAK
+// pixels, which keeps the warps of the list kernels on similar work and their reads close together — and is
+// the same from run to run.
+constexpr int CW_THREADS = 256;
+constexpr int CW_BLOCKS_PER_SM = 4;
+__device__ __forceinline__ void compact_range(const StageArgs& a, int& begin, int& end) {
   const int total = a.W * a.H;
+  const int n_warps = gridDim.x * (CW_THREADS / 32);
+  int chunk = (total + n_warps - 1) / n_warps;
+  chunk = (chunk + 31) & ~31;
+  const int w = blockIdx.x * (CW_THREADS / 32) + (threadIdx.x >> 5);
+  begin = imin(w * chunk, total);
+  end = imin(begin + chunk, total);
+}
+__global__ void __launch_bounds__(CW_THREADS) k_weak_count(const __grid_constant__ KernelParams P) {
+  const StageArgs& a = P.a;
+  int begin, end;
+  compact_range(a, begin, end);
   const int lane = threadIdx.x & 31;
-  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total; base += gridDim.x * blockDim.x) {
+  int n0 = 0, n1 = 0;
+  for (int base = begin; base < end; base += 32) {
     const int i = base + lane;
-    const bool weak = i < total && a.state[i] == DPE_WEAK;
-    const int colour = weak ? (((i % a.W) + (i / a.W)) & 1) : 0;
+    const bool weak = i < end && a.state[i] == DPE_WEAK;
+    const int colour = ((i % a.W) + (i / a.W)) & 1;
+    n0 += __popc(__ballot_sync(0xffffffffu, weak && colour == 0));
+    n1 += __popc(__ballot_sync(0xffffffffu, weak && colour == 1));
+  }
+  if (lane == 0) {
+    const int w = blockIdx.x * (CW_THREADS / 32) + (threadIdx.x >> 5);
+    a.weak_scan[2 * w] = n0; a.weak_scan[2 * w + 1] = n1;
+  }
+}
+// exclusive scan of the per-warp counts (n entries per colour, interleaved), one CTA
+__global__ void __launch_bounds__(1024) k_weak_scan(int* __restrict__ scan, const int n, int* __restrict__ count) {
+  __shared__ int s_sum[2][32];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int per = (n + 1023) / 1024;
+  const int b = imin(t * per, n), e = imin(b + per, n);
+  int loc[2] = {0, 0};
+  for (int i = b; i < e; ++i) { loc[0] += scan[2 * i]; loc[1] += scan[2 * i + 1]; }
+  int pre[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    int v = loc[c];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+    if (lane == 31) s_sum[c][wid] = v;
+    pre[c] = v - loc[c];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int own = s_sum[c][lane];
+      int v = own;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+      s_sum[c][lane] = v - own;
+      if (lane == 31) count[c] = v;
+    }
+  }
+  __syncthreads();
+  int run[2] = {pre[0] + s_sum[0][wid], pre[1] + s_sum[1][wid]};
+  for (int i = b; i < e; ++i) {
+    const int c0 = scan[2 * i], c1 = scan[2 * i + 1];
+    scan[2 * i] = run[0]; scan[2 * i + 1] = run[1];
+    run[0] += c0; run[1] += c1;
+  }
+}
+__global__ void __launch_bounds__(CW_THREADS) k_weak_scatter(const __grid_constant__ KernelParams P) {
+  const StageArgs& a = P.a;
+  int begin, end;
+  compact_range(a, begin, end);
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (CW_THREADS / 32) + (threadIdx.x >> 5);
+  int off[2] = {a.weak_scan[2 * w], a.weak_scan[2 * w + 1]};
+  const unsigned lt = (1u << lane) - 1u;
+  for (int base = begin; base < end; base += 32) {
+    const int i = base + lane;
+    const bool weak = i < end && a.state[i] == DPE_WEAK;
+    const int colour = ((i % a.W) + (i / a.W)) & 1;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const unsigned m = __ballot_sync(0xffffffffu, weak && colour == c);
-      if (m == 0u) continue;
-      int off = 0;
-      if (lane == (__ffs(m) - 1)) off = atomicAdd(&a.weak_count[c], __popc(m));
-      off = __shfl_sync(0xffffffffu, off, __ffs(m) - 1);
-      if (weak && colour == c) a.weak_list[c * a.list_stride + off + __popc(m & ((1u << lane) - 1u))] = i;
+      if (weak && colour == c) a.weak_list[c * a.list_stride + off[c] + __popc(m & lt)] = i;
+      off[c] += __popc(m);
     }
   }
 }
@@ -485,7 +753,8 @@ __global__ void __launch_bounds__(NTW, WEAK_CTAS_PER_SM) k_weak_list(const __gri
 #undef PHASE_SYNC
 
 // ---- light per-pixel kernels ------------------------------------------------------------
-enum LightOp { L_EXTRACT = 0, L_MEDIAN = 1, L_FINISH = 2, L_EDGE_INFO = 3, L_NEAREST = 4, L_NEIGH = 5, L_FIT = 6, L_LOAD = 7 };
+enum LightOp { L_EXTRACT = 0, L_MEDIAN = 1, L_FINISH = 2, L_EDGE_INFO = 3, L_NEAREST = 4, L_NEIGH = 5, L_FIT = 6, L_LOAD = 7,
+               L_LABEL_BOUNDARY = 8, L_FIT_COPY = 9 };
 
 template <int OP>
 __global__ void __launch_bounds__(256) k_light(const __grid_constant__ KernelParams P) {
@@ -511,6 +780,26 @@ __global__ void __launch_bounds__(256) k_light(const __grid_constant__ KernelPar
     else if (OP == L_NEIGH) gen_neighbours_pixel(a, x, y);
     else if (OP == L_FIT) fit_plane_pixel(a, x, y);
     else if (OP == L_LOAD) load_pixel(a, x, y);
+    else if (OP == L_LABEL_BOUNDARY) label_boundary_pixel(a, x, y);
+    else if (OP == L_FIT_COPY) { if (a.state[i] != DPE_WEAK) a.fit_planes[i] = a.planes[i]; }  // DPE.cu:2945
+  }
+}
+
+// The same per-pixel functions over the compacted WEAK lists (both colours): one thread per WEAK pixel, warps
+// full of WEAK pixels instead of one here and there in an image-sized launch.  A pixel another thread demoted
+// after the list was built (NeigbourUpdate) is skipped by the functions' own state test.
+template <int OP, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_list(const __grid_constant__ KernelParams P) {
+  StageArgs a = P.a;
+  a.rc = &P.rc;
+  const int n0 = a.weak_count[0], total = n0 + a.weak_count[1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int center = i < n0 ? a.weak_list[i] : a.weak_list[a.list_stride + (i - n0)];
+    const int x = center % a.W, y = center / a.W;
+    if (OP == L_NEAREST) nearest_strong_pixel(a, x, y);
+    else if (OP == L_LABEL_BOUNDARY) label_boundary_pixel(a, x, y);
+    else if (OP == L_NEIGH) gen_neighbours_pixel(a, x, y);
+    else if (OP == L_FIT) fit_plane_pixel(a, x, y);
   }
 }
 
@@ -538,7 +827,9 @@ void launch_classify_refine(const KernelParams& P0, const LaunchCfg& cfg, cudaSt
   KernelParams P = P0;
   P.a.tiles_x = (P.a.W + TILE_W - 1) / TILE_W;
   P.a.tiles_y = (P.a.H + 3) / 4;
-  k_full<OP_CLASSIFY><<<persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, CTAS_PER_SM), NT, 0, stream>>>(P);
+  const int g = persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, CTAS_PER_SM);
+  if (P.a.variants & DPE_VARIANT_CLASSIFY_PER_PIXEL) k_full<OP_CLASSIFY><<<g, NT, 0, stream>>>(P);
+  else k_classify_warp<<<g, NT, 0, stream>>>(P);
   count(cfg);
 }
 void launch_strong(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t stream) {
@@ -555,22 +846,48 @@ void launch_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t strea
   count(cfg);
 }
 void launch_compact_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream) {
-  cudaMemsetAsync(P.a.weak_count, 0, 2 * sizeof(int), stream);
-  k_compact_weak<<<cfg.num_sms * 8, 256, 0, stream>>>(P);
-  count(cfg);
+  const int blocks = cfg.num_sms * CW_BLOCKS_PER_SM;
+  k_weak_count<<<blocks, CW_THREADS, 0, stream>>>(P);
+  k_weak_scan<<<1, 1024, 0, stream>>>(P.a.weak_scan, blocks * (CW_THREADS / 32), P.a.weak_count);
+  k_weak_scatter<<<blocks, CW_THREADS, 0, stream>>>(P);
+  count(cfg); count(cfg); count(cfg);
 }
+int compact_scan_entries(int num_sms) { return 2 * num_sms * CW_BLOCKS_PER_SM * (CW_THREADS / 32); }
 template <int OP>
 static void launch_light(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream) {
   k_light<OP><<<cfg.num_sms * 8, 256, 0, stream>>>(P);
   count(cfg);
 }
+template <int OP, int THREADS>
+static void launch_list(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream, int blocks_per_sm) {
+  k_list<OP, THREADS><<<cfg.num_sms * blocks_per_sm, THREADS, 0, stream>>>(P);
+  count(cfg);
+}
+static inline bool full_image(const KernelParams& P) { return (P.a.variants & DPE_VARIANT_LIGHT_FULL_IMAGE) != 0; }
 void launch_extract(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_EXTRACT>(P, cfg, s); }
 void launch_median(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_MEDIAN>(P, cfg, s); }
 void launch_finish(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_FINISH>(P, cfg, s); }
-void launch_edge_info(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_EDGE_INFO>(P, cfg, s); }
-void launch_nearest_strong(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_NEAREST>(P, cfg, s); }
-void launch_gen_neighbours(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_NEIGH>(P, cfg, s); }
-void launch_fit_plane(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_FIT>(P, cfg, s); }
+// GenEdgeInform: the per-pixel part over the image, the WEAK-only label-boundary walk over the list
+void launch_edge_info(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) {
+  launch_light<L_EDGE_INFO>(P, cfg, s);
+  if (full_image(P)) launch_light<L_LABEL_BOUNDARY>(P, cfg, s);
+  else launch_list<L_LABEL_BOUNDARY, 128>(P, cfg, s, 16);
+}
+void launch_nearest_strong(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) {
+  if (full_image(P)) { launch_light<L_NEAREST>(P, cfg, s); return; }
+  // every pixel that is not WEAK holds (-1, -1) (DPE.cu:2858)
+  cudaMemsetAsync(P.a.nearest_strong, 0xFF, (size_t)P.a.W * P.a.H * sizeof(short2), s);
+  launch_list<L_NEAREST, 128>(P, cfg, s, 16);
+}
+void launch_gen_neighbours(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) {
+  if (full_image(P)) launch_light<L_NEIGH>(P, cfg, s);
+  else launch_list<L_NEIGH, 64>(P, cfg, s, 16);
+}
+void launch_fit_plane(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) {
+  if (full_image(P)) { launch_light<L_FIT>(P, cfg, s); return; }
+  launch_light<L_FIT_COPY>(P, cfg, s);
+  launch_list<L_FIT, 64>(P, cfg, s, 16);
+}
 void launch_load(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) { launch_light<L_LOAD>(P, cfg, s); }
 
 // ---- result export ---------------------------------------------------------------------------

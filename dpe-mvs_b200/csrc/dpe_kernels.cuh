@@ -31,7 +31,10 @@ void launch_finish(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t str
 void launch_edge_info(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
 void launch_nearest_strong(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
 void launch_gen_neighbours(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
-void launch_compact_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);  // after gen_neighbours
+// WEAK pixels of each colour into raster-ordered lists; before the anchor search (its input) and again after it
+// (it demotes unreliable pixels).  compact_scan_entries = ints StageArgs::weak_scan needs.
+void launch_compact_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
+int compact_scan_entries(int num_sms);
 void launch_fit_plane(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);
 void launch_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);  // one colour, one iter
 

@@ -46,6 +46,13 @@ struct RefConst {
   SrcConst src[DPE_MAX_SRC];
 };
 
+// kernel variants (StageArgs::variants, test hook dpe_debug_set_variants)
+enum {
+  DPE_VARIANT_CLASSIFY_PER_PIXEL = 1,  // DepthToWeak + LocalRefine one thread per pixel (the definition, dpe_core.cuh)
+  DPE_VARIANT_CLASSIFY_MUL_ADD = 2,    // warp-cooperative form accumulating with separate multiply and add
+  DPE_VARIANT_LIGHT_FULL_IMAGE = 4     // anchor search / plane fit over the whole image instead of the WEAK list
+};
+
 // Kernel argument block for one (view, stage).
 struct StageArgs {
   const RefConst* rc;
@@ -77,6 +84,7 @@ struct StageArgs {
   int* weak_list;
   int* weak_count;
   int list_stride;
+  int* weak_scan;  // scratch of the ordered compaction: per-warp counts / offsets (compact_scan_entries ints)
   // state carried in from the previous stage (possibly at the previous scale)
   const float4* prev_planes;  // (world normal, depth)
   const uint8_t* prev_state;
@@ -95,6 +103,7 @@ struct StageArgs {
   int exact;     // 1: homography, source coordinates, bilateral weights and geometric consistency in the reference's fp32 operation order
   int cost_raw;  // cost arithmetic: 1 = moments on raw intensities like the reference, 0 = centred (dpe_core.cuh)
   int ref_race;  // 1: edge-mode direction 4 samples its own colour like the reference, racy
+  int variants;  // DPE_VARIANT_* bits (dpe_debug_set_variants): earlier forms of a kernel, kept for A/B tests
   Xorwow* rng;  // per-pixel XORWOW state of this stage (dpe_rng.h), starts as curand_init(seed, y, x)
   unsigned long long* eval_units;  // optional counter (36-tap units)
   int tiles_x, tiles_y;

@@ -113,6 +113,13 @@ DPE_HDN void edge_info_pixel(const StageArgs& a, const int x, const int y) {
     density = fmaxf(density, (float)(bound_pix / tot_pix));  // integer division
     a.complexity[center] = (float)(1.0f / (1.0f + exp(-25.0 * (density - 0.35))));  // double arithmetic, DPE.cu:2554
   }
+}
+
+// the use_label part of GenEdgeInform (DPE.cu:2560-2590): only WEAK pixels with a positive label take part
+DPE_HDN void label_boundary_pixel(const StageArgs& a, const int x, const int y) {
+  const int W = a.W, H = a.H, center = y * W + x;
+  const int dirx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
+  const int diry[8] = {-1, 1, 0, 0, -1, 1, 1, -1};
   if (a.state[center] == DPE_WEAK) {  // use_label
     const int center_label = a.label[center];
     if (center_label > 0) {

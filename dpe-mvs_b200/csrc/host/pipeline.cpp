@@ -262,7 +262,7 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     if (!jpeg_image_size(dec, image_path(0), &width, &height, &err) || width <= 0 || height <= 0) return bail("Images may error, check it!");
     P = (size_t)width * height;
     if (cudaHostAlloc((void**)&gray_slab, P * n_views, cudaHostAllocPortable) != cudaSuccess) return bail("DPE-MVS: cannot allocate pinned memory");
-    const int n_load = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 8, n_views}));
+    const int n_load = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 16, n_views}));
     std::vector<JpegDecoder*> decs(n_load, nullptr);
     decs[0] = dec;
     std::atomic<int> bad(0), bad_cam(0), next_dec(0);

@@ -201,7 +201,7 @@ static int hostsim_stage_impl(int W, int H, int full_w, int full_h, int n_src, c
 
   if (p->state != DPE_FIRST_INIT) for_all([&](int x, int y) { load_pixel(a, x, y); });
   if (p->use_apd) {
-    for_all([&](int x, int y) { edge_info_pixel(a, x, y); });
+    for_all([&](int x, int y) { edge_info_pixel(a, x, y); label_boundary_pixel(a, x, y); });
     for_all([&](int x, int y) { nearest_strong_pixel(a, x, y); });
     for_all([&](int x, int y) { gen_neighbours_pixel(a, x, y); });
   }

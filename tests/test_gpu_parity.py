@@ -328,6 +328,58 @@ def test_results_do_not_depend_on_sharding():
         c.close()
 
 
+def _prep_for(grays, ns):
+    lib = capi.load()
+    import ctypes as C
+    out = []
+    for g in grays:
+        h, w = g.shape
+        per = []
+        for k in range(ns):
+            ss = 1 << (ns - 1 - k)
+            f = np.float32(1.0) / np.float32(ss)
+            cw, ch = int(np.floor(float(np.float32(w) * f) + 0.5)), int(np.floor(float(np.float32(h) * f) + 0.5))
+            e = np.empty((ch, cw), np.uint8); l = np.empty((ch, cw), np.int32)
+            gg = np.ascontiguousarray(g)
+            lib.dpe_host_problem_edges(gg.ctypes.data_as(C.c_void_p), w, h, ss, e.ctypes.data_as(C.c_void_p), l.ctypes.data_as(C.c_void_p))
+            per.append((e, l))
+        out.append(per)
+    return out
+
+
+def _full_run(variants, grays, cams, drs, pairs, ns, prep, seed=11):
+    ctx = capi.Context(0)
+    ctx.scene_begin(len(grays), grays[0].shape[1], grays[0].shape[0], ns)
+    for v, (img, (K, R, t), (dmin, dmax)) in enumerate(zip(grays, cams, drs)):
+        ctx.set_view(v, img, K, R, t, dmin, dmax)
+        ctx.set_pairs(v, pairs[v])
+        for k, (e, l) in enumerate(prep[v]):
+            ctx.set_prep(v, k, e, l)
+    ctx.commit()
+    ctx.debug_set_variants(variants)
+    _run_schedule(ctx, ns, seed)
+    maps = [ctx.get_maps(v, ns - 1) for v in range(len(grays))]
+    ctx.close()
+    return maps
+
+
+def test_kernel_variants_give_identical_maps():
+    """The warp-cooperative DepthToWeak + LocalRefine kernel (pairs of (pixel, hypothesis) dealt to all lanes, view by
+    view) and the WEAK-list forms of the anchor search / plane fit against their one-thread-per-pixel definitions
+    (dpe_debug_set_variants): every map of every view after the whole schedule, bit for bit.  The scene has
+    low-texture planes, so the weak path and the classifier's WEAK branch are exercised."""
+    spec, grays, cams, drs, pairs, gt = small_scene("c4", 0.08, 5)
+    ns = 2
+    prep = _prep_for(grays, ns)
+    want = _full_run(1 | 4, grays, cams, drs, pairs, ns, prep)      # definitions: per-pixel classifier, full-image light kernels
+    got = _full_run(0, grays, cams, drs, pairs, ns, prep)           # product default
+    n_weak = sum(int((m["state"] == capi.WEAK).sum()) for m in want)
+    assert n_weak > 500, n_weak
+    for v, (a, b) in enumerate(zip(got, want)):
+        for key in ("depth", "normal", "state", "selected"):
+            assert np.array_equal(a[key], b[key]), (v, key, float((a[key] != b[key]).mean()))
+
+
 def test_edge_cases_sizes_and_source_counts():
     """Ragged image sizes (not multiples of the 32x8 tile), the maximum of 31 source views, a view without any
     source, a source that is not itself a reference view: the whole schedule runs, maps have the

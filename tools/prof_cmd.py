@@ -12,7 +12,9 @@ from bench import ensure_scene, load_scene_arrays, product_prep
 n_prof = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 cfg = sys.argv[2] if len(sys.argv) > 2 else "c2"
 n_views = int(sys.argv[3]) if len(sys.argv) > 3 else 12
-folder = ensure_scene(cfg, n_views, f"{cfg}v{n_views}")
+variants = int(sys.argv[4]) if len(sys.argv) > 4 else 0      # dpe_debug_set_variants
+scale = float(sys.argv[5]) if len(sys.argv) > 5 else 1.0
+folder = ensure_scene(cfg, n_views, f"{cfg}v{n_views}s{scale}", scale)
 grays, cams, drs, pairs = load_scene_arrays(folder)
 V = len(grays); H, W = grays[0].shape
 lib = capi.load()
@@ -24,6 +26,7 @@ for v in range(V):
     for k, (e, l) in enumerate(product_prep(lib, grays[v], ns)):
         ctx.set_prep(v, k, e, l)
 ctx.commit()
+ctx.debug_set_variants(variants)
 sched = capi.stage_schedule(ns)
 for (k, p) in sched:                      # warm pass: every view gets real depth maps
     ctx.run_stage(k, p, 20261018); ctx.stage_commit()
@@ -37,6 +40,7 @@ t0 = time.time()
 for (k, p) in sched:
     ctx.run_stage(k, p, 20261018)
     ctx.stage_commit()
+print("config", cfg, "views", V, "size", W, H, "variants", variants)
 print("wall", time.time() - t0, "gpu_ms", ctx.stage_gpu_ms(), "launches", ctx.kernel_launches())
 for k, v in ctx.get_profile().items():
     print(f"{k:16s} ms={v['ms']:10.3f} launches={v['launches']:4d} units={v['units']:.4g}" + (f"  Gunits/s={v['units']/v['ms']/1e6:.2f}" if v['units'] else ""))
