@@ -19,6 +19,12 @@ LIB = HERE / "lib"
 BIN = HERE / "bin"
 OBJ = HERE / "build"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+# experiments: DPE_BUILD_TAG=<tag> DPE_BUILD_DEFS="-DDPE_CTAS_PER_SM=5" builds lib/libdpe_b200_<tag>.so beside the
+# product library (capi.py loads it when DPE_LIB points at it)
+TAG = os.environ.get("DPE_BUILD_TAG", "")
+DEFS = os.environ.get("DPE_BUILD_DEFS", "").split()
+if TAG:
+    OBJ = HERE / f"build_{TAG}"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
@@ -62,9 +68,9 @@ def build_lib(verbose=False, force=False) -> Path:
                 # division / sqrt / exp / sin / cos and flush-to-zero.  The kernels follow the reference's
                 # expressions, so the same flag gives the same kind of rounding in the same places.
                 extra = extra + ["--use_fast_math"]
-            _run([NVCC, *ARCH, *COMMON, *extra, "-I", CSRC, "-I", HERE.parent / "include", "-c", src, "-o", o], verbose)
+            _run([NVCC, *ARCH, *COMMON, *extra, *DEFS, "-I", CSRC, "-I", HERE.parent / "include", "-c", src, "-o", o], verbose)
         objs.append(o)
-    so = LIB / "libdpe_b200.so"
+    so = LIB / (f"libdpe_b200_{TAG}.so" if TAG else "libdpe_b200.so")
     if force or _newer(so, objs):
         _run([NVCC, *ARCH, "-shared", "-o", so, *objs, "-lnvjpeg", "-lcudart", "-lpthread", "-ldl"], verbose)
     return so

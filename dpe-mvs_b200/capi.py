@@ -11,7 +11,8 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "lib" / "libdpe_b200.so"
+import os
+LIB_PATH = Path(os.environ["DPE_LIB"]) if os.environ.get("DPE_LIB") else HERE / "lib" / "libdpe_b200.so"
 
 FIRST_INIT, REFINE_INIT, REFINE_ITER = 0, 1, 2
 WEAK, STRONG, UNKNOWN = 0, 1, 2
@@ -62,7 +63,7 @@ def load(build=True):
     global _lib
     if _lib is not None:
         return _lib
-    if build:
+    if build and not os.environ.get("DPE_LIB"):
         import importlib.util
         spec = importlib.util.spec_from_file_location("dpe_build", HERE / "build.py")
         b = importlib.util.module_from_spec(spec)

@@ -849,10 +849,13 @@ int dpe_stage_begin(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t see
     // an external profiler started with --profile-from-start off sees exactly the profiled views
     if (ctx->profile && li == 0) cudaProfilerStart();
     if (ctx->profile && li == ctx->profile_views) cudaProfilerStop();
-    Scratch& s = ctx->scratch[(prof_view || ctx->gauss_seidel) ? 0 : li % ns];
+    const int si = (prof_view || ctx->gauss_seidel) ? 0 : li % ns;
+    Scratch& s = ctx->scratch[si];
     KernelParams KP;
     fill_args(ctx, view, k, p, seed, s, &KP);
     StageArgs& a = KP.a;
+    a.slot = si;
+    launch_set_ref_const(si, &KP.rc, s.stream);  // stream-ordered: lands after the previous view's kernels on this stream
     // outputs: the other map buffer when the scale changes, in place otherwise
     const int out_buf = map_buffer_of_scale(ctx, k);
     float4* new_planes; uint8_t* new_state; uint32_t* new_sel;
@@ -1176,6 +1179,8 @@ int dpe_cost_eval(dpe_ctx* ctx, int view, int k, int n_pix, const int* xy, const
   CK(cudaMemcpy(d_pl, planes, (size_t)n_pix * sizeof(float4), cudaMemcpyHostToDevice));
   CK(cudaDeviceSynchronize());
   launch_set_scale_tex((unsigned long long)ctx->scale_tex[k], 0);
+  KP.a.slot = DPE_RC_SLOTS - 1;
+  launch_set_ref_const(KP.a.slot, &KP.rc, 0);
   launch_cost_eval(KP, n_pix, d_xy, d_pl, mode, 0ull, d_out, cfg_of(ctx), 0);
   CK(cudaGetLastError());
   CK(cudaMemcpy(out, d_out, (size_t)n_pix * N * sizeof(float), cudaMemcpyDeviceToHost));
@@ -1197,6 +1202,9 @@ int dpe_geom_eval(dpe_ctx* ctx, int view, int k, int n_pix, const int* xy, const
   CK(dmalloc(&d_out, (size_t)n_pix * N * sizeof(float)));
   CK(cudaMemcpy(d_xy, xy, (size_t)n_pix * 2 * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_pl, planes, (size_t)n_pix * sizeof(float4), cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize());
+  KP.a.slot = DPE_RC_SLOTS - 1;
+  launch_set_ref_const(KP.a.slot, &KP.rc, 0);
   launch_geom_eval(KP, n_pix, d_xy, d_pl, d_out, cfg_of(ctx), 0);
   CK(cudaGetLastError());
   CK(cudaMemcpy(out, d_out, (size_t)n_pix * N * sizeof(float), cudaMemcpyDeviceToHost));
@@ -1299,6 +1307,8 @@ int dpe_bench_ncc(dpe_ctx* ctx, int view, int variant, int n_cand, int reps, dou
   const LaunchCfg cfg = cfg_of(ctx);
   CK(cudaDeviceSynchronize());
   launch_set_scale_tex((unsigned long long)ctx->scale_tex[k], 0);
+  KP.a.slot = DPE_RC_SLOTS - 1;
+  launch_set_ref_const(KP.a.slot, &KP.rc, 0);
   launch_ncc_bench(KP, v.planes, n_cand, variant, out, cfg, 0);
   CK(cudaEventRecord(ctx->ev0, 0));
   for (int r = 0; r < reps; ++r) launch_ncc_bench(KP, v.planes, n_cand, variant, out, cfg, 0);

@@ -37,10 +37,20 @@ constexpr int SMW = TILE_W + 2 * HALO;  // 42
 // per-unique-handle loop.
 __constant__ cudaTextureObject_t c_scale_tex;
 
+// Folded cameras of the view-stages in flight: one slot per stream of the stage (dpe_capi.cu queues a
+// stream-ordered copy into the slot in front of a view-stage's kernels).  Kernels and the non-inlined cost
+// functions index c_rc[slot] directly, which the compiler turns into constant-bank loads with a uniform index —
+// the 8 KB block used to ride along as a __grid_constant__ kernel parameter, and a device function that received
+// a pointer into it could only read it with generic loads.
+__constant__ RefConst c_rc[DPE_RC_SLOTS];
+
 struct DevEnv {
   const float2* tbl;  // &table[threadIdx.x]; tap t lives at tbl[t * NT]
   const float* img;   // reference image (for the far-away anchor patches of the weak path)
   int W, H;
+  int slot;           // which c_rc block this view-stage uses
+  __device__ __forceinline__ const RefConst& rc() const { return c_rc[slot]; }
+  __device__ __forceinline__ const SrcConst& src(int v) const { return c_rc[slot].src[v]; }
   __device__ __forceinline__ float ref(int x, int y) const {
     return __ldg(&img[(size_t)iclamp(y, 0, H - 1) * W + iclamp(x, 0, W - 1)]);
   }
@@ -87,18 +97,18 @@ __device__ __forceinline__ void flush_evals(unsigned long long* counter, unsigne
 enum FullOp { OP_INIT = 0, OP_CLASSIFY = 1 };
 
 template <int OP>
-__global__ void __launch_bounds__(NT, CTAS_PER_SM) k_full(const __grid_constant__ KernelParams P) {
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) k_full(const __grid_constant__ StageArgs A) {
   __shared__ float2 s_tbl[36 * NT];
   __shared__ float s_tile[SMW * (4 + 2 * HALO)];
-  StageArgs a = P.a;
-  a.rc = &P.rc;
+  StageArgs a = A;
+  a.rc = &c_rc[a.slot];
   const int n_tiles = a.tiles_x * a.tiles_y;
   unsigned evals = 0;
   RefTile<4> tile;
   tile.s = s_tile;
   DevEnv env;
   env.tbl = s_tbl + threadIdx.x;
-  env.img = a.ref_img; env.W = a.W; env.H = a.H;
+  env.img = a.ref_img; env.W = a.W; env.H = a.H; env.slot = a.slot;
   TblStore st;
   st.tbl = s_tbl + threadIdx.x;
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -117,219 +127,22 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_full(const __grid_constant_
   flush_evals(a.eval_units, evals);
 }
 
-// ---- DepthToWeak + LocalRefine, warp-cooperative ----------------------------------------------
-// classify_refine_pixel (dpe_core.cuh) is the definition: per pixel, 61 disparity hypotheses x the pixel's
-// selected views.  One thread per pixel leaves the lanes of a warp idle whenever their pixel has not selected
-// the view the warp is walking (a warp walks the union of its 32 pixels' selections: 23-26 of 32 lanes
-// active, profiles/r01_ncu_v5_classify.txt).  Here a warp still owns 32 neighbouring pixels, but for each view
-// v the (pixel, hypothesis) pairs of the pixels that selected v are dealt round-robin to all 32 lanes: lane L
-// of round j scores pair i = 32 j + L = (pixel of rank i mod n among the n selecting pixels, hypothesis
-// i / n), so a round works on neighbouring pixels at the same or adjacent disparities (texture locality as
-// before) and every lane is busy.  Costs go back to the owning lane by shuffle; each owner adds them to its
-// 61-entry profile in ascending view order, which is the order of the per-pixel loop, so the sums are bit
-// for bit the same.
-struct ClsPix {
-  float nx, ny, nz;   // plane normal in reference-camera coordinates
-  float fxB, disp;    // fx * mean baseline, current disparity
-  float r0, c0, inv_sw, mean_r, var_r;  // PatchStats
-  int klo, khi;       // hypothesis range: -30..30, or -5..5 on the 6-pixel border (LocalRefine only)
-  int pad;            // 13 words: lanes reading different pixels' records hit different banks
-};
-
-__global__ void __launch_bounds__(NT, CTAS_PER_SM) k_classify_warp(const __grid_constant__ KernelParams P) {
-  __shared__ float2 s_tbl[36 * NT];
-  __shared__ float s_tile[SMW * (4 + 2 * HALO)];
-  __shared__ ClsPix s_pix[NT];
-  StageArgs a = P.a;
-  a.rc = &P.rc;
-  const RefConst& rc = P.rc;
-  const int n_tiles = a.tiles_x * a.tiles_y;
-  const int W = a.W, H = a.H, N = rc.n_src;
-  unsigned evals = 0;
-  RefTile<4> tile;
-  tile.s = s_tile;
-  TblStore st;
-  st.tbl = s_tbl + threadIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  ClsPix* wpix = s_pix + warp * 32;
-  const bool mul_add = (a.variants & DPE_VARIANT_CLASSIFY_MUL_ADD) != 0;
-  float prof[61];
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int tx0 = (t % a.tiles_x) * TILE_W, ty0 = (t / a.tiles_x) * 4;
-    __syncthreads();
-    tile.stage(a.ref_img, W, H, tx0, ty0);
-    __pipeline_wait_prior(0);
-    __syncthreads();
-    const int x = tx0 + lane, y = ty0 + warp;
-    const int center = y * W + x;
-    // ---- per-pixel set-up (the head of classify_refine_pixel)
-    bool active = false, classify = false, refine = false;
-    uint8_t new_state = DPE_UNKNOWN;
-    uint32_t sel = 0u;
-    ViewW vw; vw.clear();
-    float origin_depth = 0.f, weight_normal = 0.f, fxB = 0.f, disp = 0.f;
-    float4 pl = make_float4(0.f, 0.f, 1.f, 0.f);
-    if (x < W && y < H) {
-      const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact != 0);
-      const bool border = (x < 6 || y < 6 || x >= W - 6 || y >= H - 6);
-      new_state = a.state[center];
-      classify = true;
-      if (border) { new_state = DPE_UNKNOWN; classify = false; }
-      const float4 pw = a.planes[center];
-      origin_depth = pw.w;
-      pl = world_to_cam_normal(rc, pw);
-      if (origin_depth == 0.f) {
-        if (classify) new_state = DPE_UNKNOWN;
-        a.state[center] = new_state;
-      } else {
-        sel = a.selected[center];
-        vw = ViewW::unpack(a.view_w[center]);
-        float base_line = 0.f;
-        int valid = 0;
-        for (int v = 0; v < N; ++v)
-          if ((sel >> v) & 1u) { base_line += rc.src[v].baseline; weight_normal += (float)vw.get(v); valid++; }
-        if (valid == 0) {
-          if (classify) new_state = DPE_UNKNOWN;
-          a.state[center] = new_state;
-        } else {
-          base_line /= valid;
-          disp = rc.fx * base_line / origin_depth;
-          fxB = rc.fx * base_line;
-          refine = !(weight_normal == 0.f);
-          active = true;
-          ClsPix& cp = wpix[lane];
-          cp.nx = pl.x; cp.ny = pl.y; cp.nz = pl.z; cp.fxB = fxB; cp.disp = disp;
-          cp.r0 = ps.r0; cp.c0 = ps.c0; cp.inv_sw = ps.inv_sw; cp.mean_r = ps.mean_r; cp.var_r = ps.var_r;
-          cp.klo = classify ? -30 : -5; cp.khi = classify ? 30 : 5;
-        }
-      }
-    }
-    if (!active) sel = 0u;
-#pragma unroll 1
-    for (int kk = 0; kk < 61; ++kk) prof[kk] = 0.f;
-    __syncwarp();
-    // ---- the profile, view by view
-#pragma unroll 1
-    for (int v = 0; v < N; ++v) {
-      const unsigned S = __ballot_sync(0xffffffffu, (sel >> v) & 1u);
-      if (S == 0u) continue;
-      const int n = __popc(S);
-      const int total = n * 61;
-      const bool mine = (S >> lane) & 1u;
-      const int my_rank = __popc(S & lt_mask);
-      const float wf = (float)vw.get(v);
-      const int per_round = (32 + n - 1) / n;  // at most this many pairs of one pixel in a round
-      const SrcConst& sc = rc.src[v];
-#pragma unroll 1
-      for (int base = 0; base < total; base += 32) {
-        const int i = base + lane;
-        float c = 0.f;
-        bool ok = false;
-        if (i < total) {
-          const int kk = i / n, r = i - kk * n;
-          const int pl_lane = __fns(S, 0, r + 1);
-          const ClsPix cp = wpix[pl_lane];
-          const int k = kk - 30;
-          if (k >= cp.klo && k <= cp.khi) {
-            const float p_depth = cp.fxB / (cp.disp + k);
-            if (!(p_depth < rc.depth_min || p_depth > rc.depth_max)) {
-              const int px = tx0 + pl_lane;
-              float4 hp = make_float4(cp.nx, cp.ny, cp.nz, 0.f);
-              hp.w = dist2origin(rc, px, y, p_depth, hp);
-              const float3 m = plane_to_m(rc, hp);
-              PatchStats ps;
-              ps.r0 = cp.r0; ps.c0 = cp.c0; ps.exact = a.exact; ps.inv_sw = cp.inv_sw; ps.mean_r = cp.mean_r; ps.var_r = cp.var_r;
-              DevEnv env;
-              env.tbl = s_tbl + warp * 32 + pl_lane;
-              env.img = a.ref_img; env.W = W; env.H = H;
-              const float g = a.geom ? a.geom_factor * geom_cost(a, rc, sc, hp, px, y) : 0.f;
-              c = ncc_old(env, ps, rc, sc, hp, m, px, y);
-              evals += c < 2.0f;
-              if (a.geom) c += g;
-              ok = true;
-            }
-          }
-        }
-        const unsigned okm = __ballot_sync(0xffffffffu, ok);
-        // hand the costs to their owners: pixel of rank r holds pairs i = r, r + n, r + 2n, ...
-        int mi = base + ((my_rank - base % n) + n) % n;  // this owner's first pair of the round
-#pragma unroll 1
-        for (int q = 0; q < per_round; ++q, mi += n) {
-          const int src = mi - base;
-          const float cv = __shfl_sync(0xffffffffu, c, src & 31);
-          if (mine && src < 32 && mi < total && ((okm >> src) & 1u)) {
-            const int kk = mi / n;
-            prof[kk] = mul_add ? add_rn(mul_rn(cv, wf), prof[kk]) : fmaf(cv, wf, prof[kk]);
-          }
-        }
-      }
-    }
-    // ---- per-pixel tail: LocalRefine's arg-min over k in [-5, 5], the classifier on the profile
-    if (active) {
-      float lr_min = 2.0f, lr_best_depth = origin_depth, lr_now = 0.f;
-      bool need_extra = false;
-      const int k_lo = classify ? -30 : -5, k_hi = classify ? 30 : 5;
-#pragma unroll 1
-      for (int k = k_lo; k <= k_hi; ++k) {
-        const float p_depth = fxB / (disp + k);
-        const bool in_range = !(p_depth < rc.depth_min || p_depth > rc.depth_max);
-        const float pc = in_range ? prof[k + 30] / weight_normal : 2.0f;
-        if (in_range && k >= -5 && k <= 5 && refine) {
-          if (pc < lr_min) { lr_min = pc; lr_best_depth = p_depth; }
-        }
-        if (k == 0) {
-          if (in_range) lr_now = pc;
-          else if (refine) need_extra = true;
-        }
-        if (classify) prof[k + 30] = (2.0f > pc) ? pc : 2.0f;
-      }
-      if (need_extra) {  // LocalRefine scores the current depth even when disparity 0 is out of range (rare)
-        float4 hp = pl;
-        hp.w = dist2origin(rc, x, y, origin_depth, hp);
-        const float3 m = plane_to_m(rc, hp);
-        PatchStats ps;
-        const ClsPix cp = wpix[lane];
-        ps.r0 = cp.r0; ps.c0 = cp.c0; ps.exact = a.exact; ps.inv_sw = cp.inv_sw; ps.mean_r = cp.mean_r; ps.var_r = cp.var_r;
-        DevEnv env;
-        env.tbl = s_tbl + threadIdx.x; env.img = a.ref_img; env.W = W; env.H = H;
-        float acc = 0.f;
-        for (int v = 0; v < N; ++v) {
-          if ((sel >> v) & 1u) {
-            const float g = a.geom ? a.geom_factor * geom_cost(a, rc, rc.src[v], hp, x, y) : 0.f;
-            float c = ncc_old(env, ps, rc, rc.src[v], hp, m, x, y);
-            evals += c < 2.0f;
-            if (a.geom) c += g;
-            acc = mul_add ? add_rn(mul_rn(c, (float)vw.get(v)), acc) : fmaf(c, (float)vw.get(v), acc);
-          }
-        }
-        lr_now = acc / weight_normal;
-      }
-      if (classify) new_state = classify_profile(prof, a.weak_peak_radius);
-      a.state[center] = new_state;
-      if (refine && (lr_now - lr_min > 0.1)) a.planes[center].w = lr_best_depth;  // double comparison, DPE.cu:2832
-    }
-    __syncwarp();
-  }
-  flush_evals(a.eval_units, evals);
-}
-
 // ---- red/black half sweeps: tile = 32 x 8 pixels, one thread per pixel of one colour ----
 enum HalfOp { OP_STRONG = 0, OP_STRONG_EDGE = 1 };
 
 template <int OP>
-__global__ void __launch_bounds__(NT, CTAS_PER_SM) k_half(const __grid_constant__ KernelParams P) {
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) k_half(const __grid_constant__ StageArgs A) {
   __shared__ float2 s_tbl[36 * NT];
   __shared__ float s_tile[SMW * (8 + 2 * HALO)];
-  StageArgs a = P.a;
-  a.rc = &P.rc;
+  StageArgs a = A;
+  a.rc = &c_rc[a.slot];
   const int n_tiles = a.tiles_x * a.tiles_y;
   unsigned evals = 0;
   RefTile<8> tile;
   tile.s = s_tile;
   DevEnv env;
   env.tbl = s_tbl + threadIdx.x;
-  env.img = a.ref_img; env.W = a.W; env.H = a.H;
+  env.img = a.ref_img; env.W = a.W; env.H = a.H; env.slot = a.slot;
   TblStore st;
   st.tbl = s_tbl + threadIdx.x;
   float cost_arr[9 * DPE_MAX_IMAGES];
@@ -381,8 +194,8 @@ __device__ __forceinline__ void compact_range(const StageArgs& a, int& begin, in
   begin = imin(w * chunk, total);
   end = imin(begin + chunk, total);
 }
-__global__ void __launch_bounds__(CW_THREADS) k_weak_count(const __grid_constant__ KernelParams P) {
-  const StageArgs& a = P.a;
+__global__ void __launch_bounds__(CW_THREADS) k_weak_count(const __grid_constant__ StageArgs A) {
+  const StageArgs& a = A;
   int begin, end;
   compact_range(a, begin, end);
   const int lane = threadIdx.x & 31;
@@ -436,8 +249,8 @@ __global__ void __launch_bounds__(1024) k_weak_scan(int* __restrict__ scan, cons
     run[0] += c0; run[1] += c1;
   }
 }
-__global__ void __launch_bounds__(CW_THREADS) k_weak_scatter(const __grid_constant__ KernelParams P) {
-  const StageArgs& a = P.a;
+__global__ void __launch_bounds__(CW_THREADS) k_weak_scatter(const __grid_constant__ StageArgs A) {
+  const StageArgs& a = A;
   int begin, end;
   compact_range(a, begin, end);
   const int lane = threadIdx.x & 31;
@@ -468,6 +281,9 @@ struct WarpEnv {
   const float2* tbl36;  // strong-patch table of the centre pixel (final re-score), shared memory
   const float* img;
   int W, H;
+  int slot;
+  __device__ __forceinline__ const RefConst& rc() const { return c_rc[slot]; }
+  __device__ __forceinline__ const SrcConst& src(int v) const { return c_rc[slot].src[v]; }
   __device__ __forceinline__ float ref(int x, int y) const {
     return __ldg(&img[(size_t)iclamp(y, 0, H - 1) * W + iclamp(x, 0, W - 1)]);
   }
@@ -504,7 +320,7 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
   const bool writer = live && lane == 0;  // the lane that publishes this pixel's results
   const int W = a.W, H = a.H, N = rc.n_src, center = y * W + x;
   const int iter = a.iter;
-  WarpEnv env{S.tbl36, a.ref_img, W, H};
+  WarpEnv env{S.tbl36, a.ref_img, W, H, a.slot};
   GlobalRef ref{a.ref_img, W, H};
   WeakTab& T = S.T;
   // ---- set-up: anchors, strong-patch table + statistics (lane 0), deformable table (lanes 0..8)
@@ -717,7 +533,7 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
     const float3 m = plane_to_m(rc, final_plane);
     if (lane < nv) {
       const int v = vlist_lo;
-      const float cv = ncc_old(env, ps, rc, rc.src[v], final_plane, m, x, y);
+      const float cv = ncc_old(env, ps, v, final_plane, m, x, y);
       S.hcost[v] = cv;
       if (cv < 2.0f) taps += 36;
     }
@@ -729,10 +545,10 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
 
 constexpr int NTW = 128;  // threads per CTA of the weak sweep: 4 warps = 4 pixels in phase lock-step
 constexpr int WEAK_CTAS_PER_SM = 6;
-__global__ void __launch_bounds__(NTW, WEAK_CTAS_PER_SM) k_weak_list(const __grid_constant__ KernelParams P) {
+__global__ void __launch_bounds__(NTW, WEAK_CTAS_PER_SM) k_weak_list(const __grid_constant__ StageArgs A) {
   __shared__ WeakWarpSmem s_w[NTW / 32];
-  StageArgs a = P.a;
-  a.rc = &P.rc;
+  StageArgs a = A;
+  a.rc = &c_rc[a.slot];
   const int count = a.weak_count[a.colour];
   const int* list = a.weak_list + a.colour * a.list_stride;
   int taps = 0;
@@ -746,7 +562,7 @@ __global__ void __launch_bounds__(NTW, WEAK_CTAS_PER_SM) k_weak_list(const __gri
     const int i = g * warps_per_cta + wid;
     const bool live = i < count;
     const int center = list[live ? i : count - 1];
-    weak_update_warp(a, P.rc, center % a.W, center / a.W, s_w[wid], taps, live);
+    weak_update_warp(a, c_rc[a.slot], center % a.W, center / a.W, s_w[wid], taps, live);
   }
   flush_evals(a.eval_units, (unsigned)((taps + 18) / 36));
 }
@@ -757,9 +573,9 @@ enum LightOp { L_EXTRACT = 0, L_MEDIAN = 1, L_FINISH = 2, L_EDGE_INFO = 3, L_NEA
                L_LABEL_BOUNDARY = 8, L_FIT_COPY = 9 };
 
 template <int OP>
-__global__ void __launch_bounds__(256) k_light(const __grid_constant__ KernelParams P) {
-  StageArgs a = P.a;
-  a.rc = &P.rc;
+__global__ void __launch_bounds__(256) k_light(const __grid_constant__ StageArgs A) {
+  StageArgs a = A;
+  a.rc = &c_rc[a.slot];
   const int total = (OP == L_MEDIAN) ? a.W * ((a.H + 1) / 2) : a.W * a.H;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int x, y;
@@ -789,9 +605,9 @@ __global__ void __launch_bounds__(256) k_light(const __grid_constant__ KernelPar
 // full of WEAK pixels instead of one here and there in an image-sized launch.  A pixel another thread demoted
 // after the list was built (NeigbourUpdate) is skipped by the functions' own state test.
 template <int OP, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_list(const __grid_constant__ KernelParams P) {
-  StageArgs a = P.a;
-  a.rc = &P.rc;
+__global__ void __launch_bounds__(THREADS) k_list(const __grid_constant__ StageArgs A) {
+  StageArgs a = A;
+  a.rc = &c_rc[a.slot];
   const int n0 = a.weak_count[0], total = n0 + a.weak_count[1];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int center = i < n0 ? a.weak_list[i] : a.weak_list[a.list_stride + (i - n0)];
@@ -801,6 +617,12 @@ __global__ void __launch_bounds__(THREADS) k_list(const __grid_constant__ Kernel
     else if (OP == L_NEIGH) gen_neighbours_pixel(a, x, y);
     else if (OP == L_FIT) fit_plane_pixel(a, x, y);
   }
+}
+
+void launch_set_ref_const(int slot, const RefConst* rc, cudaStream_t stream) {
+  // n_src <= 31 sources are in use; the tail of src[] need not travel
+  const size_t bytes = offsetof(RefConst, src) + (size_t)rc->n_src * sizeof(SrcConst);
+  cudaMemcpyToSymbolAsync(c_rc, rc, bytes, (size_t)slot * sizeof(RefConst), cudaMemcpyHostToDevice, stream);
 }
 
 void launch_set_scale_tex(unsigned long long tex, cudaStream_t stream) {
@@ -820,16 +642,14 @@ void launch_init(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t stre
   KernelParams P = P0;
   P.a.tiles_x = (P.a.W + TILE_W - 1) / TILE_W;
   P.a.tiles_y = (P.a.H + 3) / 4;
-  k_full<OP_INIT><<<persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, CTAS_PER_SM), NT, 0, stream>>>(P);
+  k_full<OP_INIT><<<persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, CTAS_PER_SM), NT, 0, stream>>>(P.a);
   count(cfg);
 }
 void launch_classify_refine(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t stream) {
   KernelParams P = P0;
   P.a.tiles_x = (P.a.W + TILE_W - 1) / TILE_W;
   P.a.tiles_y = (P.a.H + 3) / 4;
-  const int g = persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, CTAS_PER_SM);
-  if (P.a.variants & DPE_VARIANT_CLASSIFY_PER_PIXEL) k_full<OP_CLASSIFY><<<g, NT, 0, stream>>>(P);
-  else k_classify_warp<<<g, NT, 0, stream>>>(P);
+  k_full<OP_CLASSIFY><<<persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, CTAS_PER_SM), NT, 0, stream>>>(P.a);
   count(cfg);
 }
 void launch_strong(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t stream) {
@@ -837,30 +657,30 @@ void launch_strong(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t st
   P.a.tiles_x = (P.a.W + TILE_W - 1) / TILE_W;
   P.a.tiles_y = (P.a.H + 7) / 8;
   const int g = persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, CTAS_PER_SM);
-  if (P.a.use_apd) k_half<OP_STRONG_EDGE><<<g, NT, 0, stream>>>(P);
-  else k_half<OP_STRONG><<<g, NT, 0, stream>>>(P);
+  if (P.a.use_apd) k_half<OP_STRONG_EDGE><<<g, NT, 0, stream>>>(P.a);
+  else k_half<OP_STRONG><<<g, NT, 0, stream>>>(P.a);
   count(cfg);
 }
 void launch_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream) {
-  k_weak_list<<<cfg.num_sms * WEAK_CTAS_PER_SM, NTW, 0, stream>>>(P);
+  k_weak_list<<<cfg.num_sms * WEAK_CTAS_PER_SM, NTW, 0, stream>>>(P.a);
   count(cfg);
 }
 void launch_compact_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream) {
   const int blocks = cfg.num_sms * CW_BLOCKS_PER_SM;
-  k_weak_count<<<blocks, CW_THREADS, 0, stream>>>(P);
+  k_weak_count<<<blocks, CW_THREADS, 0, stream>>>(P.a);
   k_weak_scan<<<1, 1024, 0, stream>>>(P.a.weak_scan, blocks * (CW_THREADS / 32), P.a.weak_count);
-  k_weak_scatter<<<blocks, CW_THREADS, 0, stream>>>(P);
+  k_weak_scatter<<<blocks, CW_THREADS, 0, stream>>>(P.a);
   count(cfg); count(cfg); count(cfg);
 }
 int compact_scan_entries(int num_sms) { return 2 * num_sms * CW_BLOCKS_PER_SM * (CW_THREADS / 32); }
 template <int OP>
 static void launch_light(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream) {
-  k_light<OP><<<cfg.num_sms * 8, 256, 0, stream>>>(P);
+  k_light<OP><<<cfg.num_sms * 8, 256, 0, stream>>>(P.a);
   count(cfg);
 }
 template <int OP, int THREADS>
 static void launch_list(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream, int blocks_per_sm) {
-  k_list<OP, THREADS><<<cfg.num_sms * blocks_per_sm, THREADS, 0, stream>>>(P);
+  k_list<OP, THREADS><<<cfg.num_sms * blocks_per_sm, THREADS, 0, stream>>>(P.a);
   count(cfg);
 }
 static inline bool full_image(const KernelParams& P) { return (P.a.variants & DPE_VARIANT_LIGHT_FULL_IMAGE) != 0; }
@@ -976,6 +796,9 @@ void launch_resize_linear(const float* src, int sw, int sh, float* dst, int dw, 
 // the linear filter returns the texel itself).
 struct DevEnvExact {
   const float2* tbl;
+  int slot;
+  __device__ __forceinline__ const RefConst& rc() const { return c_rc[slot]; }
+  __device__ __forceinline__ const SrcConst& src(int v) const { return c_rc[slot].src[v]; }
   __device__ __forceinline__ float tex(const SrcConst& sc, float u, float v) const {
     const float xb = u - 0.5f, yb = v - 0.5f;
     const float fx0 = floorf(xb), fy0 = floorf(yb);
@@ -989,43 +812,43 @@ struct DevEnvExact {
   __device__ __forceinline__ float2 pw(int t) const { return tbl[t * NT]; }
 };
 
-__global__ void __launch_bounds__(NT) k_cost_eval(const __grid_constant__ KernelParams P, int n_pix,
+__global__ void __launch_bounds__(NT) k_cost_eval(const __grid_constant__ StageArgs A, int n_pix,
                                                   const int* __restrict__ xy, const float4* __restrict__ planes,
                                                   int mode, float* __restrict__ out) {
   __shared__ float2 s_tbl[36 * NT];
-  const RefConst& rc = P.rc;
+  const RefConst& rc = c_rc[A.slot];
   const int i = blockIdx.x * NT + threadIdx.x;
   if (i >= n_pix) return;
   const int x = xy[2 * i], y = xy[2 * i + 1];
-  GlobalRef ref{P.a.ref_img, P.a.W, P.a.H};
+  GlobalRef ref{A.ref_img, A.W, A.H};
   TblStore st{s_tbl + threadIdx.x};
-  const PatchStats ps = build_patch(ref, x, y, st, P.a.cost_raw != 0, P.a.exact != 0);
+  const PatchStats ps = build_patch(ref, x, y, st, A.cost_raw != 0, A.exact != 0);
   const float3 m = plane_to_m(rc, planes[i]);
   if (mode == 0) {
-    DevEnv env{s_tbl + threadIdx.x, P.a.ref_img, P.a.W, P.a.H};
-    for (int v = 0; v < rc.n_src; ++v) out[(size_t)i * rc.n_src + v] = ncc_old(env, ps, rc, rc.src[v], planes[i], m, x, y);
+    DevEnv env{s_tbl + threadIdx.x, A.ref_img, A.W, A.H, A.slot};
+    for (int v = 0; v < rc.n_src; ++v) out[(size_t)i * rc.n_src + v] = ncc_old(env, ps, v, planes[i], m, x, y);
   } else {
-    DevEnvExact env{s_tbl + threadIdx.x};
-    for (int v = 0; v < rc.n_src; ++v) out[(size_t)i * rc.n_src + v] = ncc_old(env, ps, rc, rc.src[v], planes[i], m, x, y);
+    DevEnvExact env{s_tbl + threadIdx.x, A.slot};
+    for (int v = 0; v < rc.n_src; ++v) out[(size_t)i * rc.n_src + v] = ncc_old(env, ps, v, planes[i], m, x, y);
   }
 }
 void launch_cost_eval(const KernelParams& P, int n_pix, const int* xy, const float4* planes, int mode,
                       unsigned long long, float* out, const LaunchCfg& cfg, cudaStream_t stream) {
-  k_cost_eval<<<(n_pix + NT - 1) / NT, NT, 0, stream>>>(P, n_pix, xy, planes, mode, out);
+  k_cost_eval<<<(n_pix + NT - 1) / NT, NT, 0, stream>>>(P.a, n_pix, xy, planes, mode, out);
   count(cfg);
 }
 
-__global__ void k_geom_eval(const __grid_constant__ KernelParams P, int n_pix, const int* __restrict__ xy,
+__global__ void k_geom_eval(const __grid_constant__ StageArgs A, int n_pix, const int* __restrict__ xy,
                             const float4* __restrict__ planes, float* __restrict__ out) {
-  const RefConst& rc = P.rc;
+  const RefConst& rc = c_rc[A.slot];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pix) return;
   for (int v = 0; v < rc.n_src; ++v)
-    out[(size_t)i * rc.n_src + v] = geom_cost(P.a, rc, rc.src[v], planes[i], xy[2 * i], xy[2 * i + 1]);
+    out[(size_t)i * rc.n_src + v] = geom_cost(A, rc, rc.src[v], planes[i], xy[2 * i], xy[2 * i + 1]);
 }
 void launch_geom_eval(const KernelParams& P, int n_pix, const int* xy, const float4* planes, float* out,
                       const LaunchCfg& cfg, cudaStream_t stream) {
-  k_geom_eval<<<(n_pix + 127) / 128, 128, 0, stream>>>(P, n_pix, xy, planes, out);
+  k_geom_eval<<<(n_pix + 127) / 128, 128, 0, stream>>>(P.a, n_pix, xy, planes, out);
   count(cfg);
 }
 
@@ -1035,18 +858,18 @@ void launch_geom_eval(const KernelParams& P, int n_pix, const int* xy, const flo
 // views.  ROWS = tap rows fetched before any is consumed (texture results in flight per thread =
 // 6 * ROWS); MINB = CTAs per SM the register allocation is tuned for.
 template <int ROWS, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_ncc_bench(const __grid_constant__ KernelParams P, const float4* __restrict__ world_planes,
+__global__ void __launch_bounds__(NT, MINB) k_ncc_bench(const __grid_constant__ StageArgs A, const float4* __restrict__ world_planes,
                                                         int n_cand, float* __restrict__ out) {
   __shared__ float2 s_tbl[36 * NT];
   __shared__ float s_tile[SMW * (8 + 2 * HALO)];
-  StageArgs a = P.a;
-  const RefConst& rc = P.rc;
+  StageArgs a = A;
+  const RefConst& rc = c_rc[A.slot];
   const int tiles_x = (a.W + TILE_W - 1) / TILE_W, tiles_y = (a.H + 7) / 8;
   RefTile<8> tile;
   tile.s = s_tile;
   DevEnv env;
   env.tbl = s_tbl + threadIdx.x;
-  env.img = a.ref_img; env.W = a.W; env.H = a.H;
+  env.img = a.ref_img; env.W = a.W; env.H = a.H; env.slot = a.slot;
   TblStore st;
   st.tbl = s_tbl + threadIdx.x;
   const int offx[8] = {0, 0, -1, 1, -3, 3, 5, -7}, offy[8] = {-1, 1, 0, 0, 5, -5, 3, 2};
@@ -1068,7 +891,7 @@ __global__ void __launch_bounds__(NT, MINB) k_ncc_bench(const __grid_constant__ 
         pl.w = dist2origin(rc, nx, ny, pw.w > 0.f ? pw.w : 1.0f, pl);
         const float3 m = plane_to_m(rc, pl);
         for (int v = 0; v < rc.n_src; ++v) {
-          acc += ncc_old(env, ps, rc, rc.src[v], pl, m, x, y);
+          acc += ncc_old(env, ps, v, pl, m, x, y);
         }
       }
       out[y * a.W + x] = acc;
@@ -1080,8 +903,8 @@ void launch_ncc_bench(const KernelParams& P, const float4* world_planes, int n_c
   const int tiles = ((P.a.W + TILE_W - 1) / TILE_W) * ((P.a.H + 7) / 8);
   auto g = [&](int per_sm) { return persistent_grid(tiles, cfg.num_sms, per_sm); };
   switch (variant) {
-    case 0: k_ncc_bench<0, 4><<<g(4), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
-    case 1: k_ncc_bench<0, 3><<<g(3), NT, 0, stream>>>(P, world_planes, n_cand, out); break;
+    case 0: k_ncc_bench<0, 4><<<g(4), NT, 0, stream>>>(P.a, world_planes, n_cand, out); break;
+    case 1: k_ncc_bench<0, 3><<<g(3), NT, 0, stream>>>(P.a, world_planes, n_cand, out); break;
     default: break;
   }
   count(cfg);

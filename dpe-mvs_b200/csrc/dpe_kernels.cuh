@@ -18,6 +18,9 @@ struct LaunchCfg {
 // selects the scale whose layered image texture the following kernels sample (device-wide constant:
 // all kernels in flight on a device must be of the same scale — a stage is)
 void launch_set_scale_tex(unsigned long long tex, cudaStream_t stream);
+// copies a view-stage's folded cameras into constant-memory block `slot`, ordered on `stream` in front of the
+// kernels that use it (StageArgs::slot); the host copy may be reused as soon as the call returns
+void launch_set_ref_const(int slot, const RefConst* rc, cudaStream_t stream);
 
 // stage kernels (one view, one stage); all asynchronous on `stream`
 void launch_load(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream);

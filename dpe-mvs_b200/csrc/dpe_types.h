@@ -48,14 +48,15 @@ struct RefConst {
 
 // kernel variants (StageArgs::variants, test hook dpe_debug_set_variants)
 enum {
-  DPE_VARIANT_CLASSIFY_PER_PIXEL = 1,  // DepthToWeak + LocalRefine one thread per pixel (the definition, dpe_core.cuh)
-  DPE_VARIANT_CLASSIFY_MUL_ADD = 2,    // warp-cooperative form accumulating with separate multiply and add
-  DPE_VARIANT_LIGHT_FULL_IMAGE = 4     // anchor search / plane fit over the whole image instead of the WEAK list
+  DPE_VARIANT_LIGHT_FULL_IMAGE = 4     // label boundary / nearest strong / anchor search / plane fit over the whole image instead of the WEAK lists
 };
 
 // Kernel argument block for one (view, stage).
+#define DPE_RC_SLOTS 5  // folded-camera blocks in constant memory: one per stream of a stage + one for the test hooks
+
 struct StageArgs {
-  const RefConst* rc;
+  const RefConst* rc;    // set inside the kernels: &c_rc[slot]
+  int slot;              // which constant-memory RefConst block this view-stage uses
   const float* ref_img;  // W*H float, row-major (the reference image at this scale)
   int W, H;
   // PatchMatch state (DPE.h:61-81)

@@ -875,7 +875,7 @@ DPE_HDN void weak_update_pixel(const Env& env, const PatchStats& ps, const Stage
     for (int v = 0; v < N; ++v) {
       const int w = vw.get(v);
       if (w > 0) {
-        const float cv = ncc_old(env, ps, rc, rc.src[v], final_plane, m, x, y);
+        const float cv = ncc_old(env, ps, v, final_plane, m, x, y);
         c += w * cv;
         if (cv < 2.0f) taps += 36;
       }

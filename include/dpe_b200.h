@@ -168,9 +168,9 @@ DPE_API int dpe_set_cost_arithmetic(dpe_ctx* ctx, int mode);
  * makes a sweep race-free and bit-reproducible; 1 samples the reference's positions (own colour, read while
  * the same launch writes it: DPE.cu:1274-1278) for parity runs. */
 DPE_API int dpe_set_reference_race(dpe_ctx* ctx, int on);
-/* test hook: run earlier forms of some kernels, for A/B comparisons of results and speed.  Bits: 1 DepthToWeak +
- * LocalRefine one thread per pixel (the definition the warp-cooperative kernel is held to), 2 the warp-cooperative
- * form with separate multiply and add, 4 anchor search / plane fit over the whole image instead of the WEAK list. */
+/* test hook: run earlier forms of some kernels, for A/B comparisons of results and speed.  Bit 4: the WEAK-only
+ * steps (label-boundary walk, nearest strong pixel, anchor search, plane fit) as image-sized launches, one thread
+ * per pixel, instead of over the compacted WEAK lists. */
 DPE_API int dpe_debug_set_variants(dpe_ctx* ctx, int mask);
 /* test hook: scratch arrays of the view that ran last on the first stream.  what: 0 anchors (P x 9 short2),
  * 1 fit planes (P float4), 2 radius (P int32), 3 costs (P float), 4 weak_reliable (P u8), 5 nearest strong

@@ -34,6 +34,34 @@
 #endif
 #define clock64() (DPE_REF_SEED)
 
+// Measurement only: the reference follows every kernel launch with cudaDeviceSynchronize() (26 + 1 per
+// RunPatchMatch, DPE.cu:3150-3226), so the wall time its host thread spends inside those calls is the GPU time
+// of its kernels (minus a few microseconds of launch latency each).  The call sites are redirected to a timing
+// wrapper; with DPE_REF_TIMING=<file> set, the totals are written there at exit (bench.py --impl reference
+// reports them as the reference's GPU-only time).
+#include <chrono>
+namespace dpe_ref_timing {
+struct Totals {
+  double sync_wait_s = 0.0;
+  long long syncs = 0;
+  ~Totals() {
+    if (const char* path = getenv("DPE_REF_TIMING")) {
+      if (FILE* f = fopen(path, "w")) { fprintf(f, "{\"sync_wait_s\": %.6f, \"syncs\": %lld}\n", sync_wait_s, syncs); fclose(f); }
+    }
+  }
+};
+inline Totals& totals() { static Totals t; return t; }
+inline cudaError_t timed_sync() {
+  const auto t0 = std::chrono::steady_clock::now();
+  const cudaError_t e = (cudaDeviceSynchronize)();
+  Totals& t = totals();
+  t.sync_wait_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  t.syncs++;
+  return e;
+}
+}  // namespace dpe_ref_timing
+#define cudaDeviceSynchronize() (::dpe_ref_timing::timed_sync())
+
 typedef unsigned char uchar;
 #ifndef MIN
 #define MIN(a, b) ((a) > (b) ? (b) : (a))
@@ -184,6 +212,26 @@ class Mat {
   void convertTo(Mat& dst, int rtype, double alpha = 1.0, double beta = 0.0) const {
     const int cn = channels(), sd = depth(), dd = CV_MAT_DEPTH(rtype);
     Mat out(rows, cols, CV_MAKETYPE(dd, cn));
+    // plain typed loops for the conversions the reference makes per image (uchar <-> float, unscaled): the
+    // generic path below goes through a double and a switch per element
+    if (alpha == 1.0 && beta == 0.0 && sd == CV_8U && dd == CV_32F) {
+      for (int r = 0; r < rows; ++r) {
+        const uchar* sp = data + r * step.p[0]; float* dp = (float*)(out.data + r * out.step.p[0]);
+        for (int c = 0; c < cols * cn; ++c) dp[c] = (float)sp[c];
+      }
+      dst = out; return;
+    }
+    if (alpha == 1.0 && beta == 0.0 && sd == CV_32F && dd == CV_8U) {
+      for (int r = 0; r < rows; ++r) {
+        const float* sp = (const float*)(data + r * step.p[0]); uchar* dp = out.data + r * out.step.p[0];
+        for (int c = 0; c < cols * cn; ++c) { const float v = sp[c]; dp[c] = (uchar)(v < 0 ? 0 : (v > 255 ? 255 : (int)lrintf(v))); }
+      }
+      dst = out; return;
+    }
+    if (alpha == 1.0 && beta == 0.0 && sd == dd) {
+      for (int r = 0; r < rows; ++r) memcpy(out.data + r * out.step.p[0], data + r * step.p[0], out.step.p[0]);
+      dst = out; return;
+    }
     for (int r = 0; r < rows; ++r)
       for (int c = 0; c < cols * cn; ++c) {
         const double v = load(data + r * step.p[0] + c * depth_size(sd), sd) * alpha + beta;
@@ -242,6 +290,44 @@ inline void resize(const Mat& src_in, Mat& dst, Size dsize, double = 0, double =
   const int cn = src.channels(), d = src.depth();
   Mat out(dsize.height, dsize.width, src.type());
   const double sx_ = (double)src.cols / dsize.width, sy_ = (double)src.rows / dsize.height;
+  if (cn == 1 && (d == CV_32F || d == CV_8U)) {
+    // the same arithmetic as the generic path below, with the column taps tabulated once and typed rows
+    std::vector<int> x0(dsize.width), x1(dsize.width);
+    std::vector<float> fxv(dsize.width);
+    for (int dx = 0; dx < dsize.width; ++dx) {
+      float fx = (float)((dx + 0.5) * sx_ - 0.5);
+      int sx = (int)floorf(fx); fx -= sx;
+      if (sx < 0) { fx = 0; sx = 0; }
+      if (sx >= src.cols - 1) { fx = 0; sx = src.cols - 1; }
+      x0[dx] = sx; x1[dx] = MIN(sx + 1, src.cols - 1); fxv[dx] = fx;
+    }
+    for (int dy = 0; dy < dsize.height; ++dy) {
+      float fy = (float)((dy + 0.5) * sy_ - 0.5);
+      int sy = (int)floorf(fy); fy -= sy;
+      if (sy < 0) { fy = 0; sy = 0; }
+      if (sy >= src.rows - 1) { fy = 0; sy = src.rows - 1; }
+      const int sy1 = MIN(sy + 1, src.rows - 1);
+      if (d == CV_32F) {
+        const float* r0p = (const float*)(src.data + sy * src.step.p[0]); const float* r1p = (const float*)(src.data + sy1 * src.step.p[0]);
+        float* op = (float*)(out.data + dy * out.step.p[0]);
+        for (int dx = 0; dx < dsize.width; ++dx) {
+          const float fx = fxv[dx];
+          const float r0 = r0p[x0[dx]] * (1.f - fx) + r0p[x1[dx]] * fx, r1 = r1p[x0[dx]] * (1.f - fx) + r1p[x1[dx]] * fx;
+          op[dx] = (float)(double)(r0 * (1.f - fy) + r1 * fy);
+        }
+      } else {
+        const uchar* r0p = src.data + sy * src.step.p[0]; const uchar* r1p = src.data + sy1 * src.step.p[0];
+        uchar* op = out.data + dy * out.step.p[0];
+        for (int dx = 0; dx < dsize.width; ++dx) {
+          const float fx = fxv[dx];
+          const float r0 = (float)r0p[x0[dx]] * (1.f - fx) + (float)r0p[x1[dx]] * fx, r1 = (float)r1p[x0[dx]] * (1.f - fx) + (float)r1p[x1[dx]] * fx;
+          Mat::store(op + dx, CV_8U, r0 * (1.f - fy) + r1 * fy);
+        }
+      }
+    }
+    dst = out;
+    return;
+  }
   for (int dy = 0; dy < dsize.height; ++dy) {
     float fy = (float)((dy + 0.5) * sy_ - 0.5);
     int sy = (int)floorf(fy); fy -= sy;

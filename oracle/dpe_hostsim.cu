@@ -44,6 +44,9 @@ struct HostEnv {
   float2 tbl[36];
   const float* img;
   int W, H;
+  const RefConst* rcp;
+  const RefConst& rc() const { return *rcp; }
+  const SrcConst& src(int v) const { return rcp->src[v]; }
   float tex(const SrcConst& sc, float u, float v) const { return host_tex((const HostImage*)sc.tex, u, v); }
   float2 pw(int t) const { return tbl[t]; }
   float ref(int x, int y) const { return img[(size_t)iclamp(y, 0, H - 1) * W + iclamp(x, 0, W - 1)]; }
@@ -79,14 +82,14 @@ int dpe_hostsim_cost_eval(int W, int H, int full_w, int full_h, const float* ref
     rc->src[i].tex = (unsigned long long)&imgs[i];
   }
   for (int i = 0; i < n_pix; ++i) {
-    HostEnv env; env.img = ref_img; env.W = W; env.H = H;
+    HostEnv env; env.img = ref_img; env.W = W; env.H = H; env.rcp = rc;
     HostRef ref{ref_img, W, H};
     HostStore st{env.tbl};
     const int x = xy[2 * i], y = xy[2 * i + 1];
     const PatchStats ps = build_patch(ref, x, y, st, getenv("DPE_HOSTSIM_CENTRED") == nullptr, getenv("DPE_HOSTSIM_EXACT") != nullptr);
     const float4 pl = make_float4(planes[4 * i], planes[4 * i + 1], planes[4 * i + 2], planes[4 * i + 3]);
     const float3 m = plane_to_m(*rc, pl);
-    for (int v = 0; v < n_src; ++v) out[(size_t)i * n_src + v] = ncc_old(env, ps, *rc, rc->src[v], pl, m, x, y);
+    for (int v = 0; v < n_src; ++v) out[(size_t)i * n_src + v] = ncc_old(env, ps, v, pl, m, x, y);
   }
   delete rc;
   return 0;
@@ -188,7 +191,7 @@ static int hostsim_stage_impl(int W, int H, int full_w, int full_h, int n_src, c
       for (int x = (y + colour) & 1; x < W; x += 2) fn(x, y);
   };
   auto with_patch = [&](int x, int y, auto&& fn) {
-    HostEnv env; env.img = images[0]; env.W = W; env.H = H;
+    HostEnv env; env.img = images[0]; env.W = W; env.H = H; env.rcp = a.rc;
     HostStore st{env.tbl};
     const PatchStats ps = build_patch(ref, x, y, st, a.cost_raw != 0, a.exact != 0);
     unsigned ev = 0;

@@ -364,20 +364,23 @@ def _full_run(variants, grays, cams, drs, pairs, ns, prep, seed=11):
 
 
 def test_kernel_variants_give_identical_maps():
-    """The warp-cooperative DepthToWeak + LocalRefine kernel (pairs of (pixel, hypothesis) dealt to all lanes, view by
-    view) and the WEAK-list forms of the anchor search / plane fit against their one-thread-per-pixel definitions
-    (dpe_debug_set_variants): every map of every view after the whole schedule, bit for bit.  The scene has
-    low-texture planes, so the weak path and the classifier's WEAK branch are exercised."""
+    """The WEAK-list forms of the label-boundary walk, nearest-strong search, anchor search and plane fit (ordered
+    compaction + one thread per WEAK pixel) against the image-sized launches they replace (dpe_debug_set_variants):
+    every map of every view after the whole schedule, bit for bit.  The scene has low-texture planes, so the weak
+    path is exercised."""
     spec, grays, cams, drs, pairs, gt = small_scene("c4", 0.08, 5)
     ns = 2
     prep = _prep_for(grays, ns)
-    want = _full_run(1 | 4, grays, cams, drs, pairs, ns, prep)      # definitions: per-pixel classifier, full-image light kernels
+    want = _full_run(4, grays, cams, drs, pairs, ns, prep)          # image-sized launches
     got = _full_run(0, grays, cams, drs, pairs, ns, prep)           # product default
     n_weak = sum(int((m["state"] == capi.WEAK).sum()) for m in want)
     assert n_weak > 500, n_weak
     for v, (a, b) in enumerate(zip(got, want)):
         for key in ("depth", "normal", "state", "selected"):
-            assert np.array_equal(a[key], b[key]), (v, key, float((a[key] != b[key]).mean()))
+            x, y = np.ascontiguousarray(a[key]), np.ascontiguousarray(b[key])
+            if x.dtype == np.float32:       # bit patterns: NaN depths of degenerate planes compare equal to themselves
+                x, y = x.view(np.uint32), y.view(np.uint32)
+            assert np.array_equal(x, y), (v, key, float((x != y).mean()))
 
 
 def test_edge_cases_sizes_and_source_counts():

@@ -21,11 +21,13 @@ for (k, p) in capi.stage_schedule(ns):
     ctx.run_stage(k, p, 20261018); ctx.stage_commit()
 names = {0: "as-is/4", 1: "rows6/3"}
 out = []
-for var in sorted(names):
-    best, cs = 0.0, None
-    for view in (0, 5):
-        r, c = ctx.bench_ncc(view, var, 8, 3)
-        best = max(best, r); cs = c if view == 0 else cs
-    out.append(dict(variant=names[var], gunits=best / 1e9, checksum=cs))
-    print(out[-1], flush=True)
+for arith, aname in ((1, "fast"), (2, "reference, operation by operation")):
+    ctx.set_cost_arithmetic(arith)
+    for var in sorted(names):
+        best, cs = 0.0, None
+        for view in (0, 5):
+            r, c = ctx.bench_ncc(view, var, 8, 3)
+            best = max(best, r); cs = c if view == 0 else cs
+        out.append(dict(arithmetic=aname, variant=names[var], gunits=best / 1e9, checksum=cs))
+        print(out[-1], flush=True)
 (ROOT / "gpurun_out" / "ncc_study.json").write_text(json.dumps(out, indent=1))
