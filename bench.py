@@ -39,7 +39,11 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT / "dpe-mvs_b200"))
 
 SEED = 20261018
-WORKLOAD = "c2: 49 views 1600x1200, 10 src/view, 2 scales x 4 stages (DTU-shape synthetic)"
+WORKLOADS = {
+    "c2": "c2: 49 views 1600x1200, 10 src/view, 2 scales x 4 stages (DTU-shape synthetic)",
+    "c4": "c4: 20 views 3024x2016, 10 src/view, 3 scales x 4 stages, >= 60 % low-texture planes, weak=True edge=True (ETH3D-shape synthetic)",
+}
+WORKLOAD = WORKLOADS["c2"]
 
 
 # ------------------------------------------------------------------------------------------
@@ -164,10 +168,11 @@ def run_ours(args):
         cpu_group = dist.new_group(backend="gloo")
     lib = capi.load()
 
-    tag = "c2"
+    tag = args.config
+    workload = WORKLOADS[tag]
     folder = scene_dir(tag)
     if rank == 0:
-        ensure_scene("c2", None, tag)
+        ensure_scene(tag, None, tag)
     if use_dist:
         dist.barrier()
     grays, cams, drs, pairs = load_scene_arrays(folder)
@@ -330,44 +335,62 @@ def run_ours(args):
         tj = folder / "timing.json"
         os.environ["DPE_TIMING_JSON"] = str(tj)
         runs = []
-        for rep in range(3):        # the first call also brings up CUDA contexts (and, N > 1, the NCCL communicator) on the GPUs
+        weak_out = tag == "c4"      # BASELINE.json configs[3]: weak=True edge=True
+        for rep in range(3 if tag == "c2" else 1):        # the first call also brings up CUDA contexts (and, N > 1, the NCCL communicator) on the GPUs
             shutil.rmtree(folder / "DPE", ignore_errors=True)
             t0 = time.perf_counter()
-            DPE_MVS.dpe_mvs(str(folder), local if world == 1 else -1, False, False, False, True, False, False, False)
+            DPE_MVS.dpe_mvs(str(folder), local if world == 1 else -1, False, False, False, True, False, weak_out, weak_out)
             dt = time.perf_counter() - t0
             try:
                 bd = json.loads(tj.read_text())
             except Exception:
                 bd = None
             runs.append((dt, bd))
-        order = sorted(range(3), key=lambda i: runs[i][0])
-        e2e_s, bd = runs[order[1]]
+        order = sorted(range(len(runs)), key=lambda i: runs[i][0])
+        e2e_s, bd = runs[order[len(runs) // 2]]
         px = [(int(np.floor(W / (1 << (n_scales - 1 - k)) + 0.5)) * int(np.floor(H / (1 << (n_scales - 1 - k)) + 0.5))) for k in range(n_scales)]
         h2d = V * W * H + V * sum(5 * p for p in px)                 # images once (broadcast over NVLink) + edge(1)+label(4) per scale
         d2h = V * W * H + V * W * H * 4                              # nvJPEG luma back to host + depth.npy payload
         e2e = {"value": V / e2e_s, "unit": "depth maps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "seconds": e2e_s, "seconds_all_runs": [r[0] for r in runs], "statistic": "median of 3 calls",
-               "api": "DPE_MVS.dpe_mvs(dense_folder, depth=True)", "breakdown": bd}
+               "seconds": e2e_s, "seconds_all_runs": [r[0] for r in runs], "statistic": f"median of {len(runs)} call(s)",
+               "api": "DPE_MVS.dpe_mvs(dense_folder, depth=True" + (", weak=True, edge=True)" if weak_out else ")"), "breakdown": bd}
     if use_dist:
         dist.barrier(group=cpu_group)
 
-    # ---- cpu baseline: float64 oracle port of the NCC, one core, bounded sample
+    # ---- baseline leg (rank 0, N = 1): the reference has no CPU PatchMatch path, so the baseline BASELINE.json names is
+    # its own CUDA build on this box — a bounded sample (2 views, ~10 s) of the same scene, host stages on the host
+    # cores; the float64 NCC port on one core is kept beside it as the scalar-CPU figure
     cpu = None
     if rank == 0 and world == 1:
         cpu = cpu_baseline_port(grays, cams, pairs, prof)
+        try:
+            if tag == "c2" and (ROOT / "oracle" / "_ref" / "DPE_ref").exists():
+                ref = ReferenceSample(2, local)
+                ref.step()
+                dt, gpu_s = ref.step()
+                port = cpu
+                cpu = {"value": 2 / dt, "unit": "depth maps/s", "cores": 1, "kind": "reference", "sample": ref.describe(),
+                       "gpu_only_depth_maps_per_s": (2 / gpu_s) if gpu_s else None,
+                       "scalar_port": port}
+        except Exception as e:      # the baseline leg must not take the bench line down
+            cpu = dict(cpu or {}, reference_sample_error=str(e)[:200])
 
     if rank == 0:
         line = {
             "metric": "depth maps/s per scene", "value": value, "unit": "depth maps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "views": V, "width": W, "height": H, "src_per_view": len(pairs[0]),
+            "config": {"workload": workload, "views": V, "width": W, "height": H, "src_per_view": len(pairs[0]),
                        "view_stages_per_step": V * len(sched), "parallelism": f"reference views sharded over {world} GPU(s); per stage one in-place ncclAllGather per view slot of the depth atlas, issued by libdpe_b200.so behind each view's last kernel",
                        "l2": "inputs larger than L2 (per view-stage ~0.5 GB of state + 11 images; 49 views cycle through)",
                        "rng_seed": SEED,
                        "cost_arithmetic": {2: "reference, operation by operation (default)", 1: "reference moments, constant-folded homography (DPE_ARITH=fast)", 0: "centred (DPE_ARITH=centred)"}[arith]},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "value_fast_arithmetic": fast_value,
+            "vs_reference_sample": None if not (cpu and cpu.get("kind") == "reference") else {
+                "e2e_ratio": (e2e["value"] / cpu["value"]) if e2e else None,
+                "gpu_only_ratio": (value / cpu["gpu_only_depth_maps_per_s"]) if cpu.get("gpu_only_depth_maps_per_s") else None,
+                "note": "ours (49 views) against the 2-view reference sample of this same run; the driver computes the official ratio from --impl reference"},
             "wall_ms_per_step": wall_ms / args.steps, "allgather_ms_per_step": gather_ms / args.steps,
             "allgather_wait_ms_per_step_slowest_rank": gather_wait_ms / args.steps,
         }
@@ -411,10 +434,73 @@ def cpu_baseline_port(grays, cams, pairs, prof):
 
 
 # ------------------------------------------------------------------------------------------
+class ReferenceSample:
+    """The reference's own CUDA build (oracle/_ref/DPE_ref: unmodified sources, sm_100, RNG seed pinned) on a bounded
+    sample of the bench scene: the first M reference views, all stages, all 49 images present; the depth maps of
+    source-only views are supplied as files, because the reference reads its sources' depths.dmb from disk
+    (DPE.cpp:826-844).  Its GPU-only time is the wall time its host thread spends inside the cudaDeviceSynchronize
+    that follows every launch (oracle/cvshim: dpe_ref_timing), BASELINE.md section 3b."""
+
+    def __init__(self, M, local):
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import prep_cv2
+        self.prep_cv2 = prep_cv2
+        self.exe = ROOT / "oracle" / "_ref" / "DPE_ref"
+        self.M, self.local = M, local
+        self.folder = ensure_scene("c2", None, "c2")
+        grays, cams, drs, pairs = load_scene_arrays(self.folder)
+        self.V, (self.H, self.W), self.n_src = len(grays), grays[0].shape, len(pairs[0])
+        self.n_scales = 2
+        self.sample = Path(str(self.folder) + f"_refsample{M}")
+        shutil.rmtree(self.sample, ignore_errors=True)
+        self.sample.mkdir(parents=True)
+        os.symlink(self.folder / "images", self.sample / "images")
+        os.symlink(self.folder / "cams", self.sample / "cams")
+        with open(self.sample / "pair.txt", "w") as f:
+            f.write(f"{M}\n")
+            for v in range(M):
+                f.write(f"{v}\n{len(pairs[v])} " + " ".join(f"{j} 100.0" for j in pairs[v]) + "\n")
+        t0 = time.perf_counter()
+        self.prep = {v: [prep_cv2.problem_edges(grays[v], 1 << j)[1:] for j in range(self.n_scales)] for v in range(M)}
+        self.prep_s_per_view = (time.perf_counter() - t0) / M        # cv2 Canny / Hough / CCL: GetProblemEdges, not in the timed call
+
+    def _prepare(self):
+        shutil.rmtree(self.sample / "DPE", ignore_errors=True)
+        for v in range(self.V):
+            d = self.sample / "DPE" / f"{v:08d}"
+            d.mkdir(parents=True)
+            if v < self.M:
+                for j in range(self.n_scales):
+                    self.prep_cv2.write_dmb(d / f"edges_{j}.dmb", self.prep[v][j][0])
+                    self.prep_cv2.write_dmb(d / f"labels_{j}.dmb", self.prep[v][j][1])
+            else:
+                self.prep_cv2.write_dmb(d / "depths.dmb", np.load(self.folder / "gt" / f"{v:08d}_depth.npy").astype(np.float32))
+
+    def step(self):
+        """One timed call of the reference CLI; returns (wall seconds, GPU-only seconds)."""
+        self._prepare()
+        tfile = self.sample / "ref_timing.json"
+        env = dict(os.environ, DPE_REF_TIMING=str(tfile))
+        t0 = time.perf_counter()
+        p = subprocess.run([str(self.exe), str(self.sample), str(self.local), "0", "0", "0", "1", "0", "0", "0"], capture_output=True, text=True, env=env)
+        dt = time.perf_counter() - t0
+        if p.returncode != 0:
+            raise RuntimeError("DPE_ref failed: " + p.stderr[-500:])
+        try:
+            gpu_s = float(json.loads(tfile.read_text())["sync_wait_s"])
+        except Exception:
+            gpu_s = None
+        return dt, gpu_s
+
+    def describe(self):
+        return (f"{self.M} reference views of the 49-view c2 scene (1600x1200, {self.n_src} sources each, all 8 stages), unmodified "
+                f"reference CUDA build for sm_100 on one B200 through its CLI, host stages on the box's cores ({os.cpu_count()} present, "
+                f"single-threaded as written); images read from pre-decoded sidecars (no JPEG decode: favours the reference), "
+                f"edges/labels precomputed with cv2 ({self.prep_s_per_view:.2f} s per view, not timed: favours the reference), "
+                f"sources' depth maps supplied as files")
+
+
 def run_reference(args):
-    """The reference's own CUDA build on a bounded sample: M reference views of the c2 scene
-    (all 49 images present; the depth maps of source-only views are supplied as files, because
-    the reference reads sources' depths.dmb from disk, DPE.cpp:826-844)."""
     rank, world, local = dist_env()
     if rank != 0:
         return
@@ -425,63 +511,27 @@ def run_reference(args):
     if not exe.exists():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/DPE_ref is not built (run __graft_entry__.build() where /root/reference exists)"}))
         return
-    sys.path.insert(0, str(ROOT / "oracle"))
-    import prep_cv2
-    import synth
-    M = int(os.environ.get("DPE_REF_SAMPLE_VIEWS", "3"))
-    folder = ensure_scene("c2", None, "c2")
-    grays, cams, drs, pairs = load_scene_arrays(folder)
-    V = len(grays)
-    H, W = grays[0].shape
-    n_scales = 2
-    sample = Path(str(folder) + "_refsample")
-    shutil.rmtree(sample, ignore_errors=True)
-    sample.mkdir(parents=True)
-    os.symlink(folder / "images", sample / "images")
-    os.symlink(folder / "cams", sample / "cams")
-    with open(sample / "pair.txt", "w") as f:
-        f.write(f"{M}\n")
-        for v in range(M):
-            f.write(f"{v}\n{len(pairs[v])} " + " ".join(f"{j} 100.0" for j in pairs[v]) + "\n")
-    prep = {v: [prep_cv2.problem_edges(grays[v], 1 << j)[1:] for j in range(n_scales)] for v in range(M)}
-
-    def prepare():
-        shutil.rmtree(sample / "DPE", ignore_errors=True)
-        for v in range(V):
-            d = sample / "DPE" / f"{v:08d}"
-            d.mkdir(parents=True)
-            if v < M:
-                for j in range(n_scales):
-                    prep_cv2.write_dmb(d / f"edges_{j}.dmb", prep[v][j][0])
-                    prep_cv2.write_dmb(d / f"labels_{j}.dmb", prep[v][j][1])
-            else:
-                prep_cv2.write_dmb(d / "depths.dmb", np.load(folder / "gt" / f"{v:08d}_depth.npy").astype(np.float32))
-
-    def one_step():
-        prepare()
-        t0 = time.perf_counter()
-        p = subprocess.run([str(exe), str(sample), str(local), "0", "0", "0", "1", "0", "0", "0"], capture_output=True, text=True)
-        dt = time.perf_counter() - t0
-        if p.returncode != 0:
-            raise RuntimeError("DPE_ref failed: " + p.stderr[-500:])
-        return dt
-
+    M = int(os.environ.get("DPE_REF_SAMPLE_VIEWS", "5"))
+    ref = ReferenceSample(M, local)
     for _ in range(args.warmup):
-        one_step()
+        ref.step()
     sampler = ClockSampler(local)
     sampler.start()
-    times = [one_step() for _ in range(args.steps)]
+    runs = [ref.step() for _ in range(args.steps)]
     clocks = sampler.stop()
-    sec = float(np.mean(times))
+    sec = float(np.mean([r[0] for r in runs]))
+    gpu = [r[1] for r in runs if r[1] is not None]
+    gpu_s = float(np.mean(gpu)) if gpu else None
     value = M / sec
-    desc = (f"{M} reference views of the 49-view c2 scene (1600x1200, 10 sources each, all 8 stages), unmodified reference CUDA "
-            f"build for sm_100 on one B200, host stages on {os.cpu_count()} host cores (single-threaded as written); edges/labels "
-            f"precomputed with cv2 (not timed), sources' depth maps supplied as files")
     line = dict(base)
     line.update({"value": value, "ms_per_step": sec * 1e3,
-                 "config": {"workload": WORKLOAD, "sample_views": M, "width": W, "height": H, "src_per_view": len(pairs[0])},
-                 "cpu_baseline": {"value": value, "unit": "depth maps/s", "cores": 1, "kind": "reference", "sample": desc},
+                 "config": {"workload": WORKLOAD, "sample_views": M, "width": ref.W, "height": ref.H, "src_per_view": ref.n_src},
+                 "cpu_baseline": {"value": value, "unit": "depth maps/s", "cores": 1, "kind": "reference", "sample": ref.describe()},
                  "e2e": {"value": value, "unit": "depth maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "gpu_only": None if gpu_s is None else {"seconds_per_view": gpu_s / M, "depth_maps_per_s": M / gpu_s,
+                                                         "how": "wall time inside the cudaDeviceSynchronize after each of the reference's launches"},
+                 "host_split": None if gpu_s is None else {"gpu_s_per_view": gpu_s / M, "host_s_per_view": (sec - gpu_s) / M,
+                                                           "prep_s_per_view_not_timed": ref.prep_s_per_view},
                  "clocks": clocks, "gpu_launches": 0})
     print(json.dumps(line))
 
@@ -492,6 +542,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS), help="c2 = the headline workload (default); c4 = the weak-texture scene")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
