@@ -60,10 +60,6 @@ struct ViewData {
   int cur_buf = 0;     // which of the two map buffers holds them (a stage at a new scale writes the other one)
 };
 
-struct FuseData {
-  float* depth = nullptr; float* normal = nullptr; uint8_t* state = nullptr; uint8_t* bgr = nullptr; uint8_t* mask = nullptr;
-};
-
 struct Scratch {
   float4* planes = nullptr; float* costs = nullptr; uint32_t* selected = nullptr; uint4* view_w = nullptr;
   uint8_t* state = nullptr; float4* fit_planes = nullptr; int* radius = nullptr; short2* edge_neigh = nullptr;
@@ -170,8 +166,13 @@ struct dpe_ctx {
   int variants = 0;           // dpe_debug_set_variants
   // scratch
   std::vector<Scratch> scratch;
-  // device fusion (dpe_fuse_*): per-view maps at full resolution + the fused cloud (host)
-  std::vector<FuseData> fuse;
+  // device fusion (dpe_fuse_*): maps of all views at full resolution (own copies, or the carried maps themselves on
+  // one GPU), colour images, marks, and the fused cloud (host)
+  float4* fuse_planes = nullptr; uint8_t* fuse_state = nullptr;          // what dpe_fuse_run reads
+  float4* fuse_planes_own = nullptr; uint8_t* fuse_state_own = nullptr;  // allocations (host-provided or gathered maps)
+  uint8_t* fuse_bgr = nullptr; uint16_t* fuse_mask = nullptr;
+  std::vector<char> fuse_have;
+  bool fuse_resident = false;
   std::vector<FusedPointDev> cloud;
   // initial XORWOW states per scale for rng_seed (dpe_rng.h): table[k][y*w+x] = curand_init(seed, y, x)
   std::vector<Xorwow*> rng_table;
@@ -296,8 +297,10 @@ static void free_scene(dpe_ctx* ctx) {
   ctx->view_done.clear();
   dfree(ctx->exp_depth); dfree(ctx->exp_normal); dfree(ctx->exp_weak);
   ctx->exp_depth = nullptr; ctx->exp_normal = nullptr; ctx->exp_weak = nullptr;
-  for (auto& f : ctx->fuse) { dfree(f.depth); dfree(f.normal); dfree(f.state); dfree(f.bgr); dfree(f.mask); }
-  ctx->fuse.clear(); ctx->cloud.clear();
+  dfree(ctx->fuse_planes_own); dfree(ctx->fuse_state_own); dfree(ctx->fuse_bgr); dfree(ctx->fuse_mask);
+  ctx->fuse_planes_own = nullptr; ctx->fuse_state_own = nullptr; ctx->fuse_bgr = nullptr; ctx->fuse_mask = nullptr;
+  ctx->fuse_planes = nullptr; ctx->fuse_state = nullptr; ctx->fuse_have.clear(); ctx->fuse_resident = false;
+  ctx->cloud.clear();
   for (auto p : ctx->rng_table) dfree(p);
   ctx->rng_table.clear(); ctx->rng_ready = false;
   dfree(ctx->zero_edge); ctx->zero_edge = nullptr;
@@ -1013,36 +1016,126 @@ int dpe_set_view_order(dpe_ctx* ctx, int sequential) {
 }
 
 // ---- device fusion (RunFusion, DPE.cpp:1220-1370) ---------------------------------------------
+// Fusion reads, for every view, its final (world normal, depth) planes, pixel states and colour image, and keeps a
+// mark per pixel.  The maps either come from the host (dpe_fuse_set_view: tests, external maps) or are the ones
+// the last stage left on the GPUs (dpe_fuse_prepare: no trip through the host; with several ranks the blocks are
+// all-gathered with NCCL so that every rank holds the maps of every view its own views use as sources).
+static int fuse_slot(const dpe_ctx* ctx, int view) {  // rank-major: the layout one all-gather of padded blocks produces
+  if (ctx->n_ranks == 1 || view >= ctx->n_problems) return view;
+  int first = 0, count = 0, r = 0;
+  for (; r < ctx->n_ranks; ++r) {
+    dpe_shard_range(ctx->n_problems, ctx->n_ranks, r, &first, &count);
+    if (view < first + count) break;
+  }
+  return r * ctx->slots_per_rank + (view - first);
+}
+static int fuse_total_slots(const dpe_ctx* ctx) {
+  return ctx->n_ranks == 1 ? ctx->n_views : ctx->slots_per_rank * ctx->n_ranks;
+}
+static int fuse_ensure(dpe_ctx* ctx, bool own_maps) {
+  const size_t P = (size_t)ctx->W * ctx->H;
+  const size_t slots = (size_t)fuse_total_slots(ctx);
+  if (own_maps && !ctx->fuse_planes_own) {
+    CK(dmalloc(&ctx->fuse_planes_own, slots * P * sizeof(float4)));
+    CK(dmalloc(&ctx->fuse_state_own, slots * P));
+  }
+  if (!ctx->fuse_bgr) {
+    CK(dmalloc(&ctx->fuse_bgr, (size_t)ctx->n_views * P * 3));
+    CK(cudaMemsetAsync(ctx->fuse_bgr, 0, (size_t)ctx->n_views * P * 3, ctx->upload_stream));
+  }
+  if (!ctx->fuse_mask) CK(dmalloc(&ctx->fuse_mask, (size_t)ctx->n_views * P * sizeof(uint16_t)));
+  if (ctx->fuse_have.empty()) ctx->fuse_have.assign(ctx->n_views, 0);
+  return DPE_OK;
+}
+
 int dpe_fuse_set_view(dpe_ctx* ctx, int view, const float* depth, const float* normal3, const uint8_t* state, const uint8_t* bgr) {
   if (!ctx || view < 0 || view >= ctx->n_views || !depth || !normal3 || !state || !bgr) return DPE_ERR_ARG;
+  if (ctx->n_ranks != 1) FAIL(DPE_ERR_STATE, "host-provided fusion maps need an unsharded context");
   CK(cudaSetDevice(ctx->device));
-  if (ctx->fuse.empty()) ctx->fuse.assign(ctx->n_views, FuseData());
-  FuseData& f = ctx->fuse[view];
+  if (int rc = fuse_ensure(ctx, true)) return rc;
+  ctx->fuse_resident = false;
   const size_t P = (size_t)ctx->W * ctx->H;
-  if (!f.depth) {
-    CK(dmalloc(&f.depth, P * 4)); CK(dmalloc(&f.normal, P * 12)); CK(dmalloc(&f.state, P)); CK(dmalloc(&f.bgr, P * 3));
-    CK(dmalloc(&f.mask, P));
+  std::vector<float4> h(P);
+  for (size_t i = 0; i < P; ++i) h[i] = make_float4(normal3[3 * i], normal3[3 * i + 1], normal3[3 * i + 2], depth[i]);
+  CK(cudaMemcpy(ctx->fuse_planes_own + (size_t)view * P, h.data(), P * sizeof(float4), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->fuse_state_own + (size_t)view * P, state, P, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->fuse_bgr + (size_t)view * P * 3, bgr, P * 3, cudaMemcpyHostToDevice));
+  ctx->fuse_have[view] = 1;
+  return DPE_OK;
+}
+
+int dpe_fuse_set_color(dpe_ctx* ctx, int view, const uint8_t* bgr) {
+  if (!ctx || view < 0 || view >= ctx->n_views || !bgr) return DPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = fuse_ensure(ctx, false)) return rc;
+  const size_t P = (size_t)ctx->W * ctx->H;
+  CK(cudaMemcpyAsync(ctx->fuse_bgr + (size_t)view * P * 3, bgr, P * 3, cudaMemcpyHostToDevice, ctx->upload_stream));
+  return DPE_OK;
+}
+
+int dpe_fuse_broadcast_colors(dpe_ctx* ctx, int root) {
+  if (!ctx || root < 0 || root >= ctx->n_ranks) return DPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = fuse_ensure(ctx, false)) return rc;
+  if (ctx->n_ranks > 1) {
+    if (!ctx->comm) FAIL(DPE_ERR_STATE, "no communicator");
+    NCK(nccl_api().Broadcast(ctx->fuse_bgr, ctx->fuse_bgr, (size_t)ctx->n_views * ctx->W * ctx->H * 3, ncclUint8, root, ctx->comm, ctx->upload_stream));
   }
-  CK(cudaMemcpy(f.depth, depth, P * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(f.normal, normal3, P * 12, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(f.state, state, P, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(f.bgr, bgr, P * 3, cudaMemcpyHostToDevice));
+  CK(cudaStreamSynchronize(ctx->upload_stream));
+  return DPE_OK;
+}
+
+int dpe_fuse_prepare(dpe_ctx* ctx) {
+  if (!ctx) return DPE_ERR_ARG;
+  if (!ctx->committed) FAIL(DPE_ERR_STATE, "scene not committed");
+  if (ctx->stage_open) if (int rc = dpe_stage_end(ctx)) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const int top = ctx->n_scales - 1;
+  for (int li = 0; li < ctx->n_local; ++li)
+    if (ctx->views[ctx->first_view + li].cur_scale != top) FAIL(DPE_ERR_STATE, "fusion needs the maps of the finest scale (run the whole schedule first)");
+  const size_t P = (size_t)ctx->W * ctx->H;
+  const int b = map_buffer_of_scale(ctx, top);  // = 0: stride P per view, the local block is contiguous
+  if (ctx->n_ranks == 1 && ctx->first_view == 0) {
+    if (int rc = fuse_ensure(ctx, false)) return rc;
+    ctx->fuse_planes = ctx->maps_planes[b]; ctx->fuse_state = ctx->maps_state[b];  // the carried maps themselves
+  } else {
+    if (int rc = fuse_ensure(ctx, true)) return rc;
+    if (ctx->n_ranks > 1 && !ctx->comm) FAIL(DPE_ERR_STATE, "no communicator");
+    const size_t spr = (size_t)ctx->slots_per_rank;
+    float4* mine_p = ctx->fuse_planes_own + (size_t)ctx->rank * spr * P;
+    uint8_t* mine_s = ctx->fuse_state_own + (size_t)ctx->rank * spr * P;
+    CK(cudaMemcpyAsync(mine_p, ctx->maps_planes[b], (size_t)ctx->n_local * P * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->comm_stream));
+    CK(cudaMemcpyAsync(mine_s, ctx->maps_state[b], (size_t)ctx->n_local * P, cudaMemcpyDeviceToDevice, ctx->comm_stream));
+    if (ctx->n_ranks > 1) {
+      NCK(nccl_api().AllGather(mine_p, ctx->fuse_planes_own, spr * P * 4, ncclFloat, ctx->comm, ctx->comm_stream));
+      NCK(nccl_api().AllGather(mine_s, ctx->fuse_state_own, spr * P, ncclUint8, ctx->comm, ctx->comm_stream));
+    }
+    CK(cudaStreamSynchronize(ctx->comm_stream));
+    ctx->fuse_planes = ctx->fuse_planes_own; ctx->fuse_state = ctx->fuse_state_own;
+  }
+  ctx->fuse_resident = true;
+  for (int v = 0; v < ctx->n_views; ++v) ctx->fuse_have[v] = v < ctx->n_problems ? 1 : 0;
   return DPE_OK;
 }
 
 int dpe_fuse_run(dpe_ctx* ctx, size_t* n_points) {
   if (!ctx || !n_points) return DPE_ERR_ARG;
-  if (ctx->fuse.empty()) FAIL(DPE_ERR_STATE, "no fusion inputs (dpe_fuse_set_view)");
+  if (ctx->fuse_have.empty()) FAIL(DPE_ERR_STATE, "no fusion inputs (dpe_fuse_set_view / dpe_fuse_prepare)");
   CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->upload_stream));
+  if (!ctx->fuse_resident) { ctx->fuse_planes = ctx->fuse_planes_own; ctx->fuse_state = ctx->fuse_state_own; }
   const int V = ctx->n_views, W = ctx->W, H = ctx->H;
   const size_t P = (size_t)W * H;
   std::vector<FuseView> hv(V);
+  CK(cudaMemset(ctx->fuse_mask, 0, (size_t)V * P * sizeof(uint16_t)));
   for (int v = 0; v < V; ++v) {
     FuseView& fv = hv[v];
     memset(&fv, 0, sizeof(fv));
-    const FuseData& f = ctx->fuse[v];
-    fv.depth = f.depth; fv.normal = f.normal; fv.state = f.state; fv.bgr = f.bgr; fv.mask = f.mask;
-    if (f.mask) CK(cudaMemset(f.mask, 0, P));
+    if (ctx->fuse_have[v]) {
+      const size_t slot = ctx->fuse_resident ? (size_t)fuse_slot(ctx, v) : (size_t)v;
+      fv.planes = ctx->fuse_planes + slot * P; fv.state = ctx->fuse_state + slot * P;
+    }
+    fv.bgr = ctx->fuse_bgr + (size_t)v * P * 3; fv.mask = ctx->fuse_mask + (size_t)v * P;
     const HostCam& c = ctx->views[v].cam;
     for (int i = 0; i < 9; ++i) { fv.K[i] = (float)c.K[i]; fv.R[i] = (float)c.R[i]; }
     for (int i = 0; i < 3; ++i) fv.t[i] = (float)c.t[i];
@@ -1057,12 +1150,15 @@ int dpe_fuse_run(dpe_ctx* ctx, size_t* n_points) {
   const size_t temp_bytes = fuse_select_temp_bytes((int)P);
   CK(dmalloc(&temp, temp_bytes ? temp_bytes : 1));
   ctx->cloud.clear();
-  for (int i = 0; i < V; ++i) {  // views in order: a view sees every mark of the views before it
-    if (!hv[i].depth) continue;
+  // resident maps: this rank's block of views; host-provided maps: every view that has maps.  Views in order: a
+  // view sees every mark of the views before it.
+  const int v0 = ctx->fuse_resident ? ctx->first_view : 0, v1 = ctx->fuse_resident ? ctx->first_view + ctx->n_local : V;
+  for (int i = v0; i < v1; ++i) {
+    if (!hv[i].planes) continue;
     FuseSrcList sl; memset(&sl, 0, sizeof(sl));
     const std::vector<int>& src = ctx->views[i].src;
     sl.n = (int)src.size();
-    for (int j = 0; j < sl.n; ++j) sl.id[j] = ctx->fuse[src[j]].depth ? src[j] : -1;
+    for (int j = 0; j < sl.n; ++j) sl.id[j] = ctx->fuse_have[src[j]] ? src[j] : -1;
     launch_fuse_view(dv, i, sl, W, H, pts, accept, ctx->num_sms, 0);
     launch_fuse_select(temp, temp_bytes, pts, accept, sel, d_n, (int)P, 0);
     ctx->launches += 2;

@@ -5,9 +5,12 @@
 // (< 1 %) and normal angle (< 10 deg), accept the point if sum exp(-(e + 200 dd + 10 ang)) exceeds
 // 0.3 (0.45 for WEAK pixels) per consistent view, and mark the source pixels it used so that later
 // pixels / views skip them.  Here views are still processed in order (one launch per view: a later view
-// sees every mark of an earlier one), the pixels of a view in parallel; marks are plain byte stores.  The
-// one semantic difference: two pixels of the SAME view that land on the same source pixel can both use it,
-// where the reference's raster order gives it to the first — a slightly denser cloud, same points.
+// sees every mark of an earlier one), the pixels of a view in parallel.  A mark records WHICH view set it
+// (view index + 1), and a launch ignores the marks of its own view, so what a pixel sees never depends on
+// how the launch was scheduled: the cloud is the same from run to run.  The one semantic difference: two
+// pixels of the SAME view that land on the same source pixel both use it, where the reference's raster order
+// gives it to the first — a slightly denser cloud, same points.  With several GPUs every rank fuses its own
+// block of views against its own marks (marks do not cross ranks), which adds duplicates at the seams.
 // Accepted points are compacted per view with cub::DeviceSelect (stable: points come out in raster
 // order, like the reference's) and appended to the host cloud.
 #include <cuda_runtime.h>
@@ -35,14 +38,16 @@ __device__ __forceinline__ void fuse_project(const FuseView& c, const float X[3]
 __global__ void __launch_bounds__(256) k_fuse_view(const FuseView* __restrict__ views, const int i, const FuseSrcList srcs, const int W,
                                                    const int H, FusedPointDev* __restrict__ pts, uint8_t* __restrict__ accept) {
   const FuseView& ref = views[i];
+  const uint16_t epoch = (uint16_t)(i + 1);
   const int total = W * H;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     accept[idx] = 0;
-    if (ref.mask[idx] == 1) continue;
-    const float ref_depth = ref.depth[idx];
+    if (ref.mask[idx] != 0) continue;  // marked by an earlier view (a view is never its own source)
+    const float4 rp = ref.planes[idx];
+    const float ref_depth = rp.w;
     if (ref_depth <= 0.0f) continue;
     const int r = idx / W, c = idx - r * W;
-    const float rn0 = ref.normal[3 * idx], rn1 = ref.normal[3 * idx + 1], rn2 = ref.normal[3 * idx + 2];
+    const float rn0 = rp.x, rn1 = rp.y, rn2 = rp.z;
     float X[3];
     fuse_world_point(ref, (float)c, (float)r, ref_depth, X);
     int num_consistent = 0;
@@ -53,21 +58,23 @@ __global__ void __launch_bounds__(256) k_fuse_view(const FuseView* __restrict__ 
       const int s = srcs.id[j];
       if (s < 0) continue;
       const FuseView& sv = views[s];
-      if (sv.depth == nullptr) continue;
+      if (sv.planes == nullptr) continue;
       float u, v, pd;
       fuse_project(sv, X, &u, &v, &pd);
       const int sr = (int)(v + 0.5f), sc = (int)(u + 0.5f);
       if (!(sc >= 0 && sc < W && sr >= 0 && sr < H)) continue;
       const int sidx = sr * W + sc;
-      if (sv.mask[sidx] == 1) continue;
-      const float sd = sv.depth[sidx];
+      const uint16_t sm = sv.mask[sidx];
+      if (sm != 0 && sm != epoch) continue;  // marks of this launch do not count (see the header comment)
+      const float4 sp4 = sv.planes[sidx];
+      const float sd = sp4.w;
       if (sd <= 0.0f) continue;
       float Y[3], bu, bv;
       fuse_world_point(sv, (float)sc, (float)sr, sd, Y);
       fuse_project(ref, Y, &bu, &bv, &pd);
       const float reproj = sqrtf((c - bu) * (c - bu) + (r - bv) * (r - bv));
       const float rel = fabsf(pd - ref_depth) / ref_depth;
-      float angle = acosf(rn0 * sv.normal[3 * sidx] + rn1 * sv.normal[3 * sidx + 1] + rn2 * sv.normal[3 * sidx + 2]);
+      float angle = acosf(rn0 * sp4.x + rn1 * sp4.y + rn2 * sp4.z);
       if (angle != angle) angle = 0.0f;
       if (reproj < 2.0f && rel < 0.01f && angle < 0.174533f) {
         used[j] = sidx;
@@ -82,7 +89,7 @@ __global__ void __launch_bounds__(256) k_fuse_view(const FuseView* __restrict__ 
       for (int j = 0; j < srcs.n; ++j) {
         if (used[j] < 0) continue;
         const FuseView& sv = views[srcs.id[j]];
-        sv.mask[used[j]] = 1;
+        sv.mask[used[j]] = epoch;
         const uint8_t* sp = sv.bgr + 3 * (size_t)used[j];
         col[0] += sp[0]; col[1] += sp[1]; col[2] += sp[2];
       }

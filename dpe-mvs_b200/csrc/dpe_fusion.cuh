@@ -7,11 +7,10 @@
 namespace dpe {
 
 struct FuseView {
-  const float* depth;    // H*W, 0 = invalid; nullptr = view has no maps (source-only image)
-  const float* normal;   // H*W*3, world space
+  const float4* planes;  // H*W (world normal, depth); depth 0 = invalid; nullptr = view has no maps (source-only image)
   const uint8_t* state;  // PixelState
   const uint8_t* bgr;    // H*W*3
-  uint8_t* mask;         // H*W, 1 = already fused into a point
+  uint16_t* mask;        // H*W: 0 = free, e = fused into a point while view e - 1 was the reference view
   float K[9], R[9], t[3], C[3];
 };
 struct FuseSrcList {

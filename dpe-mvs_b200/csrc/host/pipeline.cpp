@@ -173,6 +173,13 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
   const std::string out_root = dense + "/DPE";
   mkdir(out_root.c_str(), 0777);
 
+  if (fusion && file_exists(dense + "/blocks")) {
+    // RunFusion gates pixels with <dense>/blocks/mask_<id>.jpg when that folder exists (DPE.cpp:1243-1247, 1296);
+    // that gate is not implemented here, and silently fusing without it would give a different cloud
+    std::cerr << "DPE-MVS: " << dense << "/blocks exists: fusion with block masks is not supported\n";
+    return 1;
+  }
+
   // ---- GenerateSampleList --------------------------------------------------------------------
   std::vector<ProblemDesc> problems;
   if (!read_pairs(dense + "/pair.txt", &problems) || problems.empty()) {
@@ -342,6 +349,36 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     });
     prep_done_at = now_s();
   });
+  // ---- fusion: colour images (cv::IMREAD_COLOR, DPE.cpp:1253) decode in the background too -----------------------
+  std::vector<uint8_t> color_slab;
+  std::atomic<int> color_bad(0);
+  std::thread color_thread;
+  if (fusion) {
+    color_slab.resize(P * 3 * (size_t)n_problems);
+    color_thread = std::thread([&]() {
+      const int n_dec = std::max(1, std::min(4, n_problems));
+      std::vector<JpegDecoder*> cd(n_dec, nullptr);
+      std::atomic<int> next_dec(0);
+      parallel_for(n_problems, n_dec, [&](int v) {
+        thread_local int my = -1;
+        thread_local const void* owner = nullptr;
+        if (my < 0 || owner != (const void*)&cd) {
+          my = next_dec++; owner = (const void*)&cd;
+          cudaSetDevice(gpus[0]);
+          std::string e; cd[my] = jpeg_decoder_create(&e);
+        }
+        std::vector<uint8_t> c;
+        std::string e;
+        int w = 0, h = 0;
+        uint8_t* dst = color_slab.data() + P * 3 * (size_t)v;
+        if (cd[my] && jpeg_decode_bgr(cd[my], image_path(v), &c, &w, &h, &e) && w == width && h == height) memcpy(dst, c.data(), P * 3);
+        else  // grey-only JPEG: replicate luma (what cv::imread(IMREAD_COLOR) returns for it)
+          for (size_t i = 0; i < P; ++i) dst[3 * i] = dst[3 * i + 1] = dst[3 * i + 2] = gray_slab[P * v + i];
+      });
+      for (auto* d : cd) jpeg_decoder_destroy(d);
+    });
+  }
+
   auto wait_prep = [&](int v) {
     std::unique_lock<std::mutex> lk(prep_m);
     prep_cv.wait(lk, [&]() { return prep_left[v] == 0; });
@@ -352,6 +389,7 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
   tm.ctx = now_s() - t_ctx0;
   auto fail = [&](const std::string& what) {
     if (prep_thread.joinable()) prep_thread.join();
+    if (color_thread.joinable()) color_thread.join();
     if (G > 1) dpe_comm_reset_all();
     destroy_all();
     jpeg_decoder_destroy(dec);
@@ -419,7 +457,9 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
 
   // ---- one worker per GPU: scene upload, the whole schedule, export of its views ----------------------
   std::atomic<bool> abort_flag(false);
-  std::vector<double> t_upload(G, 0.0), t_stages(G, 0.0), t_prep_wait(G, 0.0), t_up_views(G, 0.0), t_up_commit(G, 0.0);
+  std::vector<double> t_upload(G, 0.0), t_stages(G, 0.0), t_prep_wait(G, 0.0), t_up_views(G, 0.0), t_up_commit(G, 0.0), t_fuse(G, 0.0);
+  std::vector<std::vector<float>> cloud_xyz(G);
+  std::vector<std::vector<uint8_t>> cloud_bgr(G);
   auto worker = [&](int g) {
     dpe_ctx* c = ctxs[g];
     auto bad = [&](const char* what) {
@@ -487,6 +527,23 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
       }
     }
     t_stages[g] = now_s() - ts0;
+    if (fusion) {
+      // the maps stay where the last stage left them: all-gather of the final planes + states (NCCL), colours
+      // uploaded by the first GPU and broadcast, then every GPU fuses its own block of views
+      const double tf0 = now_s();
+      if (dpe_fuse_prepare(c)) return bad("fuse_prepare");
+      if (g == 0) {
+        if (color_thread.joinable()) color_thread.join();
+        for (int v = 0; v < n_problems; ++v)
+          if (dpe_fuse_set_color(c, v, color_slab.data() + P * 3 * (size_t)v)) return bad("fuse_set_color");
+      }
+      if (dpe_fuse_broadcast_colors(c, 0)) return bad("fuse_broadcast_colors");
+      size_t n_points = 0;
+      if (dpe_fuse_run(c, &n_points)) return bad("fuse_run");
+      cloud_xyz[g].resize(n_points * 3); cloud_bgr[g].resize(n_points * 3);
+      if (n_points && dpe_fuse_get(c, cloud_xyz[g].data(), cloud_bgr[g].data())) return bad("fuse_get");
+      t_fuse[g] = now_s() - tf0;
+    }
   };
   t0 = now_s();
   if (G == 1) worker(0);
@@ -503,37 +560,27 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     tm.upload = std::max(tm.upload, t_upload[g]); tm.stages = std::max(tm.stages, t_stages[g]);
     tm.prep_wait = std::max(tm.prep_wait, t_prep_wait[g]);
   }
-  tm.output = std::max(0.0, now_s() - t0 - tm.upload - tm.stages);  // what the writers needed beyond the last stage
+  { double mf = 0; for (int g = 0; g < G; ++g) mf = std::max(mf, t_fuse[g]);
+    tm.output = std::max(0.0, now_s() - t0 - tm.upload - tm.stages - mf); }  // what the writers needed beyond the last stage
   for (int g = 0; g < G; ++g) if (!errs[g].empty()) return fail(errs[g]);
   if (write_fail.load()) return fail("cannot write the .npy outputs");
   for (int g = 0; g < G; ++g) { tm.gpu_ms = std::max(tm.gpu_ms, dpe_stage_gpu_ms(ctxs[g])); tm.launches += dpe_kernel_launches(ctxs[g]); }
 
+  if (color_thread.joinable()) color_thread.join();
   if (fusion) {
-    // on the device of the first context: maps of every problem view + colour images go up, the cloud comes back
+    // the ranks' clouds in rank order = view order (ExportPointCloud, DPE.cpp:532-572)
     t0 = now_s();
-    dpe_ctx* fc = ctxs[0];
-    std::vector<uint8_t> color;
-    std::vector<float> fd(P), fn(P * 3);
-    std::vector<uint8_t> fs(P);
-    for (int v = 0; v < n_problems; ++v) {
-      int w, h;
-      cudaSetDevice(gpus[0]);
-      if (!jpeg_decode_bgr(dec, image_path(v), &color, &w, &h, &err)) {
-        color.resize(P * 3);  // grey-only JPEG: replicate luma
-        for (size_t i = 0; i < P; ++i) color[3 * i] = color[3 * i + 1] = color[3 * i + 2] = gray_slab[P * v + i];
-      }
-      int owner = 0, first = 0, count = 0;
-      for (; owner < G; ++owner) { dpe_shard_range(n_problems, G, owner, &first, &count); if (v < first + count) break; }
-      if (dpe_get_maps(ctxs[owner], v, fd.data(), fn.data(), fs.data(), nullptr)) return fail(std::string("get_maps: ") + dpe_last_error(ctxs[owner]));
-      if (dpe_fuse_set_view(fc, v, fd.data(), fn.data(), fs.data(), color.data())) return fail(std::string("fuse_set_view: ") + dpe_last_error(fc));
-    }
     size_t n_points = 0;
-    if (dpe_fuse_run(fc, &n_points)) return fail(std::string("fuse_run: ") + dpe_last_error(fc));
-    std::vector<float> xyz(n_points * 3);
-    std::vector<uint8_t> bgr(n_points * 3);
-    if (n_points && dpe_fuse_get(fc, xyz.data(), bgr.data())) return fail(std::string("fuse_get: ") + dpe_last_error(fc));
+    for (int g = 0; g < G; ++g) n_points += cloud_xyz[g].size() / 3;
+    std::vector<float> xyz; std::vector<uint8_t> bgr;
+    xyz.reserve(n_points * 3); bgr.reserve(n_points * 3);
+    for (int g = 0; g < G; ++g) {
+      xyz.insert(xyz.end(), cloud_xyz[g].begin(), cloud_xyz[g].end()); bgr.insert(bgr.end(), cloud_bgr[g].begin(), cloud_bgr[g].end());
+      std::vector<float>().swap(cloud_xyz[g]); std::vector<uint8_t>().swap(cloud_bgr[g]);
+    }
     if (!write_ply(dense + "/DPE/DPE.ply", xyz.data(), bgr.data(), n_points)) return fail("cannot write DPE.ply");
-    tm.fusion = now_s() - t0;
+    for (int g = 0; g < G; ++g) tm.fusion = std::max(tm.fusion, t_fuse[g]);
+    tm.fusion += now_s() - t0;
   }
   const double t_destroy0 = now_s();
   if (G == 1) destroy_all();

@@ -246,12 +246,23 @@ DPE_API int dpe_bench_ncc(dpe_ctx* ctx, int view, int variant, int n_cand, int r
 
 /* --- depth-map fusion on the device (replaces DPE::RunFusion, DPE.cpp:1220-1370, and the point list
  *     ExportPointCloud writes, DPE.cpp:532-572) -----------------------------------------------------
- * Inputs are the final maps of every problem view at full resolution (as dpe_get_maps returns them,
- * depth already zeroed where the pixel state is UNKNOWN) and the colour image (B,G,R interleaved);
- * cameras and source lists are the scene's.  Views without maps are skipped as sources.  dpe_fuse_run
- * fuses the views in index order; dpe_fuse_get copies the cloud out (n_points x 3 each). */
+ * Fusion reads the final (world normal, depth) map, pixel states and colour image (B,G,R interleaved) of every
+ * problem view; cameras and source lists are the scene's.  Two ways to give it the maps:
+ *   dpe_fuse_prepare   the maps the last stage left on the GPU(s) — nothing goes through the host; with several
+ *                      ranks it is a collective that all-gathers the ranks' blocks with NCCL, after which every
+ *                      rank fuses its own block of views (dpe_fuse_run) against its own marks;
+ *   dpe_fuse_set_view  maps from the host (what the reference reads from depths.dmb / normals.dmb / weak.bin:
+ *                      depth zeroed where out of range), unsharded contexts only.
+ * Colours: dpe_fuse_set_view, or dpe_fuse_set_color (asynchronous; rank `root` alone may upload and
+ * dpe_fuse_broadcast_colors, a collective, hands them to the other ranks).  dpe_fuse_run fuses the views in index
+ * order; the cloud is the same from run to run.  dpe_fuse_get copies it out (n_points x 3 each).  The reference's
+ * optional <dense>/blocks/mask_<id>.jpg gate (DPE.cpp:1243-1247, 1296) is not implemented: dpe_run_pipeline
+ * refuses to fuse when that folder exists. */
+DPE_API int dpe_fuse_prepare(dpe_ctx* ctx);
 DPE_API int dpe_fuse_set_view(dpe_ctx* ctx, int view, const float* depth, const float* normal3, const uint8_t* state,
                       const uint8_t* bgr);
+DPE_API int dpe_fuse_set_color(dpe_ctx* ctx, int view, const uint8_t* bgr);
+DPE_API int dpe_fuse_broadcast_colors(dpe_ctx* ctx, int root);
 DPE_API int dpe_fuse_run(dpe_ctx* ctx, size_t* n_points);
 DPE_API int dpe_fuse_get(dpe_ctx* ctx, float* xyz, uint8_t* bgr);
 

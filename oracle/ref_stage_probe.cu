@@ -172,6 +172,24 @@ int main(int argc, char** argv) {
   GenNeighbours<<<gf, bf>>>(hd);
   NeigbourUpdate<<<gf, bf>>>(hd);
   dump(0);
+  if (argc > 3) {
+    // optional: the outputs of GenEdgeInform / FindNearestStrongPoint themselves (DPE.cu:2483-2591, 2855-2889), per pixel:
+    // edge_neigh (8 x short2), complex (float), label_boundary (8 x short2, (-2,-2) where the pixel is not WEAK),
+    // weak_nearest_strong (short2)
+    std::vector<short2> en(P * 8), lbc((size_t)(weak_count + 1) * 8), lbx(P * 8), ns(P);
+    std::vector<float> cx(P);
+    cudaMemcpy(en.data(), h.edge_neigh_cuda, en.size() * sizeof(short2), cudaMemcpyDeviceToHost);
+    cudaMemcpy(cx.data(), h.complex_cuda, 4 * P, cudaMemcpyDeviceToHost);
+    cudaMemcpy(lbc.data(), h.label_boundary_cuda, lbc.size() * sizeof(short2), cudaMemcpyDeviceToHost);
+    cudaMemcpy(ns.data(), h.weak_nearest_strong, P * sizeof(short2), cudaMemcpyDeviceToHost);
+    for (size_t i = 0; i < P; ++i)
+      for (int k = 0; k < 8; ++k) lbx[i * 8 + k] = (params.use_APD && weak[i] == WEAK) ? lbc[(size_t)nmap[i] * 8 + k] : make_short2(-2, -2);
+    FILE* ex = fopen(argv[3], "wb");
+    if (!ex) return 2;
+    fwrite(en.data(), sizeof(short2), en.size(), ex); fwrite(cx.data(), 4, P, ex);
+    fwrite(lbx.data(), sizeof(short2), lbx.size(), ex); fwrite(ns.data(), sizeof(short2), P, ex);
+    fclose(ex);
+  }
   RandomInitialization<<<gf, bf>>>(hd);
   dump(1);
   for (int i = 0; i < params.max_iterations; ++i) {
