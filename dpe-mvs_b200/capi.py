@@ -127,7 +127,7 @@ def load(build=True):
     lib.dpe_fuse_prepare.argtypes = [vp]
     lib.dpe_fuse_set_color.argtypes = [vp, ci, vp]
     lib.dpe_fuse_broadcast_colors.argtypes = [vp, ci]
-    lib.dpe_fuse_run.argtypes = [vp, C.POINTER(C.c_size_t)]
+    lib.dpe_fuse_run.argtypes = [vp, ci, ci, C.POINTER(C.c_size_t)]
     lib.dpe_fuse_get.argtypes = [vp, vp, vp]
     lib.dpe_debug_read.argtypes = [vp, ci, vp, C.c_size_t]
     lib.dpe_debug_stop_after.argtypes = [vp, ci]
@@ -370,7 +370,7 @@ class Context:
             st = np.ascontiguousarray(m["state"], np.uint8); c = np.ascontiguousarray(colours[v], np.uint8)
             self._ck(self.lib.dpe_fuse_set_view(self.h, v, d.ctypes.data, n.ctypes.data, st.ctypes.data, c.ctypes.data))
         n = C.c_size_t()
-        self._ck(self.lib.dpe_fuse_run(self.h, C.byref(n)))
+        self._ck(self.lib.dpe_fuse_run(self.h, 0, self.n_views, C.byref(n)))
         xyz = np.empty((n.value, 3), np.float32); bgr = np.empty((n.value, 3), np.uint8)
         if n.value:
             self._ck(self.lib.dpe_fuse_get(self.h, xyz.ctypes.data, bgr.ctypes.data))
@@ -384,7 +384,7 @@ class Context:
             self._ck(self.lib.dpe_fuse_set_color(self.h, v, c.ctypes.data))
         self._ck(self.lib.dpe_fuse_broadcast_colors(self.h, 0))
         n = C.c_size_t()
-        self._ck(self.lib.dpe_fuse_run(self.h, C.byref(n)))
+        self._ck(self.lib.dpe_fuse_run(self.h, 0, self.n_views, C.byref(n)))
         xyz = np.empty((n.value, 3), np.float32); bgr = np.empty((n.value, 3), np.uint8)
         if n.value:
             self._ck(self.lib.dpe_fuse_get(self.h, xyz.ctypes.data, bgr.ctypes.data))

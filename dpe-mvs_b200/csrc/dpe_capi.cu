@@ -1118,8 +1118,8 @@ int dpe_fuse_prepare(dpe_ctx* ctx) {
   return DPE_OK;
 }
 
-int dpe_fuse_run(dpe_ctx* ctx, size_t* n_points) {
-  if (!ctx || !n_points) return DPE_ERR_ARG;
+int dpe_fuse_run(dpe_ctx* ctx, int first_view, int count, size_t* n_points) {
+  if (!ctx || !n_points || first_view < 0 || count < 0 || first_view + count > ctx->n_views) return DPE_ERR_ARG;
   if (ctx->fuse_have.empty()) FAIL(DPE_ERR_STATE, "no fusion inputs (dpe_fuse_set_view / dpe_fuse_prepare)");
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->upload_stream));
@@ -1150,10 +1150,8 @@ int dpe_fuse_run(dpe_ctx* ctx, size_t* n_points) {
   const size_t temp_bytes = fuse_select_temp_bytes((int)P);
   CK(dmalloc(&temp, temp_bytes ? temp_bytes : 1));
   ctx->cloud.clear();
-  // resident maps: this rank's block of views; host-provided maps: every view that has maps.  Views in order: a
-  // view sees every mark of the views before it.
-  const int v0 = ctx->fuse_resident ? ctx->first_view : 0, v1 = ctx->fuse_resident ? ctx->first_view + ctx->n_local : V;
-  for (int i = v0; i < v1; ++i) {
+  // views in order: a view sees every mark of the views before it
+  for (int i = first_view; i < first_view + count; ++i) {
     if (!hv[i].planes) continue;
     FuseSrcList sl; memset(&sl, 0, sizeof(sl));
     const std::vector<int>& src = ctx->views[i].src;
@@ -1252,6 +1250,8 @@ int dpe_debug_read(dpe_ctx* ctx, int what, void* out, size_t bytes) {
     case 8: src = s.selected; n = P * sizeof(uint32_t); break;
     case 9: src = s.state; n = P; break;
     case 11: src = s.fit_planes; n = P; break;  // accepted-candidate codes of a stage truncated after a strong sweep
+    case 12: src = s.edge_neigh; n = P * 8 * sizeof(short2); break;
+    case 13: src = s.label_boundary; n = P * 8 * sizeof(short2); break;
     case 10: src = ctx->views[ctx->first_view].scales[ctx->last_stage_scale].lin; n = P * sizeof(float); break;
     default: return DPE_ERR_ARG;
   }

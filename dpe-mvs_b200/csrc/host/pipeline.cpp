@@ -426,6 +426,8 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     arith = m == "fast" ? DPE_COST_REFERENCE : (m == "centred" ? DPE_COST_CENTRED : DPE_COST_REFERENCE_EXACT);
   }
   const std::vector<Stage> schedule = make_schedule(round_num);
+  bool fusion_sharded = false;
+  if (const char* e = getenv("DPE_FUSION_SHARDED")) fusion_sharded = atoi(e) != 0 && G > 1;
 
   // ---- .npy writers (main.cpp:570-575) run behind the GPU workers -------------------------------------
   const bool any_output = depth || normal || weak || edge;
@@ -529,7 +531,10 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     t_stages[g] = now_s() - ts0;
     if (fusion) {
       // the maps stay where the last stage left them: all-gather of the final planes + states (NCCL), colours
-      // uploaded by the first GPU and broadcast, then every GPU fuses its own block of views
+      // uploaded by the first GPU.  Default: the first GPU fuses all views in order, like the reference (a view sees
+      // the marks of every view before it).  DPE_FUSION_SHARDED=1: colours broadcast, every GPU fuses its own block of
+      // views against its own marks — G times faster, but surface seen from two blocks is fused twice (measured on a
+      // 24-view ring scene, 2 GPUs: 14.6 M points instead of 11.9 M).
       const double tf0 = now_s();
       if (dpe_fuse_prepare(c)) return bad("fuse_prepare");
       if (g == 0) {
@@ -537,11 +542,13 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
         for (int v = 0; v < n_problems; ++v)
           if (dpe_fuse_set_color(c, v, color_slab.data() + P * 3 * (size_t)v)) return bad("fuse_set_color");
       }
-      if (dpe_fuse_broadcast_colors(c, 0)) return bad("fuse_broadcast_colors");
-      size_t n_points = 0;
-      if (dpe_fuse_run(c, &n_points)) return bad("fuse_run");
-      cloud_xyz[g].resize(n_points * 3); cloud_bgr[g].resize(n_points * 3);
-      if (n_points && dpe_fuse_get(c, cloud_xyz[g].data(), cloud_bgr[g].data())) return bad("fuse_get");
+      if (fusion_sharded && dpe_fuse_broadcast_colors(c, 0)) return bad("fuse_broadcast_colors");
+      if (fusion_sharded || g == 0) {
+        size_t n_points = 0;
+        if (dpe_fuse_run(c, fusion_sharded ? first : 0, fusion_sharded ? count : n_problems, &n_points)) return bad("fuse_run");
+        cloud_xyz[g].resize(n_points * 3); cloud_bgr[g].resize(n_points * 3);
+        if (n_points && dpe_fuse_get(c, cloud_xyz[g].data(), cloud_bgr[g].data())) return bad("fuse_get");
+      }
       t_fuse[g] = now_s() - tf0;
     }
   };

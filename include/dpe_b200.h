@@ -176,7 +176,8 @@ DPE_API int dpe_debug_set_variants(dpe_ctx* ctx, int mask);
  * 1 fit planes (P float4), 2 radius (P int32), 3 costs (P float), 4 weak_reliable (P u8), 5 nearest strong
  * (P short2), 6 complexity (P float), 7 plane hypotheses in reference-camera coordinates (P float4), 8 selected
  * views (P uint32), 9 pixel state (P u8), 10 the image of the shard's first view at that scale (P float), 11 after a stage truncated at a strong sweep (step 2, 5, 8):
- * which candidate each pixel took in it (P u8: 0 kept, 1..8 propagation slot + 1, 10..14 refinement hypothesis). */
+ * which candidate each pixel took in it (P u8: 0 kept, 1..8 propagation slot + 1, 10..14 refinement hypothesis), 12 nearest edge
+ * pixel per direction (P x 8 short2), 13 label boundary per direction (P x 8 short2; defined for WEAK pixels with a label > 0). */
 DPE_API int dpe_debug_read(dpe_ctx* ctx, int what, void* out, size_t bytes);
 /* test hook: the following stages stop after `step` of every view-stage, in the numbering of
  * DPE::RunPatchMatch's launch sequence (DPE.cu:3126-3249) used by oracle/ref_stage_probe.cu: 0 anchor search,
@@ -250,12 +251,15 @@ DPE_API int dpe_bench_ncc(dpe_ctx* ctx, int view, int variant, int n_cand, int r
  * problem view; cameras and source lists are the scene's.  Two ways to give it the maps:
  *   dpe_fuse_prepare   the maps the last stage left on the GPU(s) — nothing goes through the host; with several
  *                      ranks it is a collective that all-gathers the ranks' blocks with NCCL, after which every
- *                      rank fuses its own block of views (dpe_fuse_run) against its own marks;
+ *                      rank holds the maps of all problem views: one rank can fuse all of them in order (the
+ *                      reference's semantics), or every rank its own block against its own marks (faster; marks
+ *                      do not cross ranks, so surface seen from two blocks is fused twice);
  *   dpe_fuse_set_view  maps from the host (what the reference reads from depths.dmb / normals.dmb / weak.bin:
  *                      depth zeroed where out of range), unsharded contexts only.
  * Colours: dpe_fuse_set_view, or dpe_fuse_set_color (asynchronous; rank `root` alone may upload and
- * dpe_fuse_broadcast_colors, a collective, hands them to the other ranks).  dpe_fuse_run fuses the views in index
- * order; the cloud is the same from run to run.  dpe_fuse_get copies it out (n_points x 3 each).  The reference's
+ * dpe_fuse_broadcast_colors, a collective, hands them to the other ranks).  dpe_fuse_run fuses views
+ * [first_view, first_view + count) in index order, starting from a clean set of marks; the cloud is the same from
+ * run to run.  dpe_fuse_get copies it out (n_points x 3 each).  The reference's
  * optional <dense>/blocks/mask_<id>.jpg gate (DPE.cpp:1243-1247, 1296) is not implemented: dpe_run_pipeline
  * refuses to fuse when that folder exists. */
 DPE_API int dpe_fuse_prepare(dpe_ctx* ctx);
@@ -263,7 +267,7 @@ DPE_API int dpe_fuse_set_view(dpe_ctx* ctx, int view, const float* depth, const 
                       const uint8_t* bgr);
 DPE_API int dpe_fuse_set_color(dpe_ctx* ctx, int view, const uint8_t* bgr);
 DPE_API int dpe_fuse_broadcast_colors(dpe_ctx* ctx, int root);
-DPE_API int dpe_fuse_run(dpe_ctx* ctx, size_t* n_points);
+DPE_API int dpe_fuse_run(dpe_ctx* ctx, int first_view, int count, size_t* n_points);
 DPE_API int dpe_fuse_get(dpe_ctx* ctx, float* xyz, uint8_t* bgr);
 
 /* --- micro-benchmarks used for the roofline denominators ------------------ */

@@ -55,6 +55,10 @@ def test_first_stage_follows_the_reference_kernels(arith, thr):
         ctx.run_stage(k, p, SEED)
         ctx.stage_commit()
         got[step] = (ctx.debug_read(7, (ch, cw, 4), np.float32), ctx.debug_read(8, (ch, cw), np.uint32))
+    ctx.debug_stop_after(-1)         # the whole stage: + GetDepthandNormal, median filter, DepthToWeak, LocalRefine, host tail
+    ctx.run_stage(k, p, SEED)
+    ctx.stage_commit()
+    fin = ctx.get_maps(v, 0)
     ctx.close()
     # RandomInitialization: the same random planes bit for bit, the same initial view selection
     assert (got[1][0] == fx["s1_planes"]).all(-1).mean() > 0.999                # 1.000 / 1.000
@@ -64,10 +68,21 @@ def test_first_stage_follows_the_reference_kernels(arith, thr):
     assert _identical(got[8][0], fx["s8_planes"]) > thr["s8"]                   # 0.887 / 1.000 (bit for bit)
     if arith == 2:      # the reference's arithmetic: the whole stage bit for bit, costs included
         assert (got[8][0] == fx["s8_planes"]).all(-1).mean() > 0.998 and (got[8][1] == fx["s8_selected"]).mean() > 0.998
+        # ... and the stage's final maps (K10-K13 + the host tail of ProcessProblem, main.cpp:427-437): measured 100 %
+        dr = fx["drange"]
+        rd = fx["s11_planes"][..., 3].copy(); rst = fx["s11_state"].copy()
+        dmin, dmax = np.float32(dr[0]) * np.float32(0.6), np.float32(dr[1]) * np.float32(1.2)
+        oob = (rd < dmin) | (rd > dmax)
+        rd[oob] = 0; rst[oob] = 2
+        assert (fin["state"] == rst).mean() > 0.999
+        same_d = (fin["depth"] == rd) | (np.isnan(fin["depth"]) & np.isnan(rd))
+        assert same_d.mean() > 0.998, same_d.mean()
+        assert (fin["normal"] == fx["s11_planes"][..., :3]).all(-1)[rd > 0].mean() > 0.998
+        assert (fin["selected"] == fx["s11_selected"]).mean() > 0.998
 
 
 @pytest.mark.parametrize("arith,thr", [(1, dict(s2=0.96, s4=0.955, s4w=0.95, s10=0.87, fit=0.74, state=0.995, depth=0.98, normal=0.87)),
-                                       (2, dict(s2=0.995, s4=0.993, s4w=0.98, s10=0.985, fit=0.95, state=0.999, depth=0.995, normal=0.985))])
+                                       (2, dict(s2=0.995, s4=0.993, s4w=0.98, s10=0.985, fit=0.97, state=0.999, depth=0.995, normal=0.985))])
 def test_weak_stage_follows_the_reference_kernels(arith, thr):
     """stage 6 (REFINE_ITER at the fine scale): anchor search, edge-adaptive sampling, plane fit + adaptive
     radius, deformable NCC, geometric consistency, classification — replayed from the stored inputs with the
@@ -104,7 +119,18 @@ def test_weak_stage_follows_the_reference_kernels(arith, thr):
     assert (ctx.debug_read(9, (H, W), np.uint8) == fx["s0_state"]).mean() > 0.999           # which WEAK pixels stay WEAK
     assert (ctx.debug_read(4, (H, W), np.uint8)[weak] == fx["s0_reliable"][weak]).mean() > 0.999
     nb = ctx.debug_read(0, (H, W, 9, 2), np.int16)
-    assert (nb[weak] == fx["s0_neighbours"][weak]).all(-1).all(-1).mean() > 0.96            # anchors incl. their order: 0.983
+    anchors_equal = (nb[weak] == fx["s0_neighbours"][weak]).all(-1).all(-1).mean()          # anchors incl. their order
+    assert anchors_equal > (0.995 if arith == 2 else 0.96), anchors_equal                   # 0.983 / 1.000
+    k2k3 = GOLD / "ref_stage_weak_k2k3.npz"
+    if k2k3.exists():   # the outputs of GenEdgeInform and FindNearestStrongPoint themselves (oracle/make_k2k3_golden.py)
+        g2 = np.load(k2k3)
+        assert np.array_equal(ctx.debug_read(12, (H, W, 8, 2), np.int16), g2["s0_edge_neigh"])          # nearest edge pixel per direction
+        assert np.array_equal(ctx.debug_read(5, (H, W, 2), np.int16), g2["s0_nearest_strong"])           # nearest STRONG pixel of WEAK pixels
+        cx = ctx.debug_read(6, (H, W), np.float32)
+        assert (cx == g2["s0_complex"]).mean() > 0.999 and np.abs(cx - g2["s0_complex"]).max() < 1e-6  # edge-density sigmoid
+        lab = weak & (fx["label"] > 0)
+        if lab.any():
+            assert np.array_equal(ctx.debug_read(13, (H, W, 8, 2), np.int16)[lab], g2["s0_label_boundary"][lab])
     run(1)          # RandomInitialization (REFINE: re-scores the carried planes)
     assert _identical(ctx.debug_read(7, (H, W, 4), np.float32), fx["s1_planes"]) > 0.999    # 1.000
     assert (ctx.debug_read(8, (H, W), np.uint32) == fx["s1_selected"]).mean() > 0.999
@@ -113,7 +139,7 @@ def test_weak_stage_follows_the_reference_kernels(arith, thr):
     run(3)          # RANSACToGetFitPlane + adaptive radius
     assert (ctx.debug_read(2, (H, W), np.int32)[weak] == fx["s3_radius"][weak]).mean() > 0.995  # 1.000
     dn = np.abs(ctx.debug_read(1, (H, W, 4), np.float32)[..., :3] - fx["s3_fit"][..., :3]).max(-1)
-    assert (dn[weak] < 1e-4).mean() > thr["fit"] - 0.1                                       # after iteration 0
+    assert (dn[weak] < 1e-4).mean() > thr["fit"]                                             # after iteration 0: 0.975 with the reference arithmetic
     run(4)          # weak sweeps (deformable NCC + geometric consistency)
     pl = ctx.debug_read(7, (H, W, 4), np.float32)
     assert _identical(pl, fx["s4_planes"]) > thr["s4"]                                       # 0.977 / 0.993
