@@ -50,7 +50,7 @@ struct ViewData {
   bool have_cam = false;
   bool have_img = false;
   std::vector<int> src;
-  std::vector<float> relpose;  // per source: R_rel[9], t_rel[3] as the device computes them (k_relative_pose)
+  std::vector<float> relpose;  // per source: R_rel[9], t_rel[3], baseline as the device computes them (k_relative_pose)
   std::vector<ScaleImg> scales;
   // state carried between stages (owner only): pointers into dpe_ctx::maps_*[cur_buf]
   float4* planes = nullptr;  // (world normal, depth)
@@ -699,12 +699,14 @@ int dpe_scene_commit(dpe_ctx* ctx) {
         for (int i = 0; i < 3; ++i) in.push_back((float)r.t[i]);
         for (int i = 0; i < 9; ++i) in.push_back((float)sc.R[i]);
         for (int i = 0; i < 3; ++i) in.push_back((float)sc.t[i]);
+        for (int i = 0; i < 3; ++i) in.push_back((float)r.C[i]);
+        for (int i = 0; i < 3; ++i) in.push_back((float)sc.C[i]);
         ++n_pairs;
       }
     }
     if (n_pairs) {
       float *d_in = nullptr, *d_out = nullptr;
-      std::vector<float> out(n_pairs * 12);
+      std::vector<float> out(n_pairs * 13);
       CK(dmalloc(&d_in, in.size() * sizeof(float))); CK(dmalloc(&d_out, out.size() * sizeof(float)));
       CK(cudaMemcpy(d_in, in.data(), in.size() * sizeof(float), cudaMemcpyHostToDevice));
       launch_relative_pose(d_in, d_out, (int)n_pairs, 0);
@@ -714,8 +716,8 @@ int dpe_scene_commit(dpe_ctx* ctx) {
       size_t o = 0;
       for (int v = 0; v < ctx->n_views; ++v) {
         ViewData& rv = ctx->views[v];
-        rv.relpose.assign(out.begin() + o, out.begin() + o + rv.src.size() * 12);
-        o += rv.src.size() * 12;
+        rv.relpose.assign(out.begin() + o, out.begin() + o + rv.src.size() * 13);
+        o += rv.src.size() * 13;
       }
     }
   }
@@ -748,9 +750,10 @@ static void build_ref_const(const dpe_ctx* ctx, int view, int k, bool geom, RefC
     const int sv = rv.src[si];
     SrcConst& sc = rc->src[si];
     fold_pair(rv.cam, ctx->views[sv].cam, w, h, ctx->W, ctx->H, &sc);
-    if (rv.relpose.size() >= (size_t)(si + 1) * 12) {
-      memcpy(sc.Rrel, &rv.relpose[(size_t)si * 12], 9 * sizeof(float));
-      memcpy(sc.trel, &rv.relpose[(size_t)si * 12 + 9], 3 * sizeof(float));
+    if (rv.relpose.size() >= (size_t)(si + 1) * 13) {
+      memcpy(sc.Rrel, &rv.relpose[(size_t)si * 13], 9 * sizeof(float));
+      memcpy(sc.trel, &rv.relpose[(size_t)si * 13 + 9], 3 * sizeof(float));
+      sc.baseline = rv.relpose[(size_t)si * 13 + 12];  // the device's value (k_relative_pose)
     }
     sc.src_view = sv;
     sc.tex = 0;

@@ -544,7 +544,10 @@ __device__ void weak_update_warp(const StageArgs& a, const RefConst& rc, const i
 }
 
 constexpr int NTW = 128;  // threads per CTA of the weak sweep: 4 warps = 4 pixels in phase lock-step
-constexpr int WEAK_CTAS_PER_SM = 6;
+#ifndef DPE_WEAK_CTAS_PER_SM
+#define DPE_WEAK_CTAS_PER_SM 6
+#endif
+constexpr int WEAK_CTAS_PER_SM = DPE_WEAK_CTAS_PER_SM;
 __global__ void __launch_bounds__(NTW, WEAK_CTAS_PER_SM) k_weak_list(const __grid_constant__ StageArgs A) {
   __shared__ WeakWarpSmem s_w[NTW / 32];
   StageArgs a = A;
@@ -771,12 +774,26 @@ __global__ void k_resize_linear(const float* __restrict__ src, int sw, int sh, f
 // Relative pose of every (reference, source) pair of the scene, computed by the DEVICE compiler from the same
 // expressions ComputeHomography evaluates per call (DPE.cu:455-481): the reference's nvcc contracts these
 // multiply-adds, a host compiler would not, and the last bit of R_rel / t_rel is enough to move a tap across a
-// 1/256 filter-weight bin.  in: n x (ref R[9], ref t[3], src R[9], src t[3]); out: n x (R_rel[9], t_rel[3]).
+// 1/256 filter-weight bin.  in: n x (ref R[9], ref t[3], src R[9], src t[3], ref c[3], src c[3]);
+// out: n x (R_rel[9], t_rel[3], baseline).
 __global__ void k_relative_pose(const float* __restrict__ in, float* __restrict__ out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float* c = in + (size_t)i * 24;
-  relative_pose_ref(c, c + 9, c + 12, c + 21, out + (size_t)i * 12, out + (size_t)i * 12 + 9);
+  const float* c = in + (size_t)i * 30;
+  float* o = out + (size_t)i * 13;
+  relative_pose_ref(c, c + 9, c + 12, c + 21, o, o + 9);
+  // baseline of the pair as DepthToWeak / LocalRefine form it per pixel (DPE.cu:2640-2645, 2783-2788): float
+  // differences of the stored camera centres, the squared norm promoted to double, sqrtf of it — which under
+  // --use_fast_math is the approximate single-precision root; a host sqrtf can differ from it in the last bit, and
+  // the disparity steps of both kernels (and with them the depths LocalRefine writes) hang on that bit
+  const float* rc3 = c + 24;
+  const float* sc3 = c + 27;
+  float c_dist[3];
+  c_dist[0] = rc3[0] - sc3[0];
+  c_dist[1] = rc3[1] - sc3[1];
+  c_dist[2] = rc3[2] - sc3[2];
+  double temp_val = c_dist[0] * c_dist[0] + c_dist[1] * c_dist[1] + c_dist[2] * c_dist[2];
+  o[12] = sqrtf(temp_val);
 }
 void launch_relative_pose(const float* in, float* out, int n, cudaStream_t stream) {
   k_relative_pose<<<(n + 127) / 128, 128, 0, stream>>>(in, out, n);

@@ -63,6 +63,10 @@ typedef struct dpe_ctx dpe_ctx;
 
 /* --- lifetime (replaces DPE::DPE / ~DPE, DPE.cpp:674-731, and
  *     cudaSetDevice in RunDPEPipeline, main.cpp:478) ----------------------- */
+/* One context per GPU at a time: the texture handle of the running scale and the folded cameras of the views in
+ * flight live in per-device constant memory, so two contexts must not run stages on the same device concurrently
+ * (one after the other is fine).  Device memory comes from the device's stream-ordered pool and stays with the
+ * process after dpe_ctx_destroy unless DPE_RELEASE_MEMORY=1. */
 DPE_API int dpe_ctx_create(dpe_ctx** out, int gpu_index);
 DPE_API void dpe_ctx_destroy(dpe_ctx* ctx);
 DPE_API const char* dpe_last_error(const dpe_ctx* ctx);
