@@ -246,8 +246,9 @@ def write_cam(path, K, R, t, dmin, dmax):
         f.write(f"\n{dmin:.8f} {interval:.8f} 192 {dmax:.8f}\n")
 
 
-def write_scene(spec: SceneSpec, out_dir, device=None, save_gt=True, jpeg_quality=98, sidecar=True):
-    """Writes the colmap2mvsnet layout; returns dict with per-view GT arrays (if kept)."""
+def write_scene(spec: SceneSpec, out_dir, device=None, save_gt=True, jpeg_quality=98, sidecar=True, gt_every=1):
+    """Writes the colmap2mvsnet layout; returns the source lists.  save_gt: True (depth + normal), "depth", or False;
+    gt_every = K keeps the ground truth of every K-th view only (large scenes)."""
     import cv2
     out = Path(out_dir)
     (out / "images").mkdir(parents=True, exist_ok=True)
@@ -269,7 +270,7 @@ def write_scene(spec: SceneSpec, out_dir, device=None, save_gt=True, jpeg_qualit
         dmax = float(np.percentile(valid, 99)) * 1.25
         K, R, t = spec.cams[v]
         write_cam(out / "cams" / f"{v:08d}_cam.txt", K, R, t, dmin, dmax)
-        if save_gt:
+        if save_gt and v % gt_every == 0:
             np.save(out / "gt" / f"{v:08d}_depth.npy", depth)
             if save_gt != "depth":
                 np.save(out / "gt" / f"{v:08d}_normal.npy", normal)
