@@ -150,6 +150,7 @@ struct dpe_ctx {
   bool comm_owned = false;  // created by dpe_comm_init_rank (destroyed with the context); cached ones are not
   cudaStream_t comm_stream = nullptr, upload_stream = nullptr, copy_stream = nullptr;
   std::vector<cudaEvent_t> view_done;  // per local view: its last kernel of the running stage
+  RefConst* h_rc = nullptr;            // pinned: folded cameras of the running stage's views (source of the async copies into c_rc)
   cudaEvent_t comm_done = nullptr;
   bool comm_queued = false;  // the running stage has all-gathers in flight
   // device staging of dpe_export_view (depth, normal3, weak as the .npy files hold them)
@@ -295,6 +296,8 @@ static void free_scene(dpe_ctx* ctx) {
   ctx->scratch.clear();
   for (auto e : ctx->view_done) cudaEventDestroy(e);
   ctx->view_done.clear();
+  if (ctx->h_rc) cudaFreeHost(ctx->h_rc);
+  ctx->h_rc = nullptr;
   dfree(ctx->exp_depth); dfree(ctx->exp_normal); dfree(ctx->exp_weak);
   ctx->exp_depth = nullptr; ctx->exp_normal = nullptr; ctx->exp_weak = nullptr;
   dfree(ctx->fuse_planes_own); dfree(ctx->fuse_state_own); dfree(ctx->fuse_bgr); dfree(ctx->fuse_mask);
@@ -662,6 +665,7 @@ int dpe_scene_commit(dpe_ctx* ctx) {
   }
   ctx->view_done.assign(ctx->n_local, nullptr);
   for (auto& e : ctx->view_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CK(cudaHostAlloc((void**)&ctx->h_rc, (size_t)nl * sizeof(RefConst), cudaHostAllocDefault));
   CK(dmalloc(&ctx->exp_depth, P * sizeof(float))); CK(dmalloc(&ctx->exp_normal, P * 3 * sizeof(float)));
   CK(dmalloc(&ctx->exp_weak, P));
   trace("prep + map slabs");
@@ -861,7 +865,10 @@ int dpe_stage_begin(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t see
     fill_args(ctx, view, k, p, seed, s, &KP);
     StageArgs& a = KP.a;
     a.slot = si;
-    launch_set_ref_const(si, &KP.rc, s.stream);  // stream-ordered: lands after the previous view's kernels on this stream
+    // stream-ordered: lands after the previous view's kernels on this stream; from pinned memory, so the host does not
+    // wait for that stream to drain (a pageable source would make every view-stage's enqueue block on the one before)
+    memcpy(&ctx->h_rc[li], &KP.rc, offsetof(RefConst, src) + (size_t)KP.rc.n_src * sizeof(SrcConst));
+    launch_set_ref_const(si, &ctx->h_rc[li], s.stream);
     // outputs: the other map buffer when the scale changes, in place otherwise
     const int out_buf = map_buffer_of_scale(ctx, k);
     float4* new_planes; uint8_t* new_state; uint32_t* new_sel;

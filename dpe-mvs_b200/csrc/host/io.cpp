@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <nvjpeg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
 
@@ -136,6 +137,7 @@ struct JpegDecoder {
   unsigned char* dev = nullptr;
   size_t dev_bytes = 0;
   std::vector<unsigned char> file;
+  std::vector<uint8_t> scratch;  // padded luma plane of the host decoder
 };
 
 JpegDecoder* jpeg_decoder_create(std::string* err) {
@@ -175,6 +177,22 @@ static bool jpeg_decode_to(JpegDecoder* d, const std::string& path, nvjpegOutput
   }
   const int w = ws[0], h = hs[0];
   const size_t need = (size_t)w * h * ch;
+  if (fmt == NVJPEG_OUTPUT_Y) {
+    // grey images: the host decoder that reproduces libjpeg's pixels (jpeg_luma.cpp) unless DPE_JPEG_DECODER=nvjpeg;
+    // files it does not handle (progressive, ..) go through nvJPEG below
+    const char* force = getenv("DPE_JPEG_DECODER");
+    if (!(force && std::string(force) == "nvjpeg")) {
+      uint8_t* out = dst;
+      size_t out_cap = cap;
+      if (grow) { grow->resize(need); out = grow->data(); out_cap = need; }
+      int ew = 0, eh = 0;
+      std::string e2;
+      if (need <= out_cap && jpeg_decode_luma_islow(d->file.data(), d->file.size(), &d->scratch, out, out_cap, &ew, &eh, &e2) && ew == w && eh == h) {
+        *width = w; *height = h;
+        return true;
+      }
+    }
+  }
   if (need > d->dev_bytes) {
     cudaFree(d->dev);
     if (cudaMalloc(&d->dev, need) != cudaSuccess) { if (err) *err = "cudaMalloc failed in jpeg decode"; d->dev_bytes = 0; return false; }

@@ -39,6 +39,10 @@ JpegDecoder* jpeg_decoder_create(std::string* err);
 void jpeg_decoder_destroy(JpegDecoder* d);
 bool jpeg_decode_gray(JpegDecoder* d, const std::string& path, std::vector<uint8_t>* gray, int* width, int* height,
                       std::string* err);
+// baseline JPEG -> luma exactly as libjpeg(-turbo) / cv::imread(IMREAD_GRAYSCALE) decode it (jpeg_luma.cpp); false for
+// file types it does not handle (progressive, arithmetic, 12-bit, ..): the caller falls back to nvJPEG
+bool jpeg_decode_luma_islow(const uint8_t* data, size_t size, std::vector<uint8_t>* scratch, uint8_t* dst, size_t cap, int* width,
+                            int* height, std::string* err);
 // image size from the JPEG header alone
 bool jpeg_image_size(JpegDecoder* d, const std::string& path, int* width, int* height, std::string* err);
 // the same into caller-provided host memory of `cap` bytes (e.g. a slot of a pinned slab)

@@ -1,0 +1,59 @@
+"""The host JPEG luma decoder (csrc/host/jpeg_luma.cpp: Huffman + integer dequantisation + jpeg_idct_islow) against
+cv2.imread(..., IMREAD_GRAYSCALE), i.e. libjpeg-turbo — the pixels the reference feeds PatchMatch (DPE.cpp:745).
+Bit-identical on greyscale and colour files, subsampled or not, any size, with restart intervals.  CPU only."""
+import ctypes as C
+
+import cv2
+import numpy as np
+import pytest
+
+import capi
+
+
+def _decode(path):
+    lib = capi.load()
+    raw = np.fromfile(path, np.uint8)
+    out = np.zeros(1 << 24, np.uint8)
+    w, h = C.c_int(), C.c_int()
+    rc = lib.dpe_host_decode_luma_islow(raw.ctypes.data_as(C.c_void_p), C.c_long(raw.size), out.ctypes.data_as(C.c_void_p), C.c_long(out.size),
+                                        C.byref(w), C.byref(h))
+    if rc != 0:
+        return None
+    return out[:w.value * h.value].reshape(h.value, w.value)
+
+
+def _image(h, w, color, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = 128 + 60 * np.sin(xx / 7.3 + seed) * np.cos(yy / 5.1) + 30 * np.sin((xx + yy) / 23.0)
+    img = base[..., None] + rng.normal(0, 12, (h, w, 3 if color else 1)) + (np.array([20, -10, 5]) if color else 0)
+    img = np.clip(img, 0, 255).astype(np.uint8)
+    img[: h // 8] = 255; img[-h // 8:] = 0          # saturated regions: exercises the range limit
+    return img if color else img[..., 0]
+
+
+CASES = [(120, 160, False, [cv2.IMWRITE_JPEG_QUALITY, 98]), (97, 131, False, [cv2.IMWRITE_JPEG_QUALITY, 75]),
+         (120, 160, True, [cv2.IMWRITE_JPEG_QUALITY, 95]), (101, 67, True, [cv2.IMWRITE_JPEG_QUALITY, 50]),
+         (64, 200, True, [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, 3]),
+         (33, 45, False, [cv2.IMWRITE_JPEG_QUALITY, 100, cv2.IMWRITE_JPEG_OPTIMIZE, 1]),
+         (80, 96, True, [cv2.IMWRITE_JPEG_QUALITY, 92, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, 0x111111])]
+
+
+@pytest.mark.parametrize("h,w,color,params", CASES)
+def test_luma_decoder_equals_libjpeg(tmp_path, h, w, color, params):
+    p = str(tmp_path / "t.jpg")
+    try:
+        ok = cv2.imwrite(p, _image(h, w, color, h + w), params)
+    except cv2.error:
+        pytest.skip("this OpenCV build does not know the parameter")
+    assert ok
+    want = cv2.imread(p, cv2.IMREAD_GRAYSCALE)
+    got = _decode(p)
+    assert got is not None and got.shape == want.shape
+    assert np.array_equal(got, want), (int(np.abs(got.astype(int) - want.astype(int)).max()), float((got != want).mean()))
+
+
+def test_progressive_files_are_declined(tmp_path):
+    p = str(tmp_path / "p.jpg")
+    assert cv2.imwrite(p, _image(64, 64, True, 1), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    assert _decode(p) is None        # the pipeline then falls back to nvJPEG

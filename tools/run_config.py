@@ -11,13 +11,17 @@ ap.add_argument("config"); ap.add_argument("--views", type=int, default=None); a
 ap.add_argument("--fusion", action="store_true"); ap.add_argument("--gpus", type=int, default=1)
 ap.add_argument("--sharded-fusion", action="store_true"); ap.add_argument("--repeat", type=int, default=1)
 ap.add_argument("--no-sidecar", action="store_true", help="skip the .gray sidecars (only the reference build's imread stand-in needs them)")
+ap.add_argument("--no-normal", action="store_true", help="do not write normal.npy (25 MB per 1920x1080 view)")
+ap.add_argument("--keep-scene", action="store_true", help="reuse the scene folder of an earlier invocation")
 args = ap.parse_args()
 tag = f"{args.config}_v{args.views}_s{args.scale}_g{args.gpus}" + ("_shardedfusion" if args.sharded_fusion else "")
-folder = Path("/tmp") / f"cfg_{tag}"
-shutil.rmtree(folder, ignore_errors=True)
+folder = Path("/tmp") / f"cfg_{args.config}_v{args.views}_s{args.scale}"
 spec = synth.make_scene(args.config, scale=args.scale, n_views=args.views)
 gt_every = max(1, spec.n_views // 8)
-t0 = time.time(); synth.write_scene(spec, folder, save_gt="depth", sidecar=not args.no_sidecar, gt_every=gt_every); t_gen = time.time() - t0
+t_gen = 0.0
+if not (args.keep_scene and (folder / "pair.txt").exists()):
+    shutil.rmtree(folder, ignore_errors=True)
+    t0 = time.time(); synth.write_scene(spec, folder, save_gt="depth", sidecar=not args.no_sidecar, gt_every=gt_every); t_gen = time.time() - t0
 if args.sharded_fusion:
     os.environ["DPE_FUSION_SHARDED"] = "1"
 if args.gpus > 1:
@@ -28,7 +32,7 @@ runs = []
 for rep in range(args.repeat):          # the first call of a process also brings up CUDA contexts and the NCCL communicator
     shutil.rmtree(folder / "DPE", ignore_errors=True)
     t0 = time.perf_counter()
-    DPE_MVS.dpe_mvs(str(folder), 0 if args.gpus == 1 else -1, False, args.fusion, False, True, True, weak, weak)
+    DPE_MVS.dpe_mvs(str(folder), 0 if args.gpus == 1 else -1, False, args.fusion, False, True, not args.no_normal, weak, weak)
     runs.append((time.perf_counter() - t0, json.loads(tj.read_text())))
 dt = runs[-1][0]
 out = dict(config=args.config, views=spec.n_views, width=spec.width, height=spec.height, n_src=spec.n_src, gpus=args.gpus,
