@@ -9,10 +9,11 @@ assertions are written against (the literal 99 % / 1 degree of BASELINE.json is 
 itself).  Modes of this implementation:
   matched   the reference's view order (sequential) and its racy direction-4 sampling positions, same pixels and
             prep arrays as the reference reads                                  (dpe_set_view_order, dpe_set_reference_race)
-  default   what dpe_mvs() runs on one GPU: sequential order, race-free direction 4
-  jacobi    what several GPUs run: every view reads the previous stage's depth maps
-  jpeg      the product end to end, DPE_MVS.dpe_mvs(folder): nvJPEG decode + native Canny / Hough prep instead of the
-            sidecar pixels and cv2 prep the reference is fed (quantifies SURVEY 8f N3 / N1 on the final maps)
+  default   a bare C-ABI context: sequential order, race-free direction 4 (what DPE_DETERMINISTIC=1 selects in dpe_mvs())
+  jacobi    every view reads the previous stage's depth maps (the order several GPUs need), race-free direction 4
+  jpeg      the product end to end, DPE_MVS.dpe_mvs(folder) on one GPU: its own JPEG decode (host/jpeg_luma.cpp) and native
+            Canny / Hough prep instead of the sidecar pixels and cv2 prep the reference is fed, the reference's view
+            order and sampling positions (the product default) — SURVEY 8f N3 / N1 on the final maps
 The numbers are printed and, when gpurun_out/ exists, written to gpurun_out/gate2_<scene>.json.
 """
 import json
@@ -145,27 +146,29 @@ def test_gate2_c1_against_the_reference_build(tmp_path):
     rr = r["ref_vs_ref"]
     # two reference runs agree on ~98 % of the depths and ~92 % of the normals on this scene (round 1: 0.982 / 0.917)
     assert rr["depth_1pct"] > 0.95 and rr["weak_agree"] > 0.98
-    # measured on B200 (gpurun_out/gate2_c1.json, round 2), depth within 1 % / normal within 1 deg / 5 deg / weak map:
-    #   reference vs reference   0.982 / 0.917 / 0.971 / 0.9957
-    #   matched   vs reference   0.980 / 0.814 / 0.961 / 0.9921        (ours vs ours, matched: 0.987 / 0.932 / 0.979 / 0.9969)
-    #   default   vs reference   0.985 / 0.649 / 0.950 / 0.9810
-    #   jacobi    vs reference   0.984 / 0.647 / 0.949 / 0.9808
-    #   jpeg      vs reference   0.984 / 0.617 / 0.945 / 0.9804
+    # measured on B200 (profiles/r02_gate2_c1.json), depth within 1 % / normal within 1 deg / 5 deg / weak map:
+    #   reference vs reference   0.982 / 0.922 / 0.972 / 0.9957
+    #   matched   vs reference   0.981 / 0.846 / 0.966 / 0.9942        (ours vs ours, matched: 0.984-0.987 / 0.930-0.943 / 0.976-0.981 / 0.997)
+    #   jpeg      vs reference   0.981 / 0.845 / 0.966 / 0.9941        (with nvJPEG's luma instead of libjpeg's: 0.978 / 0.617 / 0.939 / 0.989)
+    #   default   vs reference   0.985 / 0.650 / 0.950 / 0.9809
+    #   jacobi    vs reference   0.984 / 0.647 / 0.949 / 0.9806
     for mode in ("matched", "default", "jacobi", "jpeg"):
         m = r[f"{mode}_vs_ref"]
+        close = mode in ("matched", "jpeg")
         # depth: every mode within one point of what the reference reaches against itself
         assert m["depth_1pct"] >= rr["depth_1pct"] - 0.01, (mode, m, rr)
-        # weak / strong classification: matched within one point, the race-free and JPEG-fed modes within two
-        assert m["weak_agree"] >= rr["weak_agree"] - (0.01 if mode == "matched" else 0.02), (mode, m, rr)
-        assert m["normal_5deg"] >= rr["normal_5deg"] - (0.02 if mode == "matched" else 0.035), (mode, m, rr)
-    # normals within 1 degree: BASELINE.json's literal 99 % is not met by the reference against itself (0.917); the
-    # round-1 review's target for the matched mode is reference-vs-reference minus 3 points — NOT met: the gap is 10
-    # points (its seed is the fine-stage remainder of tests/test_gpu_stage_golden.py, amplified over 8 stages; two of
-    # OUR runs in this mode agree on 0.932).  The assertions hold what is measured, half a dozen points of slack for
-    # the run-to-run spread of a racy sweep:
-    assert r["matched_vs_ref"]["normal_1deg"] >= rr["normal_1deg"] - 0.16, (r["matched_vs_ref"], rr)
-    assert r["default_vs_ref"]["normal_1deg"] >= 0.58 and r["jacobi_vs_ref"]["normal_1deg"] >= 0.58, r
-    assert r["jpeg_vs_ref"]["normal_1deg"] >= 0.55, r
+        # weak / strong classification: matched within half a point, the race-free modes within two
+        assert m["weak_agree"] >= rr["weak_agree"] - (0.005 if close else 0.02), (mode, m, rr)
+        assert m["normal_5deg"] >= rr["normal_5deg"] - (0.015 if close else 0.035), (mode, m, rr)
+    # normals within 1 degree: BASELINE.json's literal 99 % is not met by the reference against itself (0.92); the
+    # round-1 review's target for the matched mode is reference-vs-reference minus 3 points — not met yet: the gap is
+    # 7.5 points (10 before LocalRefine's baseline / cost_now were made bit-exact; what remains is the fine-stage
+    # remainder of tests/test_gpu_stage_golden.py amplified over the four fine stages; two of OUR runs in this mode
+    # agree on 0.93-0.94).  The assertions hold what is measured, with four points of slack for the run-to-run spread
+    # of a racy sweep:
+    assert r["matched_vs_ref"]["normal_1deg"] >= rr["normal_1deg"] - 0.115, (r["matched_vs_ref"], rr)
+    assert r["jpeg_vs_ref"]["normal_1deg"] >= rr["normal_1deg"] - 0.115, (r["jpeg_vs_ref"], rr)
+    assert r["default_vs_ref"]["normal_1deg"] >= 0.60 and r["jacobi_vs_ref"]["normal_1deg"] >= 0.60, r
     assert r["matched_vs_matched"]["depth_1pct"] >= rr["depth_1pct"] - 0.005
 
 
@@ -173,7 +176,11 @@ def test_gate2_c1_against_the_reference_build(tmp_path):
 def test_gate2_c4_shape_against_the_reference_build(tmp_path):
     r = _gate2(tmp_path, "c4", 0.5, 6, "c4_half_v6")
     rr = r["ref_vs_ref"]
+    # measured (profiles/r02_gate2_c4_half_v6.json): reference vs reference 0.974 / 0.572 / 0.929 / 0.977; matched and
+    # jpeg vs reference 0.971 / 0.426 / 0.913 / 0.975; default / jacobi 0.971 / 0.37 / 0.904 / 0.974
     for mode in ("matched", "default", "jacobi", "jpeg"):
         m = r[f"{mode}_vs_ref"]
-        assert m["depth_1pct"] >= rr["depth_1pct"] - 0.015, (mode, m, rr)
-        assert m["weak_agree"] >= rr["weak_agree"] - 0.01, (mode, m, rr)
+        assert m["depth_1pct"] >= rr["depth_1pct"] - 0.01, (mode, m, rr)
+        assert m["weak_agree"] >= rr["weak_agree"] - 0.007, (mode, m, rr)
+        assert m["normal_5deg"] >= rr["normal_5deg"] - 0.035, (mode, m, rr)
+    assert r["matched_vs_ref"]["normal_1deg"] >= rr["normal_1deg"] - 0.20 and r["jpeg_vs_ref"]["normal_1deg"] >= rr["normal_1deg"] - 0.20
