@@ -24,6 +24,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 #include "dpe_kernels.cuh"
@@ -819,6 +820,16 @@ static void fill_args(dpe_ctx* ctx, int view, int k, const dpe_stage_params* p, 
   (void)seed;
 }
 
+// host-side unpacking of the cloud on a few threads (10^8 points are seconds of work for one)
+template <class F>
+static void cloud_parallel(size_t n, F fn) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  const size_t nt = n < (1u << 20) ? 1 : (hw ? (hw > 16 ? 16 : hw) : 4);
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < nt; ++t) th.emplace_back([=]() { for (size_t i = n * t / nt; i < n * (t + 1) / nt; ++i) fn(i); });
+  for (auto& x : th) x.join();
+}
+
 // the carried-map buffers of local view li in buffer b
 static void map_buffers(dpe_ctx* ctx, int li, int b, float4** planes, uint8_t** state, uint32_t** sel) {
   const size_t P = map_stride(ctx, b);
@@ -1154,11 +1165,23 @@ int dpe_fuse_run(dpe_ctx* ctx, int first_view, int count, size_t* n_points) {
   }
   FuseView* dv; CK(dmalloc(&dv, V * sizeof(FuseView)));
   CK(cudaMemcpy(dv, hv.data(), V * sizeof(FuseView), cudaMemcpyHostToDevice));
-  FusedPointDev *pts, *sel; uint8_t* accept; int* d_n; void* temp;
-  CK(dmalloc(&pts, P * sizeof(FusedPointDev))); CK(dmalloc(&sel, P * sizeof(FusedPointDev)));
-  CK(dmalloc(&accept, P)); CK(dmalloc(&d_n, sizeof(int)));
-  const size_t temp_bytes = fuse_select_temp_bytes((int)P);
-  CK(dmalloc(&temp, temp_bytes ? temp_bytes : 1));
+  // the cloud is assembled on the device (ordered append, the running total stays on the device) and copied out once;
+  // capacity: every pixel of every fused view, or what the pool still gives
+  FusedPointDev *pts = nullptr, *cloud_dev = nullptr; uint8_t* accept = nullptr; int* warp_counts = nullptr;
+  unsigned long long* running = nullptr;
+  CK(dmalloc(&pts, P * sizeof(FusedPointDev)));
+  CK(dmalloc(&accept, P)); CK(dmalloc(&warp_counts, (size_t)fuse_append_blocks(ctx->num_sms) * 8 * sizeof(int)));
+  CK(dmalloc(&running, 3 * sizeof(unsigned long long)));
+  CK(cudaMemset(running, 0, 3 * sizeof(unsigned long long)));
+  int n_fuse = 0;
+  for (int i = first_view; i < first_view + count; ++i) if (hv[i].planes) ++n_fuse;
+  unsigned long long capacity = (unsigned long long)(n_fuse > 0 ? n_fuse : 1) * P;
+  while (capacity >= P && dmalloc(&cloud_dev, capacity * sizeof(FusedPointDev)) != cudaSuccess) {
+    cudaGetLastError();
+    cloud_dev = nullptr;
+    capacity /= 2;
+  }
+  if (!cloud_dev) FAIL(DPE_ERR_CUDA, "no device memory for the fused cloud");
   ctx->cloud.clear();
   // views in order: a view sees every mark of the views before it
   for (int i = first_view; i < first_view + count; ++i) {
@@ -1168,27 +1191,41 @@ int dpe_fuse_run(dpe_ctx* ctx, int first_view, int count, size_t* n_points) {
     sl.n = (int)src.size();
     for (int j = 0; j < sl.n; ++j) sl.id[j] = ctx->fuse_have[src[j]] ? src[j] : -1;
     launch_fuse_view(dv, i, sl, W, H, pts, accept, ctx->num_sms, 0);
-    launch_fuse_select(temp, temp_bytes, pts, accept, sel, d_n, (int)P, 0);
-    ctx->launches += 2;
-    int n = 0;
-    CK(cudaMemcpy(&n, d_n, sizeof(int), cudaMemcpyDeviceToHost));
-    const size_t at = ctx->cloud.size();
-    ctx->cloud.resize(at + n);
-    if (n) CK(cudaMemcpy(ctx->cloud.data() + at, sel, (size_t)n * sizeof(FusedPointDev), cudaMemcpyDeviceToHost));
+    launch_fuse_append(pts, accept, (int)P, warp_counts, running, capacity, cloud_dev, ctx->num_sms, 0);
+    ctx->launches += 4;
   }
   CK(cudaGetLastError());
-  dfree(dv); dfree(pts); dfree(sel); dfree(accept); dfree(d_n); dfree(temp);
+  unsigned long long h_run[3] = {0, 0, 0};
+  CK(cudaMemcpy(h_run, running, sizeof(h_run), cudaMemcpyDeviceToHost));
+  ctx->cloud.resize((size_t)h_run[0]);
+  if (h_run[0]) CK(cudaMemcpy(ctx->cloud.data(), cloud_dev, (size_t)h_run[0] * sizeof(FusedPointDev), cudaMemcpyDeviceToHost));
+  dfree(dv); dfree(pts); dfree(accept); dfree(warp_counts); dfree(running); dfree(cloud_dev);
+  if (h_run[2]) FAIL(DPE_ERR_CUDA, "the fused cloud did not fit into device memory");
   *n_points = ctx->cloud.size();
   return DPE_OK;
 }
 
 int dpe_fuse_get(dpe_ctx* ctx, float* xyz, uint8_t* bgr) {
   if (!ctx || !xyz || !bgr) return DPE_ERR_ARG;
-  for (size_t i = 0; i < ctx->cloud.size(); ++i) {
-    const FusedPointDev& p = ctx->cloud[i];
+  const FusedPointDev* c = ctx->cloud.data();
+  cloud_parallel(ctx->cloud.size(), [=](size_t i) {
+    const FusedPointDev& p = c[i];
     xyz[3 * i] = p.x; xyz[3 * i + 1] = p.y; xyz[3 * i + 2] = p.z;
     bgr[3 * i] = (uint8_t)(p.bgr & 255u); bgr[3 * i + 1] = (uint8_t)((p.bgr >> 8) & 255u); bgr[3 * i + 2] = (uint8_t)((p.bgr >> 16) & 255u);
-  }
+  });
+  return DPE_OK;
+}
+
+int dpe_fuse_get_ply_records(dpe_ctx* ctx, void* out) {
+  if (!ctx || !out) return DPE_ERR_ARG;
+  const FusedPointDev* c = ctx->cloud.data();
+  uint8_t* o = (uint8_t*)out;
+  cloud_parallel(ctx->cloud.size(), [=](size_t i) {
+    const FusedPointDev& p = c[i];
+    uint8_t* r = o + 15 * i;
+    memcpy(r, &p.x, 12);
+    r[12] = (uint8_t)(p.bgr & 255u); r[13] = (uint8_t)((p.bgr >> 8) & 255u); r[14] = (uint8_t)((p.bgr >> 16) & 255u);
+  });
   return DPE_OK;
 }
 

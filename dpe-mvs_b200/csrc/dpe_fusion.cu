@@ -11,10 +11,9 @@
 // pixels of the SAME view that land on the same source pixel both use it, where the reference's raster order
 // gives it to the first — a slightly denser cloud, same points.  With several GPUs every rank fuses its own
 // block of views against its own marks (marks do not cross ranks), which adds duplicates at the seams.
-// Accepted points are compacted per view with cub::DeviceSelect (stable: points come out in raster
-// order, like the reference's) and appended to the host cloud.
+// Accepted points are appended to the cloud on the device, view after view, in raster order like the
+// reference's (ordered compaction below); the cloud is copied out once at the end.
 #include <cuda_runtime.h>
-#include <cub/device/device_select.cuh>
 
 #include "dpe_fusion.cuh"
 
@@ -109,14 +108,91 @@ void launch_fuse_view(const FuseView* views, int i, const FuseSrcList& srcs, int
   k_fuse_view<<<num_sms * 8, 256, 0, stream>>>(views, i, srcs, W, H, pts, accept);
 }
 
-size_t fuse_select_temp_bytes(int n) {
-  size_t bytes = 0;
-  cub::DeviceSelect::Flagged(nullptr, bytes, (const FusedPointDev*)nullptr, (const uint8_t*)nullptr, (FusedPointDev*)nullptr, (int*)nullptr, n);
-  return bytes;
+// ---- appending a view's accepted points to the cloud on the device ----------------------------------------------
+// Ordered compaction in three small passes (count per warp, one-CTA scan, scatter) with the running total kept on
+// the device: points of a view land behind the points of the views before it, in raster order like the
+// reference's cloud (DPE.cpp:1286-1364), and the host never has to read a count back between views.
+constexpr int FC_THREADS = 256;
+__device__ __forceinline__ void fuse_range(int total, int& begin, int& end) {
+  const int n_warps = gridDim.x * (FC_THREADS / 32);
+  int chunk = (total + n_warps - 1) / n_warps;
+  chunk = (chunk + 31) & ~31;
+  const int w = blockIdx.x * (FC_THREADS / 32) + (threadIdx.x >> 5);
+  begin = min(w * chunk, total);
+  end = min(begin + chunk, total);
 }
-void launch_fuse_select(void* temp, size_t temp_bytes, const FusedPointDev* pts, const uint8_t* accept, FusedPointDev* out, int* n_out, int n,
-                        cudaStream_t stream) {
-  cub::DeviceSelect::Flagged(temp, temp_bytes, pts, accept, out, n_out, n, stream);
+__global__ void __launch_bounds__(FC_THREADS) k_fuse_count(const uint8_t* __restrict__ accept, int total, int* __restrict__ warp_counts) {
+  int begin, end;
+  fuse_range(total, begin, end);
+  const int lane = threadIdx.x & 31;
+  int n = 0;
+  for (int base = begin; base < end; base += 32) {
+    const int i = base + lane;
+    n += __popc(__ballot_sync(0xffffffffu, i < end && accept[i] != 0));
+  }
+  if (lane == 0) warp_counts[blockIdx.x * (FC_THREADS / 32) + (threadIdx.x >> 5)] = n;
+}
+// exclusive scan of the warp counts, offset by the running total; the running total moves on (clamped to capacity)
+__global__ void __launch_bounds__(1024) k_fuse_scan(int* __restrict__ warp_counts, int n, unsigned long long* __restrict__ running,
+                                                    unsigned long long capacity) {
+  __shared__ unsigned long long s_sum[32];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int per = (n + 1023) / 1024;
+  const int b = min(t * per, n), e = min(b + per, n);
+  unsigned long long loc = 0;
+  for (int i = b; i < e; ++i) loc += (unsigned long long)warp_counts[i];
+  unsigned long long v = loc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned long long u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+  if (lane == 31) s_sum[wid] = v;
+  const unsigned long long pre = v - loc;
+  __syncthreads();
+  if (wid == 0) {
+    const unsigned long long own = s_sum[lane];
+    unsigned long long w = own;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += u; }
+    s_sum[lane] = w - own;
+    if (lane == 31) {  // w = this view's point count
+      const unsigned long long base = running[0];
+      running[1] = base;                                              // where this view's points start
+      running[0] = base + w <= capacity ? base + w : base;            // a view that does not fit is dropped (running[2] counts)
+      if (base + w > capacity) running[2] += 1;
+    }
+  }
+  __syncthreads();
+  unsigned long long run = pre + s_sum[wid];
+  for (int i = b; i < e; ++i) {
+    const int c = warp_counts[i];
+    warp_counts[i] = (int)run;  // offset inside the view (< P)
+    run += (unsigned long long)c;
+  }
+}
+__global__ void __launch_bounds__(FC_THREADS) k_fuse_scatter(const FusedPointDev* __restrict__ pts, const uint8_t* __restrict__ accept, int total,
+                                                             const int* __restrict__ warp_offsets, const unsigned long long* __restrict__ running,
+                                                             unsigned long long capacity, FusedPointDev* __restrict__ cloud) {
+  int begin, end;
+  fuse_range(total, begin, end);
+  const unsigned long long base = running[1];
+  if (running[0] == base) return;  // nothing accepted, or the view did not fit
+  const int lane = threadIdx.x & 31;
+  int off = warp_offsets[blockIdx.x * (FC_THREADS / 32) + (threadIdx.x >> 5)];
+  const unsigned lt = (1u << lane) - 1u;
+  for (int b = begin; b < end; b += 32) {
+    const int i = b + lane;
+    const bool a = i < end && accept[i] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, a);
+    if (a) cloud[base + (unsigned long long)(off + __popc(m & lt))] = pts[i];
+    off += __popc(m);
+  }
+}
+int fuse_append_blocks(int num_sms) { return num_sms * 4; }
+void launch_fuse_append(const FusedPointDev* pts, const uint8_t* accept, int n, int* warp_counts, unsigned long long* running,
+                        unsigned long long capacity, FusedPointDev* cloud, int num_sms, cudaStream_t stream) {
+  const int blocks = fuse_append_blocks(num_sms);
+  k_fuse_count<<<blocks, FC_THREADS, 0, stream>>>(accept, n, warp_counts);
+  k_fuse_scan<<<1, 1024, 0, stream>>>(warp_counts, blocks * (FC_THREADS / 32), running, capacity);
+  k_fuse_scatter<<<blocks, FC_THREADS, 0, stream>>>(pts, accept, n, warp_counts, running, capacity, cloud);
 }
 
 }  // namespace dpe

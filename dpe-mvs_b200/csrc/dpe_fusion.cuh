@@ -24,8 +24,10 @@ struct FusedPointDev {
 
 void launch_fuse_view(const FuseView* views, int i, const FuseSrcList& srcs, int W, int H, FusedPointDev* pts, uint8_t* accept,
                       int num_sms, cudaStream_t stream);
-size_t fuse_select_temp_bytes(int n);
-void launch_fuse_select(void* temp, size_t temp_bytes, const FusedPointDev* pts, const uint8_t* accept, FusedPointDev* out, int* n_out,
-                        int n, cudaStream_t stream);
+// appends the accepted points of one view to `cloud` (device) behind running[0] points; running = {total so far,
+// start of this view, views dropped for lack of capacity}; warp_counts: fuse_append_blocks(num_sms) * 8 ints
+int fuse_append_blocks(int num_sms);
+void launch_fuse_append(const FusedPointDev* pts, const uint8_t* accept, int n, int* warp_counts, unsigned long long* running,
+                        unsigned long long capacity, FusedPointDev* cloud, int num_sms, cudaStream_t stream);
 
 }  // namespace dpe

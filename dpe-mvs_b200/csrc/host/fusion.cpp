@@ -2,6 +2,8 @@
 // runs on the device: csrc/dpe_fusion.cu through dpe_fuse_* of the C ABI.
 #include "fusion.h"
 
+#include <stdio.h>
+
 #include <fstream>
 
 namespace dpe_host {
@@ -21,6 +23,20 @@ bool write_ply(const std::string& path, const float* xyz, const uint8_t* bgr, si
   return out.good();
 }
 
-
+// the same file from ready-made vertex records (15 bytes each: dpe_fuse_get_ply_records), several parts in order
+bool write_ply_records(const std::string& path, const std::vector<const uint8_t*>& parts, const std::vector<size_t>& counts) {
+  size_t n = 0;
+  for (size_t c : counts) n += c;
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) return false;
+  fprintf(f, "ply\nformat binary_little_endian 1.0\nelement vertex %lld\n", (long long)n);
+  fprintf(f, "property float x\nproperty float y\nproperty float z\n");
+  fprintf(f, "property uchar diffuse_blue\nproperty uchar diffuse_green\nproperty uchar diffuse_red\nend_header\n");
+  bool ok = true;
+  for (size_t i = 0; i < parts.size(); ++i)
+    if (counts[i]) ok = ok && fwrite(parts[i], 15, counts[i], f) == counts[i];
+  ok = fclose(f) == 0 && ok;
+  return ok;
+}
 
 }  // namespace dpe_host

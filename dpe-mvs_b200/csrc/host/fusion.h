@@ -10,5 +10,6 @@ namespace dpe_host {
 
 // binary little-endian PLY: x y z float + diffuse_blue/green/red uchar per vertex
 bool write_ply(const std::string& path, const float* xyz, const uint8_t* bgr, size_t n);
+bool write_ply_records(const std::string& path, const std::vector<const uint8_t*>& parts, const std::vector<size_t>& counts);
 
 }  // namespace dpe_host

@@ -466,8 +466,7 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
   // ---- one worker per GPU: scene upload, the whole schedule, export of its views ----------------------
   std::atomic<bool> abort_flag(false);
   std::vector<double> t_upload(G, 0.0), t_stages(G, 0.0), t_prep_wait(G, 0.0), t_up_views(G, 0.0), t_up_commit(G, 0.0), t_fuse(G, 0.0);
-  std::vector<std::vector<float>> cloud_xyz(G);
-  std::vector<std::vector<uint8_t>> cloud_bgr(G);
+  std::vector<std::vector<uint8_t>> cloud_records(G);  // per rank: the PLY vertex records of its views' points
   auto worker = [&](int g) {
     dpe_ctx* c = ctxs[g];
     auto bad = [&](const char* what) {
@@ -553,8 +552,8 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
       if (fusion_sharded || g == 0) {
         size_t n_points = 0;
         if (dpe_fuse_run(c, fusion_sharded ? first : 0, fusion_sharded ? count : n_problems, &n_points)) return bad("fuse_run");
-        cloud_xyz[g].resize(n_points * 3); cloud_bgr[g].resize(n_points * 3);
-        if (n_points && dpe_fuse_get(c, cloud_xyz[g].data(), cloud_bgr[g].data())) return bad("fuse_get");
+        cloud_records[g].resize(n_points * 15);
+        if (n_points && dpe_fuse_get_ply_records(c, cloud_records[g].data())) return bad("fuse_get_ply_records");
       }
       t_fuse[g] = now_s() - tf0;
     }
@@ -584,15 +583,9 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
   if (fusion) {
     // the ranks' clouds in rank order = view order (ExportPointCloud, DPE.cpp:532-572)
     t0 = now_s();
-    size_t n_points = 0;
-    for (int g = 0; g < G; ++g) n_points += cloud_xyz[g].size() / 3;
-    std::vector<float> xyz; std::vector<uint8_t> bgr;
-    xyz.reserve(n_points * 3); bgr.reserve(n_points * 3);
-    for (int g = 0; g < G; ++g) {
-      xyz.insert(xyz.end(), cloud_xyz[g].begin(), cloud_xyz[g].end()); bgr.insert(bgr.end(), cloud_bgr[g].begin(), cloud_bgr[g].end());
-      std::vector<float>().swap(cloud_xyz[g]); std::vector<uint8_t>().swap(cloud_bgr[g]);
-    }
-    if (!write_ply(dense + "/DPE/DPE.ply", xyz.data(), bgr.data(), n_points)) return fail("cannot write DPE.ply");
+    std::vector<const uint8_t*> parts; std::vector<size_t> counts;
+    for (int g = 0; g < G; ++g) { parts.push_back(cloud_records[g].data()); counts.push_back(cloud_records[g].size() / 15); }
+    if (!write_ply_records(dense + "/DPE/DPE.ply", parts, counts)) return fail("cannot write DPE.ply");
     for (int g = 0; g < G; ++g) tm.fusion = std::max(tm.fusion, t_fuse[g]);
     tm.fusion += now_s() - t0;
   }

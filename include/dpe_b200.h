@@ -273,6 +273,9 @@ DPE_API int dpe_fuse_set_color(dpe_ctx* ctx, int view, const uint8_t* bgr);
 DPE_API int dpe_fuse_broadcast_colors(dpe_ctx* ctx, int root);
 DPE_API int dpe_fuse_run(dpe_ctx* ctx, int first_view, int count, size_t* n_points);
 DPE_API int dpe_fuse_get(dpe_ctx* ctx, float* xyz, uint8_t* bgr);
+/* the same cloud as the vertex records of the PLY file ExportPointCloud writes (DPE.cpp:553-569): n_points x 15 bytes,
+ * x y z float32 little-endian + blue green red uint8 */
+DPE_API int dpe_fuse_get_ply_records(dpe_ctx* ctx, void* records);
 
 /* --- micro-benchmarks used for the roofline denominators ------------------ */
 /* filtered tex2D<float> taps per second on a WxH float texture */
