@@ -156,6 +156,7 @@ struct dpe_ctx {
   bool comm_queued = false;  // the running stage has all-gathers in flight
   // device staging of dpe_export_view (depth, normal3, weak as the .npy files hold them)
   float* exp_depth = nullptr; float* exp_normal = nullptr; int8_t* exp_weak = nullptr;
+  uint8_t* viz_bgr = nullptr;  // dpe_viz_render: three BGR images
   // depth atlas per scale: front = committed (read by geom stages), back = being written
   std::vector<float*> atlas_front, atlas_back;
   int last_stage_scale = -1;
@@ -301,6 +302,7 @@ static void free_scene(dpe_ctx* ctx) {
   ctx->h_rc = nullptr;
   dfree(ctx->exp_depth); dfree(ctx->exp_normal); dfree(ctx->exp_weak);
   ctx->exp_depth = nullptr; ctx->exp_normal = nullptr; ctx->exp_weak = nullptr;
+  dfree(ctx->viz_bgr); ctx->viz_bgr = nullptr;
   dfree(ctx->fuse_planes_own); dfree(ctx->fuse_state_own); dfree(ctx->fuse_bgr); dfree(ctx->fuse_mask);
   ctx->fuse_planes_own = nullptr; ctx->fuse_state_own = nullptr; ctx->fuse_bgr = nullptr; ctx->fuse_mask = nullptr;
   ctx->fuse_planes = nullptr; ctx->fuse_state = nullptr; ctx->fuse_have.clear(); ctx->fuse_resident = false;
@@ -1396,6 +1398,28 @@ int dpe_export_view(dpe_ctx* ctx, int view, float* depth, float* normal3, int8_t
   if (weak) CK(cudaMemcpyAsync(weak, ctx->exp_weak, P, cudaMemcpyDeviceToHost, ctx->copy_stream));
   CK(cudaStreamSynchronize(ctx->copy_stream));
   CK(cudaGetLastError());
+  return DPE_OK;
+}
+
+// viz=True: the three colour images of a view's current maps, rendered into device staging (valid until the next call)
+int dpe_viz_render(dpe_ctx* ctx, int view, void** bgr_depth, void** bgr_normal, void** bgr_weak, int* width, int* height) {
+  if (!ctx || view < 0 || view >= ctx->n_views || !bgr_depth || !bgr_normal || !bgr_weak) return DPE_ERR_ARG;
+  ViewData& v = ctx->views[view];
+  if (v.cur_scale < 0 || !v.planes) FAIL(DPE_ERR_STATE, "view has no result on this context");
+  CK(cudaSetDevice(ctx->device));
+  const size_t Pf = (size_t)ctx->W * ctx->H;
+  if (!ctx->viz_bgr) CK(dmalloc(&ctx->viz_bgr, 3 * Pf * 3));
+  if (ctx->stage_open) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->view_done[view - ctx->first_view], 0));
+  const int k = v.cur_scale;
+  const size_t P = (size_t)ctx->sw[k] * ctx->sh[k];
+  uint8_t* d0 = ctx->viz_bgr; uint8_t* d1 = d0 + Pf * 3; uint8_t* d2 = d1 + Pf * 3;
+  // GetDepthMin / GetDepthMax of the view-stage: the PatchMatch range (cam file min * 0.6, max * 1.2, DPE.cpp:788-789)
+  launch_viz(v.planes, v.state, v.cam.depth_min * 0.6f, v.cam.depth_max * 1.2f, d0, d1, d2, (int)P, cfg_of(ctx), ctx->copy_stream);
+  CK(cudaStreamSynchronize(ctx->copy_stream));
+  CK(cudaGetLastError());
+  *bgr_depth = d0; *bgr_normal = d1; *bgr_weak = d2;
+  if (width) *width = ctx->sw[k];
+  if (height) *height = ctx->sh[k];
   return DPE_OK;
 }
 

@@ -702,9 +702,15 @@ void launch_nearest_strong(const KernelParams& P, const LaunchCfg& cfg, cudaStre
   cudaMemsetAsync(P.a.nearest_strong, 0xFF, (size_t)P.a.W * P.a.H * sizeof(short2), s);
   launch_list<L_NEAREST, 128>(P, cfg, s, 16);
 }
+// The anchor search keeps ~3 KB of arrays per thread in local memory: how many of its warps are resident decides
+// whether their stacks stay in L2 (126 MB) or thrash through DRAM (round-2 ncu at 32 warps/SM: 12 GB of DRAM reads
+// in one 10 ms launch).
+#ifndef DPE_NEIGH_BLOCKS_PER_SM
+#define DPE_NEIGH_BLOCKS_PER_SM 16
+#endif
 void launch_gen_neighbours(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) {
   if (full_image(P)) launch_light<L_NEIGH>(P, cfg, s);
-  else launch_list<L_NEIGH, 64>(P, cfg, s, 16);
+  else launch_list<L_NEIGH, 64>(P, cfg, s, DPE_NEIGH_BLOCKS_PER_SM);
 }
 void launch_fit_plane(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t s) {
   if (full_image(P)) { launch_light<L_FIT>(P, cfg, s); return; }
@@ -731,6 +737,46 @@ __global__ void __launch_bounds__(256) k_export(const float4* __restrict__ plane
 void launch_export(const float4* planes, const uint8_t* state, float* depth, float* normal3, int8_t* weak, int n,
                    const LaunchCfg& cfg, cudaStream_t stream) {
   k_export<<<cfg.num_sms * 8, 256, 0, stream>>>(planes, state, depth, normal3, weak, n);
+  count(cfg);
+}
+
+// ---- viz: the colour-mapped images ShowDepthMap / ShowNormalMap / ShowWeakImage write per view-stage when
+// viz=True (DPE.cpp:384-503, main.cpp:448-454), rendered on the device as interleaved BGR; JPEG encoding is the
+// caller's (nvJPEG, host/io.cpp).  planes = the view's carried (world normal, depth) map.
+__global__ void __launch_bounds__(256) k_viz(const float4* __restrict__ planes, const uint8_t* __restrict__ state, float depth_min,
+                                             float depth_max, uint8_t* __restrict__ bgr_depth, uint8_t* __restrict__ bgr_normal,
+                                             uint8_t* __restrict__ bgr_weak, int n) {
+  const float delta = depth_max - depth_min;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = planes[i];
+    // ShowDepthMap: blue -> cyan -> green -> yellow -> red ramp over (depth_max - d) / (depth_max - depth_min)
+    uint8_t b = 0, g = 0, r = 0;
+    if (!(p.w < depth_min || p.w > depth_max || p.w != p.w)) {
+      float v = (depth_max - p.w) / delta;
+      v = fminf(fmaxf(v, 0.f), 1.f) * 255.f;
+      if (v <= 51.f) { b = 255; g = (uint8_t)(v * 5.f); r = 0; }
+      else if (v <= 102.f) { v -= 51.f; b = (uint8_t)(255.f - v * 5.f); g = 255; r = 0; }
+      else if (v <= 153.f) { v -= 102.f; b = 0; g = 255; r = (uint8_t)(v * 5.f); }
+      else if (v <= 204.f) { v -= 153.f; b = 0; g = (uint8_t)(255 - (uint8_t)(v * 128.0 / 51 + 0.5)); r = 255; }
+      else { v -= 204.f; b = 0; g = (uint8_t)(127 - (uint8_t)(v * 127.0 / 51 + 0.5)); r = 255; }
+    }
+    bgr_depth[3 * i] = b; bgr_depth[3 * i + 1] = g; bgr_depth[3 * i + 2] = r;
+    // ShowNormalMap: normalised normal * 127.5 + 127.5, rounded and saturated (cv::Mat::convertTo)
+    const float norm = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+    const float inv = norm == 0.f ? 0.f : 1.0f / norm;
+    const float c3[3] = {p.x * inv, p.y * inv, p.z * inv};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) bgr_normal[3 * i + k] = (uint8_t)fminf(fmaxf(rintf(c3[k] * 127.5f + 127.5f), 0.f), 255.f);
+    // ShowWeakImage: WEAK white, STRONG green, UNKNOWN red
+    const uint8_t st = state[i];
+    bgr_weak[3 * i] = st == DPE_WEAK ? 255 : 0;
+    bgr_weak[3 * i + 1] = st == DPE_UNKNOWN ? 0 : 255;
+    bgr_weak[3 * i + 2] = st == DPE_STRONG ? 0 : 255;
+  }
+}
+void launch_viz(const float4* planes, const uint8_t* state, float depth_min, float depth_max, uint8_t* bgr_depth, uint8_t* bgr_normal,
+                uint8_t* bgr_weak, int n, const LaunchCfg& cfg, cudaStream_t stream) {
+  k_viz<<<cfg.num_sms * 8, 256, 0, stream>>>(planes, state, depth_min, depth_max, bgr_depth, bgr_normal, bgr_weak, n);
   count(cfg);
 }
 

@@ -45,6 +45,10 @@ void launch_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t strea
 void launch_export(const float4* planes, const uint8_t* state, float* depth, float* normal3, int8_t* weak, int n,
                    const LaunchCfg& cfg, cudaStream_t stream);
 
+// viz=True images of a view (depth ramp, normals, pixel classes) as interleaved BGR
+void launch_viz(const float4* planes, const uint8_t* state, float depth_min, float depth_max, uint8_t* bgr_depth, uint8_t* bgr_normal,
+                uint8_t* bgr_weak, int n, const LaunchCfg& cfg, cudaStream_t stream);
+
 // scene preparation
 void launch_u8_to_f32(const uint8_t* src, float* dst, int n, const LaunchCfg& cfg, cudaStream_t stream);
 // cv::resize(INTER_LINEAR) of a float image (DPE.cpp:808)

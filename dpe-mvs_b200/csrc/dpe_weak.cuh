@@ -291,8 +291,10 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
 
   float4 best_plane = make_float4(0.f, 0.f, 0.f, 0.f);
   bool has_valid_plane = false;
+  // per-thread arrays live in local memory (~3 KB here): what can be recomputed from the anchor positions is
+  // (the anchors' normals, their normalised image coordinates) — the stacks of the resident warps should stay in L2
   short2 spv[MAXP];
-  float3 spv3d[MAXP], spvn[MAXP];
+  float3 spv3d[MAXP];
   int valid_count = 0;
   float X[3];
   point3d(rc, x, y, a.planes[center].w, X);
@@ -306,8 +308,6 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
       const float4 spl = a.planes[spc];
       point3d(rc, sp.x, sp.y, spl.w, X);
       spv3d[valid_count] = make_float3(X[0], X[1], X[2]);
-      const float4 n4 = world_to_cam_normal(rc, spl);
-      spvn[valid_count] = make_float3(n4.x, n4.y, n4.z);
       valid_count++;
     }
   }
@@ -320,14 +320,11 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
     float temp_thr = ransac_threshold;
     PairCache<MAXP> edge_test;
     edge_test.clear();
-    // pixel -> normalised image coordinates of every anchor, once (the reference recomputes the two
-    // divisions for every anchor of every RANSAC draw, DPE.cu:2383-2385)
-    float fxs[MAXP], fys[MAXP];
-    for (int si = 0; si < valid_count; ++si) {
-      fxs[si] = fast_div(spv[si].x - rc.cx, rc.fx);
-      fys[si] = fast_div(spv[si].y - rc.cy, rc.fy);
-    }
     const float fx_c = fast_div(x - rc.cx, rc.fx), fy_c = fast_div(y - rc.cy, rc.fy);
+    auto anchor_normal = [&](const int i) {
+      const float4 n4 = world_to_cam_normal(rc, a.planes[spv[i].x + spv[i].y * W]);
+      return make_float3(n4.x, n4.y, n4.z);
+    };
     bool has_consist_normal_plane = false;
     bool must_in_triangle = !(center_label > 0 && edge_limit);
     while (iteration > 0 && max_iter > 0) {
@@ -343,7 +340,7 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
       }
       bool normal_consistency = false;
       if (a.geom && edge_limit) {
-        const float3 AN = spvn[ai], BN = spvn[bi], CN = spvn[ci];
+        const float3 AN = anchor_normal(ai), BN = anchor_normal(bi), CN = anchor_normal(ci);
         normal_consistency = true;
         // the threshold is a double literal in the reference (DPE.cu:2347)
         if (AN.x * BN.x + AN.y * BN.y + AN.z * BN.z < 0.8660254 || AN.x * CN.x + AN.y * CN.y + AN.z * CN.z < 0.8660254 ||
@@ -364,7 +361,8 @@ DPE_HDN void gen_neighbours_pixel(const StageArgs& a, const int x, const int y) 
       cv.w = -(cv.x * A.x + cv.y * A.y + cv.z * A.z);
       int temp_count = 0;
       for (int si = 0; si < valid_count; ++si) {
-        const float fit_depth = fast_div(-cv.w, cv.x * fxs[si] + cv.y * fys[si] + cv.z);
+        const float fxs = fast_div(spv[si].x - rc.cx, rc.fx), fys = fast_div(spv[si].y - rc.cy, rc.fy);  // DPE.cu:2383-2385
+        const float fit_depth = fast_div(-cv.w, cv.x * fxs + cv.y * fys + cv.z);
         const float distance = fabsf(fit_depth - spv3d[si].z);
         residuals[si] = distance;
         if (distance < temp_thr) temp_count++;

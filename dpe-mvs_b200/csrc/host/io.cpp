@@ -250,6 +250,54 @@ bool jpeg_decode_bgr(JpegDecoder* d, const std::string& path, std::vector<uint8_
   return jpeg_decode(d, path, NVJPEG_OUTPUT_BGRI, 3, bgr, width, height, err);
 }
 
+// ---- nvJPEG encoder (viz=True images) ---------------------------------------------------------
+struct JpegEncoder {
+  nvjpegHandle_t handle = nullptr;
+  nvjpegEncoderState_t state = nullptr;
+  nvjpegEncoderParams_t params = nullptr;
+  cudaStream_t stream = nullptr;
+};
+JpegEncoder* jpeg_encoder_create(std::string* err) {
+  JpegEncoder* e = new JpegEncoder();
+  cudaStreamCreate(&e->stream);
+  if (nvjpegCreateSimple(&e->handle) != NVJPEG_STATUS_SUCCESS || nvjpegEncoderStateCreate(e->handle, &e->state, e->stream) != NVJPEG_STATUS_SUCCESS ||
+      nvjpegEncoderParamsCreate(e->handle, &e->params, e->stream) != NVJPEG_STATUS_SUCCESS) {
+    if (err) *err = "nvjpeg encoder initialisation failed";
+    jpeg_encoder_destroy(e);
+    return nullptr;
+  }
+  nvjpegEncoderParamsSetQuality(e->params, 95, e->stream);                       // cv::imwrite's default
+  nvjpegEncoderParamsSetSamplingFactors(e->params, NVJPEG_CSS_420, e->stream);  // libjpeg's default for YCbCr
+  return e;
+}
+void jpeg_encoder_destroy(JpegEncoder* e) {
+  if (!e) return;
+  if (e->params) nvjpegEncoderParamsDestroy(e->params);
+  if (e->state) nvjpegEncoderStateDestroy(e->state);
+  if (e->handle) nvjpegDestroy(e->handle);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+bool jpeg_encode_bgr_dev(JpegEncoder* e, const void* bgr_dev, int width, int height, const std::string& path, std::string* err) {
+  nvjpegImage_t img;
+  memset(&img, 0, sizeof(img));
+  img.channel[0] = (unsigned char*)bgr_dev;
+  img.pitch[0] = (size_t)width * 3;
+  if (nvjpegEncodeImage(e->handle, e->state, e->params, &img, NVJPEG_INPUT_BGRI, width, height, e->stream) != NVJPEG_STATUS_SUCCESS) {
+    if (err) *err = "nvjpegEncodeImage failed";
+    return false;
+  }
+  size_t len = 0;
+  if (nvjpegEncodeRetrieveBitstream(e->handle, e->state, nullptr, &len, e->stream) != NVJPEG_STATUS_SUCCESS) { if (err) *err = "nvjpeg bitstream size"; return false; }
+  std::vector<unsigned char> buf(len);
+  if (nvjpegEncodeRetrieveBitstream(e->handle, e->state, buf.data(), &len, e->stream) != NVJPEG_STATUS_SUCCESS ||
+      cudaStreamSynchronize(e->stream) != cudaSuccess) { if (err) *err = "nvjpeg bitstream"; return false; }
+  std::ofstream out(path, std::ios::binary);
+  if (!out.is_open()) { if (err) *err = "cannot write " + path; return false; }
+  out.write((const char*)buf.data(), (std::streamsize)len);
+  return out.good();
+}
+
 }  // namespace dpe_host
 
 // C hooks for the CPU tests (tests/test_io.py)

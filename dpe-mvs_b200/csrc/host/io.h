@@ -52,4 +52,10 @@ bool jpeg_decode_gray_into(JpegDecoder* d, const std::string& path, uint8_t* dst
 bool jpeg_decode_bgr(JpegDecoder* d, const std::string& path, std::vector<uint8_t>* bgr, int* width, int* height,
                      std::string* err);
 
+// JPEG encoding of an interleaved BGR image that lives on the current device (viz=True outputs), quality 95, 4:2:0
+struct JpegEncoder;
+JpegEncoder* jpeg_encoder_create(std::string* err);
+void jpeg_encoder_destroy(JpegEncoder* e);
+bool jpeg_encode_bgr_dev(JpegEncoder* e, const void* bgr_dev, int width, int height, const std::string& path, std::string* err);
+
 }  // namespace dpe_host

@@ -166,7 +166,8 @@ class ExportQueue {
 
 extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_index, int verbose, int fusion, int viz,
                                         int depth, int normal, int weak, int edge) {
-  (void)viz;  // visualisation jpgs are out of scope; the flag is accepted
+  // viz: depth_<i>.jpg / normal_<i>.jpg / weak_<i>.jpg per view and iteration like the reference
+  // (main.cpp:448-454); its rawedge_k / connect_k jpgs of the prep stage and the complex.jpg residue (Q12) are not written
   const double t_begin = now_s();
   Timing tm;
   const std::string dense = dense_folder_c ? dense_folder_c : "";
@@ -494,6 +495,8 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     t_upload[g] = now_s() - tu0;
     int first = 0, count = 0;
     dpe_shard_range(n_problems, G, g, &first, &count);
+    JpegEncoder* venc = nullptr;  // viz images (created on first use, on this worker's GPU)
+    struct EncGuard { JpegEncoder*& e; ~EncGuard() { jpeg_encoder_destroy(e); e = nullptr; } } enc_guard{venc};
     const double ts0 = now_s();
     bool prep_up = false;
     for (size_t si = 0; si < schedule.size(); ++si) {
@@ -529,6 +532,18 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
       }
       if (dpe_stage_end(c)) return bad("stage_end");
       if (dpe_stage_commit(c)) return bad("stage_commit");
+      if (viz) {
+        if (!venc) { std::string e; cudaSetDevice(gpus[g]); venc = jpeg_encoder_create(&e); }
+        for (int v = first; venc && v < first + count; ++v) {
+          void *d0, *d1, *d2; int vw = 0, vh = 0;
+          if (dpe_viz_render(c, v, &d0, &d1, &d2, &vw, &vh)) return bad("viz_render");
+          const std::string dir = out_root + "/" + format_index(view_ids[v]) + "/";
+          std::string e;
+          jpeg_encode_bgr_dev(venc, d0, vw, vh, dir + "depth_" + std::to_string(si) + ".jpg", &e);
+          jpeg_encode_bgr_dev(venc, d1, vw, vh, dir + "normal_" + std::to_string(si) + ".jpg", &e);
+          jpeg_encode_bgr_dev(venc, d2, vw, vh, dir + "weak_" + std::to_string(si) + ".jpg", &e);
+        }
+      }
       if (g == 0 && verbose) {
         std::cout << "Iteration " << si + 1 << " / " << iteration_num << " done" << std::endl;
         if (st.resolution_up) std::cout << "Resolution up" << std::endl;

@@ -221,6 +221,10 @@ DPE_API int dpe_get_maps(dpe_ctx* ctx, int view, float* depth, float* normal3, u
  * packed on the device, copied on a stream of their own (pinned destinations overlap running stages).  Any pointer
  * may be NULL. */
 DPE_API int dpe_export_view(dpe_ctx* ctx, int view, float* depth, float* normal3, int8_t* weak);
+/* viz=True (ShowDepthMap / ShowNormalMap / ShowWeakImage, DPE.cpp:384-503, called per view-stage at main.cpp:448-454): the
+ * three colour-mapped images of `view`'s current maps, interleaved B,G,R, rendered on the device.  The pointers are
+ * DEVICE pointers into a staging buffer of the context, valid until the next call; the size is that of the view's scale. */
+DPE_API int dpe_viz_render(dpe_ctx* ctx, int view, void** bgr_depth, void** bgr_normal, void** bgr_weak, int* width, int* height);
 /* number of (pixel,hypothesis,view) bilateral-NCC units evaluated so far
  * (NCCOld = 1 unit = 36 taps, NCCNew = taps/36); 0 unless counting is on. */
 DPE_API int dpe_set_count_evals(dpe_ctx* ctx, int on);

@@ -499,6 +499,33 @@ def test_pipeline_python_api_and_cli(c1_folder):
         assert not (d / "edge.npy").exists()
 
 
+def test_pipeline_viz_images(c1_folder):
+    """viz=True: depth_<i>.jpg / normal_<i>.jpg / weak_<i>.jpg per view and iteration like the reference's ProcessProblem
+    (main.cpp:448-454; ShowDepthMap / ShowNormalMap / ShowWeakImage, DPE.cpp:384-503): decodable, of the stage's size, and
+    the last weak image shows the classes of weak.npy in the reference's colours."""
+    import cv2
+    import DPE_MVS
+    spec, folder = c1_folder
+    shutil.rmtree(folder / "DPE", ignore_errors=True)
+    assert DPE_MVS.dpe_mvs(str(folder), 0, False, False, True, True, False, True, False) == 0
+    d = folder / "DPE" / "00000000"
+    H, W = spec.height, spec.width
+    for it in range(8):
+        for name in ("depth", "normal", "weak"):
+            img = cv2.imread(str(d / f"{name}_{it}.jpg"), cv2.IMREAD_COLOR)
+            assert img is not None, (name, it)
+            assert img.shape == ((H // 2, W // 2, 3) if it < 4 else (H, W, 3)), (name, it, img.shape)
+    weak = np.load(d / "weak.npy")
+    img = cv2.imread(str(d / "weak_7.jpg"), cv2.IMREAD_COLOR).astype(int)
+    ref = {0: (0, 0, 255), 1: (255, 255, 255), 2: (0, 255, 0)}      # unknown red, weak white, strong green (B, G, R)
+    err = np.zeros(weak.shape)
+    for cls, col in ref.items():
+        err[weak == cls] = np.abs(img[weak == cls] - np.array(col)).max(-1)
+    assert (err < 80).mean() > 0.97, float((err < 80).mean())     # JPEG ringing at class borders
+    depth_img = cv2.imread(str(d / "depth_7.jpg"), cv2.IMREAD_COLOR)
+    assert depth_img.std() > 10                                       # a colour ramp, not a blank image
+
+
 def _read_ply(path):
     raw = Path(path).read_bytes()
     head, body = raw.split(b"end_header\n", 1)
