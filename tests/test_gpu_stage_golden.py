@@ -136,7 +136,9 @@ def test_weak_stage_follows_the_reference_kernels(arith, thr):
     assert _identical(ctx.debug_read(7, (H, W, 4), np.float32), fx["s1_planes"]) > 0.999    # 1.000
     assert (ctx.debug_read(8, (H, W), np.uint32) == fx["s1_selected"]).mean() > 0.999
     run(2)          # strong sweeps, edge-adaptive sampling, on converged maps (near-ties are frequent)
-    assert _identical(ctx.debug_read(7, (H, W, 4), np.float32), fx["s2_planes"]) > thr["s2"]   # 0.981 / 0.995
+    p2 = ctx.debug_read(7, (H, W, 4), np.float32)
+    print("stage 6 after the first strong sweep: planes bit-identical", float((p2 == fx["s2_planes"]).all(-1).mean()), "arith", arith)
+    assert _identical(p2, fx["s2_planes"]) > thr["s2"]   # 0.981 / 0.995
     run(3)          # RANSACToGetFitPlane + adaptive radius
     assert (ctx.debug_read(2, (H, W), np.int32)[weak] == fx["s3_radius"][weak]).mean() > 0.995  # 1.000
     dn = np.abs(ctx.debug_read(1, (H, W, 4), np.float32)[..., :3] - fx["s3_fit"][..., :3]).max(-1)
@@ -146,7 +148,9 @@ def test_weak_stage_follows_the_reference_kernels(arith, thr):
     assert _identical(pl, fx["s4_planes"]) > thr["s4"]                                       # 0.977 / 0.993
     assert _identical(pl, fx["s4_planes"], weak) > thr["s4w"]                                # 0.974 / 0.987
     run(10)         # after the third iteration
-    assert _identical(ctx.debug_read(7, (H, W, 4), np.float32), fx["s10_planes"]) > thr["s10"]  # 0.898 / 0.964
+    p10 = ctx.debug_read(7, (H, W, 4), np.float32)
+    print("stage 6 after the third iteration: planes bit-identical", float((p10 == fx["s10_planes"]).all(-1).mean()))
+    assert _identical(p10, fx["s10_planes"]) > thr["s10"]  # 0.898 / 0.964
     run(-1)         # the whole stage: + GetDepthandNormal, median filter, DepthToWeak, LocalRefine, host tail
     fin = ctx.get_maps(0, 1)
     ctx.close()
