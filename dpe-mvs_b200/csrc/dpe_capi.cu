@@ -68,6 +68,7 @@ struct Scratch {
   short2* nearest_strong = nullptr; short2* neighbours = nullptr;
   Xorwow* rng = nullptr;
   int* weak_list = nullptr; int* weak_count = nullptr; int* weak_scan = nullptr;
+  float4* snap_planes = nullptr; float* snap_costs = nullptr;  // dpe_set_reference_race(ctx, 2), allocated on first use
   cudaStream_t stream = nullptr;
 };
 
@@ -163,7 +164,7 @@ struct dpe_ctx {
   bool stage_pending = false;
   bool stage_open = false;    // between dpe_stage_begin and dpe_stage_end
   bool gauss_seidel = false;  // dpe_set_view_order
-  bool ref_race = false;      // dpe_set_reference_race
+  int ref_race = 0;           // dpe_set_reference_race
   bool cost_raw = true;       // dpe_set_cost_arithmetic
   bool exact = true;          // dpe_set_cost_arithmetic: DPE_COST_REFERENCE_EXACT is the default
   int variants = 0;           // dpe_debug_set_variants
@@ -293,6 +294,7 @@ static void free_scene(dpe_ctx* ctx) {
     dfree(s.fit_planes); dfree(s.radius); dfree(s.edge_neigh); dfree(s.complexity);
     dfree(s.label_boundary); dfree(s.weak_reliable); dfree(s.nearest_strong); dfree(s.neighbours);
     dfree(s.rng); dfree(s.weak_list); dfree(s.weak_count); dfree(s.weak_scan);
+    dfree(s.snap_planes); dfree(s.snap_costs);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   ctx->scratch.clear();
@@ -605,8 +607,10 @@ int dpe_scene_commit(dpe_ctx* ctx) {
   CK(cudaStreamSynchronize(ctx->upload_stream));  // images (uploads and / or the broadcast)
   trace("images arrived");
   ctx->scale_arr.assign(ctx->n_scales, nullptr); ctx->scale_tex.assign(ctx->n_scales, 0);
+  // DPE_TEX_F16=1 (experiment): the full-resolution level holds integers 0..255, which fp16 texels represent exactly
+  const bool top_f16 = getenv("DPE_TEX_F16") && atoi(getenv("DPE_TEX_F16")) != 0;
   for (int k = 0; k < ctx->n_scales; ++k) {
-    cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+    cudaChannelFormatDesc cd = (top_f16 && k == top) ? cudaCreateChannelDescHalf() : cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
     CK(cudaMalloc3DArray(&ctx->scale_arr[k], &cd, make_cudaExtent(ctx->sw[k], ctx->sh[k], ctx->n_views), cudaArrayLayered));
     cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
     rd.resType = cudaResourceTypeArray; rd.res.array.array = ctx->scale_arr[k];
@@ -621,6 +625,7 @@ int dpe_scene_commit(dpe_ctx* ctx) {
   for (int k = 0; k < ctx->n_scales; ++k)
     CK(dmalloc(&ctx->lin_slab[k], (size_t)ctx->n_views * ctx->sw[k] * ctx->sh[k] * sizeof(float)));
   const size_t P = (size_t)ctx->W * ctx->H;
+  uint16_t* half_tmp = nullptr;
   for (int vi = 0; vi < ctx->n_views; ++vi) {
     ViewData& v = ctx->views[vi];
     for (int k = 0; k < ctx->n_scales; ++k) v.scales[k].lin = ctx->lin_slab[k] + (size_t)vi * ctx->sw[k] * ctx->sh[k];
@@ -632,6 +637,11 @@ int dpe_scene_commit(dpe_ctx* ctx) {
       const int w = ctx->sw[k], h = ctx->sh[k];
       cudaMemcpy3DParms cp; memset(&cp, 0, sizeof(cp));
       cp.srcPtr = make_cudaPitchedPtr(v.scales[k].lin, (size_t)w * sizeof(float), w, h);
+      if (top_f16 && k == top) {
+        if (!half_tmp) CK(dmalloc(&half_tmp, P * 2));
+        launch_u8_to_f16(ctx->gray_slab + P * vi, half_tmp, ctx->W * ctx->H, cfg, 0);
+        cp.srcPtr = make_cudaPitchedPtr(half_tmp, (size_t)w * 2, w, h);
+      }
       cp.dstArray = ctx->scale_arr[k];
       cp.dstPos = make_cudaPos(0, 0, vi);
       cp.extent = make_cudaExtent(w, h, 1);
@@ -639,6 +649,7 @@ int dpe_scene_commit(dpe_ctx* ctx) {
       CK(cudaMemcpy3DAsync(&cp, 0));
     }
   }
+  if (half_tmp) dfree(half_tmp);   // stream-ordered: after the copies above
   trace("pyramids + textures");
   // depth atlases
   const int slots = total_slots(ctx);
@@ -804,7 +815,8 @@ static void fill_args(dpe_ctx* ctx, int view, int k, const dpe_stage_params* p, 
   a.label_boundary = s.label_boundary; a.weak_reliable = s.weak_reliable; a.nearest_strong = s.nearest_strong;
   a.neighbours = s.neighbours;
   a.rng = s.rng;
-  a.ref_race = ctx->ref_race ? 1 : 0;
+  a.ref_race = ctx->ref_race;
+  a.snap_planes = s.snap_planes; a.snap_costs = s.snap_costs;
   a.cost_raw = ctx->cost_raw ? 1 : 0;
   a.exact = ctx->exact ? 1 : 0;
   a.variants = ctx->variants;
@@ -860,6 +872,10 @@ int dpe_stage_begin(dpe_ctx* ctx, int k, const dpe_stage_params* p, uint64_t see
   // all views of a scale are layers of one texture (layer = view, linear filter, clamp); the handle sits in a
   // device-wide constant, so nothing of another scale may be in flight (it is not: dpe_stage_end drained it)
   launch_set_scale_tex((unsigned long long)ctx->scale_tex[k], 0);
+  if (ctx->ref_race == 2 && !ctx->scratch.empty() && !ctx->scratch[0].snap_planes) {
+    const size_t Pmax = (size_t)ctx->sw[ctx->n_scales - 1] * ctx->sh[ctx->n_scales - 1];
+    for (auto& s : ctx->scratch) { CK(dmalloc(&s.snap_planes, Pmax * sizeof(float4))); CK(dmalloc(&s.snap_costs, Pmax * sizeof(float))); }
+  }
   CK(cudaEventRecord(ctx->ev0, 0));
   for (auto& s : ctx->scratch) CK(cudaStreamWaitEvent(s.stream, ctx->ev0, 0));
   const int stop = ctx->debug_stop_after;
@@ -1246,7 +1262,7 @@ int dpe_debug_set_variants(dpe_ctx* ctx, int mask) {
 
 int dpe_set_reference_race(dpe_ctx* ctx, int on) {
   if (!ctx) return DPE_ERR_ARG;
-  ctx->ref_race = on != 0;
+  ctx->ref_race = on == 2 ? 2 : (on != 0);
   return DPE_OK;
 }
 

@@ -13,6 +13,7 @@
 //    through the texture unit's bilinear filter, and the three moment sums are FMAs;
 //  * red/black sweeps read only the other colour, so a sweep is race-free and
 //    deterministic.
+#include <cuda_fp16.h>
 #include <cuda_pipeline.h>
 #include "dpe_core.cuh"
 #include "dpe_consts.h"
@@ -660,6 +661,11 @@ void launch_strong(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t st
   P.a.tiles_x = (P.a.W + TILE_W - 1) / TILE_W;
   P.a.tiles_y = (P.a.H + 7) / 8;
   const int g = persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, CTAS_PER_SM);
+  if (P.a.use_apd && P.a.ref_race == 2 && P.a.snap_planes) {
+    const size_t n = (size_t)P.a.W * P.a.H;
+    cudaMemcpyAsync((void*)P.a.snap_planes, P.a.planes, n * sizeof(float4), cudaMemcpyDeviceToDevice, stream);
+    cudaMemcpyAsync((void*)P.a.snap_costs, P.a.costs, n * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+  }
   if (P.a.use_apd) k_half<OP_STRONG_EDGE><<<g, NT, 0, stream>>>(P.a);
   else k_half<OP_STRONG><<<g, NT, 0, stream>>>(P.a);
   count(cfg);
@@ -786,6 +792,13 @@ __global__ void k_u8_to_f32(const uint8_t* __restrict__ src, float* __restrict__
 }
 void launch_u8_to_f32(const uint8_t* src, float* dst, int n, const LaunchCfg& cfg, cudaStream_t stream) {
   k_u8_to_f32<<<cfg.num_sms * 8, 256, 0, stream>>>(src, dst, n);
+  count(cfg);
+}
+__global__ void k_u8_to_f16(const uint8_t* __restrict__ src, __half* __restrict__ dst, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = __int2half_rn((int)src[i]);
+}
+void launch_u8_to_f16(const uint8_t* src, void* dst, int n, const LaunchCfg& cfg, cudaStream_t stream) {
+  k_u8_to_f16<<<cfg.num_sms * 8, 256, 0, stream>>>(src, (__half*)dst, n);
   count(cfg);
 }
 

@@ -103,7 +103,11 @@ struct StageArgs {
   unsigned char* debug_accept;  // test hook (dpe_debug_stop_after at a strong-sweep step): per pixel, which candidate the sweep took
   int exact;     // 1: homography, source coordinates, bilateral weights and geometric consistency in the reference's fp32 operation order
   int cost_raw;  // cost arithmetic: 1 = moments on raw intensities like the reference, 0 = centred (dpe_core.cuh)
-  int ref_race;  // 1: edge-mode direction 4 samples its own colour like the reference, racy
+  int ref_race;  // 1: edge-mode direction 4 samples its own colour like the reference, racy;
+                 // 2: the same positions read from a copy of the maps taken before the launch (what a reference thread
+                 //    sees when the pixels up-left of it are still in flight): deterministic
+  const float4* snap_planes;  // ref_race == 2: planes / costs as they were before this half-sweep
+  const float* snap_costs;
   int variants;  // DPE_VARIANT_* bits (dpe_debug_set_variants): earlier forms of a kernel, kept for A/B tests
   Xorwow* rng;  // per-pixel XORWOW state of this stage (dpe_rng.h), starts as curand_init(seed, y, x)
   unsigned long long* eval_units;  // optional counter (36-tap units)

@@ -170,7 +170,9 @@ enum { DPE_COST_CENTRED = 0, DPE_COST_REFERENCE = 1, DPE_COST_REFERENCE_EXACT = 
 DPE_API int dpe_set_cost_arithmetic(dpe_ctx* ctx, int mode);
 /* Edge-mode propagation, direction 4: 0 (default) samples the other colour like directions 5-7, which
  * makes a sweep race-free and bit-reproducible; 1 samples the reference's positions (own colour, read while
- * the same launch writes it: DPE.cu:1274-1278) for parity runs. */
+ * the same launch writes it: DPE.cu:1274-1278) for parity runs; 2 samples the reference's positions
+ * from a copy of the maps taken before each half-sweep (what a reference thread reads while the pixels up-left
+ * of it are still in flight, the usual case): the reference's positions without its nondeterminism. */
 DPE_API int dpe_set_reference_race(dpe_ctx* ctx, int on);
 /* test hook: run earlier forms of some kernels, for A/B comparisons of results and speed.  Bit 4: the WEAK-only
  * steps (label-boundary walk, nearest strong pixel, anchor search, plane fit) as image-sized launches, one thread

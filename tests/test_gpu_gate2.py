@@ -9,6 +9,8 @@ assertions are written against (the literal 99 % / 1 degree of BASELINE.json is 
 itself).  Modes of this implementation:
   matched   the reference's view order (sequential) and its racy direction-4 sampling positions, same pixels and
             prep arrays as the reference reads                                  (dpe_set_view_order, dpe_set_reference_race)
+  snapshot  like matched, the direction-4 positions read from the maps as they were before each half-sweep
+            (dpe_set_reference_race(ctx, 2)): the reference's positions, deterministic
   default   a bare C-ABI context: sequential order, race-free direction 4 (what DPE_DETERMINISTIC=1 selects in dpe_mvs())
   jacobi    every view reads the previous stage's depth maps (the order several GPUs need), race-free direction 4
   jpeg      the product end to end, DPE_MVS.dpe_mvs(folder) on one GPU: its own JPEG decode (host/jpeg_luma.cpp) and native
@@ -81,7 +83,7 @@ def _run_ours(grays, cams, drs, pairs, n_scales, prep, matched, sequential):
     if sequential:
         ctx.set_view_order(1)
     if matched:
-        ctx.set_reference_race(1)
+        ctx.set_reference_race(int(matched))
     for (k, p) in capi.stage_schedule(n_scales):
         ctx.run_stage(k, p, SEED)
         ctx.stage_commit()
@@ -122,7 +124,7 @@ def _gate2(tmp, config, scale, n_views, tag):
     ref_b = _run_reference(folder, V, n_scales, prep)
     res = {"scene": tag, "views": V, "size": [int(grays[0].shape[1]), int(grays[0].shape[0])]}
     res["ref_vs_ref"] = _mean([_compare(ref_b[v], ref_a[v]) for v in range(V)])
-    for name, (matched, sequential) in {"matched": (True, True), "default": (False, True), "jacobi": (False, False)}.items():
+    for name, (matched, sequential) in {"matched": (1, True), "snapshot": (2, True), "default": (0, True), "jacobi": (0, False)}.items():
         ours = _run_ours(grays, cams, drs, pairs, n_scales, prep, matched, sequential)
         res[f"{name}_vs_ref"] = _mean([_compare(ours[v], ref_a[v]) for v in range(V)])
         if name == "matched":
