@@ -205,6 +205,8 @@ def run_ours(args):
     # which dpe_mvs() honours too (host/pipeline.cpp)
     arith = {"fast": 1, "centred": 0}.get(os.environ.get("DPE_ARITH", ""), 2)
     ctx.set_cost_arithmetic(arith)
+    # edge-mode direction 4 as dpe_mvs() runs it: the reference's positions, read from the pre-sweep copy of the maps
+    ctx.set_reference_race({"live": 1, "shifted": 0}.get(os.environ.get("DPE_DIRECTION4", ""), 2))
     sched = capi.stage_schedule(n_scales)
 
     def one_step():

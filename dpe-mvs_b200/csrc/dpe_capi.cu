@@ -607,10 +607,8 @@ int dpe_scene_commit(dpe_ctx* ctx) {
   CK(cudaStreamSynchronize(ctx->upload_stream));  // images (uploads and / or the broadcast)
   trace("images arrived");
   ctx->scale_arr.assign(ctx->n_scales, nullptr); ctx->scale_tex.assign(ctx->n_scales, 0);
-  // DPE_TEX_F16=1 (experiment): the full-resolution level holds integers 0..255, which fp16 texels represent exactly
-  const bool top_f16 = getenv("DPE_TEX_F16") && atoi(getenv("DPE_TEX_F16")) != 0;
   for (int k = 0; k < ctx->n_scales; ++k) {
-    cudaChannelFormatDesc cd = (top_f16 && k == top) ? cudaCreateChannelDescHalf() : cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
     CK(cudaMalloc3DArray(&ctx->scale_arr[k], &cd, make_cudaExtent(ctx->sw[k], ctx->sh[k], ctx->n_views), cudaArrayLayered));
     cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
     rd.resType = cudaResourceTypeArray; rd.res.array.array = ctx->scale_arr[k];
@@ -625,7 +623,6 @@ int dpe_scene_commit(dpe_ctx* ctx) {
   for (int k = 0; k < ctx->n_scales; ++k)
     CK(dmalloc(&ctx->lin_slab[k], (size_t)ctx->n_views * ctx->sw[k] * ctx->sh[k] * sizeof(float)));
   const size_t P = (size_t)ctx->W * ctx->H;
-  uint16_t* half_tmp = nullptr;
   for (int vi = 0; vi < ctx->n_views; ++vi) {
     ViewData& v = ctx->views[vi];
     for (int k = 0; k < ctx->n_scales; ++k) v.scales[k].lin = ctx->lin_slab[k] + (size_t)vi * ctx->sw[k] * ctx->sh[k];
@@ -637,11 +634,6 @@ int dpe_scene_commit(dpe_ctx* ctx) {
       const int w = ctx->sw[k], h = ctx->sh[k];
       cudaMemcpy3DParms cp; memset(&cp, 0, sizeof(cp));
       cp.srcPtr = make_cudaPitchedPtr(v.scales[k].lin, (size_t)w * sizeof(float), w, h);
-      if (top_f16 && k == top) {
-        if (!half_tmp) CK(dmalloc(&half_tmp, P * 2));
-        launch_u8_to_f16(ctx->gray_slab + P * vi, half_tmp, ctx->W * ctx->H, cfg, 0);
-        cp.srcPtr = make_cudaPitchedPtr(half_tmp, (size_t)w * 2, w, h);
-      }
       cp.dstArray = ctx->scale_arr[k];
       cp.dstPos = make_cudaPos(0, 0, vi);
       cp.extent = make_cudaExtent(w, h, 1);
@@ -649,7 +641,6 @@ int dpe_scene_commit(dpe_ctx* ctx) {
       CK(cudaMemcpy3DAsync(&cp, 0));
     }
   }
-  if (half_tmp) dfree(half_tmp);   // stream-ordered: after the copies above
   trace("pyramids + textures");
   // depth atlases
   const int slots = total_slots(ctx);

@@ -70,7 +70,7 @@ struct RefTile {
   int x0, y0;
   __device__ __forceinline__ void stage(const float* __restrict__ img, int W, int H, int tx0, int ty0) {
     x0 = tx0; y0 = ty0;
-    for (int i = threadIdx.x; i < SMW * SMH; i += NT) {
+    for (int i = threadIdx.x; i < SMW * SMH; i += blockDim.x) {
       const int gx = iclamp(tx0 - HALO + (i % SMW), 0, W - 1);
       const int gy = iclamp(ty0 - HALO + (i / SMW), 0, H - 1);
       __pipeline_memcpy_async(&s[i], &img[(size_t)gy * W + gx], sizeof(float));
@@ -160,6 +160,45 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_half(const __grid_constant_
         const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact != 0);
         strong_update_pixel<OP == OP_STRONG_EDGE>(env, ps, a, x, y, cost_arr, evals);
       }
+    }
+  }
+  flush_evals(a.eval_units, evals);
+}
+
+// The edge-mode strong sweep in the REFERENCE's launch geometry, for dpe_set_reference_race(ctx, 1): one CTA of
+// 16 warps per 32 x 32 pixel block, warp w on the row pair 2w / 2w+1, CTAs handed out in raster order, one per SM
+// (128 registers x 512 threads) — BlackPixelUpdateStrong<<<(W/32, H/2/16), (32,16)>>> (DPE.cu:3129-3148, 3199-3201).
+// What a direction-4 read of the launch's own colour sees depends on which threads have already written: warps whose
+// pixels are cheap (views outside the source images) finish long before their block mates, earlier waves of blocks
+// before later ones.  The same geometry reproduces those systematic parts of the reference's race; the persistent
+// 8-row tiles of k_half do not.  The per-thread table keeps its stride of NT: four groups of 128 threads.
+constexpr int REFGEOM_THREADS = 512;
+constexpr int REFGEOM_SMEM = 4 * 36 * NT * (int)sizeof(float2) + SMW * (32 + 2 * HALO) * (int)sizeof(float);
+template <int OP>
+__global__ void __launch_bounds__(REFGEOM_THREADS, 1) k_half_refgeom(const __grid_constant__ StageArgs A) {
+  extern __shared__ float2 s_dyn[];
+  float2* s_tbl = s_dyn + (threadIdx.x / NT) * 36 * NT + (threadIdx.x % NT);
+  StageArgs a = A;
+  a.rc = &c_rc[a.slot];
+  unsigned evals = 0;
+  RefTile<32> tile;
+  tile.s = reinterpret_cast<float*>(s_dyn + 4 * 36 * NT);
+  DevEnv env;
+  env.tbl = s_tbl;
+  env.img = a.ref_img; env.W = a.W; env.H = a.H; env.slot = a.slot;
+  TblStore st;
+  st.tbl = s_tbl;
+  float cost_arr[9 * DPE_MAX_IMAGES];
+  const int tx0 = (blockIdx.x % a.tiles_x) * TILE_W, ty0 = (blockIdx.x / a.tiles_x) * 32;
+  tile.stage(a.ref_img, a.W, a.H, tx0, ty0);
+  __pipeline_wait_prior(0);
+  __syncthreads();
+  const int lx = threadIdx.x & 31;
+  const int x = tx0 + lx, y = ty0 + 2 * (threadIdx.x >> 5) + ((lx + a.colour) & 1);
+  if (x < a.W && y < a.H) {
+    if (a.state[y * a.W + x] != DPE_WEAK) {
+      const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact != 0);
+      strong_update_pixel<OP == OP_STRONG_EDGE, true>(env, ps, a, x, y, cost_arr, evals);
     }
   }
   flush_evals(a.eval_units, evals);
@@ -666,7 +705,11 @@ void launch_strong(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t st
     cudaMemcpyAsync((void*)P.a.snap_planes, P.a.planes, n * sizeof(float4), cudaMemcpyDeviceToDevice, stream);
     cudaMemcpyAsync((void*)P.a.snap_costs, P.a.costs, n * sizeof(float), cudaMemcpyDeviceToDevice, stream);
   }
-  if (P.a.use_apd) k_half<OP_STRONG_EDGE><<<g, NT, 0, stream>>>(P.a);
+  if (P.a.use_apd && P.a.ref_race == 1) {
+    cudaFuncSetAttribute(k_half_refgeom<OP_STRONG_EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, REFGEOM_SMEM);  // per device
+    P.a.tiles_y = (P.a.H + 31) / 32;
+    k_half_refgeom<OP_STRONG_EDGE><<<P.a.tiles_x * P.a.tiles_y, REFGEOM_THREADS, REFGEOM_SMEM, stream>>>(P.a);
+  } else if (P.a.use_apd) k_half<OP_STRONG_EDGE><<<g, NT, 0, stream>>>(P.a);
   else k_half<OP_STRONG><<<g, NT, 0, stream>>>(P.a);
   count(cfg);
 }
@@ -792,13 +835,6 @@ __global__ void k_u8_to_f32(const uint8_t* __restrict__ src, float* __restrict__
 }
 void launch_u8_to_f32(const uint8_t* src, float* dst, int n, const LaunchCfg& cfg, cudaStream_t stream) {
   k_u8_to_f32<<<cfg.num_sms * 8, 256, 0, stream>>>(src, dst, n);
-  count(cfg);
-}
-__global__ void k_u8_to_f16(const uint8_t* __restrict__ src, __half* __restrict__ dst, int n) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = __int2half_rn((int)src[i]);
-}
-void launch_u8_to_f16(const uint8_t* src, void* dst, int n, const LaunchCfg& cfg, cudaStream_t stream) {
-  k_u8_to_f16<<<cfg.num_sms * 8, 256, 0, stream>>>(src, (__half*)dst, n);
   count(cfg);
 }
 

@@ -51,7 +51,6 @@ void launch_viz(const float4* planes, const uint8_t* state, float depth_min, flo
 
 // scene preparation
 void launch_u8_to_f32(const uint8_t* src, float* dst, int n, const LaunchCfg& cfg, cudaStream_t stream);
-void launch_u8_to_f16(const uint8_t* src, void* dst, int n, const LaunchCfg& cfg, cudaStream_t stream);  // __half, exact: 0..255
 // cv::resize(INTER_LINEAR) of a float image (DPE.cpp:808)
 void launch_relative_pose(const float* in, float* out, int n, cudaStream_t stream);
 void launch_resize_linear(const float* src, int sw, int sh, float* dst, int dw, int dh,

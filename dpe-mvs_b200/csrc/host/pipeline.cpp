@@ -426,12 +426,18 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     const std::string m(e);
     arith = m == "fast" ? DPE_COST_REFERENCE : (m == "centred" ? DPE_COST_CENTRED : DPE_COST_REFERENCE_EXACT);
   }
-  // edge-mode propagation, direction 4: the reference's sampling positions (own colour, read while the same launch
-  // writes it — SURVEY Q3) are the default of the product surface, because they are what agrees best with the
-  // reference end to end (tests/test_gpu_gate2.py); like the reference, two runs then differ in the last digits.
-  // DPE_DETERMINISTIC=1 selects the shifted, race-free positions: bit-reproducible runs.
-  bool reference_positions = true;
-  if (const char* e = getenv("DPE_DETERMINISTIC")) reference_positions = atoi(e) == 0;
+  // edge-mode propagation, direction 4 samples pixels of the colour the same launch is writing in the reference
+  // (SURVEY Q3).  Default of the product surface: the reference's positions, read from a copy of the maps taken before
+  // each half-sweep (dpe_set_reference_race(c, 2)) — what agrees best with the reference end to end
+  // (tests/test_gpu_gate2.py) and, unlike the reference, the same result every run.  DPE_DIRECTION4=live reads them
+  // live (racy exactly like the reference: two runs differ in the last digits), DPE_DIRECTION4=shifted (or the older
+  // DPE_DETERMINISTIC=1) shifts direction 4 onto the other colour like directions 5-7.
+  int direction4 = 2;
+  if (const char* e = getenv("DPE_DETERMINISTIC")) direction4 = atoi(e) != 0 ? 0 : 2;
+  if (const char* e = getenv("DPE_DIRECTION4")) {
+    const std::string m(e);
+    direction4 = m == "live" ? 1 : (m == "shifted" ? 0 : 2);
+  }
   const std::vector<Stage> schedule = make_schedule(round_num);
   bool fusion_sharded = false;
   if (const char* e = getenv("DPE_FUSION_SHARDED")) fusion_sharded = atoi(e) != 0 && G > 1;
@@ -491,7 +497,7 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     t_up_commit[g] = now_s() - tu0 - t_up_views[g];
     if (sequential) dpe_set_view_order(c, 1);
     if (arith >= 0) dpe_set_cost_arithmetic(c, arith);
-    dpe_set_reference_race(c, reference_positions ? 1 : 0);
+    dpe_set_reference_race(c, direction4);
     t_upload[g] = now_s() - tu0;
     int first = 0, count = 0;
     dpe_shard_range(n_problems, G, g, &first, &count);

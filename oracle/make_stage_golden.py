@@ -9,6 +9,7 @@ Runs on a GPU box:   python oracle/make_stage_golden.py      -> tests/golden/ref
 tests/test_stage_golden.py replays the stored inputs through the CPU logic simulator step by step.
 """
 import ctypes as C
+import os
 import struct
 import subprocess
 import sys
@@ -110,7 +111,7 @@ def all_stages(report, grays, cams, drs, pairs, prep, sizes, sched, v):
     for vv in range(len(grays)):
         for kk in range(2):
             ctx.set_prep(vv, kk, *prep[vv][kk])
-    ctx.set_reference_race(1)
+    ctx.set_reference_race(int(os.environ.get("DPE_STAGE_DIFF_RACE", "1")))   # 1 live, 2 pre-sweep copy
     ctx.set_profile(len(grays))
     out = {}
     prev_k = None

@@ -80,3 +80,32 @@ for colour, name in ((first, "first"), (~first, "second")):
         if colour is first:
             print(f"  ({x},{y}) state {st[y, x]} edge {fx['edge'][y, x]} our code {acc[y, x]} | {tag} | ref source {src[:2]} | our source {osrc[:2]} | ref cost {fx['s2_costs'][y, x]:.7f} our cost {cost[y, x]:.7f} before {fx['s1_costs'][y, x]:.7f}")
     print(name, "colour:", kinds)
+
+# ---- is every difference a race difference?  A first-colour pixel is "sensitive" when the direction-4 candidate it would
+# pick from the maps as they were BEFORE the launch (s1) is not the one it would pick from the maps AFTER it (s2: other
+# position, other plane, or none because the costs along the ray became NaN).  Iteration 0 on this scene: offset 5, step 2.
+def pick(c, x, y):
+    best, pos = np.float32(3.4e38), None
+    for s in range(11):
+        qx, qy = x - 5 - 2 * s, y - 5 - 2 * s
+        if qx < 0 or qy < 0:
+            break
+        if best > c[qy, qx]:
+            best, pos = c[qy, qx], (qx, qy)
+    return pos
+
+
+c1, c2 = fx["s1_costs"], fx["s2_costs"]
+sens = np.zeros((H, W), bool)
+for y in range(H):
+    for x in range(y & 1, W, 2):
+        if st[y, x] == 0:
+            continue
+        po, pn = pick(c1, x, y), pick(c2, x, y)
+        if po is None and pn is None:
+            continue
+        sens[y, x] = (po is None) != (pn is None) or po != pn or not (b(s1[po[1], po[0]]) == b(s2[pn[1], pn[0]])).all()
+d1 = diff & first
+print(f"first-colour pixels whose direction-4 candidate was rewritten during the launch: {int(sens.sum())}; "
+      f"differing first-colour pixels among them: {int((d1 & sens).sum())} of {int(d1.sum())} "
+      f"(a differing pixel that is NOT among them would be an arithmetic difference: {int((d1 & ~sens).sum())})")
