@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(REFGEOM_THREADS, 1) k_half_refgeom(const __gri
   if (x < a.W && y < a.H) {
     if (a.state[y * a.W + x] != DPE_WEAK) {
       const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact != 0);
-      strong_update_pixel<OP == OP_STRONG_EDGE, true>(env, ps, a, x, y, cost_arr, evals);
+      strong_update_pixel<OP == OP_STRONG_EDGE>(env, ps, a, x, y, cost_arr, evals);
     }
   }
   flush_evals(a.eval_units, evals);

@@ -153,6 +153,16 @@ def all_stages(report, grays, cams, drs, pairs, prep, sizes, sched, v):
         prev_k = k
         r = final_compare(maps[v], dumps[11], drs[v])
         r.update(steps)
+        if os.environ.get("DPE_STAGE_DIFF_REFREF") and si > 0:
+            # the reference against itself: the same probe once more on the same inputs (its direction-4 race)
+            d2 = run_probe(f"all{si}b", imgs, [cams[i] for i in ids], (W, H), drs[v], p, planes, state, sel, src_d, edge, edge_low, label)
+            rr = {f"step{st_}_plane_bitwise": float((d2[st_]["planes"].view(np.uint32) == dumps[st_]["planes"].view(np.uint32)).all(-1).mean())
+                  for st_ in ((1, 2, 5, 8) if not p.use_apd else (1, 2, 4, 7, 10))}
+            ok2 = (d2[11]["planes"][..., 3] > 0) & (dumps[11]["planes"][..., 3] > 0)
+            dn2 = np.abs(d2[11]["planes"][..., :3] - dumps[11]["planes"][..., :3]).max(-1)
+            rr["final_normal_identical"] = float((dn2[ok2] < 1e-4).mean())
+            rr["final_state_equal"] = float((d2[11]["state"] == dumps[11]["state"]).mean())
+            r["ref_vs_ref"] = rr
         r["selected_equal"] = float((maps[v]["selected"] == dumps[11]["selected"]).mean())
         r["weak_frac"] = float((maps[v]["state"] == 0).mean())
         out[f"stage{si}"] = r

@@ -149,27 +149,31 @@ def test_gate2_c1_against_the_reference_build(tmp_path):
     # two reference runs agree on ~98 % of the depths and ~92 % of the normals on this scene (round 1: 0.982 / 0.917)
     assert rr["depth_1pct"] > 0.95 and rr["weak_agree"] > 0.98
     # measured on B200 (profiles/r02_gate2_c1.json), depth within 1 % / normal within 1 deg / 5 deg / weak map:
-    #   reference vs reference   0.982 / 0.922 / 0.972 / 0.9957
-    #   matched   vs reference   0.981 / 0.846 / 0.966 / 0.9942        (ours vs ours, matched: 0.984-0.987 / 0.930-0.943 / 0.976-0.981 / 0.997)
-    #   jpeg      vs reference   0.981 / 0.845 / 0.966 / 0.9941        (with nvJPEG's luma instead of libjpeg's: 0.978 / 0.617 / 0.939 / 0.989)
+    #   reference vs reference   0.982 / 0.920-0.923 / 0.972 / 0.9957
+    #   matched   vs reference   0.981 / 0.859-0.868 / 0.965 / 0.9941   (live reads in the reference's launch geometry; ours vs ours: 0.91-0.95 at 1 deg)
+    #   snapshot  vs reference   0.981 / 0.854 / 0.965 / 0.9941         (the same on every run)
+    #   jpeg      vs reference   0.981 / 0.854 / 0.965 / 0.9941         (the product default = snapshot; with nvJPEG's luma instead of libjpeg's: 0.978 / 0.617 / 0.939 / 0.989)
     #   default   vs reference   0.985 / 0.650 / 0.950 / 0.9809
     #   jacobi    vs reference   0.984 / 0.647 / 0.949 / 0.9806
-    for mode in ("matched", "default", "jacobi", "jpeg"):
+    for mode in ("matched", "snapshot", "default", "jacobi", "jpeg"):
         m = r[f"{mode}_vs_ref"]
-        close = mode in ("matched", "jpeg")
+        close = mode in ("matched", "snapshot", "jpeg")
         # depth: every mode within one point of what the reference reaches against itself
         assert m["depth_1pct"] >= rr["depth_1pct"] - 0.01, (mode, m, rr)
         # weak / strong classification: matched within half a point, the race-free modes within two
         assert m["weak_agree"] >= rr["weak_agree"] - (0.005 if close else 0.02), (mode, m, rr)
         assert m["normal_5deg"] >= rr["normal_5deg"] - (0.015 if close else 0.035), (mode, m, rr)
     # normals within 1 degree: BASELINE.json's literal 99 % is not met by the reference against itself (0.92); the
-    # round-1 review's target for the matched mode is reference-vs-reference minus 3 points — not met yet: the gap is
-    # 7.5 points (10 before LocalRefine's baseline / cost_now were made bit-exact; what remains is the fine-stage
-    # remainder of tests/test_gpu_stage_golden.py amplified over the four fine stages; two of OUR runs in this mode
-    # agree on 0.93-0.94).  The assertions hold what is measured, with four points of slack for the run-to-run spread
-    # of a racy sweep:
-    assert r["matched_vs_ref"]["normal_1deg"] >= rr["normal_1deg"] - 0.115, (r["matched_vs_ref"], rr)
-    assert r["jpeg_vs_ref"]["normal_1deg"] >= rr["normal_1deg"] - 0.115, (r["jpeg_vs_ref"], rr)
+    # round-1 review's target for the matched mode is reference-vs-reference minus 3 points — not met: the gap is
+    # 5.5-7 points.  Every pixel that differs after a fine sweep is one whose direction-4 sample was rewritten during that
+    # launch (tools/sweep_seeds_scene.py: 753 of 754 at 640x480, 18 of 18 on the replay scene); which of those reads see
+    # the new value is a property of the reference's timing on this GPU that it reproduces run after run (its own two
+    # runs differ on 0.06 % of the pixels after a sweep, ours from it on 0.3-0.8 %), and those fractions of a percent per
+    # sweep are what twelve fine sweeps amplify into these points.  The assertions hold what is measured, with three
+    # points of slack for the run-to-run spread of a racy sweep:
+    assert r["matched_vs_ref"]["normal_1deg"] >= rr["normal_1deg"] - 0.09, (r["matched_vs_ref"], rr)
+    assert r["snapshot_vs_ref"]["normal_1deg"] >= rr["normal_1deg"] - 0.09, (r["snapshot_vs_ref"], rr)
+    assert r["jpeg_vs_ref"]["normal_1deg"] >= rr["normal_1deg"] - 0.09, (r["jpeg_vs_ref"], rr)
     assert r["default_vs_ref"]["normal_1deg"] >= 0.60 and r["jacobi_vs_ref"]["normal_1deg"] >= 0.60, r
     assert r["matched_vs_matched"]["depth_1pct"] >= rr["depth_1pct"] - 0.005
 
@@ -178,11 +182,12 @@ def test_gate2_c1_against_the_reference_build(tmp_path):
 def test_gate2_c4_shape_against_the_reference_build(tmp_path):
     r = _gate2(tmp_path, "c4", 0.5, 6, "c4_half_v6")
     rr = r["ref_vs_ref"]
-    # measured (profiles/r02_gate2_c4_half_v6.json): reference vs reference 0.974 / 0.572 / 0.929 / 0.977; matched and
-    # jpeg vs reference 0.971 / 0.426 / 0.913 / 0.975; default / jacobi 0.971 / 0.37 / 0.904 / 0.974
-    for mode in ("matched", "default", "jacobi", "jpeg"):
+    # measured (profiles/r02_gate2_c4_half_v6.json): reference vs reference 0.974 / 0.573 / 0.929 / 0.977; matched
+    # 0.971 / 0.44-0.47 / 0.915 / 0.975; snapshot = jpeg 0.971 / 0.454 / 0.915 / 0.976; default / jacobi 0.971 / 0.37 / 0.904 / 0.974
+    for mode in ("matched", "snapshot", "default", "jacobi", "jpeg"):
         m = r[f"{mode}_vs_ref"]
         assert m["depth_1pct"] >= rr["depth_1pct"] - 0.01, (mode, m, rr)
         assert m["weak_agree"] >= rr["weak_agree"] - 0.007, (mode, m, rr)
         assert m["normal_5deg"] >= rr["normal_5deg"] - 0.035, (mode, m, rr)
-    assert r["matched_vs_ref"]["normal_1deg"] >= rr["normal_1deg"] - 0.20 and r["jpeg_vs_ref"]["normal_1deg"] >= rr["normal_1deg"] - 0.20
+    for mode in ("matched", "snapshot", "jpeg"):
+        assert r[f"{mode}_vs_ref"]["normal_1deg"] >= rr["normal_1deg"] - 0.16, (mode, r[f"{mode}_vs_ref"], rr)
