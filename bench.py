@@ -507,7 +507,8 @@ def run_reference(args):
     if rank != 0:
         return
     exe = ROOT / "oracle" / "_ref" / "DPE_ref"
-    base = {"impl": "reference", "metric": "depth maps/s per scene", "unit": "depth maps/s", "n_gpus": 1,
+    # n_gpus echoes the launch (the driver pairs the two arms by N); the reference itself is a single-GPU, single-process program
+    base = {"impl": "reference", "metric": "depth maps/s per scene", "unit": "depth maps/s", "n_gpus": int(args.gpus), "gpus_used": 1,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic"}
     if not exe.exists():
