@@ -140,15 +140,45 @@ struct JpegDecoder {
   std::vector<uint8_t> scratch;  // padded luma plane of the host decoder
 };
 
+// The nvJPEG handle (tens to hundreds of milliseconds to create, and a CUDA context on the calling thread) comes up on
+// first use: grey decodes of baseline files never need it (jpeg_luma.cpp), only colour, progressive files and
+// DPE_JPEG_DECODER=nvjpeg do.
 JpegDecoder* jpeg_decoder_create(std::string* err) {
-  JpegDecoder* d = new JpegDecoder();
+  (void)err;
+  return new JpegDecoder();
+}
+static bool ensure_nvjpeg(JpegDecoder* d, std::string* err) {
+  if (d->handle) return true;
   if (nvjpegCreateSimple(&d->handle) != NVJPEG_STATUS_SUCCESS || nvjpegJpegStateCreate(d->handle, &d->state) != NVJPEG_STATUS_SUCCESS) {
+    if (d->handle) { nvjpegDestroy(d->handle); d->handle = nullptr; }
     if (err) *err = "nvjpeg initialisation failed";
-    delete d;
-    return nullptr;
+    return false;
   }
   cudaStreamCreate(&d->stream);
-  return d;
+  return true;
+}
+
+// frame size from the SOFn marker of a JPEG stream (ITU T.81 B.2.2); false if none is found in the bytes given
+static bool jpeg_frame_size(const unsigned char* p, size_t n, int* width, int* height) {
+  if (n < 4 || p[0] != 0xFF || p[1] != 0xD8) return false;
+  size_t i = 2;
+  while (i + 4 <= n) {
+    if (p[i] != 0xFF) { ++i; continue; }
+    const unsigned char m = p[i + 1];
+    if (m == 0xFF) { ++i; continue; }                                     // fill byte
+    if (m == 0x01 || (m >= 0xD0 && m <= 0xD8)) { i += 2; continue; }      // TEM, RSTn, SOI: no length
+    if (m == 0xD9 || m == 0xDA) return false;                             // EOI / start of scan before any frame header
+    const size_t len = ((size_t)p[i + 2] << 8) | p[i + 3];
+    if (len < 2) return false;
+    if (m >= 0xC0 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+      if (i + 9 > n) return false;
+      *height = (p[i + 5] << 8) | p[i + 6];
+      *width = (p[i + 7] << 8) | p[i + 8];
+      return *width > 0 && *height > 0;
+    }
+    i += 2 + len;
+  }
+  return false;
 }
 
 void jpeg_decoder_destroy(JpegDecoder* d) {
@@ -169,13 +199,11 @@ static bool jpeg_decode_to(JpegDecoder* d, const std::string& path, nvjpegOutput
   in.seekg(0);
   d->file.resize((size_t)n);
   in.read((char*)d->file.data(), n);
-  int comps = 0, ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
-  nvjpegChromaSubsampling_t ss;
-  if (nvjpegGetImageInfo(d->handle, d->file.data(), d->file.size(), &comps, &ss, ws, hs) != NVJPEG_STATUS_SUCCESS) {
+  int w = 0, h = 0;
+  if (!jpeg_frame_size(d->file.data(), d->file.size(), &w, &h)) {
     if (err) *err = "not a decodable JPEG: " + path;
     return false;
   }
-  const int w = ws[0], h = hs[0];
   const size_t need = (size_t)w * h * ch;
   if (fmt == NVJPEG_OUTPUT_Y) {
     // grey images: the host decoder that reproduces libjpeg's pixels (jpeg_luma.cpp) unless DPE_JPEG_DECODER=nvjpeg;
@@ -191,6 +219,15 @@ static bool jpeg_decode_to(JpegDecoder* d, const std::string& path, nvjpegOutput
         *width = w; *height = h;
         return true;
       }
+    }
+  }
+  if (!ensure_nvjpeg(d, err)) return false;
+  {
+    int comps = 0, ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
+    nvjpegChromaSubsampling_t ss;
+    if (nvjpegGetImageInfo(d->handle, d->file.data(), d->file.size(), &comps, &ss, ws, hs) != NVJPEG_STATUS_SUCCESS || ws[0] != w || hs[0] != h) {
+      if (err) *err = "not a decodable JPEG: " + path;
+      return false;
     }
   }
   if (need > d->dev_bytes) {
@@ -225,17 +262,15 @@ static bool jpeg_decode(JpegDecoder* d, const std::string& path, nvjpegOutputFor
 bool jpeg_image_size(JpegDecoder* d, const std::string& path, int* width, int* height, std::string* err) {
   std::ifstream in(path, std::ios::binary);
   if (!in.good()) { if (err) *err = "cannot open " + path; return false; }
-  // the frame header sits in the first kilobytes; nvjpegGetImageInfo needs no entropy data
+  // the frame header sits in the first kilobytes
   std::vector<unsigned char> head(65536);
   in.read((char*)head.data(), (std::streamsize)head.size());
   const size_t n = (size_t)in.gcount();
-  int comps = 0, ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
-  nvjpegChromaSubsampling_t ss;
-  if (nvjpegGetImageInfo(d->handle, head.data(), n, &comps, &ss, ws, hs) != NVJPEG_STATUS_SUCCESS) {
+  (void)d;
+  if (!jpeg_frame_size(head.data(), n, width, height)) {
     if (err) *err = "not a decodable JPEG: " + path;
     return false;
   }
-  *width = ws[0]; *height = hs[0];
   return true;
 }
 
@@ -327,6 +362,15 @@ DPE_TEST_API int dpe_host_read_pairs(const char* path, int* out, int cap) {
   }
   return n;
 }
+}
+
+extern "C" DPE_TEST_API int dpe_host_jpeg_size(const char* path, int* w, int* h) {
+  std::string err;
+  dpe_host::JpegDecoder* d = dpe_host::jpeg_decoder_create(&err);
+  if (!d) return -1;
+  const bool ok = dpe_host::jpeg_image_size(d, path, w, h, &err);
+  dpe_host::jpeg_decoder_destroy(d);
+  return ok ? 0 : -2;
 }
 
 extern "C" DPE_TEST_API int dpe_host_decode_gray(const char* path, unsigned char* out, int cap, int* w, int* h) {

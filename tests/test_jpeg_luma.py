@@ -57,3 +57,23 @@ def test_progressive_files_are_declined(tmp_path):
     p = str(tmp_path / "p.jpg")
     assert cv2.imwrite(p, _image(64, 64, True, 1), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
     assert _decode(p) is None        # the pipeline then falls back to nvJPEG
+
+
+def test_frame_size_and_path_decode_need_no_gpu(tmp_path):
+    """the size comes from the SOFn marker and baseline files decode on the host: neither touches nvJPEG (whose handle is
+    only created for colour, progressive files and DPE_JPEG_DECODER=nvjpeg), so both work in a process without a GPU"""
+    lib = capi.load()
+    for i, (h, w, color, params) in enumerate([(97, 131, False, [cv2.IMWRITE_JPEG_QUALITY, 75]), (64, 200, True, [cv2.IMWRITE_JPEG_QUALITY, 90]),
+                                               (48, 80, True, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])]):
+        p = str(tmp_path / f"s{i}.jpg")
+        assert cv2.imwrite(p, _image(h, w, color, 3 + i), params)
+        ww, hh = C.c_int(), C.c_int()
+        assert lib.dpe_host_jpeg_size(p.encode(), C.byref(ww), C.byref(hh)) == 0
+        assert (hh.value, ww.value) == (h, w)
+        if i < 2:
+            out = np.zeros(h * w, np.uint8)
+            assert lib.dpe_host_decode_gray(p.encode(), out.ctypes.data_as(C.c_void_p), out.size, C.byref(ww), C.byref(hh)) == 0
+            assert np.array_equal(out.reshape(h, w), cv2.imread(p, cv2.IMREAD_GRAYSCALE))
+    bad = tmp_path / "bad.jpg"
+    bad.write_bytes(b"\xff\xd8\xff\xd9")
+    assert lib.dpe_host_jpeg_size(str(bad).encode(), C.byref(ww), C.byref(hh)) != 0
