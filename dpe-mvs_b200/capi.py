@@ -31,7 +31,7 @@ SYMBOLS = [
     "dpe_scene_set_view", "dpe_scene_set_pairs", "dpe_scene_set_prep", "dpe_scene_set_shard", "dpe_scene_commit",
     "dpe_run_stage", "dpe_stage_begin", "dpe_stage_wait_view", "dpe_stage_end", "dpe_stage_atlas", "dpe_view_slot", "dpe_stage_commit",
     "dpe_shard_range", "dpe_comm_get_unique_id", "dpe_comm_init_rank", "dpe_comm_init_all", "dpe_comm_reset_all",
-    "dpe_scene_broadcast_images", "dpe_export_view", "dpe_scene_set_active", "dpe_stage_comm_ms", "dpe_debug_set_variants", "dpe_fuse_prepare", "dpe_fuse_set_color", "dpe_fuse_broadcast_colors", "dpe_fuse_get_ply_records", "dpe_viz_render", "dpe_cost_eval", "dpe_geom_eval", "dpe_get_size",
+    "dpe_scene_broadcast_images", "dpe_export_view", "dpe_scene_set_active", "dpe_stage_comm_ms", "dpe_debug_set_variants", "dpe_fuse_prepare", "dpe_fuse_set_color", "dpe_fuse_set_block", "dpe_fuse_broadcast_colors", "dpe_fuse_get_ply_records", "dpe_viz_render", "dpe_cost_eval", "dpe_geom_eval", "dpe_get_size",
     "dpe_get_maps", "dpe_set_count_evals", "dpe_eval_units", "dpe_stage_gpu_ms", "dpe_probe_tex_rate",
     "dpe_probe_fma_rate", "dpe_probe_tex_pattern", "dpe_probe_tex_weights", "dpe_run_pipeline", "dpe_set_profile", "dpe_get_profile", "dpe_set_view_order", "dpe_bench_ncc", "dpe_set_reference_race", "dpe_debug_read", "dpe_debug_stop_after", "dpe_debug_set_maps", "dpe_set_cost_arithmetic", "dpe_fuse_set_view", "dpe_fuse_run", "dpe_fuse_get",
 ]
@@ -362,9 +362,13 @@ class Context:
         self._ck(self.lib.dpe_bench_ncc(self.h, view, variant, n_cand, reps, C.byref(r), C.byref(c)))
         return r.value, c.value
 
-    def fuse(self, maps, colours):
-        """maps[v] = dict(depth, normal, state) at full resolution (None = no maps), colours[v] = HxWx3 uint8 BGR.
-        Returns (xyz Nx3 float32, bgr Nx3 uint8)."""
+    def fuse(self, maps, colours, blocks=None):
+        """maps[v] = dict(depth, normal, state) at full resolution (None = no maps), colours[v] = HxWx3 uint8 BGR,
+        blocks[v] = HxW uint8 block mask (<dense>/blocks/mask_<id>.jpg) or None.  Returns (xyz Nx3 float32, bgr Nx3 uint8)."""
+        for v, b in enumerate(blocks or []):
+            if b is not None:
+                bb = np.ascontiguousarray(b, np.uint8)
+                self._ck(self.lib.dpe_fuse_set_block(self.h, v, bb.ctypes.data))
         for v, m in enumerate(maps):
             if m is None:
                 continue

@@ -175,6 +175,7 @@ struct dpe_ctx {
   float4* fuse_planes = nullptr; uint8_t* fuse_state = nullptr;          // what dpe_fuse_run reads
   float4* fuse_planes_own = nullptr; uint8_t* fuse_state_own = nullptr;  // allocations (host-provided or gathered maps)
   uint8_t* fuse_bgr = nullptr; uint16_t* fuse_mask = nullptr;
+  uint8_t* fuse_block = nullptr; std::vector<char> fuse_block_have;  // dpe_fuse_set_block
   std::vector<char> fuse_have;
   bool fuse_resident = false;
   std::vector<FusedPointDev> cloud;
@@ -305,8 +306,9 @@ static void free_scene(dpe_ctx* ctx) {
   dfree(ctx->exp_depth); dfree(ctx->exp_normal); dfree(ctx->exp_weak);
   ctx->exp_depth = nullptr; ctx->exp_normal = nullptr; ctx->exp_weak = nullptr;
   dfree(ctx->viz_bgr); ctx->viz_bgr = nullptr;
-  dfree(ctx->fuse_planes_own); dfree(ctx->fuse_state_own); dfree(ctx->fuse_bgr); dfree(ctx->fuse_mask);
+  dfree(ctx->fuse_planes_own); dfree(ctx->fuse_state_own); dfree(ctx->fuse_bgr); dfree(ctx->fuse_mask); dfree(ctx->fuse_block);
   ctx->fuse_planes_own = nullptr; ctx->fuse_state_own = nullptr; ctx->fuse_bgr = nullptr; ctx->fuse_mask = nullptr;
+  ctx->fuse_block = nullptr; ctx->fuse_block_have.clear();
   ctx->fuse_planes = nullptr; ctx->fuse_state = nullptr; ctx->fuse_have.clear(); ctx->fuse_resident = false;
   ctx->cloud.clear();
   for (auto p : ctx->rng_table) dfree(p);
@@ -1103,6 +1105,22 @@ int dpe_fuse_set_color(dpe_ctx* ctx, int view, const uint8_t* bgr) {
   return DPE_OK;
 }
 
+int dpe_fuse_set_block(dpe_ctx* ctx, int view, const uint8_t* mask) {
+  if (!ctx || view < 0 || view >= ctx->n_views || !mask) return DPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = fuse_ensure(ctx, false)) return rc;
+  const size_t P = (size_t)ctx->W * ctx->H;
+  if (!ctx->fuse_block) {
+    CK(dmalloc(&ctx->fuse_block, (size_t)ctx->n_views * P));
+    ctx->fuse_block_have.assign(ctx->n_views, 0);
+  }
+  // pageable or pinned source alike: the copy is complete (or staged) when the call returns
+  CK(cudaMemcpyAsync(ctx->fuse_block + (size_t)view * P, mask, P, cudaMemcpyHostToDevice, ctx->upload_stream));
+  CK(cudaStreamSynchronize(ctx->upload_stream));
+  ctx->fuse_block_have[view] = 1;
+  return DPE_OK;
+}
+
 int dpe_fuse_broadcast_colors(dpe_ctx* ctx, int root) {
   if (!ctx || root < 0 || root >= ctx->n_ranks) return DPE_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
@@ -1166,6 +1184,7 @@ int dpe_fuse_run(dpe_ctx* ctx, int first_view, int count, size_t* n_points) {
       fv.planes = ctx->fuse_planes + slot * P; fv.state = ctx->fuse_state + slot * P;
     }
     fv.bgr = ctx->fuse_bgr + (size_t)v * P * 3; fv.mask = ctx->fuse_mask + (size_t)v * P;
+    if (ctx->fuse_block && ctx->fuse_block_have[v]) fv.block = ctx->fuse_block + (size_t)v * P;
     const HostCam& c = ctx->views[v].cam;
     for (int i = 0; i < 9; ++i) { fv.K[i] = (float)c.K[i]; fv.R[i] = (float)c.R[i]; }
     for (int i = 0; i < 3; ++i) fv.t[i] = (float)c.t[i];

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(256) k_fuse_view(const FuseView* __restrict__ 
   const int total = W * H;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     accept[idx] = 0;
+    if (ref.block != nullptr && ref.block[idx] < 128) continue;  // block mask (DPE.cpp:1296-1298): gates the reference pixel only
     if (ref.mask[idx] != 0) continue;  // marked by an earlier view (a view is never its own source)
     const float4 rp = ref.planes[idx];
     const float ref_depth = rp.w;

@@ -11,6 +11,7 @@ struct FuseView {
   const uint8_t* state;  // PixelState
   const uint8_t* bgr;    // H*W*3
   uint16_t* mask;        // H*W: 0 = free, e = fused into a point while view e - 1 was the reference view
+  const uint8_t* block;  // H*W or nullptr: <dense>/blocks/mask_<id>.jpg; below 128 = not fused as a reference pixel (DPE.cpp:1296)
   float K[9], R[9], t[3], C[3];
 };
 struct FuseSrcList {

@@ -174,12 +174,8 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
   const std::string out_root = dense + "/DPE";
   mkdir(out_root.c_str(), 0777);
 
-  if (fusion && file_exists(dense + "/blocks")) {
-    // RunFusion gates pixels with <dense>/blocks/mask_<id>.jpg when that folder exists (DPE.cpp:1243-1247, 1296);
-    // that gate is not implemented here, and silently fusing without it would give a different cloud
-    std::cerr << "DPE-MVS: " << dense << "/blocks exists: fusion with block masks is not supported\n";
-    return 1;
-  }
+  // RunFusion gates reference pixels with <dense>/blocks/mask_<id>.jpg when that folder exists (DPE.cpp:1242-1268, 1296)
+  const bool use_block = fusion && file_exists(dense + "/blocks");
 
   // ---- GenerateSampleList --------------------------------------------------------------------
   std::vector<ProblemDesc> problems;
@@ -351,11 +347,12 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     prep_done_at = now_s();
   });
   // ---- fusion: colour images (cv::IMREAD_COLOR, DPE.cpp:1253) decode in the background too -----------------------
-  std::vector<uint8_t> color_slab;
-  std::atomic<int> color_bad(0);
+  std::vector<uint8_t> color_slab, block_slab;
+  std::atomic<int> color_bad(0), block_bad(0);
   std::thread color_thread;
   if (fusion) {
     color_slab.resize(P * 3 * (size_t)n_problems);
+    if (use_block) block_slab.resize(P * (size_t)n_problems);
     color_thread = std::thread([&]() {
       const int n_dec = std::max(1, std::min(4, n_problems));
       std::vector<JpegDecoder*> cd(n_dec, nullptr);
@@ -375,6 +372,12 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
         if (cd[my] && jpeg_decode_bgr(cd[my], image_path(v), &c, &w, &h, &e) && w == width && h == height) memcpy(dst, c.data(), P * 3);
         else  // grey-only JPEG: replicate luma (what cv::imread(IMREAD_COLOR) returns for it)
           for (size_t i = 0; i < P; ++i) dst[3 * i] = dst[3 * i + 1] = dst[3 * i + 2] = gray_slab[P * v + i];
+        if (use_block) {  // cv::imread(IMREAD_GRAYSCALE) of blocks/mask_<id>.jpg, the id printed without padding (DPE.cpp:1265-1267)
+          const std::string bp = dense + "/blocks/mask_" + std::to_string(view_ids[v]) + ".jpg";
+          int bw = 0, bh = 0;
+          if (!cd[my] || !jpeg_decode_gray_into(cd[my], bp, block_slab.data() + P * (size_t)v, P, &bw, &bh, &e) || bw != width || bh != height)
+            block_bad++;
+        }
       });
       for (auto* d : cd) jpeg_decoder_destroy(d);
     });
@@ -569,7 +572,14 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
         for (int v = 0; v < n_problems; ++v)
           if (dpe_fuse_set_color(c, v, color_slab.data() + P * 3 * (size_t)v)) return bad("fuse_set_color");
       }
-      if (fusion_sharded && dpe_fuse_broadcast_colors(c, 0)) return bad("fuse_broadcast_colors");
+      if (fusion_sharded && dpe_fuse_broadcast_colors(c, 0)) return bad("fuse_broadcast_colors");   // also: the colour thread has ended
+      if (use_block) {
+        // the reference reads an empty Mat for a missing mask and indexes it; here a missing or mis-sized mask is an error
+        if (block_bad.load()) { errs[g] = "a blocks/mask_<id>.jpg is missing, undecodable or not of the images' size"; return; }
+        const int b0 = fusion_sharded ? first : 0, b1 = fusion_sharded ? first + count : (g == 0 ? n_problems : 0);
+        for (int v = b0; v < b1; ++v)
+          if (dpe_fuse_set_block(c, v, block_slab.data() + P * (size_t)v)) return bad("fuse_set_block");
+      }
       if (fusion_sharded || g == 0) {
         size_t n_points = 0;
         if (dpe_fuse_run(c, fusion_sharded ? first : 0, fusion_sharded ? count : n_problems, &n_points)) return bad("fuse_run");

@@ -269,13 +269,16 @@ DPE_API int dpe_bench_ncc(dpe_ctx* ctx, int view, int variant, int n_cand, int r
  * Colours: dpe_fuse_set_view, or dpe_fuse_set_color (asynchronous; rank `root` alone may upload and
  * dpe_fuse_broadcast_colors, a collective, hands them to the other ranks).  dpe_fuse_run fuses views
  * [first_view, first_view + count) in index order, starting from a clean set of marks; the cloud is the same from
- * run to run.  dpe_fuse_get copies it out (n_points x 3 each).  The reference's
- * optional <dense>/blocks/mask_<id>.jpg gate (DPE.cpp:1243-1247, 1296) is not implemented: dpe_run_pipeline
- * refuses to fuse when that folder exists. */
+ * run to run.  dpe_fuse_get copies it out (n_points x 3 each).
+ * dpe_fuse_set_block: the reference's optional <dense>/blocks/mask_<id>.jpg gate (DPE.cpp:1242-1268, 1296-1298) — a
+ * grey image of the view's size; a pixel of that view whose mask value is below 128 is not fused as a reference pixel
+ * (it still serves as a source pixel of other views).  Set it on the context that fuses the view; views without a mask
+ * are not gated.  dpe_run_pipeline reads the folder when it exists. */
 DPE_API int dpe_fuse_prepare(dpe_ctx* ctx);
 DPE_API int dpe_fuse_set_view(dpe_ctx* ctx, int view, const float* depth, const float* normal3, const uint8_t* state,
                       const uint8_t* bgr);
 DPE_API int dpe_fuse_set_color(dpe_ctx* ctx, int view, const uint8_t* bgr);
+DPE_API int dpe_fuse_set_block(dpe_ctx* ctx, int view, const uint8_t* mask);
 DPE_API int dpe_fuse_broadcast_colors(dpe_ctx* ctx, int root);
 DPE_API int dpe_fuse_run(dpe_ctx* ctx, int first_view, int count, size_t* n_points);
 DPE_API int dpe_fuse_get(dpe_ctx* ctx, float* xyz, uint8_t* bgr);

@@ -18,6 +18,7 @@ struct FusionInput {
   const std::vector<std::vector<uint8_t>>* state = nullptr;
   const std::vector<std::vector<uint8_t>>* bgr = nullptr;
   const std::vector<CamFile>* cams = nullptr;
+  const std::vector<std::vector<uint8_t>>* blocks = nullptr;  // optional <dense>/blocks/mask_<id>.jpg, grey (DPE.cpp:1242-1268)
   std::vector<std::vector<int>> src;
 };
 struct FusedPoint { float x, y, z; uint8_t b, g, r; };
@@ -69,6 +70,7 @@ void fuse_views(const FusionInput& in, std::vector<FusedPoint>* cloud) {
     for (int r = 0; r < H; ++r) {
       for (int c = 0; c < W; ++c) {
         const size_t idx = (size_t)r * W + c;
+        if (in.blocks && (*in.blocks)[i][idx] < 128) continue;  // DPE.cpp:1296-1298: only the reference pixel is gated
         if (masks[i][idx] == 1) continue;
         const float ref_depth = depth[idx];
         if (ref_depth <= 0.0f) continue;
@@ -151,6 +153,39 @@ extern "C" long fusion_oracle_run(int n_views, int width, int height, const floa
     in.src.push_back(s);
   }
   in.depth = &d; in.normal = &n; in.state = &st; in.bgr = &c; in.cams = &cams;
+  std::vector<FusedPoint> cloud;
+  fuse_views(in, &cloud);
+  for (long i = 0; i < (long)cloud.size() && i < cap; ++i) {
+    xyz[3 * i] = cloud[i].x; xyz[3 * i + 1] = cloud[i].y; xyz[3 * i + 2] = cloud[i].z;
+    out_bgr[3 * i] = cloud[i].b; out_bgr[3 * i + 1] = cloud[i].g; out_bgr[3 * i + 2] = cloud[i].r;
+  }
+  return (long)cloud.size();
+}
+
+// the same with block masks: blocks = n_views x (H*W) grey values (a reference pixel below 128 is skipped)
+extern "C" long fusion_oracle_run_blocks(int n_views, int width, int height, const float* depth, const float* normal, const uint8_t* state,
+                                         const uint8_t* bgr, const uint8_t* blocks, const float* K, const float* R, const float* t,
+                                         const int* src, int max_src, float* xyz, uint8_t* out_bgr, long cap) {
+  using namespace dpe_host;
+  const size_t P = (size_t)width * height;
+  std::vector<std::vector<float>> d(n_views), n(n_views);
+  std::vector<std::vector<uint8_t>> st(n_views), c(n_views), bl(n_views);
+  std::vector<CamFile> cams(n_views);
+  FusionInput in;
+  in.width = width; in.height = height; in.n_views = n_views;
+  for (int v = 0; v < n_views; ++v) {
+    d[v].assign(depth + v * P, depth + (v + 1) * P);
+    n[v].assign(normal + v * P * 3, normal + (v + 1) * P * 3);
+    st[v].assign(state + v * P, state + (v + 1) * P);
+    c[v].assign(bgr + v * P * 3, bgr + (v + 1) * P * 3);
+    bl[v].assign(blocks + v * P, blocks + (v + 1) * P);
+    for (int i = 0; i < 9; ++i) { cams[v].K[i] = K[v * 9 + i]; cams[v].R[i] = R[v * 9 + i]; }
+    for (int i = 0; i < 3; ++i) cams[v].t[i] = t[v * 3 + i];
+    std::vector<int> s;
+    for (int j = 0; j < max_src; ++j) if (src[v * max_src + j] >= 0) s.push_back(src[v * max_src + j]);
+    in.src.push_back(s);
+  }
+  in.depth = &d; in.normal = &n; in.state = &st; in.bgr = &c; in.cams = &cams; in.blocks = &bl;
   std::vector<FusedPoint> cloud;
   fuse_views(in, &cloud);
   for (long i = 0; i < (long)cloud.size() && i < cap; ++i) {

@@ -62,6 +62,16 @@ def main():
                 f.write(f"{v}\n{len(pairs[v])} " + " ".join(f"{j} 100.0" for j in pairs[v]) + "\n")
         subprocess.check_call([str(ROOT / "oracle" / "_ref" / "ref_fusion_probe"), str(folder)])
         xyz, bgr = read_ply(folder / "DPE" / "DPE.ply")
+        # once more with <dense>/blocks/mask_<id>.jpg (DPE.cpp:1242-1268, 1296): grey masks, a reference pixel below 128 is skipped
+        yy, xx = np.mgrid[0:H, 0:W]
+        blocks = np.stack([np.where(((xx // 16 + yy // 12 + v) % 3) == 0, 40 + 20 * v, 130 + 25 * v).astype(np.uint8) for v in range(V)])
+        blocks[:, :, :7] = 127; blocks[:, :, -7:] = 128            # both sides of the threshold
+        (folder / "blocks").mkdir()
+        for v in range(V):
+            with open(folder / "blocks" / f"mask_{v}.gray", "wb") as f:       # the shim's imread reads the sidecar of mask_<id>.jpg
+                f.write(np.array([H, W], np.int32).tobytes()); f.write(np.ascontiguousarray(blocks[v]).tobytes())
+        subprocess.check_call([str(ROOT / "oracle" / "_ref" / "ref_fusion_probe"), str(folder)])
+        xyz_b, bgr_b = read_ply(folder / "DPE" / "DPE.ply")
         # the cameras as the reference parsed them from the cam files (what both fusions must be fed)
         cam_rt = [synth.read_cam(folder / "cams" / f"{v:08d}_cam.txt") for v in range(V)]
     out = ROOT / "tests" / "golden" / "ref_fusion_c1.npz"
@@ -69,6 +79,9 @@ def main():
                         gray=np.stack(grays), K=np.stack([c[0] for c in cam_rt]), R=np.stack([c[1] for c in cam_rt]),
                         t=np.stack([c[2] for c in cam_rt]), pairs=np.array(pairs, np.int32), ref_xyz=xyz, ref_bgr=bgr)
     print("wrote", out, "points", len(xyz), "bytes", out.stat().st_size)
+    out_b = ROOT / "tests" / "golden" / "ref_fusion_c1_blocks.npz"      # inputs are those of ref_fusion_c1.npz
+    np.savez_compressed(out_b, blocks=blocks, ref_xyz=xyz_b, ref_bgr=bgr_b)
+    print("wrote", out_b, "points", len(xyz_b), "bytes", out_b.stat().st_size)
 
 
 if __name__ == "__main__":

@@ -619,6 +619,71 @@ def test_device_fusion_against_the_reference_cloud():
     assert len(ref) <= len(xyz) <= 1.06 * len(ref), (len(xyz), len(ref))     # measured: see DESIGN.md section 3
 
 
+def test_device_fusion_with_block_masks_against_the_reference_cloud():
+    """<dense>/blocks/mask_<id>.jpg (DPE.cpp:1242-1268, 1296): the device fusion with dpe_fuse_set_block against the cloud the
+    reference's own RunFusion made from the same maps and masks (tests/golden/ref_fusion_c1_blocks.npz), and against the
+    CPU checker that reproduces that cloud bit for bit (tests/test_fusion_golden.py)."""
+    fx = np.load(ROOT / "tests" / "golden" / "ref_fusion_c1.npz")
+    fb = np.load(ROOT / "tests" / "golden" / "ref_fusion_c1_blocks.npz")
+    V, H, W = fx["depth"].shape
+    bgr = np.repeat(fx["gray"][..., None], 3, axis=-1)
+    maps = [dict(depth=fx["depth"][v], normal=fx["normal"][v], state=fx["state"][v]) for v in range(V)]
+    ctx = capi.Context(0)
+    capi.upload_scene(ctx, list(fx["gray"]), [(fx["K"][v], fx["R"][v], fx["t"][v]) for v in range(V)], [(1.0, 10.0)] * V,
+                      [list(p) for p in fx["pairs"]], 2)
+    xyz, col = ctx.fuse(maps, list(bgr), blocks=list(fb["blocks"]))
+    ctx.close()
+    ref = fb["ref_xyz"]
+    key = lambda a: set(map(tuple, np.round(a.astype(np.float64) * 1e4).astype(np.int64)))
+    kg, kr = key(xyz), key(ref)
+    print("fusion with block masks vs reference cloud: ours", len(xyz), "reference", len(ref), "reference points missing from ours", len(kr - kg))
+    assert len(ref) < len(fx["ref_xyz"])                                       # the masks removed points
+    assert len(kr - kg) <= 0.04 * len(kr), (len(kr - kg), len(kr))
+    assert len(ref) <= len(xyz) <= 1.06 * len(ref), (len(xyz), len(ref))
+    # no point comes from a blocked reference pixel: every point back-projects onto a pixel of SOME view whose mask is >= 128
+    # (checked through the reference's own cloud above); and the gate is really on: without masks the cloud is larger
+    ctx = capi.Context(0)
+    capi.upload_scene(ctx, list(fx["gray"]), [(fx["K"][v], fx["R"][v], fx["t"][v]) for v in range(V)], [(1.0, 10.0)] * V,
+                      [list(p) for p in fx["pairs"]], 2)
+    xyz_all, _ = ctx.fuse(maps, list(bgr))
+    ctx.close()
+    assert len(xyz) < len(xyz_all)
+
+
+def test_pipeline_fusion_honours_block_masks(c1_folder):
+    """dpe_mvs(fusion=True) on a folder with blocks/: masks are read (grey JPEG, id without padding), a missing one is an error"""
+    import cv2
+    import DPE_MVS
+    spec, folder = c1_folder
+    H, W = spec.height, spec.width
+    shutil.rmtree(folder / "DPE", ignore_errors=True)
+    shutil.rmtree(folder / "blocks", ignore_errors=True)
+    try:
+        assert DPE_MVS.dpe_mvs(str(folder), 0, False, True, False, True, False, False, False) == 0
+        n_all = _ply_points(folder / "DPE" / "DPE.ply")
+        (folder / "blocks").mkdir()
+        m = np.full((H, W), 255, np.uint8); m[:, : W // 2] = 0
+        for v in range(spec.n_views):
+            assert cv2.imwrite(str(folder / "blocks" / f"mask_{v}.jpg"), m, [cv2.IMWRITE_JPEG_QUALITY, 100])
+        shutil.rmtree(folder / "DPE", ignore_errors=True)
+        assert DPE_MVS.dpe_mvs(str(folder), 0, False, True, False, True, False, False, False) == 0
+        n_blk = _ply_points(folder / "DPE" / "DPE.ply")
+        print("fusion points without / with block masks:", n_all, n_blk)
+        assert 0 < n_blk < 0.8 * n_all
+        (folder / "blocks" / "mask_1.jpg").unlink()
+        shutil.rmtree(folder / "DPE", ignore_errors=True)
+        with pytest.raises(RuntimeError, match="DPE-MVS failed with code 1"):
+            DPE_MVS.dpe_mvs(str(folder), 0, False, True, False, True, False, False, False)
+    finally:
+        shutil.rmtree(folder / "blocks", ignore_errors=True)
+        shutil.rmtree(folder / "DPE", ignore_errors=True)
+
+
+def _ply_points(path):
+    head = Path(path).read_bytes()[:400].decode("latin1")
+    return int([l for l in head.split("\n") if l.startswith("element vertex")][0].split()[-1])
+
+
 def test_pipeline_rejects_bad_input(tmp_path):
     import DPE_MVS
     (tmp_path / "pair.txt").write_text("1\n0\n0\n")
