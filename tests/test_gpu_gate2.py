@@ -166,7 +166,7 @@ def test_gate2_c1_against_the_reference_build(tmp_path):
     # normals within 1 degree: BASELINE.json's literal 99 % is not met by the reference against itself (0.92); the
     # round-1 review's target for the matched mode is reference-vs-reference minus 3 points — not met: the gap is
     # 5.5-7 points.  Every pixel that differs after a fine sweep is one whose direction-4 sample was rewritten during that
-    # launch (tools/sweep_seeds_scene.py: 753 of 754 at 640x480, 18 of 18 on the replay scene); which of those reads see
+    # launch (tools/sweep_seeds_scene.py: 3320 of 3323 at 1120x840, 753 of 754 at 640x480, 18 of 18 on the replay scene); which of those reads see
     # the new value is a property of the reference's timing on this GPU that it reproduces run after run (its own two
     # runs differ on 0.06 % of the pixels after a sweep, ours from it on 0.3-0.8 %), and those fractions of a percent per
     # sweep are what twelve fine sweeps amplify into these points.  The assertions hold what is measured, with three
