@@ -8,12 +8,13 @@
 //    (weight, weight*ref) pairs of its pixel from it ONCE into a [tap][thread] shared
 //    table — the reference recomputes them (exp + sqrt + ref fetch per tap) for every one
 //    of the ~100 (hypothesis, view) evaluations a pixel makes per sweep;
-//  * per (hypothesis, view) the homography is 9 FMAs in registers (A - b m^T, with A and b
-//    in the constant bank via a __grid_constant__ parameter block), the 36 source taps go
-//    through the texture unit's bilinear filter, and the three moment sums are FMAs;
-//  * red/black sweeps read only the other colour, so a sweep is race-free and
-//    deterministic.
-#include <cuda_fp16.h>
+//  * per (hypothesis, view) the homography is built from the folded cameras in constant memory (c_rc[slot]) —
+//    in the reference's own operation order by default, 9 FMAs (A - b m^T) with DPE_COST_REFERENCE — the 36
+//    source taps go through the texture unit's bilinear filter, and the three moment sums are FMAs;
+//  * a red/black sweep writes one colour and reads the other, so it is race-free and deterministic; the one
+//    exception is the reference's edge-mode direction 4, which samples the colour being written: read from a
+//    pre-sweep copy (ref_race 2, deterministic), live in the reference's launch geometry (ref_race 1,
+//    k_half_refgeom), or moved onto the other colour (ref_race 0).
 #include <cuda_pipeline.h>
 #include "dpe_core.cuh"
 #include "dpe_consts.h"
