@@ -114,6 +114,56 @@ print(f"differing first-colour pixels: {len(ys)}; with a direction-4 candidate r
 for (x, y) in clean[:40]:
     print(f"   ({x},{y}) state {st[y, x]} on-edge {edge[y, x] != 0} our code {acc[y, x]} edge_neigh4 {en[y, x, 4].tolist()} ours {ours[y, x].tolist()} ref {s2[y, x].tolist()} "
           f"ref cost {c2[y, x]:.7f} before {c1[y, x]:.7f} ref changed {not (b(s1[y, x]) == b(s2[y, x])).all()} ours changed {not (b(s1[y, x]) == b(ours[y, x])).all()}")
+# where could the planes of the unexplained pixels have come from?  every candidate position of the 8 directions (both passes)
+DIRS = [(0, -1), (0, 1), (-1, 0), (1, 0), (-1, -1), (1, 1), (-1, 1), (1, -1)]
+
+
+def all_positions(x, y):
+    out = []
+    on_edge = edge[y, x] != 0
+    for d, (dx, dy) in enumerate(DIRS):
+        ex, ey = int(en[y, x, d, 0]), int(en[y, x, d, 1])
+        dist = np.float32(np.sqrt(float((ex - x) ** 2 + (ey - y) ** 2)))
+        if d >= 4:
+            dist = np.float32(dist / 1.4142135623730951)
+        if on_edge:
+            dist = np.float32(22.0)
+        elif ex == -1 or ey == -1 or dist > max_edge:
+            dist = np.float32(max_edge)
+            if d >= 4:
+                dist = np.float32(dist / 1.4142135623730951)
+        step_num = min(max(11, int(dist / np.float32(2))), 22)
+        step_len = max(int(dist / np.float32(step_num)), 2)
+        if d < 4 and step_len % 2 == 1:
+            step_len -= 1
+        fx = fy = 0
+        if d > 4:
+            if d % 2:
+                fx = dx
+            else:
+                fy = dy
+        for ps, (n, sl) in enumerate(((step_num, step_len),) + (() if on_edge else ((11, 2),))):
+            for s_ in range(n):
+                qx, qy = x + 5 * dx + s_ * sl * dx + fx, y + 5 * dy + s_ * sl * dy + fy
+                if 0 <= qx < w and 0 <= qy < h:
+                    out.append((d, ps, s_, qx, qy))
+    return out
+
+
+for (x, y) in clean[:10]:
+    pos = all_positions(x, y)
+    hit_r = [(d, ps, s_, qx, qy, float(c1[qy, qx])) for (d, ps, s_, qx, qy) in pos if (b(s1[qy, qx]) == b(s2[y, x])).all() or (b(s2[qy, qx]) == b(s2[y, x])).all()]
+    hit_o = [(d, ps, s_, qx, qy, float(c1[qy, qx])) for (d, ps, s_, qx, qy) in pos if (b(s1[qy, qx]) == b(ours[y, x])).all()]
+    best = {}
+    for (d, ps, s_, qx, qy) in pos:
+        k_ = (d, ps)
+        if k_ not in best or c1[qy, qx] < best[k_][0]:
+            best[k_] = (float(c1[qy, qx]), qx, qy, s_)
+    print(f"   ({x},{y}): reference's new plane found at candidate positions (dir, pass, step, x, y, cost before): {hit_r[:4]}; ours at {hit_o[:4]}")
+    print(f"        min-cost pick per (dir, pass) from the costs before the launch: { {k_: v for k_, v in sorted(best.items())} }")
+    nanc = [(d, ps, s_) for (d, ps, s_, qx, qy) in pos if not np.isfinite(c1[qy, qx])]
+    print(f"        non-finite costs among the candidates before the launch: {nanc[:6]}; selected-views of the pixel before / ref after: {int(dumps[1]['selected'][y, x]):#x} / {int(dumps[2]['selected'][y, x]):#x}")
+
 # how many first-colour pixels were exposed to the race at all?
 exposed = 0
 sample = [(x, y) for y in range(0, h, 3) for x in range(y & 1, w, 6) if st[y, x] != 0]
