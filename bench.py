@@ -206,7 +206,8 @@ def run_ours(args):
     arith = {"fast": 1, "centred": 0}.get(os.environ.get("DPE_ARITH", ""), 2)
     ctx.set_cost_arithmetic(arith)
     # edge-mode direction 4 as dpe_mvs() runs it: the reference's positions, read from the pre-sweep copy of the maps
-    ctx.set_reference_race({"live": 1, "shifted": 0}.get(os.environ.get("DPE_DIRECTION4", ""), 2))
+    direction4 = {"live": 1, "shifted": 0}.get(os.environ.get("DPE_DIRECTION4", ""), 2)
+    ctx.set_reference_race(direction4)
     sched = capi.stage_schedule(n_scales)
 
     def one_step():
@@ -386,7 +387,9 @@ def run_ours(args):
                        "view_stages_per_step": V * len(sched), "parallelism": f"reference views sharded over {world} GPU(s); per stage one in-place ncclAllGather per view slot of the depth atlas, issued by libdpe_b200.so behind each view's last kernel",
                        "l2": "inputs larger than L2 (per view-stage ~0.5 GB of state + 11 images; 49 views cycle through)",
                        "rng_seed": SEED,
-                       "cost_arithmetic": {2: "reference, operation by operation (default)", 1: "reference moments, constant-folded homography (DPE_ARITH=fast)", 0: "centred (DPE_ARITH=centred)"}[arith]},
+                       "cost_arithmetic": {2: "reference, operation by operation (default)", 1: "reference moments, constant-folded homography (DPE_ARITH=fast)", 0: "centred (DPE_ARITH=centred)"}[arith],
+                       "direction4": {2: "reference positions from the pre-sweep copy (default, deterministic)", 1: "reference positions, live (DPE_DIRECTION4=live)",
+                                      0: "shifted onto the other colour (DPE_DIRECTION4=shifted)"}[direction4]},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "value_fast_arithmetic": fast_value,
             "vs_reference_sample": None if not (cpu and cpu.get("kind") == "reference") else {
