@@ -118,13 +118,6 @@ std::map<std::vector<int>, CommSet> g_comm_cache;
 
 }  // namespace
 
-// Kernel forms a context starts with: DPE_DEFAULT_VARIANTS (dpe_types.h), or $DPE_VARIANTS (an integer mask of
-// DPE_VARIANT_* bits) for A/B runs of whole programs — bench.py, dpe_mvs() — without touching their code.
-static int default_variants() {
-  if (const char* e = getenv("DPE_VARIANTS")) return atoi(e);
-  return DPE_DEFAULT_VARIANTS;
-}
-
 struct dpe_ctx {
   int device = 0;
   int num_sms = 148;
@@ -174,7 +167,7 @@ struct dpe_ctx {
   int ref_race = 0;           // dpe_set_reference_race
   bool cost_raw = true;       // dpe_set_cost_arithmetic
   bool exact = true;          // dpe_set_cost_arithmetic: DPE_COST_REFERENCE_EXACT is the default
-  int variants = default_variants();  // dpe_debug_set_variants
+  int variants = 0;           // dpe_debug_set_variants
   // scratch
   std::vector<Scratch> scratch;
   // device fusion (dpe_fuse_*): maps of all views at full resolution (own copies, or the carried maps themselves on

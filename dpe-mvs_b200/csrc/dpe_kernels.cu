@@ -19,7 +19,6 @@
 #include "dpe_core.cuh"
 #include "dpe_consts.h"
 #include "dpe_weak.cuh"
-#include "dpe_coop.cuh"
 #include "dpe_kernels.cuh"
 
 namespace dpe {
@@ -97,16 +96,7 @@ __device__ __forceinline__ void flush_evals(unsigned long long* counter, unsigne
 }
 
 // ---- full-image kernels: tile = 32 x 4 pixels, one thread per pixel ---------------------
-// OP_CLASSIFY_COOP: the classifier with the (pixel, view) pairs of a warp dealt out densely over its lanes
-// (dpe_coop.cuh) — the default; OP_CLASSIFY (every thread walks its own pixel's views) stays for A/B runs
-// (DPE_VARIANT_PER_PIXEL_COSTS).
-enum FullOp { OP_INIT = 0, OP_CLASSIFY = 1, OP_CLASSIFY_COOP = 2 };
-
-__device__ __forceinline__ PatchStats no_patch() {
-  PatchStats ps;
-  ps.r0 = 0.f; ps.c0 = 0.f; ps.exact = 0; ps.inv_sw = 0.f; ps.mean_r = 0.f; ps.var_r = 0.f;
-  return ps;
-}
+enum FullOp { OP_INIT = 0, OP_CLASSIFY = 1 };
 
 template <int OP>
 __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_full(const __grid_constant__ StageArgs A) {
@@ -130,13 +120,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_full(const __grid_constant_
     __pipeline_wait_prior(0);
     __syncthreads();
     const int x = tx0 + (threadIdx.x & 31), y = ty0 + (threadIdx.x >> 5);
-    const bool act = x < a.W && y < a.H;
-    if (OP == OP_CLASSIFY_COOP) {
-      // every lane of the warp goes in: lanes without a pixel still score other lanes' pairs
-      PatchStats ps = no_patch();
-      if (act) ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact != 0);
-      classify_refine_coop(env, ps, a, x, y, act, evals);
-    } else if (act) {
+    if (x < a.W && y < a.H) {
       const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact != 0);
       if (OP == OP_INIT) init_pixel(env, ps, a, x, y, evals);
       else classify_refine_pixel(env, ps, a, x, y, evals);
@@ -146,11 +130,9 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_full(const __grid_constant_
 }
 
 // ---- red/black half sweeps: tile = 32 x 8 pixels, one thread per pixel of one colour ----
-// COOP: the refinement half of the update (current plane + 5 hypotheses over the sampled views) shared out over
-// the warp (dpe_coop.cuh) — the default; the per-pixel form stays for A/B runs (DPE_VARIANT_PER_PIXEL_COSTS).
 enum HalfOp { OP_STRONG = 0, OP_STRONG_EDGE = 1 };
 
-template <int OP, bool COOP>
+template <int OP>
 __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_half(const __grid_constant__ StageArgs A) {
   __shared__ float2 s_tbl[36 * NT];
   __shared__ float s_tile[SMW * (8 + 2 * HALO)];
@@ -174,15 +156,11 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_half(const __grid_constant_
     __syncthreads();
     const int lx = threadIdx.x & 31;
     const int x = tx0 + lx, y = ty0 + 2 * (threadIdx.x >> 5) + ((lx + a.colour) & 1);
-    bool act = x < a.W && y < a.H;
-    if (act) act = a.state[y * a.W + x] != DPE_WEAK;
-    if (COOP) {
-      PatchStats ps = no_patch();
-      if (act) ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact != 0);
-      strong_update_coop<OP == OP_STRONG_EDGE>(env, ps, a, x, y, act, cost_arr, evals);
-    } else if (act) {
-      const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact != 0);
-      strong_update_pixel<OP == OP_STRONG_EDGE>(env, ps, a, x, y, cost_arr, evals);
+    if (x < a.W && y < a.H) {
+      if (a.state[y * a.W + x] != DPE_WEAK) {
+        const PatchStats ps = build_patch(tile, x, y, st, a.cost_raw != 0, a.exact != 0);
+        strong_update_pixel<OP == OP_STRONG_EDGE>(env, ps, a, x, y, cost_arr, evals);
+      }
     }
   }
   flush_evals(a.eval_units, evals);
@@ -703,8 +681,6 @@ static inline int persistent_grid(int n_tiles, int num_sms, int per_sm) {
 static inline void count(const LaunchCfg& cfg) {
   if (cfg.launch_counter) ++*cfg.launch_counter;
 }
-// A/B hook: the forms of the sweep and the classifier in which every thread scores its own pixel's views
-static inline bool per_pixel_costs(const KernelParams& P) { return (P.a.variants & DPE_VARIANT_PER_PIXEL_COSTS) != 0; }
 
 void launch_init(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t stream) {
   KernelParams P = P0;
@@ -717,9 +693,7 @@ void launch_classify_refine(const KernelParams& P0, const LaunchCfg& cfg, cudaSt
   KernelParams P = P0;
   P.a.tiles_x = (P.a.W + TILE_W - 1) / TILE_W;
   P.a.tiles_y = (P.a.H + 3) / 4;
-  const int g = persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, CTAS_PER_SM);
-  if (per_pixel_costs(P)) k_full<OP_CLASSIFY><<<g, NT, 0, stream>>>(P.a);
-  else k_full<OP_CLASSIFY_COOP><<<g, NT, 0, stream>>>(P.a);
+  k_full<OP_CLASSIFY><<<persistent_grid(P.a.tiles_x * P.a.tiles_y, cfg.num_sms, CTAS_PER_SM), NT, 0, stream>>>(P.a);
   count(cfg);
 }
 void launch_strong(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t stream) {
@@ -736,13 +710,8 @@ void launch_strong(const KernelParams& P0, const LaunchCfg& cfg, cudaStream_t st
     cudaFuncSetAttribute(k_half_refgeom<OP_STRONG_EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, REFGEOM_SMEM);  // per device
     P.a.tiles_y = (P.a.H + 31) / 32;
     k_half_refgeom<OP_STRONG_EDGE><<<P.a.tiles_x * P.a.tiles_y, REFGEOM_THREADS, REFGEOM_SMEM, stream>>>(P.a);
-  } else if (per_pixel_costs(P)) {
-    if (P.a.use_apd) k_half<OP_STRONG_EDGE, false><<<g, NT, 0, stream>>>(P.a);
-    else k_half<OP_STRONG, false><<<g, NT, 0, stream>>>(P.a);
-  } else {
-    if (P.a.use_apd) k_half<OP_STRONG_EDGE, true><<<g, NT, 0, stream>>>(P.a);
-    else k_half<OP_STRONG, true><<<g, NT, 0, stream>>>(P.a);
-  }
+  } else if (P.a.use_apd) k_half<OP_STRONG_EDGE><<<g, NT, 0, stream>>>(P.a);
+  else k_half<OP_STRONG><<<g, NT, 0, stream>>>(P.a);
   count(cfg);
 }
 void launch_weak(const KernelParams& P, const LaunchCfg& cfg, cudaStream_t stream) {

@@ -48,11 +48,8 @@ struct RefConst {
 
 // kernel variants (StageArgs::variants, test hook dpe_debug_set_variants)
 enum {
-  DPE_VARIANT_LIGHT_FULL_IMAGE = 4,    // label boundary / nearest strong / anchor search / plane fit over the whole image instead of the WEAK lists
-  DPE_VARIANT_PER_PIXEL_COSTS = 8      // strong sweep + classifier: every thread scores its own pixel's views instead of the warp-cooperative deal (dpe_coop.cuh)
+  DPE_VARIANT_LIGHT_FULL_IMAGE = 4     // label boundary / nearest strong / anchor search / plane fit over the whole image instead of the WEAK lists
 };
-// what a new context runs (dpe_capi.cu; $DPE_VARIANTS overrides it)
-#define DPE_DEFAULT_VARIANTS DPE_VARIANT_PER_PIXEL_COSTS
 
 // Kernel argument block for one (view, stage).
 #define DPE_RC_SLOTS 5  // folded-camera blocks in constant memory: one per stream of a stage + one for the test hooks

@@ -8,14 +8,10 @@
 // (libdpe_hostsim.so) that only tests/ loads; nothing in the product links or falls back
 // to it — the C-ABI library fails with DPE_ERR_NO_DEVICE when there is no GPU.
 #include <stdint.h>
-#include <stdio.h>
 #include <stdlib.h>
-#include <ucontext.h>
-#include <functional>
 #include <vector>
 #include "dpe_core.cuh"
 #include "dpe_weak.cuh"
-#include "dpe_coop.cuh"
 #include "dpe_consts.h"
 
 using namespace dpe;
@@ -65,100 +61,7 @@ struct HostStore {
   void operator()(int t, float w, float wr) const { tbl[t] = make_float2(w, wr); }
 };
 
-// ---- a warp on the CPU -----------------------------------------------------------------------
-// dpe_coop.cuh is written against three warp primitives (lane id, ballot, indexed shuffle).  Here the 32 lanes of
-// a warp are fibers on one OS thread: a lane runs until it reaches a primitive, parks its operand and yields; when
-// every lane is parked at the same kind of primitive the exchange is resolved and the lanes run on.  A lane that
-// returns while others wait, or lanes parked at different primitives, is the CPU picture of a deadlocked or
-// divergent full-mask intrinsic: the simulator reports it and aborts the stage.
-struct WarpSim {
-  enum { NONE = 0, BALLOT = 1, SHFL = 2 };
-  static constexpr size_t STACK = 512 * 1024;
-  ucontext_t main_ctx, ctx[32];
-  std::vector<char> stacks;
-  int cur = 0;
-  bool done[32];
-  int kind[32];
-  unsigned val[32], res[32];
-  int arg[32];
-  std::function<void(int)> body;
-  const char* error = nullptr;
-  WarpSim() : stacks(32 * STACK) {}
-  static void entry(unsigned lo, unsigned hi) {
-    WarpSim* w = (WarpSim*)(((uintptr_t)hi << 32) | (uintptr_t)lo);
-    const int lane = w->cur;
-    w->body(lane);
-    w->done[lane] = true;
-    w->kind[lane] = NONE;
-    swapcontext(&w->ctx[lane], &w->main_ctx);
-  }
-  unsigned sync(int k, unsigned v, int a) {
-    const int lane = cur;
-    kind[lane] = k; val[lane] = v; arg[lane] = a;
-    swapcontext(&ctx[lane], &main_ctx);
-    kind[lane] = NONE;
-    return res[lane];
-  }
-  // runs body(lane) for the 32 lanes; false (and error set) when the lanes did not stay together
-  bool run(std::function<void(int)> fn) {
-    body = std::move(fn);
-    error = nullptr;
-    for (int l = 0; l < 32; ++l) {
-      done[l] = false; kind[l] = NONE;
-      getcontext(&ctx[l]);
-      ctx[l].uc_stack.ss_sp = stacks.data() + (size_t)l * STACK;
-      ctx[l].uc_stack.ss_size = STACK;
-      ctx[l].uc_link = &main_ctx;
-      const uintptr_t self = (uintptr_t)this;
-      makecontext(&ctx[l], (void (*)())entry, 2, (unsigned)(self & 0xffffffffu), (unsigned)(self >> 32));
-    }
-    for (;;) {
-      for (int l = 0; l < 32; ++l) {   // every lane up to its next primitive (or its end)
-        if (done[l]) continue;
-        cur = l;
-        swapcontext(&main_ctx, &ctx[l]);
-      }
-      int n_done = 0, k = NONE;
-      for (int l = 0; l < 32; ++l) n_done += done[l];
-      if (n_done == 32) return true;
-      if (n_done != 0) { error = "a lane left while others wait at a full-mask warp primitive"; return false; }
-      k = kind[0];
-      for (int l = 1; l < 32; ++l)
-        if (kind[l] != k) { error = "lanes wait at different warp primitives"; return false; }
-      if (k == BALLOT) {
-        unsigned b = 0;
-        for (int l = 0; l < 32; ++l) b |= (val[l] ? 1u : 0u) << l;
-        for (int l = 0; l < 32; ++l) res[l] = b;
-      } else {
-        for (int l = 0; l < 32; ++l) res[l] = val[arg[l] & 31];
-      }
-    }
-  }
-};
-thread_local WarpSim* g_warp = nullptr;
-
-// Env of a lane inside a simulated warp: the patch table is the warp's [36][32] array, this lane's column
-struct HostCoopEnv {
-  const float2* tbl;
-  const float* img;
-  int W, H;
-  const RefConst* rcp;
-  const RefConst& rc() const { return *rcp; }
-  const SrcConst& src(int v) const { return rcp->src[v]; }
-  float tex(const SrcConst& sc, float u, float v) const { return host_tex((const HostImage*)sc.tex, u, v); }
-  float2 pw(int t) const { return tbl[t * 32]; }
-  float ref(int x, int y) const { return img[(size_t)iclamp(y, 0, H - 1) * W + iclamp(x, 0, W - 1)]; }
-};
-struct HostCoopStore {
-  float2* col;
-  void operator()(int t, float w, float wr) const { col[t * 32] = make_float2(w, wr); }
-};
-
 }  // namespace
-
-extern "C" int dpe_hostsim_lane() { return g_warp->cur; }
-extern "C" unsigned dpe_hostsim_ballot(int pred) { return g_warp->sync(WarpSim::BALLOT, (unsigned)pred, 0); }
-extern "C" unsigned dpe_hostsim_shfl(unsigned bits, int src_lane) { return g_warp->sync(WarpSim::SHFL, bits, src_lane); }
 
 extern "C" {
 
@@ -299,40 +202,6 @@ static int hostsim_stage_impl(int W, int H, int full_w, int full_h, int n_src, c
     }
   };
 
-  // DPE_HOSTSIM_COOP: the strong sweep and the classifier through dpe_coop.cuh, a simulated warp per 32 x rows
-  // pixel strip (the kernels' lane layout), instead of pixel by pixel
-  const bool coop = getenv("DPE_HOSTSIM_COOP") != nullptr;
-  const char* warp_error = nullptr;
-  auto for_warps = [&](int rows, auto&& fn) {
-    const int wx = (W + 31) / 32, wy = (H + rows - 1) / rows;
-#pragma omp parallel
-    {
-      WarpSim sim;
-      std::vector<float2> tbl(36 * 32);
-      g_warp = &sim;
-#pragma omp for schedule(dynamic, 1)
-      for (int w = 0; w < wx * wy; ++w) {
-        const int tx0 = (w % wx) * 32, ty0 = (w / wx) * rows;
-        unsigned ev_lane[32] = {0};
-        const bool ok = sim.run([&](int lane) {
-          HostCoopEnv env; env.tbl = tbl.data() + lane; env.img = images[0]; env.W = W; env.H = H; env.rcp = a.rc;
-          fn(tx0, ty0, lane, env, tbl.data() + lane, ev_lane[lane]);
-        });
-        if (!ok) {
-#pragma omp critical
-          warp_error = sim.error;
-        }
-        double ev = 0;
-        for (int l = 0; l < 32; ++l) ev += ev_lane[l];
-        if (ev) {
-#pragma omp atomic
-          units += ev;
-        }
-      }
-      g_warp = nullptr;
-    }
-  };
-
   if (p->state != DPE_FIRST_INIT) for_all([&](int x, int y) { load_pixel(a, x, y); });
   if (p->use_apd) {
     for_all([&](int x, int y) { edge_info_pixel(a, x, y); label_boundary_pixel(a, x, y); });
@@ -346,21 +215,6 @@ static int hostsim_stage_impl(int W, int H, int full_w, int full_h, int n_src, c
     a.iter = it;
     for (int colour = 0; colour < 2; ++colour) {
       a.colour = colour;
-      if (coop) {
-        // k_half<OP, true>: warps of 32 x 2 pixels, one colour
-        for_warps(2, [&](int tx0, int ty0, int lane, HostCoopEnv& env, float2* col, unsigned& ev) {
-          const int x = tx0 + lane, y = ty0 + ((lane + colour) & 1);
-          bool act = x < W && y < H;
-          if (act) act = a.state[y * W + x] != DPE_WEAK;
-          PatchStats ps;
-          memset(&ps, 0, sizeof(ps));
-          if (act) ps = build_patch(ref, x, y, HostCoopStore{col}, a.cost_raw != 0, a.exact != 0);
-          float cost_arr[9 * DPE_MAX_IMAGES];
-          if (a.use_apd) strong_update_coop<true>(env, ps, a, x, y, act, cost_arr, ev);
-          else strong_update_coop<false>(env, ps, a, x, y, act, cost_arr, ev);
-        });
-        continue;
-      }
       for_colour(colour, [&](int x, int y) {
         if (a.state[y * W + x] == DPE_WEAK) return;
         with_patch(x, y, [&](HostEnv& env, const PatchStats& ps, unsigned& ev) {
@@ -395,20 +249,7 @@ static int hostsim_stage_impl(int W, int H, int full_w, int full_h, int n_src, c
       median_pixel(a, x, y);
     });
   }
-  if (coop) {
-    // k_full<OP_CLASSIFY_COOP>: warps of 32 x 1 pixels
-    for_warps(1, [&](int tx0, int ty0, int lane, HostCoopEnv& env, float2* col, unsigned& ev) {
-      const int x = tx0 + lane, y = ty0;
-      const bool act = x < W && y < H;
-      PatchStats ps;
-      memset(&ps, 0, sizeof(ps));
-      if (act) ps = build_patch(ref, x, y, HostCoopStore{col}, a.cost_raw != 0, a.exact != 0);
-      classify_refine_coop(env, ps, a, x, y, act, ev);
-    });
-  } else {
-    for_all([&](int x, int y) { with_patch(x, y, [&](HostEnv& env, const PatchStats& ps, unsigned& ev) { classify_refine_pixel(env, ps, a, x, y, ev); }); });
-  }
-  if (warp_error) { fprintf(stderr, "dpe_hostsim: %s\n", warp_error); delete rc; return DPE_ERR_STATE; }
+  for_all([&](int x, int y) { with_patch(x, y, [&](HostEnv& env, const PatchStats& ps, unsigned& ev) { classify_refine_pixel(env, ps, a, x, y, ev); }); });
   for_all([&](int x, int y) { finish_pixel(a, x, y); });
   if (dbg && dbg->stop_step == 11) {
     memcpy(dbg->planes, outp.data(), P * sizeof(float4));

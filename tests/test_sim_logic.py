@@ -136,42 +136,3 @@ def test_reference_arithmetic_restatement_agrees_with_the_folded_one(monkeypatch
     want = np.array([[O.bilateral_ncc_old(imgs[0], imgs[v + 1], cc[0], cc[v + 1], int(x), int(y), planes[i].astype(np.float64), quant=1)
                       for v in range(len(ids) - 1)] for i, (x, y) in enumerate(xy)])
     assert np.median(np.abs(exact - want)) < 3e-4 and np.percentile(np.abs(exact - want), 99) < 1e-2
-
-
-@pytest.mark.timeout(600)
-def test_cooperative_scoring_matches_per_pixel(monkeypatch):
-    """csrc/dpe_coop.cuh (the strong sweep's refinement half and the classifier with the (pixel, view) pairs of a
-    warp dealt out over its lanes) against the per-pixel functions of dpe_core.cuh, both through the simulator —
-    which runs the 32 lanes of a warp as fibers meeting in ballot / shuffle, and fails the stage when a lane
-    leaves while others wait (the CPU picture of a deadlocked full-mask intrinsic).  Six stages of a weak-texture
-    scene: ACMM-pattern and edge-mode sweeps, geometric-consistency stages, WEAK pixels, lanes outside the image
-    (121 is not a multiple of 32).  Every output and the unit count, bit for bit.  The same comparison on the GPU:
-    tests/test_gpu_parity.py::test_cooperative_scoring_gives_identical_maps."""
-    import ctypes as C
-    import capi
-    spec, grays, cams, drs, pairs, gt = small_scene("c4", 0.04, 4)      # 121 x 81
-    lib = capi.load()
-    H, W = grays[0].shape
-    sizes = simpipe.level_sizes(W, H, 2)
-    prep = []
-    for g in grays:
-        per = []
-        for k in range(2):
-            e = np.empty((sizes[k][1], sizes[k][0]), np.uint8)
-            l = np.empty((sizes[k][1], sizes[k][0]), np.int32)
-            gg = np.ascontiguousarray(g)
-            lib.dpe_host_problem_edges(gg.ctypes.data_as(C.c_void_p), W, H, 1 << (1 - k), e.ctypes.data_as(C.c_void_p), l.ctypes.data_as(C.c_void_p))
-            per.append((e, l))
-        prep.append(per)
-    monkeypatch.setenv("DPE_HOSTSIM_EXACT", "1")
-    want, want_units = simpipe.run(grays, cams, drs, pairs, 2, prep=prep, stages=6, seed=5)
-    monkeypatch.setenv("DPE_HOSTSIM_COOP", "1")
-    got, got_units = simpipe.run(grays, cams, drs, pairs, 2, prep=prep, stages=6, seed=5)
-    assert got_units == want_units
-    assert sum(int((w["state"] == hostsim.WEAK).sum()) for w in want) > 2000
-    for v, (a, b) in enumerate(zip(got, want)):
-        for key in ("planes", "state", "selected", "depth"):
-            x, y = a[key], b[key]
-            if x.dtype == np.float32:
-                x, y = x.view(np.uint32), y.view(np.uint32)
-            assert np.array_equal(x, y), (v, key, float((x != y).mean()))
