@@ -151,6 +151,20 @@ def product_prep(lib, gray, n_scales):
     return out
 
 
+# Wall-clock budget of one bench.py process.  The driver gives a run a fixed time limit (870 s per N in round 1's
+# scaling record) and chooses --steps itself (20 + 5 warm-up steps of ~20 s at N = 1), so the legs that only add
+# context to the line — the fast-arithmetic step, the 2nd and 3rd end-to-end call, the reference sample of the
+# baseline leg — are skipped when the budget is nearly spent; the line then says so ("statistic": median of fewer
+# calls, "value_fast_arithmetic": null, "cpu_baseline.kind": "port").  The timed steps, the roofline pass, one
+# end-to-end call and the scalar baseline always run.
+T_PROCESS_START = time.perf_counter()
+BENCH_BUDGET_S = float(os.environ.get("DPE_BENCH_BUDGET_S", "800"))
+
+
+def time_left():
+    return BENCH_BUDGET_S - (time.perf_counter() - T_PROCESS_START)
+
+
 # ------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -253,7 +267,7 @@ def run_ours(args):
     # ---- the same step once more in the fast arithmetic (constant-folded homography, DPE_ARITH=fast), reported
     # beside the headline so that the price of bit-level parity with the reference is on record
     fast_value = None
-    if arith == 2:
+    if arith == 2 and (use_dist or time_left() > 240.0):   # optional leg: skipped when a long --steps run has used up the wall-clock budget
         ctx.set_cost_arithmetic(1)
         sync_all()
         mf = ctx.stage_gpu_ms()
@@ -349,13 +363,16 @@ def run_ours(args):
             except Exception:
                 bd = None
             runs.append((dt, bd))
+            if time_left() < 1.3 * dt + 60.0:      # no room for another call and the baseline leg: report what there is
+                break
         order = sorted(range(len(runs)), key=lambda i: runs[i][0])
-        e2e_s, bd = runs[order[len(runs) // 2]]
+        e2e_s, bd = runs[order[(len(runs) - 1) // 2]]
+        statistic = {3: "median of 3 calls", 2: "faster of 2 calls (the first call of a process also creates the CUDA contexts)"}.get(len(runs), "single call")
         px = [(int(np.floor(W / (1 << (n_scales - 1 - k)) + 0.5)) * int(np.floor(H / (1 << (n_scales - 1 - k)) + 0.5))) for k in range(n_scales)]
         h2d = V * W * H + V * sum(5 * p for p in px)                 # images once (broadcast over NVLink) + edge(1)+label(4) per scale
         d2h = V * W * H + V * W * H * 4                              # nvJPEG luma back to host + depth.npy payload
         e2e = {"value": V / e2e_s, "unit": "depth maps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "seconds": e2e_s, "seconds_all_runs": [r[0] for r in runs], "statistic": f"median of {len(runs)} call(s)",
+               "seconds": e2e_s, "seconds_all_runs": [r[0] for r in runs], "statistic": statistic,
                "api": "DPE_MVS.dpe_mvs(dense_folder, depth=True" + (", weak=True, edge=True)" if weak_out else ")"), "breakdown": bd}
     if use_dist:
         dist.barrier(group=cpu_group)
@@ -367,7 +384,7 @@ def run_ours(args):
     if rank == 0 and world == 1:
         cpu = cpu_baseline_port(grays, cams, pairs, prof)
         try:
-            if tag == "c2" and (ROOT / "oracle" / "_ref" / "DPE_ref").exists():
+            if tag == "c2" and (ROOT / "oracle" / "_ref" / "DPE_ref").exists() and time_left() > 60.0:
                 ref = ReferenceSample(2, local)
                 ref.step()
                 dt, gpu_s = ref.step()
@@ -519,7 +536,21 @@ def run_reference(args):
         return
     M = int(os.environ.get("DPE_REF_SAMPLE_VIEWS", "5"))
     ref = ReferenceSample(M, local)
-    for _ in range(args.warmup):
+    # The first step doubles as a calibration: the reference's host part runs at very different speeds on different
+    # boxes (18-26 s per 5-view step seen), and the driver chooses --steps.  If warm-up + timed steps of this sample
+    # would not fit the process's wall-clock budget, the sample shrinks (never below 2 views) before anything is timed.
+    warmed = 0
+    if args.warmup + args.steps > 1 and "DPE_REF_SAMPLE_VIEWS" not in os.environ:
+        dt = ref.step()[0]
+        warmed = 1
+        todo = args.warmup + args.steps - 1
+        avail = time_left() - 30.0
+        if dt * todo > avail and M > 2:
+            M2 = max(2, int(M * avail / (dt * todo)))
+            if M2 < M:
+                M, warmed = M2, 0
+                ref = ReferenceSample(M, local)
+    for _ in range(max(args.warmup - warmed, 0)):
         ref.step()
     sampler = ClockSampler(local)
     sampler.start()
