@@ -339,21 +339,27 @@ int dpe_ctx_create(dpe_ctx** out, int gpu_index) {
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
   }
-  cudaEventCreate(&ctx->ev0);
-  cudaEventCreate(&ctx->ev1);
-  cudaEventCreate(&ctx->ev_views);
-  cudaEventCreate(&ctx->pa);
-  cudaEventCreate(&ctx->pb);
-  cudaEventCreateWithFlags(&ctx->comm_done, cudaEventDisableTiming);
+  bool ok = true;
+  ok &= cudaEventCreate(&ctx->ev0) == cudaSuccess;
+  ok &= cudaEventCreate(&ctx->ev1) == cudaSuccess;
+  ok &= cudaEventCreate(&ctx->ev_views) == cudaSuccess;
+  ok &= cudaEventCreate(&ctx->pa) == cudaSuccess;
+  ok &= cudaEventCreate(&ctx->pb) == cudaSuccess;
+  ok &= cudaEventCreateWithFlags(&ctx->comm_done, cudaEventDisableTiming) == cudaSuccess;
   // the exchange runs beside the view kernels: highest priority, so that its few CTAs are placed as soon as a
   // persistent view kernel retires
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_hi);
-  cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-  dmalloc(&ctx->d_eval_units, sizeof(unsigned long long));
-  cudaMemset(ctx->d_eval_units, 0, sizeof(unsigned long long));
+  ok &= cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+  ok &= cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok &= cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok &= dmalloc(&ctx->d_eval_units, sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaMemset(ctx->d_eval_units, 0, sizeof(unsigned long long)) == cudaSuccess;
+  if (!ok) {  // a context with a missing event or stream would fail later, somewhere less obvious
+    cudaGetLastError();
+    dpe_ctx_destroy(ctx);
+    return DPE_ERR_CUDA;
+  }
   *out = ctx;
   return DPE_OK;
 }
