@@ -333,6 +333,17 @@ bool jpeg_encode_bgr_dev(JpegEncoder* e, const void* bgr_dev, int width, int hei
   return out.good();
 }
 
+bool jpeg_encode_bgr_host(JpegEncoder* e, const uint8_t* bgr, int width, int height, const std::string& path, std::string* err) {
+  void* dev = nullptr;
+  const size_t bytes = (size_t)width * height * 3;
+  if (cudaMalloc(&dev, bytes) != cudaSuccess) { cudaGetLastError(); if (err) *err = "cudaMalloc for a viz image failed"; return false; }
+  bool ok = cudaMemcpy(dev, bgr, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (!ok && err) *err = "upload of a viz image failed";
+  ok = ok && jpeg_encode_bgr_dev(e, dev, width, height, path, err);
+  cudaFree(dev);
+  return ok;
+}
+
 }  // namespace dpe_host
 
 // C hooks for the CPU tests (tests/test_io.py)

@@ -57,5 +57,7 @@ struct JpegEncoder;
 JpegEncoder* jpeg_encoder_create(std::string* err);
 void jpeg_encoder_destroy(JpegEncoder* e);
 bool jpeg_encode_bgr_dev(JpegEncoder* e, const void* bgr_dev, int width, int height, const std::string& path, std::string* err);
+// the same for an image in host memory (staged through a temporary device buffer on the current device)
+bool jpeg_encode_bgr_host(JpegEncoder* e, const uint8_t* bgr, int width, int height, const std::string& path, std::string* err);
 
 }  // namespace dpe_host

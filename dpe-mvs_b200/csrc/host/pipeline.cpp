@@ -167,7 +167,8 @@ class ExportQueue {
 extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_index, int verbose, int fusion, int viz,
                                         int depth, int normal, int weak, int edge) {
   // viz: depth_<i>.jpg / normal_<i>.jpg / weak_<i>.jpg per view and iteration like the reference
-  // (main.cpp:448-454); its rawedge_k / connect_k jpgs of the prep stage and the complex.jpg residue (Q12) are not written
+  // (main.cpp:448-454) and the rawedge_<k>.jpg / connect_<k>.jpg images of the prep stage (main.cpp:361-364, 380-383);
+  // the complex.jpg residue (Q12) is not written
   const double t_begin = now_s();
   Timing tm;
   const std::string dense = dense_folder_c ? dense_folder_c : "";
@@ -307,7 +308,10 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
     std::vector<std::pair<int, int>> jobs;
     for (int j = 0; j < round_num; ++j)
       for (int v = 0; v < n_problems; ++v) jobs.push_back({v, j});
-    parallel_for((int)jobs.size(), std::max(1, (hw > 0 ? hw : 4) - 1), [&](int job) {
+    const int n_prep_threads = std::max(1, (hw > 0 ? hw : 4) - 1);
+    std::vector<JpegEncoder*> encs(viz ? n_prep_threads : 0, nullptr);  // viz: one nvJPEG encoder per prep thread
+    std::atomic<int> next_enc(0);
+    parallel_for((int)jobs.size(), n_prep_threads, [&](int job) {
       const int v = jobs[job].first, j = jobs[job].second;
       const std::string dir = out_root + "/" + format_index(view_ids[v]);
       const std::string ep = dir + "/edges_" + std::to_string(j) + ".dmb";
@@ -338,12 +342,49 @@ extern "C" DPE_API int dpe_run_pipeline(const char* dense_folder_c, int gpu_inde
         std::vector<int32_t> l;
         int oc, orr;
         problem_edges(gimg, 1 << j, &e, &l, &oc, &orr);
+        if (viz) {
+          // show_medium_result: the edge map as rawedge_<j>.jpg and the connected regions as connect_<j>.jpg, each only
+          // when it was computed rather than read from the cache, like the reference.  Region colours are arbitrary
+          // there (rand()); here a label hashes to its colour, background is black, the regions too small to keep
+          // (label -1) are grey.  Failing to write a picture does not fail the run.
+          thread_local int my = -1;
+          thread_local const void* owner = nullptr;
+          if (my < 0 || owner != (const void*)&encs) {
+            my = next_enc++; owner = (const void*)&encs;
+            cudaSetDevice(gpus[0]);
+            std::string ee;
+            if (my < (int)encs.size()) encs[my] = jpeg_encoder_create(&ee);
+          }
+          JpegEncoder* enc = my < (int)encs.size() ? encs[my] : nullptr;
+          const size_t n = (size_t)e.rows * e.cols;
+          if (enc && n > 0 && l.size() == n) {
+            std::vector<uint8_t> bgr(n * 3);
+            std::string ee;
+            if (!have_e) {
+              for (size_t i = 0; i < n; ++i) bgr[3 * i] = bgr[3 * i + 1] = bgr[3 * i + 2] = e.d[i];
+              jpeg_encode_bgr_host(enc, bgr.data(), e.cols, e.rows, dir + "/rawedge_" + std::to_string(j) + ".jpg", &ee);
+            }
+            if (!have_l) {
+              for (size_t i = 0; i < n; ++i) {
+                const int32_t lab = l[i];
+                uint32_t h = (uint32_t)lab * 2654435761u;
+                h ^= h >> 15;
+                const uint8_t c0 = lab == 0 ? 0 : (lab < 0 ? 96 : (uint8_t)(64 + (h & 127)));
+                const uint8_t c1 = lab == 0 ? 0 : (lab < 0 ? 96 : (uint8_t)(64 + ((h >> 8) & 127)));
+                const uint8_t c2 = lab == 0 ? 0 : (lab < 0 ? 96 : (uint8_t)(64 + ((h >> 16) & 127)));
+                bgr[3 * i] = c0; bgr[3 * i + 1] = c1; bgr[3 * i + 2] = c2;
+              }
+              jpeg_encode_bgr_host(enc, bgr.data(), e.cols, e.rows, dir + "/connect_" + std::to_string(j) + ".jpg", &ee);
+            }
+          }
+        }
         if (!have_e) prep[v].edge[j] = e;
         if (!have_l) prep[v].label[j] = l;
       }
       { std::lock_guard<std::mutex> lk(prep_m); prep_left[v]--; }
       prep_cv.notify_all();
     });
+    for (auto* enc : encs) jpeg_encoder_destroy(enc);
     prep_done_at = now_s();
   });
   // ---- fusion: colour images (cv::IMREAD_COLOR, DPE.cpp:1253) decode in the background too -----------------------

@@ -498,14 +498,26 @@ def test_pipeline_python_api_and_cli(c1_folder):
 def test_pipeline_viz_images(c1_folder):
     """viz=True: depth_<i>.jpg / normal_<i>.jpg / weak_<i>.jpg per view and iteration like the reference's ProcessProblem
     (main.cpp:448-454; ShowDepthMap / ShowNormalMap / ShowWeakImage, DPE.cpp:384-503): decodable, of the stage's size, and
-    the last weak image shows the classes of weak.npy in the reference's colours."""
+    the last weak image shows the classes of weak.npy in the reference's colours; rawedge_<k>.jpg / connect_<k>.jpg of
+    the prep stage."""
     import cv2
     import DPE_MVS
     spec, folder = c1_folder
     shutil.rmtree(folder / "DPE", ignore_errors=True)
-    assert DPE_MVS.dpe_mvs(str(folder), 0, False, False, True, True, False, True, False) == 0
+    assert DPE_MVS.dpe_mvs(str(folder), 0, False, False, True, True, False, True, True) == 0
     d = folder / "DPE" / "00000000"
     H, W = spec.height, spec.width
+    # the prep stage's pictures (main.cpp:361-364, 380-383): rawedge_<k>.jpg is the edge map of scale 2^-k — at k = 0 the
+    # map edge.npy holds — and connect_<k>.jpg its connected regions in colours on a black background
+    edge = np.load(d / "edge.npy")
+    for k in range(2):
+        raw = cv2.imread(str(d / f"rawedge_{k}.jpg"), cv2.IMREAD_GRAYSCALE)
+        con = cv2.imread(str(d / f"connect_{k}.jpg"), cv2.IMREAD_COLOR)
+        assert raw is not None and con is not None, k
+        assert raw.shape == (H >> k, W >> k) and con.shape == (H >> k, W >> k, 3), (k, raw.shape, con.shape)
+        assert (con.max(-1) > 48).mean() > 0.05, k                     # some region is coloured
+    raw0 = cv2.imread(str(d / "rawedge_0.jpg"), cv2.IMREAD_GRAYSCALE)
+    assert ((raw0 > 127) == (edge > 0)).mean() > 0.9, float(((raw0 > 127) == (edge > 0)).mean())    # JPEG ringing on one-pixel lines
     for it in range(8):
         for name in ("depth", "normal", "weak"):
             img = cv2.imread(str(d / f"{name}_{it}.jpg"), cv2.IMREAD_COLOR)
