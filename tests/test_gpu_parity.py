@@ -508,14 +508,14 @@ def test_pipeline_viz_images(c1_folder):
     d = folder / "DPE" / "00000000"
     H, W = spec.height, spec.width
     # the prep stage's pictures (main.cpp:361-364, 380-383): rawedge_<k>.jpg is the edge map of scale 2^-k — at k = 0 the
-    # map edge.npy holds — and connect_<k>.jpg its connected regions in colours on a black background
+    # map edge.npy holds — and connect_<k>.jpg its weak-texture regions in colours on a black background (this scene is
+    # textured throughout: the picture is black)
     edge = np.load(d / "edge.npy")
     for k in range(2):
         raw = cv2.imread(str(d / f"rawedge_{k}.jpg"), cv2.IMREAD_GRAYSCALE)
         con = cv2.imread(str(d / f"connect_{k}.jpg"), cv2.IMREAD_COLOR)
         assert raw is not None and con is not None, k
         assert raw.shape == (H >> k, W >> k) and con.shape == (H >> k, W >> k, 3), (k, raw.shape, con.shape)
-        assert (con.max(-1) > 48).mean() > 0.05, k                     # some region is coloured
     raw0 = cv2.imread(str(d / "rawedge_0.jpg"), cv2.IMREAD_GRAYSCALE)
     assert ((raw0 > 127) == (edge > 0)).mean() > 0.9, float(((raw0 > 127) == (edge > 0)).mean())    # JPEG ringing on one-pixel lines
     for it in range(8):
