@@ -68,6 +68,9 @@ def build_lib(verbose=False, force=False) -> Path:
                 # division / sqrt / exp / sin / cos and flush-to-zero.  The kernels follow the reference's
                 # expressions, so the same flag gives the same kind of rounding in the same places.
                 extra = extra + ["--use_fast_math"]
+            if src.name == "jpeg_luma.cpp":
+                # the IDCT's 32-bit intermediates may wrap on damaged files; wrap-around must be defined behaviour there
+                extra = extra + ["-Xcompiler", "-fwrapv"]
             _run([NVCC, *ARCH, *COMMON, *extra, *DEFS, "-I", CSRC, "-I", HERE.parent / "include", "-c", src, "-o", o], verbose)
         objs.append(o)
     so = LIB / (f"libdpe_b200_{TAG}.so" if TAG else "libdpe_b200.so")

@@ -129,6 +129,9 @@ inline uint8_t range_limit(int32_t x) {  // sample_range_limit + CENTERJSAMPLE, 
   return 0;                     // 896..1023 = -128..-1 before the centre shift: below black
 }
 
+// Coefficients of a damaged file can drive the 32-bit intermediates past INT32_MAX (libjpeg has the same arithmetic and
+// the same garbage-in, garbage-out behaviour): this file is built with -fwrapv (build.py), which makes the wrap-around
+// defined behaviour (found with -fsanitize=undefined on corrupted files; valid files never get near the limit).
 void idct_islow(const int16_t* coef, const uint16_t* quant, uint8_t* out, int stride) {
   int32_t ws[64];
   for (int c = 0; c < 8; ++c) {

@@ -77,3 +77,48 @@ def test_frame_size_and_path_decode_need_no_gpu(tmp_path):
     bad = tmp_path / "bad.jpg"
     bad.write_bytes(b"\xff\xd8\xff\xd9")
     assert lib.dpe_host_jpeg_size(str(bad).encode(), C.byref(ww), C.byref(hh)) != 0
+
+
+def test_damaged_files_are_refused_or_decoded_within_bounds(tmp_path):
+    """Truncated files, flipped bytes, runs of 0xFF, damaged headers (marker lengths, sampling factors, dimensions): the
+    decoder returns an error or some image, never writes past the capacity it was given (guard bytes behind it stay
+    intact), and still decodes the undamaged file afterwards.  The same corpus ran clean under
+    -fsanitize=address,undefined (the IDCT is built with -fwrapv: damaged coefficients may wrap its 32-bit sums)."""
+    lib = capi.load()
+    rng = np.random.default_rng(7)
+    w, h = C.c_int(), C.c_int()
+    n_ok = n_bad = 0
+    for it in range(400):
+        color = bool(it & 1)
+        params = [cv2.IMWRITE_JPEG_QUALITY, 60 + it % 40] + ([cv2.IMWRITE_JPEG_RST_INTERVAL, 2] if it % 5 == 0 else [])
+        img = _image(17 + it % 37, 23 + it % 29, color, it)
+        ok, enc = cv2.imencode(".jpg", img, params)
+        assert ok
+        raw = enc.copy().ravel()
+        mode = it % 4
+        if mode == 0:
+            raw = raw[: rng.integers(2, raw.size)]
+        elif mode == 1:
+            k = rng.integers(1, 8)
+            raw[rng.integers(0, raw.size, k)] = rng.integers(0, 256, k)
+        elif mode == 2:
+            i = rng.integers(0, raw.size - 4)
+            raw[i:i + 4] = 0xFF
+        else:
+            k = rng.integers(1, 4)
+            raw[rng.integers(2, min(raw.size, 600), k)] = rng.integers(0, 256, k)
+        raw = np.ascontiguousarray(raw)
+        for cap in (img.shape[0] * img.shape[1], 257):
+            out = np.full(cap + 64, 0xA5, np.uint8)
+            rc = lib.dpe_host_decode_luma_islow(raw.ctypes.data_as(C.c_void_p), C.c_long(raw.size), out.ctypes.data_as(C.c_void_p),
+                                                C.c_long(cap), C.byref(w), C.byref(h))
+            assert (out[cap:] == 0xA5).all(), (it, cap)
+            if rc == 0:
+                assert w.value * h.value <= cap
+            if cap > 257:
+                n_ok += rc == 0
+                n_bad += rc != 0
+    assert n_ok > 50 and n_bad > 50, (n_ok, n_bad)      # both outcomes occur
+    p = str(tmp_path / "good.jpg")
+    assert cv2.imwrite(p, _image(64, 80, True, 3), [cv2.IMWRITE_JPEG_QUALITY, 90])
+    assert np.array_equal(_decode(p), cv2.imread(p, cv2.IMREAD_GRAYSCALE))
