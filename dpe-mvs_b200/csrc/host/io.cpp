@@ -35,23 +35,25 @@ bool read_pairs(const std::string& path, std::vector<ProblemDesc>* problems) {
   int num_images = 0;
   std::getline(file, line);
   iss.str(line);
-  iss >> num_images;
+  // A count that does not parse (or overflows: the stream then stores INT_MAX) must not become a loop bound — the
+  // reference's GenerateSampleList would spin through 2^31 failed extractions on such a file; here it is an error.
+  if (!(iss >> num_images) || num_images < 0) return false;
   for (int i = 0; i < num_images; ++i) {
     ProblemDesc p;
     p.ref_image_id = 0;
     iss.clear();
-    std::getline(file, line);
+    if (!std::getline(file, line)) return false;  // fewer problems than announced
     iss.str(line);
-    iss >> p.ref_image_id;
+    if (!(iss >> p.ref_image_id)) return false;
     int n = 0;
     iss.clear();
-    std::getline(file, line);
+    if (!std::getline(file, line)) return false;
     iss.str(line);
-    iss >> n;
+    if (!(iss >> n)) return false;
     for (int j = 0; j < n; ++j) {
       int id = 0;
       float score = 0.f;
-      iss >> id >> score;
+      if (!(iss >> id >> score)) break;  // fewer sources on the line than announced: keep what is there
       if (score <= 0.0f) continue;
       p.src_image_ids.push_back(id);
     }
@@ -114,8 +116,14 @@ bool read_dmb(const std::string& path, int* rows, int* cols, int* type, std::vec
     case DMB_32FC3: es = 12; break;
     default: return false;
   }
+  // the payload must be in the file before memory is set aside for it: a foreign header can announce 2^62 elements
+  const size_t want = (size_t)h[1] * (size_t)h[2] * es;
+  in.seekg(0, std::ios::end);
+  const std::streamoff file_bytes = in.tellg();
+  if (file_bytes < 16 || (size_t)(file_bytes - 16) < want) return false;
+  in.seekg(16, std::ios::beg);
   *rows = h[1]; *cols = h[2]; *type = h[3];
-  data->resize((size_t)h[1] * h[2] * es);
+  data->resize(want);
   in.read((char*)data->data(), data->size());
   return !in.fail();
 }
@@ -375,6 +383,12 @@ DPE_TEST_API int dpe_host_read_pairs(const char* path, int* out, int cap) {
 }
 }
 
+// .dmb reader: rows / cols / type / payload bytes of a file, -1 when it is refused
+extern "C" DPE_TEST_API long dpe_host_read_dmb(const char* path, int* rows, int* cols, int* type) {
+  std::vector<uint8_t> d;
+  if (!dpe_host::read_dmb(path, rows, cols, type, &d)) return -1;
+  return (long)d.size();
+}
 extern "C" DPE_TEST_API int dpe_host_jpeg_size(const char* path, int* w, int* h) {
   std::string err;
   dpe_host::JpegDecoder* d = dpe_host::jpeg_decoder_create(&err);

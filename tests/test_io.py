@@ -45,3 +45,37 @@ def test_cam_and_pair_parsers(tmp_path):
     n = lib.dpe_host_read_pairs(str(tmp_path / "pair.txt").encode(), buf.ctypes.data_as(C.c_void_p), 64)
     assert list(buf[:n]) == [7, 2, 1, 3, 1, 0, 2, 1, 1]
     assert lib.dpe_host_read_pairs(str(tmp_path / "missing.txt").encode(), buf.ctypes.data_as(C.c_void_p), 64) == -1
+
+
+def test_malformed_inputs_are_refused_quickly(tmp_path):
+    """Files that announce more than they hold.  A count in pair.txt that overflows an int used to become the bound of a
+    loop of failed extractions (the reference's GenerateSampleList has the same loop); a .dmb header with huge
+    dimensions used to size an allocation before the payload was looked at.  Both are plain errors now — found by running
+    the parsers under -fsanitize=address,undefined on a corpus of damaged files."""
+    import struct
+    import time
+    lib = capi.load()
+    lib.dpe_host_read_dmb.restype = C.c_long
+    buf = np.zeros(64, np.int32)
+    t0 = time.perf_counter()
+    for text in ("999999999999999999999\n0\n1 1 100.0\n",            # number of problems overflows
+                 "2\n0\n999999999999999999999 1 100.0\n1\n1 0 100.0\n",  # number of sources overflows
+                 "3\n0\n1 1 100.0\n",                                 # fewer problems than announced
+                 "x\n", "", "2\n0\n"):
+        (tmp_path / "pair.txt").write_text(text)
+        assert lib.dpe_host_read_pairs(str(tmp_path / "pair.txt").encode(), buf.ctypes.data_as(C.c_void_p), 64) == -1, text
+    # fewer sources on a line than announced: what is there is kept
+    (tmp_path / "pair.txt").write_text("1\n4\n5 1 10.0 2 20.0\n")
+    n = lib.dpe_host_read_pairs(str(tmp_path / "pair.txt").encode(), buf.ctypes.data_as(C.c_void_p), 64)
+    assert list(buf[:n]) == [4, 2, 1, 2]
+    r, c, t = C.c_int(), C.c_int(), C.c_int()
+    good = struct.pack("<4i", 1, 3, 5, 0) + bytes(range(15))
+    (tmp_path / "g.dmb").write_bytes(good)
+    assert lib.dpe_host_read_dmb(str(tmp_path / "g.dmb").encode(), C.byref(r), C.byref(c), C.byref(t)) == 15 and (r.value, c.value, t.value) == (3, 5, 0)
+    for bad in (struct.pack("<4i", 1, 2**31 - 1, 2**31 - 1, 21) + b"abc",      # 2^62 elements announced
+                struct.pack("<4i", 1, 3, 5, 4) + bytes(59),                      # one byte short
+                struct.pack("<4i", 1, 3, 5, 7) + bytes(64),                      # unknown type
+                struct.pack("<4i", 2, 3, 5, 0) + bytes(15), good[:10], b""):
+        (tmp_path / "b.dmb").write_bytes(bad)
+        assert lib.dpe_host_read_dmb(str(tmp_path / "b.dmb").encode(), C.byref(r), C.byref(c), C.byref(t)) == -1
+    assert time.perf_counter() - t0 < 5.0
