@@ -19,6 +19,10 @@ static inline int c_round(float v) { return (int)roundf(v); }   // std::round, h
 // fixed-point separable path: 11-bit coefficients, horizontal pass in int, vertical pass
 // ((b*(S>>4))>>16 summed, +2, >>2).
 void resize_linear_u8(const ImageU8& src, int dcols, int drows, ImageU8* dst) {
+  if (dcols <= 0 || drows <= 0 || src.cols <= 0 || src.rows <= 0) {  // cv::resize throws here; an empty image is the answer
+    *dst = ImageU8(std::max(drows, 0), std::max(dcols, 0));
+    return;
+  }
   ImageU8 out(drows, dcols);
   const int sw = src.cols, sh = src.rows;
   const double scale_x = (double)sw / dcols, scale_y = (double)sh / drows;
@@ -73,6 +77,7 @@ void resize_linear_u8(const ImageU8& src, int dcols, int drows, ImageU8* dst) {
 
 // cv::resize(INTER_LINEAR) for CV_32FC1 (same arithmetic as the GPU pyramid kernel)
 void resize_linear_f32(const float* src, int sw, int sh, float* dst, int dw, int dh) {
+  if (dw <= 0 || dh <= 0 || sw <= 0 || sh <= 0) return;
   const double scale_x = (double)sw / dw, scale_y = (double)sh / dh;
   for (int dy = 0; dy < dh; ++dy) {
     float fy = (float)((dy + 0.5) * scale_y - 0.5);
@@ -358,6 +363,7 @@ static void threshold_binary(ImageU8* img, int thr) {
 
 static void border_clean(ImageU8* dst) {  // DPE.cpp:239-250
   const int rows = dst->rows, cols = dst->cols;
+  if (rows < 2 || cols < 2) return;  // the reference indexes column 1 / row 1 regardless; a one-pixel-wide image has none
   for (int y = 0; y < rows; y++) {
     if (dst->at(y, 1) == 0) dst->at(y, 0) = 0;
     if (dst->at(y, cols - 2) == 0) dst->at(y, cols - 1) = 0;

@@ -101,3 +101,25 @@ def test_problem_edges_matches_oracle(lib, scale_size):
     assert np.array_equal(e, e_ref)
     assert (l > 0).any(), "the weak-texture test image must contain labelled regions"
     assert np.array_equal(l, l_ref)
+
+
+def test_degenerate_image_sizes_do_not_overrun():
+    """Images a pixel or two wide, flat / binary / noisy, at scale sizes 1, 2, 4 — a target size can round to zero
+    (cv::resize would throw) and the reference's border clean-up indexes column 1 and row 1 unconditionally
+    (DPE.cpp:239-250).  The prep must come back with arrays of the rounded size; guard bytes behind them stay intact.
+    (The same cases ran clean under -fsanitize=address,undefined.)"""
+    lib = capi.load()
+    rng = np.random.default_rng(11)
+    for (h, w) in [(1, 1), (1, 5), (5, 1), (2, 2), (3, 2), (2, 7), (4, 4), (9, 3)]:
+        for kind in range(3):
+            img = (rng.integers(0, 256, (h, w)) if kind == 0 else np.full((h, w), 128) if kind == 1 else rng.integers(0, 2, (h, w)) * 255).astype(np.uint8)
+            img = np.ascontiguousarray(img)
+            for ss in (1, 2, 4):
+                f = np.float32(1.0) / np.float32(ss)
+                oc, orr = int(np.floor(float(np.float32(w) * f) + 0.5)), int(np.floor(float(np.float32(h) * f) + 0.5))     # std::round
+                n = max(oc * orr, 0)
+                e = np.full(n + 16, 0xA5, np.uint8)
+                l = np.full(n + 16, 0x5A5A5A5A, np.int32)
+                lib.dpe_host_problem_edges(img.ctypes.data_as(C.c_void_p), w, h, ss, e.ctypes.data_as(C.c_void_p), l.ctypes.data_as(C.c_void_p))
+                assert (e[n:] == 0xA5).all() and (l[n:] == 0x5A5A5A5A).all(), (h, w, kind, ss)
+                assert set(np.unique(e[:n])) <= {0, 255}
