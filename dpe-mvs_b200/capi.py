@@ -126,6 +126,7 @@ def load(build=True):
     lib.dpe_fuse_set_view.argtypes = [vp, ci, vp, vp, vp, vp]
     lib.dpe_fuse_prepare.argtypes = [vp]
     lib.dpe_fuse_set_color.argtypes = [vp, ci, vp]
+    lib.dpe_fuse_set_block.argtypes = [vp, ci, vp]
     lib.dpe_fuse_broadcast_colors.argtypes = [vp, ci]
     lib.dpe_fuse_run.argtypes = [vp, ci, ci, C.POINTER(C.c_size_t)]
     lib.dpe_fuse_get.argtypes = [vp, vp, vp]

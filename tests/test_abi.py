@@ -3,6 +3,7 @@ without a GPU (no CPU fallback).  CPU only, no compute calls."""
 import ctypes as C
 import re
 import subprocess
+import sys
 from pathlib import Path
 
 import pytest
@@ -74,3 +75,26 @@ def test_schedule_matches_reference():
     assert abs(s[4][1].ransac_threshold - 0.00875) < 1e-7 and abs(s[8][1].ransac_threshold - 0.0075) < 1e-7
     assert capi.compute_round_num(640, 480) == 2 and capi.compute_round_num(1600, 1200) == 2
     assert capi.compute_round_num(3024, 2016) == 3 and capi.compute_round_num(1920, 1080) == 3
+
+
+def test_every_entry_point_declares_its_arguments_and_survives_null():
+    """ctypes passes an undeclared Python int as a 32-bit C int: a pointer handed to an entry point without argtypes is
+    cut in half.  Every symbol of the header must have its argtypes declared in capi.py, and — called with a null context
+    and null / zero arguments, in a child process — must come back with an error code instead of crashing."""
+    lib = capi.load()
+    assert [n for n in capi.SYMBOLS if getattr(lib, n).argtypes is None] == []
+    child = r"""
+import sys, ctypes as C
+sys.path.insert(0, %r)
+import capi
+lib = capi.load()
+ints = (C.c_int, C.c_long, C.c_size_t, C.c_uint64, C.c_uint32, C.c_longlong, C.c_ulonglong)
+for name in capi.SYMBOLS:
+    f = getattr(lib, name)
+    args = [t(0) if t in ints or t in (C.c_float, C.c_double) else None for t in f.argtypes]
+    print(name, flush=True)
+    f(*args)
+print("ALL-RETURNED")
+""" % str(ROOT / "dpe-mvs_b200")
+    p = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0 and "ALL-RETURNED" in p.stdout, (p.returncode, p.stdout.splitlines()[-1:], p.stderr[-300:])
