@@ -79,3 +79,19 @@ def test_malformed_inputs_are_refused_quickly(tmp_path):
         (tmp_path / "b.dmb").write_bytes(bad)
         assert lib.dpe_host_read_dmb(str(tmp_path / "b.dmb").encode(), C.byref(r), C.byref(c), C.byref(t)) == -1
     assert time.perf_counter() - t0 < 5.0
+
+
+def test_pipeline_refuses_bad_scenes_before_touching_a_gpu(tmp_path, capfd):
+    """The checks of GenerateSampleList / CheckImages / InuputInitialization that dpe_run_pipeline makes before it needs a
+    device: no pair.txt, a reference image listed twice, more than 31 sources (DPE.cpp:762-765: "Can't process so
+    much images") — each returns non-zero with the reference's message, with or without a GPU in the box."""
+    lib = capi.load()
+    run = lambda: lib.dpe_run_pipeline(str(tmp_path).encode(), 0, 0, 0, 0, 1, 0, 0, 0)
+    assert run() != 0
+    assert "Images may error" in capfd.readouterr().err
+    (tmp_path / "pair.txt").write_text("2\n0\n1 1 100.0\n0\n1 1 100.0\n")
+    assert run() != 0
+    assert "twice" in capfd.readouterr().err
+    (tmp_path / "pair.txt").write_text("1\n0\n32 " + " ".join(f"{i + 1} 100.0" for i in range(32)) + "\n")
+    assert run() != 0
+    assert "Can't process so much images: 33" in capfd.readouterr().err
