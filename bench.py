@@ -538,15 +538,15 @@ def run_reference(args):
     ref = ReferenceSample(M, local)
     # The first step doubles as a calibration: the reference's host part runs at very different speeds on different
     # boxes (18-26 s per 5-view step seen), and the driver chooses --steps.  If warm-up + timed steps of this sample
-    # would not fit the process's wall-clock budget, the sample shrinks (never below 2 views) before anything is timed.
+    # would not fit the process's wall-clock budget, the sample shrinks (down to one view) before anything is timed.
     warmed = 0
     if args.warmup + args.steps > 1 and "DPE_REF_SAMPLE_VIEWS" not in os.environ:
         dt = ref.step()[0]
         warmed = 1
         todo = args.warmup + args.steps - 1
         avail = time_left() - 30.0
-        if dt * todo > avail and M > 2:
-            M2 = max(2, int(M * avail / (dt * todo)))
+        if dt * todo > avail and M > 1:
+            M2 = max(1, int(M * avail / (dt * todo)))
             if M2 < M:
                 M, warmed = M2, 0
                 ref = ReferenceSample(M, local)
